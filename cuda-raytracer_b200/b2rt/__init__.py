@@ -1,0 +1,325 @@
+"""Python host mirror of the reference's renderer interface for the B200 hot path.
+
+The product is `libb2rt.so` (C ABI, include/b2rt.h; CUDA for sm_100a only).  This module is a thin
+ctypes binding whose classes keep the reference's names and call order:
+
+  PathTracer   <-> class PathTracer     (src/pathtracer.h:51-257)
+  BVHAccel     <-> class BVHAccel       (src/bvh.h:99-191), batch intersect instead of per-ray virtual calls
+  CudaRenderer <-> class CudaRenderer   (src/cudaRenderer.h:173-272), progressive render()/getImage()
+
+There is NO CPU fallback: if the library is missing or no CUDA device is visible, device calls raise.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+from ._abi import Camera, Config, Light, Material, SceneDesc, Stats
+from .scene import Scene, camera_rays, place_camera, random_soup, subdivide  # noqa: F401
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(os.path.dirname(_HERE), "libb2rt.so")
+
+EXPORTS = [
+    "b2rt_last_error", "b2rt_abi_version", "b2rt_device_count", "b2rt_bvh_build", "b2rt_bvh_intersect",
+    "b2rt_bvh_occluded", "b2rt_bvh_bench_rays", "b2rt_bvh_get_stats", "b2rt_bvh_get_bbox", "b2rt_bvh_destroy",
+    "b2rt_create", "b2rt_set_config", "b2rt_set_scene", "b2rt_set_camera", "b2rt_set_frame_size", "b2rt_start",
+    "b2rt_is_done", "b2rt_wait", "b2rt_stop", "b2rt_clear", "b2rt_render", "b2rt_read_hdr", "b2rt_read_ldr",
+    "b2rt_read_rgba32f", "b2rt_get_stats", "b2rt_accum_device_ptr", "b2rt_stream_handle", "b2rt_destroy",
+    "b2rt_scene_load", "b2rt_scene_save", "b2rt_load_dae", "b2rt_scene_free", "b2rt_camera_place",
+]
+
+
+class B2rtError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"b2rt error {code}: {msg}")
+        self.code = code
+
+
+_lib = None
+
+
+def lib():
+    """Load libb2rt.so (fails loudly when it has not been built: python __graft_entry__.py build)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise FileNotFoundError(f"{LIB_PATH} not built; run `make -C cuda-raytracer_b200/csrc` "
+                                    "(or __graft_entry__.build()); there is no CPU fallback")
+        L = C.CDLL(LIB_PATH)
+        L.b2rt_last_error.restype = C.c_char_p
+        vp, u32, u64, i32 = C.c_void_p, C.c_uint32, C.c_uint64, C.c_int32
+        L.b2rt_bvh_build.argtypes = [C.POINTER(SceneDesc), u32, u32, u32, i32, C.POINTER(vp)]
+        L.b2rt_bvh_intersect.argtypes = [vp, vp, vp, vp, vp, u64, vp, vp]
+        L.b2rt_bvh_occluded.argtypes = [vp, vp, vp, vp, vp, u64, vp]
+        L.b2rt_bvh_bench_rays.argtypes = [vp, u64, C.c_int, u64, C.c_int, C.c_int, C.POINTER(C.c_double), C.POINTER(u64)]
+        L.b2rt_bvh_get_stats.argtypes = [vp, C.POINTER(Stats)]
+        L.b2rt_bvh_get_bbox.argtypes = [vp, vp]
+        L.b2rt_bvh_destroy.argtypes = [vp]; L.b2rt_bvh_destroy.restype = None
+        L.b2rt_create.argtypes = [C.POINTER(Config), C.POINTER(vp)]
+        L.b2rt_set_config.argtypes = [vp, C.POINTER(Config)]
+        L.b2rt_set_scene.argtypes = [vp, C.POINTER(SceneDesc)]
+        L.b2rt_set_camera.argtypes = [vp, C.POINTER(Camera)]
+        L.b2rt_set_frame_size.argtypes = [vp, u32, u32]
+        for f in ("b2rt_start", "b2rt_is_done", "b2rt_wait", "b2rt_stop", "b2rt_clear", "b2rt_render"):
+            getattr(L, f).argtypes = [vp]
+        L.b2rt_read_hdr.argtypes = [vp, vp, C.c_size_t]
+        L.b2rt_read_ldr.argtypes = [vp, vp, C.c_size_t]
+        L.b2rt_read_rgba32f.argtypes = [vp, vp, C.c_size_t]
+        L.b2rt_get_stats.argtypes = [vp, C.POINTER(Stats)]
+        L.b2rt_accum_device_ptr.argtypes = [vp, C.POINTER(vp), C.POINTER(C.c_size_t)]
+        L.b2rt_stream_handle.argtypes = [vp, C.POINTER(vp)]
+        L.b2rt_destroy.argtypes = [vp]; L.b2rt_destroy.restype = None
+        L.b2rt_camera_place.argtypes = [vp, vp, C.c_float, C.c_float, u32, u32, C.POINTER(Camera)]
+        _lib = L
+    return _lib
+
+
+def _check(rc):
+    if rc < 0:
+        raise B2rtError(rc, lib().b2rt_last_error().decode())
+    return rc
+
+
+def device_count():
+    return lib().b2rt_device_count()
+
+
+def _f32(a, shape=None):
+    a = np.ascontiguousarray(a, np.float32)
+    return a if shape is None else a.reshape(shape)
+
+
+class BVHAccel:
+    """BVHAccel(primitives, max_leaf_size) -- src/bvh.h:110-112; closest / any-hit queries are batched."""
+
+    def __init__(self, scene, max_leaf_size=4, width=4, treelet_bytes=0, device=-1):
+        d, keep = scene.desc()
+        h = C.c_void_p()
+        _check(lib().b2rt_bvh_build(C.byref(d), max_leaf_size, width, treelet_bytes, device, C.byref(h)))
+        self._h = h
+        self.scene = scene
+
+    def close(self):
+        if getattr(self, "_h", None):
+            lib().b2rt_bvh_destroy(self._h); self._h = None
+
+    __del__ = close
+
+    def get_bbox(self):
+        out = np.zeros(6, np.float32)
+        _check(lib().b2rt_bvh_get_bbox(self._h, out.ctypes.data))
+        return out
+
+    def _rays(self, org, dirs, tmin, tmax):
+        org = _f32(org, (-1, 3)); dirs = _f32(dirs, (-1, 3))
+        n = len(org)
+        tmin = np.zeros(n, np.float32) if tmin is None else _f32(tmin)
+        tmax = np.full(n, np.inf, np.float32) if tmax is None else _f32(tmax)
+        return org, dirs, tmin, tmax, n
+
+    def intersect(self, org, dirs, tmin=None, tmax=None):
+        """Closest hit: returns (t[n] float32 (inf on miss), prim[n] uint32 (0xFFFFFFFF on miss))."""
+        org, dirs, tmin, tmax, n = self._rays(org, dirs, tmin, tmax)
+        t = np.empty(n, np.float32); prim = np.empty(n, np.uint32)
+        _check(lib().b2rt_bvh_intersect(self._h, org.ctypes.data, dirs.ctypes.data, tmin.ctypes.data, tmax.ctypes.data, n,
+                                        t.ctypes.data, prim.ctypes.data))
+        return t, prim
+
+    def occluded(self, org, dirs, tmin=None, tmax=None):
+        org, dirs, tmin, tmax, n = self._rays(org, dirs, tmin, tmax)
+        occ = np.empty(n, np.uint8)
+        _check(lib().b2rt_bvh_occluded(self._h, org.ctypes.data, dirs.ctypes.data, tmin.ctypes.data, tmax.ctypes.data, n,
+                                       occ.ctypes.data))
+        return occ.astype(bool)
+
+    def bench_rays(self, n, mode=0, seed=1, repeats=3, any_hit=False):
+        ms = C.c_double(0); hits = C.c_uint64(0)
+        _check(lib().b2rt_bvh_bench_rays(self._h, n, mode, seed, repeats, int(any_hit), C.byref(ms), C.byref(hits)))
+        return ms.value, hits.value
+
+    def stats(self):
+        s = Stats()
+        _check(lib().b2rt_bvh_get_stats(self._h, C.byref(s)))
+        return s.as_dict()
+
+
+class PathTracer:
+    """Mirror of class PathTracer (src/pathtracer.h:51-257): same knobs, same call order.
+
+    pt = PathTracer(ns_aa=16, max_ray_depth=4, ns_area_light=1); pt.set_scene(scene); pt.set_camera(cam)
+    pt.set_frame_size(w, h); pt.start_raytracing(); while not pt.is_done(): ...; pt.save_image("out.png")
+    """
+    INIT, READY, RENDERING, DONE = "INIT", "READY", "RENDERING", "DONE"
+
+    def __init__(self, ns_aa=1, max_ray_depth=4, ns_area_light=1, ns_diff=1, ns_glsy=1, ns_refr=1, num_threads=1,
+                 envmap=None, seed=0, device=-1, bvh_width=0, max_leaf_size=0, treelet_bytes=0, max_wave_paths=0,
+                 median_threshold=0, sample_first=0, sample_stride=1, ray_eps=0.0):
+        self.cfg = Config(ns_aa=ns_aa, max_ray_depth=max_ray_depth, ns_area_light=ns_area_light, seed=seed,
+                          ray_eps=ray_eps, bvh_width=bvh_width, max_leaf_size=max_leaf_size,
+                          treelet_bytes=treelet_bytes, max_wave_paths=max_wave_paths,
+                          median_threshold=median_threshold, device=device, sample_first=sample_first,
+                          sample_stride=sample_stride)
+        h = C.c_void_p()
+        _check(lib().b2rt_create(C.byref(self.cfg), C.byref(h)))
+        self._h = h
+        self._scene = self._camera = None
+        self.width = self.height = 0
+        self.state = self.INIT
+
+    def close(self):
+        if getattr(self, "_h", None):
+            lib().b2rt_destroy(self._h); self._h = None
+
+    __del__ = close
+
+    def _maybe_ready(self):
+        if self.state == self.INIT and self._scene is not None and self._camera is not None and self.width:
+            self.state = self.READY
+
+    def set_config(self, **kw):
+        for k, v in kw.items():
+            setattr(self.cfg, k, v)
+        _check(lib().b2rt_set_config(self._h, C.byref(self.cfg)))
+
+    def set_scene(self, scene):
+        d, keep = scene.desc()
+        _check(lib().b2rt_set_scene(self._h, C.byref(d)))
+        self._scene = scene
+        if self.state != self.INIT:
+            self.state = self.READY
+        self._maybe_ready()
+
+    def set_camera(self, camera):
+        _check(lib().b2rt_set_camera(self._h, C.byref(camera)))
+        self._camera = camera
+        if self.state != self.INIT:
+            self.state = self.READY
+        self._maybe_ready()
+
+    def set_frame_size(self, width, height):
+        _check(lib().b2rt_set_frame_size(self._h, width, height))
+        self.width, self.height = width, height
+        if self.state != self.INIT:
+            self.state = self.READY      # pathtracer.cpp:105-114
+        self._maybe_ready()
+
+    def start_raytracing(self):
+        if self.state not in (self.READY, self.DONE):   # pathtracer.cpp:184 (only from READY); DONE re-renders
+            return False
+        _check(lib().b2rt_start(self._h))
+        self.state = self.RENDERING
+        return True
+
+    def is_done(self):
+        if self.state == self.RENDERING and _check(lib().b2rt_is_done(self._h)) == 1:
+            self.state = self.DONE
+        return self.state == self.DONE
+
+    def wait(self):
+        _check(lib().b2rt_wait(self._h))
+        if self.state == self.RENDERING:
+            self.state = self.DONE
+
+    def stop(self):
+        _check(lib().b2rt_stop(self._h))
+        if self.state in (self.RENDERING, self.DONE):
+            self.state = self.READY
+
+    def clear(self):
+        _check(lib().b2rt_clear(self._h))
+
+    def render(self):
+        """Blocking start + wait (accumulates ns_aa more samples, like CudaRenderer::render)."""
+        _check(lib().b2rt_render(self._h))
+        self.state = self.DONE
+
+    def increase_area_light_sample_count(self):      # pathtracer.cpp:560-564
+        self.set_config(ns_area_light=self.cfg.ns_area_light * 2)
+
+    def decrease_area_light_sample_count(self):      # pathtracer.cpp:566-570
+        self.set_config(ns_area_light=max(1, self.cfg.ns_area_light // 2))
+
+    def hdr(self):
+        """HDRImageBuffer: float32 [h, w, 3], row 0 = bottom row, index x + y*w (src/image.h:114-118)."""
+        out = np.empty((self.height, self.width, 3), np.float32)
+        _check(lib().b2rt_read_hdr(self._h, out.ctypes.data, out.size))
+        return out
+
+    def ldr(self):
+        """ImageBuffer: uint32 RGBA8 [h, w] via toColor (src/image.h:49-58,173-188)."""
+        out = np.empty((self.height, self.width), np.uint32)
+        _check(lib().b2rt_read_ldr(self._h, out.ctypes.data, out.size))
+        return out
+
+    def rgba32f(self):
+        out = np.empty((self.height, self.width, 4), np.float32)
+        _check(lib().b2rt_read_rgba32f(self._h, out.ctypes.data, out.size))
+        return out
+
+    def save_image(self, filename):
+        """PNG, vertically flipped like PathTracer::save_image (src/pathtracer.cpp:577-591)."""
+        from PIL import Image
+        ldr = self.ldr()[::-1]
+        rgba = np.stack([(ldr >> s) & 255 for s in (0, 8, 16, 24)], -1).astype(np.uint8)
+        Image.fromarray(rgba, "RGBA").save(filename)
+
+    def stats(self):
+        s = Stats()
+        _check(lib().b2rt_get_stats(self._h, C.byref(s)))
+        return s.as_dict()
+
+    def accum_device_ptr(self):
+        p = C.c_void_p(); n = C.c_size_t(0)
+        _check(lib().b2rt_accum_device_ptr(self._h, C.byref(p), C.byref(n)))
+        return p.value, n.value
+
+    def accum_tensor(self):
+        """The per-GPU accumulation buffer (rgb sum + count per pixel) as a torch CUDA tensor view, for the
+        one NCCL reduce of the multi-GPU path (b2rt/dist.py)."""
+        import torch
+        ptr, n = self.accum_device_ptr()
+
+        class _Wrap:
+            pass
+        w = _Wrap()
+        w.__cuda_array_interface__ = {"shape": (n,), "typestr": "<f4", "data": (ptr, False), "version": 2}
+        dev = self.cfg.device if self.cfg.device >= 0 else torch.cuda.current_device()
+        return torch.as_tensor(w, device=f"cuda:{dev}")
+
+
+class CudaRenderer:
+    """Mirror of cutracer::CudaRenderer (src/cudaRenderer.h:173-272): progressive accumulation."""
+
+    def __init__(self, samples_per_frame=2, max_ray_depth=3, ns_area_light=2, median_threshold=32, **kw):
+        self.pt = PathTracer(ns_aa=samples_per_frame, max_ray_depth=max_ray_depth, ns_area_light=ns_area_light,
+                             median_threshold=median_threshold, **kw)
+        self.scene = None
+        self.frames = 0
+
+    def allocOutputImage(self, width, height):
+        self.pt.set_frame_size(width, height)
+
+    def loadScene(self, scene_or_path):
+        self.scene = Scene.load(scene_or_path) if isinstance(scene_or_path, str) else scene_or_path
+        self.pt.set_scene(self.scene)
+
+    def setup(self):
+        if self.pt._camera is None:
+            self.pt.set_camera(place_camera(self.scene, self.pt.width, self.pt.height))
+
+    def setViewpoint(self, camera):
+        self.pt.set_camera(camera)       # resets accumulation, cudaRenderer.cu:1866-1869
+        self.frames = 0
+
+    def clearImage(self):
+        self.pt.clear(); self.frames = 0
+
+    def render(self):
+        # every frame draws fresh samples: shift the sample window
+        self.pt.set_config(sample_first=self.frames * self.pt.cfg.ns_aa)
+        self.pt.render()
+        self.frames += 1
+
+    def getImage(self):
+        return self.pt.rgba32f()

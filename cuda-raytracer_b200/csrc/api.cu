@@ -1,0 +1,397 @@
+// C ABI of the b2rt library (include/b2rt.h).  Thin: argument checks, handle management, host<->device
+// copies of caller buffers.  Every function documents the reference interface it replaces in b2rt.h.
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "render.cuh"
+#include "rt_device.cuh"
+
+namespace b2rt {
+static thread_local std::string g_error;
+void set_error(const std::string& msg) { g_error = msg; }
+}  // namespace b2rt
+
+using namespace b2rt;
+
+struct b2rt_bvh {
+  int device = 0;
+  DeviceBVH dbvh;
+  Tracer tracer;
+  WideBVH host_meta;     // blob released after upload; keeps levels / counts
+  cudaStream_t stream = nullptr;
+  uint64_t ray_cap = 0;
+  float4 *ray_o = nullptr, *ray_d = nullptr;
+  unsigned long long* hits = nullptr;
+  uint32_t* n_dev = nullptr;
+  b2rt_stats last{};
+};
+struct b2rt_renderer { Renderer r; };
+
+namespace {
+
+__global__ void k_pack_rays(const float* __restrict__ org, const float* __restrict__ dir, const float* __restrict__ tmin,
+                            const float* __restrict__ tmax, uint32_t n, float4* ro, float4* rd, unsigned long long* hits) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  ro[i] = make_float4(org[3 * i], org[3 * i + 1], org[3 * i + 2], tmin[i]);
+  rd[i] = make_float4(dir[3 * i], dir[3 * i + 1], dir[3 * i + 2], tmax[i]);
+  hits[i] = pack_hit(tmax[i], 0xFFFFFFFFu);
+}
+__global__ void k_unpack_hits(const unsigned long long* __restrict__ hits, uint32_t n, float* t, uint32_t* prim, uint8_t* occ) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  unsigned long long h = hits[i];
+  uint32_t p = (uint32_t)h;
+  if (occ) occ[i] = p != 0xFFFFFFFFu;
+  if (t) t[i] = p == 0xFFFFFFFFu ? __builtin_huge_valf() : __uint_as_float((uint32_t)(h >> 32));
+  if (prim) prim[i] = p;
+}
+// synthetic rays for kernel-only timing: mode 0 coherent (pinhole toward the box), mode 1 incoherent
+__global__ void k_gen_rays(uint32_t n, int mode, uint32_t k0, uint32_t k1, float3 lo, float3 hi, float4* ro, float4* rd,
+                           unsigned long long* hits) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float3 c = make_float3(0.5f * (lo.x + hi.x), 0.5f * (lo.y + hi.y), 0.5f * (lo.z + hi.z));
+  const float3 e = make_float3(hi.x - lo.x, hi.y - lo.y, hi.z - lo.z);
+  const float R = 0.5f * sqrtf(e.x * e.x + e.y * e.y + e.z * e.z);
+  f3 o, d;
+  if (mode == 0) {
+    // camera at c + (0,0,2.2R), image plane side^2 pixels, 8x4-pixel tiles per warp for coherence
+    const uint32_t side = (uint32_t)ceilf(sqrtf((float)n));
+    const uint32_t tile = i / 32, in = i % 32;
+    const uint32_t tiles_x = (side + 7) / 8;
+    const uint32_t px = (tile % tiles_x) * 8 + (in % 8), py = (tile / tiles_x) * 4 + (in / 8);
+    const uint4 r = philox4x32_10(i, 0, 0, 7, k0, k1);
+    const float sx = ((float)px + u01(r.x)) / (float)side, sy = ((float)py + u01(r.y)) / (float)(side);
+    o = mk3(c.x, c.y, c.z + 2.2f * R);
+    d = normalize3(mk3((2.f * sx - 1.f) * 0.6f, (2.f * sy - 1.f) * 0.6f, -1.f));
+  } else {
+    const uint4 r = philox4x32_10(i, 1, 0, 7, k0, k1);
+    const uint4 q = philox4x32_10(i, 2, 0, 7, k0, k1);
+    o = mk3(lo.x + e.x * u01(r.x), lo.y + e.y * u01(r.y), lo.z + e.z * u01(r.z));
+    const float z = 1.f - 2.f * u01(q.x);
+    float s, cs;
+    sincos2pi(u01(q.y), &s, &cs);
+    const float rr = sqrtf(fmaxf(0.f, 1.f - z * z));
+    d = mk3(rr * cs, rr * s, z);
+  }
+  ro[i] = make_float4(o.x, o.y, o.z, 0.f);
+  rd[i] = make_float4(d.x, d.y, d.z, __builtin_huge_valf());
+  hits[i] = pack_hit(__builtin_huge_valf(), 0xFFFFFFFFu);
+}
+__global__ void k_reset_hits(uint32_t n, const float4* rd, unsigned long long* hits) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) hits[i] = pack_hit(rd[i].w, 0xFFFFFFFFu);
+}
+__global__ void k_count_hits(uint32_t n, const unsigned long long* hits, unsigned long long* out) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  bool h = i < n && (uint32_t)hits[i] != 0xFFFFFFFFu;
+  uint32_t m = __ballot_sync(0xffffffffu, h);
+  if ((threadIdx.x & 31) == 0 && m) atomicAdd(out, (unsigned long long)__popc(m));
+}
+
+int ensure_rays(b2rt_bvh* b, uint64_t n) {
+  if (b->ray_cap >= n) return B2RT_OK;
+  if (b->ray_o) { cudaFree(b->ray_o); cudaFree(b->ray_d); cudaFree(b->hits); b->ray_o = b->ray_d = nullptr; b->hits = nullptr; }
+  b->tracer.release();
+  b->ray_cap = 0;
+  B2RT_CUDA_OK(cudaMalloc(&b->ray_o, n * sizeof(float4)));
+  B2RT_CUDA_OK(cudaMalloc(&b->ray_d, n * sizeof(float4)));
+  B2RT_CUDA_OK(cudaMalloc(&b->hits, n * 8));
+  int rc = b->tracer.init(b->dbvh, n, 6);
+  if (rc) return rc;
+  b->ray_cap = n;
+  return B2RT_OK;
+}
+
+int has_device() {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+  return n;
+}
+
+// closest / any-hit on host rays in batches (split on queue overflow)
+int intersect_host(b2rt_bvh* b, const float* org, const float* dir, const float* tmin, const float* tmax, uint64_t n,
+                   float* hit_t, uint32_t* hit_prim, uint8_t* occluded, bool any_hit) {
+  if (!b || (n && (!org || !dir || !tmin || !tmax))) { set_error("null argument"); return B2RT_ERR_INVALID; }
+  B2RT_CUDA_OK(cudaSetDevice(b->device));
+  uint64_t batch = std::min<uint64_t>(n, 1u << 22);
+  if (batch == 0) return B2RT_OK;
+  float *d_org = nullptr, *d_dir = nullptr, *d_tmin = nullptr, *d_tmax = nullptr, *d_t = nullptr;
+  uint32_t* d_prim = nullptr; uint8_t* d_occ = nullptr;
+  auto cleanup = [&]() { cudaFree(d_org); cudaFree(d_dir); cudaFree(d_tmin); cudaFree(d_tmax); cudaFree(d_t); cudaFree(d_prim); cudaFree(d_occ); };
+  int rc = ensure_rays(b, batch);
+  if (rc) return rc;
+  if (cudaMalloc(&d_org, batch * 12) || cudaMalloc(&d_dir, batch * 12) || cudaMalloc(&d_tmin, batch * 4) ||
+      cudaMalloc(&d_tmax, batch * 4) || cudaMalloc(&d_t, batch * 4) || cudaMalloc(&d_prim, batch * 4) || cudaMalloc(&d_occ, batch)) {
+    cleanup(); set_error("cudaMalloc failed for ray staging"); cudaGetLastError(); return B2RT_ERR_OOM;
+  }
+  cudaStream_t s = b->stream;
+  b->tracer.launches = 0;
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0); cudaEventCreate(&e1);
+  double ms_sum = 0;
+  uint64_t done = 0;
+  while (done < n) {
+    uint64_t m = std::min<uint64_t>(batch, n - done);
+    for (;;) {
+      cudaMemcpyAsync(d_org, org + 3 * done, m * 12, cudaMemcpyHostToDevice, s);
+      cudaMemcpyAsync(d_dir, dir + 3 * done, m * 12, cudaMemcpyHostToDevice, s);
+      cudaMemcpyAsync(d_tmin, tmin + done, m * 4, cudaMemcpyHostToDevice, s);
+      cudaMemcpyAsync(d_tmax, tmax + done, m * 4, cudaMemcpyHostToDevice, s);
+      uint32_t m32 = (uint32_t)m;
+      cudaMemcpyAsync(b->n_dev, &m32, 4, cudaMemcpyHostToDevice, s);
+      cudaEventRecord(e0, s);
+      k_pack_rays<<<(m32 + 255) / 256, 256, 0, s>>>(d_org, d_dir, d_tmin, d_tmax, m32, b->ray_o, b->ray_d, b->hits);
+      rc = b->tracer.trace(s, b->ray_o, b->ray_d, b->hits, nullptr, b->n_dev, any_hit);
+      if (rc) { cleanup(); return rc; }
+      k_unpack_hits<<<(m32 + 255) / 256, 256, 0, s>>>(b->hits, m32, d_t, d_prim, d_occ);
+      cudaEventRecord(e1, s);
+      bool ovf = false;
+      rc = b->tracer.check_overflow(s, &ovf);
+      if (rc) { cleanup(); return rc; }
+      if (!ovf) break;
+      if (m <= 1024) { cleanup(); set_error("ray queue overflow on a minimal batch"); return B2RT_ERR_OVERFLOW; }
+      m = m / 2;   // split the batch and retry
+    }
+    float ms = 0; cudaEventElapsedTime(&ms, e0, e1); ms_sum += ms;
+    if (hit_t) cudaMemcpyAsync(hit_t + done, d_t, m * 4, cudaMemcpyDeviceToHost, s);
+    if (hit_prim) cudaMemcpyAsync(hit_prim + done, d_prim, m * 4, cudaMemcpyDeviceToHost, s);
+    if (occluded) cudaMemcpyAsync(occluded + done, d_occ, m, cudaMemcpyDeviceToHost, s);
+    cudaError_t e = cudaStreamSynchronize(s);
+    if (e != cudaSuccess) { cleanup(); set_error(std::string("intersect: ") + cudaGetErrorString(e)); return B2RT_ERR_CUDA; }
+    done += m;
+  }
+  cudaEventDestroy(e0); cudaEventDestroy(e1);
+  cleanup();
+  TraceCounters tc;
+  cudaMemcpy(&tc, b->tracer.counters, sizeof tc, cudaMemcpyDeviceToHost);
+  b->last.node_visits = tc.node_visits; b->last.leaf_prim_tests = tc.prim_tests; b->last.subtree_visits = tc.subtree_visits;
+  b->last.queue_pushes = tc.pushes; b->last.kernel_launches = b->tracer.launches; b->last.ms_total = ms_sum; b->last.ms_traverse = ms_sum;
+  cudaMemset(b->tracer.counters, 0, sizeof tc);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) { set_error(std::string("intersect: ") + cudaGetErrorString(e)); return B2RT_ERR_CUDA; }
+  return B2RT_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* b2rt_last_error(void) { return g_error.c_str(); }
+int b2rt_abi_version(void) { return B2RT_ABI_VERSION; }
+int b2rt_device_count(void) { return has_device(); }
+
+int b2rt_bvh_build(const b2rt_scene_desc* scene, uint32_t max_leaf_size, uint32_t width, uint32_t treelet_bytes,
+                   int32_t device, b2rt_bvh** out) {
+  if (!out) { set_error("out is null"); return B2RT_ERR_INVALID; }
+  *out = nullptr;
+  if (!has_device()) { set_error("no CUDA device available (b2rt has no CPU fallback)"); return B2RT_ERR_NO_DEVICE; }
+  HostScene hs;
+  int rc = make_host_scene(scene, &hs);
+  if (rc) return rc;
+  b2rt_bvh* b = new (std::nothrow) b2rt_bvh();
+  if (!b) return B2RT_ERR_OOM;
+  if (device < 0) cudaGetDevice(&device);
+  b->device = device;
+  B2RT_CUDA_OK(cudaSetDevice(device));
+  rc = build_wide_bvh(hs, max_leaf_size, width, treelet_bytes, &b->host_meta);
+  if (rc) { delete b; return rc; }
+  rc = upload_bvh(b->host_meta, &b->dbvh);
+  if (rc) { delete b; return rc; }
+  b->host_meta.blob.clear(); b->host_meta.blob.shrink_to_fit();
+  B2RT_CUDA_OK(cudaStreamCreateWithFlags(&b->stream, cudaStreamNonBlocking));
+  B2RT_CUDA_OK(cudaMalloc(&b->n_dev, 4));
+  b->tracer.bvh = b->dbvh;
+  b->tracer.collect_stats = true;
+  *out = b;
+  return B2RT_OK;
+}
+
+int b2rt_bvh_intersect(b2rt_bvh* bvh, const float* org, const float* dir, const float* tmin, const float* tmax, uint64_t n,
+                       float* hit_t, uint32_t* hit_prim) {
+  return intersect_host(bvh, org, dir, tmin, tmax, n, hit_t, hit_prim, nullptr, false);
+}
+int b2rt_bvh_occluded(b2rt_bvh* bvh, const float* org, const float* dir, const float* tmin, const float* tmax, uint64_t n,
+                      uint8_t* occluded) {
+  return intersect_host(bvh, org, dir, tmin, tmax, n, nullptr, nullptr, occluded, true);
+}
+
+int b2rt_bvh_bench_rays(b2rt_bvh* b, uint64_t n, int mode, uint64_t seed, int repeats, int any_hit, double* ms_per_repeat,
+                        uint64_t* hits_out) {
+  if (!b || n == 0 || n > 0x7FFFFFFFull || repeats < 1) { set_error("bad argument"); return B2RT_ERR_INVALID; }
+  B2RT_CUDA_OK(cudaSetDevice(b->device));
+  const bool keep_stats = b->tracer.collect_stats;
+  int rc = ensure_rays(b, n);
+  if (rc) return rc;
+  cudaStream_t s = b->stream;
+  const uint32_t n32 = (uint32_t)n;
+  B2RT_CUDA_OK(cudaMemcpyAsync(b->n_dev, &n32, 4, cudaMemcpyHostToDevice, s));
+  const float* bb = b->host_meta.bbox;
+  k_gen_rays<<<(n32 + 255) / 256, 256, 0, s>>>(n32, mode, (uint32_t)seed, (uint32_t)(seed >> 32), make_float3(bb[0], bb[1], bb[2]),
+                                               make_float3(bb[3], bb[4], bb[5]), b->ray_o, b->ray_d, b->hits);
+  b->tracer.launches = 0;
+  B2RT_CUDA_OK(cudaMemsetAsync(b->tracer.counters, 0, sizeof(TraceCounters), s));
+  // one untimed pass with statistics, then `repeats` timed passes without
+  b->tracer.collect_stats = true;
+  rc = b->tracer.trace(s, b->ray_o, b->ray_d, b->hits, nullptr, b->n_dev, any_hit != 0);
+  if (rc) return rc;
+  bool ovf = false;
+  rc = b->tracer.check_overflow(s, &ovf);
+  if (rc) return rc;
+  if (ovf) { b->tracer.collect_stats = keep_stats; set_error("ray queue overflow: use fewer rays per batch"); return B2RT_ERR_OVERFLOW; }
+  TraceCounters tc;
+  B2RT_CUDA_OK(cudaMemcpy(&tc, b->tracer.counters, sizeof tc, cudaMemcpyDeviceToHost));
+  b->tracer.collect_stats = false;
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0); cudaEventCreate(&e1);
+  double total = 0;
+  for (int r = 0; r < repeats; ++r) {
+    k_reset_hits<<<(n32 + 255) / 256, 256, 0, s>>>(n32, b->ray_d, b->hits);
+    cudaEventRecord(e0, s);
+    rc = b->tracer.trace(s, b->ray_o, b->ray_d, b->hits, nullptr, b->n_dev, any_hit != 0);
+    cudaEventRecord(e1, s);
+    if (rc) return rc;
+    B2RT_CUDA_OK(cudaEventSynchronize(e1));
+    float ms = 0; cudaEventElapsedTime(&ms, e0, e1); total += ms;
+  }
+  cudaEventDestroy(e0); cudaEventDestroy(e1);
+  b->tracer.collect_stats = keep_stats;
+  if (ms_per_repeat) *ms_per_repeat = total / repeats;
+  unsigned long long* d_cnt = nullptr;
+  B2RT_CUDA_OK(cudaMalloc(&d_cnt, 8));
+  B2RT_CUDA_OK(cudaMemsetAsync(d_cnt, 0, 8, s));
+  k_count_hits<<<(n32 + 255) / 256, 256, 0, s>>>(n32, b->hits, d_cnt);
+  unsigned long long hc = 0;
+  B2RT_CUDA_OK(cudaMemcpyAsync(&hc, d_cnt, 8, cudaMemcpyDeviceToHost, s));
+  B2RT_CUDA_OK(cudaStreamSynchronize(s));
+  cudaFree(d_cnt);
+  if (hits_out) *hits_out = hc;
+  b->last.node_visits = tc.node_visits; b->last.leaf_prim_tests = tc.prim_tests; b->last.subtree_visits = tc.subtree_visits;
+  b->last.queue_pushes = tc.pushes; b->last.ms_total = total / repeats; b->last.ms_traverse = total / repeats;
+  b->last.kernel_launches = b->tracer.launches / (uint64_t)(repeats + 1);
+  b->last.rays_camera = n;
+  return B2RT_OK;
+}
+
+int b2rt_bvh_get_stats(b2rt_bvh* b, b2rt_stats* out) {
+  if (!b || !out) { set_error("null argument"); return B2RT_ERR_INVALID; }
+  *out = b->last;
+  out->ms_build = b->host_meta.build_ms;
+  out->bvh_nodes = b->host_meta.n_wide_nodes; out->bvh_subtrees = b->dbvh.n_treelets; out->bvh_levels = b->dbvh.n_levels;
+  out->bvh_width = b->dbvh.width; out->bvh_bytes = b->dbvh.blob_bytes;
+  return B2RT_OK;
+}
+int b2rt_bvh_get_bbox(b2rt_bvh* b, float* out6) {
+  if (!b || !out6) { set_error("null argument"); return B2RT_ERR_INVALID; }
+  memcpy(out6, b->host_meta.bbox, 24);
+  return B2RT_OK;
+}
+void b2rt_bvh_destroy(b2rt_bvh* b) {
+  if (!b) return;
+  cudaSetDevice(b->device);
+  if (b->stream) cudaStreamSynchronize(b->stream);
+  b->tracer.release();
+  free_bvh(&b->dbvh);
+  cudaFree(b->ray_o); cudaFree(b->ray_d); cudaFree(b->hits); cudaFree(b->n_dev);
+  if (b->stream) cudaStreamDestroy(b->stream);
+  delete b;
+}
+
+// ---- renderer ----
+int b2rt_create(const b2rt_config* cfg, b2rt_renderer** out) {
+  if (!cfg || !out) { set_error("null argument"); return B2RT_ERR_INVALID; }
+  *out = nullptr;
+  b2rt_renderer* h = new (std::nothrow) b2rt_renderer();
+  if (!h) return B2RT_ERR_OOM;
+  int rc = h->r.create(cfg);
+  if (rc) { delete h; return rc; }
+  *out = h;
+  return B2RT_OK;
+}
+int b2rt_set_config(b2rt_renderer* h, const b2rt_config* cfg) {
+  if (!h || !cfg) { set_error("null argument"); return B2RT_ERR_INVALID; }
+  if (h->r.running) { int rc = h->r.wait(); if (rc) return rc; }
+  const b2rt_config old = h->r.cfg;
+  h->r.cfg = *cfg;
+  h->r.cfg.device = old.device;  // the device is fixed at creation
+  // BVH parameters only take effect at the next set_scene
+  return B2RT_OK;
+}
+int b2rt_set_scene(b2rt_renderer* h, const b2rt_scene_desc* s) { if (!h) { set_error("null handle"); return B2RT_ERR_INVALID; } return h->r.set_scene(s); }
+int b2rt_set_camera(b2rt_renderer* h, const b2rt_camera* c) { if (!h || !c) { set_error("null argument"); return B2RT_ERR_INVALID; } return h->r.set_camera(c); }
+int b2rt_set_frame_size(b2rt_renderer* h, uint32_t w, uint32_t hh) { if (!h) { set_error("null handle"); return B2RT_ERR_INVALID; } return h->r.set_frame_size(w, hh); }
+int b2rt_start(b2rt_renderer* h) { if (!h) { set_error("null handle"); return B2RT_ERR_INVALID; } return h->r.start(); }
+int b2rt_is_done(b2rt_renderer* h) { if (!h) { set_error("null handle"); return B2RT_ERR_INVALID; } return h->r.is_done(); }
+int b2rt_wait(b2rt_renderer* h) { if (!h) { set_error("null handle"); return B2RT_ERR_INVALID; } return h->r.wait(); }
+int b2rt_stop(b2rt_renderer* h) { if (!h) { set_error("null handle"); return B2RT_ERR_INVALID; } return h->r.stop(); }
+int b2rt_clear(b2rt_renderer* h) { if (!h) { set_error("null handle"); return B2RT_ERR_INVALID; } return h->r.clear(); }
+int b2rt_render(b2rt_renderer* h) {
+  if (!h) { set_error("null handle"); return B2RT_ERR_INVALID; }
+  int rc = h->r.start();
+  if (rc) return rc;
+  return h->r.wait();
+}
+
+static int read_common(b2rt_renderer* h, bool ldr) {
+  if (!h) { set_error("null handle"); return B2RT_ERR_INVALID; }
+  return h->r.resolve(ldr);
+}
+int b2rt_read_rgba32f(b2rt_renderer* h, float* rgba, size_t n_floats) {
+  int rc = read_common(h, false);
+  if (rc) return rc;
+  const size_t np = (size_t)h->r.width * h->r.height;
+  if (!rgba || n_floats < np * 4) { set_error("output buffer too small"); return B2RT_ERR_INVALID; }
+  B2RT_CUDA_OK(cudaMemcpyAsync(rgba, h->r.resolved, np * 16, cudaMemcpyDeviceToHost, h->r.stream));
+  B2RT_CUDA_OK(cudaStreamSynchronize(h->r.stream));
+  return B2RT_OK;
+}
+int b2rt_read_hdr(b2rt_renderer* h, float* rgb, size_t n_floats) {
+  if (!h) { set_error("null handle"); return B2RT_ERR_INVALID; }
+  const size_t np = (size_t)h->r.width * h->r.height;
+  if (!rgb || n_floats < np * 3) { set_error("output buffer too small"); return B2RT_ERR_INVALID; }
+  std::vector<float> tmp(np * 4);
+  int rc = b2rt_read_rgba32f(h, tmp.data(), tmp.size());
+  if (rc) return rc;
+  for (size_t i = 0; i < np; ++i) { rgb[3 * i] = tmp[4 * i]; rgb[3 * i + 1] = tmp[4 * i + 1]; rgb[3 * i + 2] = tmp[4 * i + 2]; }
+  return B2RT_OK;
+}
+int b2rt_read_ldr(b2rt_renderer* h, uint32_t* rgba8, size_t n_pixels) {
+  int rc = read_common(h, true);
+  if (rc) return rc;
+  const size_t np = (size_t)h->r.width * h->r.height;
+  if (!rgba8 || n_pixels < np) { set_error("output buffer too small"); return B2RT_ERR_INVALID; }
+  B2RT_CUDA_OK(cudaMemcpyAsync(rgba8, h->r.ldr, np * 4, cudaMemcpyDeviceToHost, h->r.stream));
+  B2RT_CUDA_OK(cudaStreamSynchronize(h->r.stream));
+  return B2RT_OK;
+}
+int b2rt_get_stats(b2rt_renderer* h, b2rt_stats* out) {
+  if (!h || !out) { set_error("null argument"); return B2RT_ERR_INVALID; }
+  h->r.fill_stats(out);
+  return B2RT_OK;
+}
+int b2rt_accum_device_ptr(b2rt_renderer* h, void** dev_ptr, size_t* n_floats) {
+  if (!h || !dev_ptr || !h->r.accum) { set_error("no frame buffer"); return B2RT_ERR_INVALID; }
+  *dev_ptr = h->r.accum;
+  if (n_floats) *n_floats = (size_t)h->r.width * h->r.height * 4;
+  return B2RT_OK;
+}
+int b2rt_stream_handle(b2rt_renderer* h, void** s) {
+  if (!h || !s) { set_error("null argument"); return B2RT_ERR_INVALID; }
+  *s = (void*)h->r.stream;
+  return B2RT_OK;
+}
+void b2rt_destroy(b2rt_renderer* h) {
+  if (!h) return;
+  h->r.set_device();
+  h->r.destroy();
+  delete h;
+}
+
+}  // extern "C"

@@ -1,0 +1,65 @@
+// Internal types shared by the host builder and the CUDA kernels of the b2rt library.
+// Data layout in HBM is described in DESIGN.md ("Data layout").
+#pragma once
+#include <cstddef>
+#include <cstdint>
+#include <string>
+#include <vector>
+
+#include "../../include/b2rt.h"
+
+namespace b2rt {
+
+// ---- child reference encoding inside a wide node (32 bit) ----------------------------------------
+// tag = ref >> 30 : 0 INTERNAL (payload = node index local to the subtree blob)
+//                   1 LEAF     (payload = (count-1) << 24 | first primitive, local to the blob)
+//                   2 EXIT     (payload = id of the child subtree the ray must be queued at)
+//                   3 EMPTY
+constexpr uint32_t REF_INTERNAL = 0u, REF_LEAF = 1u, REF_EXIT = 2u, REF_EMPTY = 3u;
+constexpr uint32_t REF_EMPTY_WORD = 0xFFFFFFFFu;
+inline uint32_t make_ref(uint32_t tag, uint32_t payload) { return (tag << 30) | payload; }
+
+constexpr uint32_t PRIM_BYTES = 48;   // float4 x3: v0.xyz e1.x | e1.yz e2.xy | e2.z id kind pad
+constexpr uint32_t MAX_LEVELS = 32;
+constexpr uint32_t STACK_SIZE = 64;   // per-ray stack inside one subtree (bounded by the builder)
+
+inline uint32_t node_bytes(uint32_t width) { return width == 8 ? 256u : 128u; }
+
+struct TreeletDesc {      // one per subtree ("treelet"), 16 B
+  uint32_t offset16;      // blob offset / 16
+  uint32_t bytes;         // nodes + prims, multiple of 16
+  uint32_t n_nodes;
+  uint32_t n_prims;
+};
+
+struct LevelRange { uint32_t first, count; };
+
+// Host-side result of the build: one contiguous blob of subtrees, position independent.
+struct WideBVH {
+  uint32_t width = 4;
+  uint32_t n_levels = 0;
+  std::vector<uint8_t> blob;
+  std::vector<TreeletDesc> treelets;        // BFS order => levels are contiguous ranges
+  std::vector<LevelRange> levels;
+  uint32_t n_wide_nodes = 0;
+  uint32_t max_treelet_bytes = 0;
+  float bbox[6] = {0, 0, 0, 0, 0, 0};
+  double build_ms = 0;
+};
+
+// Per-primitive shading data in scene order (index = primitive id)
+struct HostScene {
+  uint32_t n_tris = 0, n_spheres = 0;
+  std::vector<float> prim_geom;       // n_prims * 12 floats (PRIM_BYTES layout, scene order)
+  std::vector<float> tri_normals;     // n_tris * 9 or empty
+  std::vector<uint32_t> prim_material;
+  std::vector<b2rt_material> materials;
+  std::vector<b2rt_light> lights;
+  uint32_t n_prims() const { return n_tris + n_spheres; }
+};
+
+void set_error(const std::string& msg);
+int make_host_scene(const b2rt_scene_desc* d, HostScene* out);
+int build_wide_bvh(const HostScene& sc, uint32_t max_leaf, uint32_t width, uint32_t treelet_bytes, WideBVH* out);
+
+}  // namespace b2rt

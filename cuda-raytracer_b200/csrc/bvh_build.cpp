@@ -1,0 +1,526 @@
+// Host BVH construction for the B200 traversal path.
+//
+// Replaces, with a different algorithm and output layout, the reference's
+//   BVHAccel::BVHAccel + splitBVHNode      src/bvh.cpp:339-365, 48-230   (binary SAH build)
+//   BVHNode::compactTree                   src/bvh.cpp:275-337           (collapse to 4-wide)
+//   BVHSubTree::compress                   src/bvh.cpp:234-273           (serialise + level lists)
+//   CuTriangle / CuBVHSubTree upload       src/cudaRenderer.cu:1757-1827
+// Pipeline here: binned-SAH binary build (O(n log n), threaded) -> SAH-ordered collapse to a W-wide
+// tree (W = 4 or 8) -> partition into shared-memory-sized subtrees ("treelets") in BFS order ->
+// one position-independent blob per subtree: SoA wide nodes (128-bit aligned rows) followed by the
+// 48-byte primitive records of its leaves.  Closest-hit results do not depend on the tree shape, so
+// this builder does not have to reproduce the reference's tree (the oracle's builder does).
+#include <algorithm>
+#include <atomic>
+#include <chrono>
+#include <cmath>
+#include <cstring>
+#include <limits>
+#include <queue>
+#include <thread>
+
+#include "b2rt_internal.h"
+
+namespace b2rt {
+
+namespace {
+
+struct Box {
+  float mn[3], mx[3];
+  void reset() {
+    for (int a = 0; a < 3; ++a) { mn[a] = std::numeric_limits<float>::infinity(); mx[a] = -std::numeric_limits<float>::infinity(); }
+  }
+  void grow(const Box& b) {
+    for (int a = 0; a < 3; ++a) { mn[a] = std::min(mn[a], b.mn[a]); mx[a] = std::max(mx[a], b.mx[a]); }
+  }
+  void grow(const float* p) {
+    for (int a = 0; a < 3; ++a) { mn[a] = std::min(mn[a], p[a]); mx[a] = std::max(mx[a], p[a]); }
+  }
+  float area() const {
+    float ex = mx[0] - mn[0], ey = mx[1] - mn[1], ez = mx[2] - mn[2];
+    if (ex < 0 || ey < 0 || ez < 0) return 0.f;
+    return 2.f * (ex * ey + ey * ez + ez * ex);
+  }
+};
+
+struct BinNode {
+  Box box;
+  uint32_t left = 0, right = 0;   // children (0 = none => leaf)
+  uint32_t start = 0, count = 0;  // primitive range in the index array
+};
+
+struct BinaryBuilder {
+  const std::vector<Box>& pbox;
+  std::vector<float> cen;          // 3 per prim
+  std::vector<uint32_t> idx;
+  std::vector<BinNode> nodes;
+  std::atomic<uint32_t> next_node{0};
+  std::atomic<int> live_threads{0};
+  uint32_t max_leaf;
+  int max_threads;
+
+  BinaryBuilder(const std::vector<Box>& pb, uint32_t ml) : pbox(pb), max_leaf(ml) {
+    size_t n = pb.size();
+    cen.resize(n * 3);
+    idx.resize(n);
+    for (size_t i = 0; i < n; ++i) {
+      idx[i] = (uint32_t)i;
+      for (int a = 0; a < 3; ++a) cen[i * 3 + a] = 0.5f * (pb[i].mn[a] + pb[i].mx[a]);
+    }
+    nodes.resize(std::max<size_t>(1, 2 * n));
+    max_threads = (int)std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
+  }
+
+  uint32_t build(uint32_t b, uint32_t e) {
+    uint32_t me = next_node.fetch_add(1);
+    BinNode& nd = nodes[me];
+    nd.box.reset();
+    Box cb; cb.reset();
+    for (uint32_t i = b; i < e; ++i) { nd.box.grow(pbox[idx[i]]); cb.grow(&cen[(size_t)idx[i] * 3]); }
+    nd.start = b; nd.count = e - b; nd.left = nd.right = 0;
+    if (e - b <= max_leaf) return me;
+
+    constexpr int NB = 16;
+    float best_cost = std::numeric_limits<float>::infinity();
+    int best_axis = -1, best_bin = -1;
+    for (int a = 0; a < 3; ++a) {
+      float lo = cb.mn[a], ext = cb.mx[a] - cb.mn[a];
+      if (!(ext > 0.f)) continue;
+      float scale = (float)NB / ext;
+      Box bb[NB]; uint32_t bc[NB];
+      for (int k = 0; k < NB; ++k) { bb[k].reset(); bc[k] = 0; }
+      for (uint32_t i = b; i < e; ++i) {
+        uint32_t p = idx[i];
+        int k = (int)((cen[(size_t)p * 3 + a] - lo) * scale);
+        k = k < 0 ? 0 : (k >= NB ? NB - 1 : k);
+        bb[k].grow(pbox[p]); bc[k]++;
+      }
+      float ra[NB]; uint32_t rc[NB];
+      Box acc; acc.reset(); uint32_t c = 0;
+      for (int k = NB - 1; k > 0; --k) { acc.grow(bb[k]); c += bc[k]; ra[k] = acc.area(); rc[k] = c; }
+      acc.reset(); c = 0;
+      for (int k = 0; k < NB - 1; ++k) {
+        acc.grow(bb[k]); c += bc[k];
+        if (c == 0 || rc[k + 1] == 0) continue;
+        float cost = acc.area() * (float)c + ra[k + 1] * (float)rc[k + 1];
+        if (cost < best_cost) { best_cost = cost; best_axis = a; best_bin = k; }
+      }
+    }
+    uint32_t mid;
+    if (best_axis >= 0) {
+      float lo = cb.mn[best_axis], scale = (float)NB / (cb.mx[best_axis] - cb.mn[best_axis]);
+      auto it = std::partition(idx.begin() + b, idx.begin() + e, [&](uint32_t p) {
+        int k = (int)((cen[(size_t)p * 3 + best_axis] - lo) * scale);
+        k = k < 0 ? 0 : (k >= NB ? NB - 1 : k);
+        return k <= best_bin;
+      });
+      mid = (uint32_t)(it - idx.begin());
+    } else {
+      mid = b;
+    }
+    if (mid == b || mid == e) {  // all centroids coincide (or binning degenerate): split by index
+      mid = b + (e - b) / 2;
+    }
+    uint32_t l, r;
+    if (e - b > 200000 && live_threads.load() < max_threads) {
+      live_threads.fetch_add(1);
+      uint32_t lres = 0;
+      std::thread t([&]() { lres = build(b, mid); live_threads.fetch_sub(1); });
+      r = build(mid, e);
+      t.join();
+      l = lres;
+    } else {
+      l = build(b, mid);
+      r = build(mid, e);
+    }
+    nodes[me].left = l; nodes[me].right = r;
+    return me;
+  }
+};
+
+struct WChild {
+  Box box;
+  int32_t node = -1;            // wide node index, or -1 for a leaf
+  uint32_t start = 0, count = 0;  // leaf primitive range (index array)
+};
+struct WNode {
+  std::vector<WChild> ch;
+  float area = 0;
+  uint64_t subtree_bytes = 0;   // this node + everything below
+  uint32_t height = 1;          // levels of wide nodes below and including this one
+  uint64_t own_bytes = 0;       // node record + its leaf primitives
+};
+
+}  // namespace
+
+int make_host_scene(const b2rt_scene_desc* d, HostScene* out) {
+  if (!d) { set_error("scene desc is null"); return B2RT_ERR_INVALID; }
+  if (d->n_tris && !d->tri_verts) { set_error("tri_verts is null"); return B2RT_ERR_INVALID; }
+  if (d->n_spheres && !d->spheres) { set_error("spheres is null"); return B2RT_ERR_INVALID; }
+  if ((uint64_t)d->n_tris + d->n_spheres >= 0xFFFFFFF0ull) { set_error("too many primitives"); return B2RT_ERR_INVALID; }
+  out->n_tris = d->n_tris; out->n_spheres = d->n_spheres;
+  const uint32_t n = out->n_prims();
+  out->prim_geom.assign((size_t)n * 12, 0.f);
+  out->prim_material.assign(n, 0u);
+  for (uint32_t i = 0; i < d->n_tris; ++i) {
+    const float* v = d->tri_verts + (size_t)i * 9;
+    float* g = &out->prim_geom[(size_t)i * 12];
+    g[0] = v[0]; g[1] = v[1]; g[2] = v[2];
+    g[3] = v[3] - v[0]; g[4] = v[4] - v[1]; g[5] = v[5] - v[2];   // e1 = p2 - p1 (triangle.cpp:172)
+    g[6] = v[6] - v[0]; g[7] = v[7] - v[1]; g[8] = v[8] - v[2];   // e2 = p3 - p1
+    uint32_t id = i, kind = 0;
+    memcpy(&g[9], &id, 4); memcpy(&g[10], &kind, 4);
+    if (d->tri_material) out->prim_material[i] = d->tri_material[i];
+  }
+  for (uint32_t i = 0; i < d->n_spheres; ++i) {
+    const float* s = d->spheres + (size_t)i * 4;
+    float* g = &out->prim_geom[((size_t)d->n_tris + i) * 12];
+    g[0] = s[0]; g[1] = s[1]; g[2] = s[2]; g[3] = s[3];
+    uint32_t id = d->n_tris + i, kind = 1;
+    memcpy(&g[9], &id, 4); memcpy(&g[10], &kind, 4);
+    if (d->sphere_material) out->prim_material[d->n_tris + i] = d->sphere_material[i];
+  }
+  if (d->tri_normals) out->tri_normals.assign(d->tri_normals, d->tri_normals + (size_t)d->n_tris * 9);
+  else out->tri_normals.clear();
+  if (d->n_materials && d->materials) out->materials.assign(d->materials, d->materials + d->n_materials);
+  else {
+    b2rt_material m; memset(&m, 0, sizeof m);
+    m.kind = B2RT_MAT_DIFFUSE; m.albedo[0] = m.albedo[1] = m.albedo[2] = 0.5f; m.ior = 1.f;
+    out->materials.assign(1, m);
+  }
+  for (uint32_t i = 0; i < n; ++i)
+    if (out->prim_material[i] >= out->materials.size()) { set_error("material index out of range"); return B2RT_ERR_INVALID; }
+  if (d->n_lights && d->lights) out->lights.assign(d->lights, d->lights + d->n_lights);
+  else out->lights.clear();
+  return B2RT_OK;
+}
+
+int build_wide_bvh(const HostScene& sc, uint32_t max_leaf, uint32_t width, uint32_t treelet_bytes, WideBVH* out) {
+  auto t0 = std::chrono::steady_clock::now();
+  if (width == 0) width = 4;
+  if (width != 4 && width != 8) { set_error("bvh width must be 4 or 8"); return B2RT_ERR_INVALID; }
+  if (max_leaf == 0) max_leaf = 4;
+  if (max_leaf > 64) { set_error("max_leaf_size must be <= 64"); return B2RT_ERR_INVALID; }
+  const uint32_t NB = node_bytes(width);
+  const uint32_t min_budget = NB + width * max_leaf * PRIM_BYTES;
+  if (treelet_bytes == 0) treelet_bytes = 48 * 1024;
+  treelet_bytes = std::max(treelet_bytes, min_budget) & ~15u;
+  if (treelet_bytes > 200 * 1024) { set_error("treelet_bytes exceeds the shared-memory budget (200 KiB)"); return B2RT_ERR_INVALID; }
+  const uint32_t depth_limit = (STACK_SIZE - 1) / (width - 1);
+
+  const uint32_t n = sc.n_prims();
+  out->width = width;
+  out->blob.clear(); out->treelets.clear(); out->levels.clear();
+
+  // primitive boxes, padded so the fp32 slab test stays conservative w.r.t. the primitive tests
+  std::vector<Box> pbox(n);
+  Box scene_box; scene_box.reset();
+  for (uint32_t i = 0; i < n; ++i) {
+    const float* g = &sc.prim_geom[(size_t)i * 12];
+    Box b; b.reset();
+    if (i < sc.n_tris) {
+      float p1[3] = {g[0], g[1], g[2]}, p2[3] = {g[0] + g[3], g[1] + g[4], g[2] + g[5]}, p3[3] = {g[0] + g[6], g[1] + g[7], g[2] + g[8]};
+      b.grow(p1); b.grow(p2); b.grow(p3);
+    } else {
+      for (int a = 0; a < 3; ++a) { b.mn[a] = g[a] - g[3]; b.mx[a] = g[a] + g[3]; }
+    }
+    pbox[i] = b;
+    scene_box.grow(b);
+  }
+  float diag = 0.f, maxabs = 0.f;
+  if (n) {
+    float ex = scene_box.mx[0] - scene_box.mn[0], ey = scene_box.mx[1] - scene_box.mn[1], ez = scene_box.mx[2] - scene_box.mn[2];
+    diag = std::sqrt(ex * ex + ey * ey + ez * ez);
+    for (int a = 0; a < 3; ++a) maxabs = std::max(maxabs, std::max(std::fabs(scene_box.mn[a]), std::fabs(scene_box.mx[a])));
+  }
+  const float pad = std::max(1e-30f, 1e-5f * std::max(diag, maxabs));
+  for (auto& b : pbox)
+    for (int a = 0; a < 3; ++a) { b.mn[a] -= pad; b.mx[a] += pad; }
+  for (int a = 0; a < 3; ++a) { out->bbox[a] = n ? scene_box.mn[a] : 0.f; out->bbox[3 + a] = n ? scene_box.mx[a] : 0.f; }
+
+  // ---- binary build ----
+  BinaryBuilder bb(pbox, max_leaf);
+  if (n) bb.build(0, n);
+
+  // ---- collapse to W-wide ----
+  std::vector<WNode> wn;
+  if (n) {
+    // iterative: (binary node) -> wide node
+    struct Item { uint32_t bin; int32_t wide; };
+    std::vector<Item> todo;
+    wn.emplace_back();
+    todo.push_back({0u, 0});
+    while (!todo.empty()) {
+      Item it = todo.back(); todo.pop_back();
+      const BinNode& root = bb.nodes[it.bin];
+      std::vector<uint32_t> kids;   // binary node ids forming the wide node's children
+      if (root.left == 0 && root.right == 0) kids.push_back(it.bin);
+      else { kids.push_back(root.left); kids.push_back(root.right); }
+      while (kids.size() < width) {
+        int best = -1; float ba = -1.f;
+        for (size_t k = 0; k < kids.size(); ++k) {
+          const BinNode& c = bb.nodes[kids[k]];
+          if (c.left == 0 && c.right == 0) continue;
+          float a = c.box.area();
+          if (a > ba) { ba = a; best = (int)k; }
+        }
+        if (best < 0) break;
+        const BinNode& c = bb.nodes[kids[best]];
+        uint32_t l = c.left, r = c.right;
+        kids[best] = l; kids.push_back(r);
+      }
+      std::vector<WChild> ch;
+      for (uint32_t k : kids) {
+        const BinNode& c = bb.nodes[k];
+        WChild w; w.box = c.box;
+        if (c.left == 0 && c.right == 0) { w.node = -1; w.start = c.start; w.count = c.count; }
+        else {
+          w.node = (int32_t)wn.size();
+          wn.emplace_back();
+          todo.push_back({k, w.node});
+        }
+        ch.push_back(w);
+      }
+      wn[it.wide].ch = std::move(ch);
+      wn[it.wide].area = root.box.area();
+    }
+    // bottom-up sizes (children have larger indices than parents => reverse order works)
+    for (int64_t i = (int64_t)wn.size() - 1; i >= 0; --i) {
+      WNode& w = wn[i];
+      w.own_bytes = NB; w.height = 1;
+      uint64_t sub = 0;
+      for (auto& c : w.ch) {
+        if (c.node < 0) w.own_bytes += (uint64_t)c.count * PRIM_BYTES;
+        else { sub += wn[c.node].subtree_bytes; w.height = std::max(w.height, wn[c.node].height + 1); }
+      }
+      w.subtree_bytes = w.own_bytes + sub;
+    }
+  }
+  out->n_wide_nodes = (uint32_t)wn.size();
+
+  // ---- partition into treelets (BFS over treelet roots => level-contiguous ids) ----
+  struct TreeletBuild { int32_t root; uint32_t level; std::vector<int32_t> nodes; };
+  std::vector<TreeletBuild> tl;
+  std::vector<int32_t> node_treelet(wn.size(), -1), node_local(wn.size(), -1);
+  if (n) {
+    tl.push_back({0, 0, {}});
+    for (size_t ti = 0; ti < tl.size(); ++ti) {
+      int32_t root = tl[ti].root;
+      uint32_t level = tl[ti].level;
+      uint64_t used = 0;
+      struct Cand { float area; int32_t node; uint32_t depth; };
+      auto cmp = [](const Cand& a, const Cand& b) { return a.area < b.area; };
+      std::priority_queue<Cand, std::vector<Cand>, decltype(cmp)> pq(cmp);
+      std::vector<int32_t> members;
+      auto include = [&](int32_t nd, uint32_t depth, auto&& self_ref) -> void {
+        members.push_back(nd);
+        used += wn[nd].own_bytes;
+        (void)depth; (void)self_ref;
+      };
+      // the root is always included
+      include(root, 1, include);
+      for (auto& c : wn[root].ch) if (c.node >= 0) pq.push({wn[c.node].area, c.node, 2});
+      std::vector<int32_t> exits;
+      while (!pq.empty()) {
+        Cand c = pq.top(); pq.pop();
+        const WNode& w = wn[c.node];
+        // whole subtree fits (bytes and stack depth): take all of it
+        if (used + w.subtree_bytes <= treelet_bytes && c.depth + w.height - 1 <= depth_limit) {
+          std::vector<int32_t> st{c.node};
+          while (!st.empty()) {
+            int32_t x = st.back(); st.pop_back();
+            include(x, 0, include);
+            for (auto& cc : wn[x].ch) if (cc.node >= 0) st.push_back(cc.node);
+          }
+          continue;
+        }
+        if (used + w.own_bytes <= treelet_bytes && c.depth <= depth_limit) {
+          include(c.node, c.depth, include);
+          for (auto& cc : w.ch) if (cc.node >= 0) pq.push({wn[cc.node].area, cc.node, c.depth + 1});
+          continue;
+        }
+        exits.push_back(c.node);
+      }
+      // local numbering: BFS from the root over members
+      for (int32_t m : members) node_treelet[m] = (int32_t)ti;
+      std::vector<int32_t> order; order.reserve(members.size());
+      order.push_back(root);
+      for (size_t q = 0; q < order.size(); ++q)
+        for (auto& cc : wn[order[q]].ch)
+          if (cc.node >= 0 && node_treelet[cc.node] == (int32_t)ti) order.push_back(cc.node);
+      for (size_t q = 0; q < order.size(); ++q) node_local[order[q]] = (int32_t)q;
+      tl[ti].nodes = std::move(order);
+      for (int32_t ex : exits) tl.push_back({ex, level + 1, {}});
+      // (exits are appended in discovery order; BFS over tl keeps levels contiguous)
+    }
+  }
+  // exits discovered from a level-L treelet have level L+1 and are appended after all level-L
+  // treelets that were already queued, so ids are sorted by level.
+  std::vector<int32_t> root_treelet(wn.size(), -1);
+  for (size_t ti = 0; ti < tl.size(); ++ti) root_treelet[tl[ti].root] = (int32_t)ti;
+
+  // ---- serialise ----
+  uint64_t total = 0;
+  out->treelets.resize(tl.size());
+  for (size_t ti = 0; ti < tl.size(); ++ti) {
+    uint64_t bytes = 0;
+    for (int32_t nd : tl[ti].nodes) bytes += wn[nd].own_bytes;
+    bytes = (bytes + 15) & ~15ull;
+    total = (total + 127) & ~127ull;
+    if (total / 16 > 0xFFFFFFFFull) { set_error("BVH blob too large"); return B2RT_ERR_INVALID; }
+    out->treelets[ti].offset16 = (uint32_t)(total / 16);
+    out->treelets[ti].bytes = (uint32_t)bytes;
+    out->treelets[ti].n_nodes = (uint32_t)tl[ti].nodes.size();
+    total += bytes;
+    out->max_treelet_bytes = std::max<uint32_t>(out->max_treelet_bytes, (uint32_t)bytes);
+  }
+  out->blob.assign((size_t)((total + 127) & ~127ull) + 128, 0);
+  const float INF = std::numeric_limits<float>::infinity();
+  for (size_t ti = 0; ti < tl.size(); ++ti) {
+    uint8_t* base = out->blob.data() + (size_t)out->treelets[ti].offset16 * 16;
+    const uint32_t nn = (uint32_t)tl[ti].nodes.size();
+    uint8_t* prim_base = base + (size_t)nn * NB;
+    uint32_t prim_cursor = 0;
+    for (uint32_t q = 0; q < nn; ++q) {
+      const WNode& w = wn[tl[ti].nodes[q]];
+      float* f = reinterpret_cast<float*>(base + (size_t)q * NB);
+      uint32_t* refs = reinterpret_cast<uint32_t*>(f + 6 * width);
+      for (uint32_t k = 0; k < width; ++k) {
+        if (k < w.ch.size()) {
+          const WChild& c = w.ch[k];
+          for (int a = 0; a < 3; ++a) { f[a * width + k] = c.box.mn[a]; f[(3 + a) * width + k] = c.box.mx[a]; }
+          if (c.node < 0) {
+            refs[k] = make_ref(REF_LEAF, ((c.count - 1) << 24) | prim_cursor);
+            for (uint32_t p = 0; p < c.count; ++p) {
+              uint32_t id = bb.idx[c.start + p];
+              memcpy(prim_base + (size_t)(prim_cursor + p) * PRIM_BYTES, &sc.prim_geom[(size_t)id * 12], PRIM_BYTES);
+            }
+            prim_cursor += c.count;
+            if (prim_cursor >= (1u << 24)) { set_error("too many primitives in one subtree"); return B2RT_ERR_INVALID; }
+          } else if (node_treelet[c.node] == (int32_t)ti) {
+            refs[k] = make_ref(REF_INTERNAL, (uint32_t)node_local[c.node]);
+          } else {
+            refs[k] = make_ref(REF_EXIT, (uint32_t)root_treelet[c.node]);
+          }
+        } else {
+          for (int a = 0; a < 3; ++a) { f[a * width + k] = INF; f[(3 + a) * width + k] = -INF; }
+          refs[k] = REF_EMPTY_WORD;
+        }
+      }
+    }
+    out->treelets[ti].n_prims = prim_cursor;
+  }
+  // levels
+  uint32_t nl = 0;
+  for (auto& t : tl) nl = std::max(nl, t.level + 1);
+  if (nl > MAX_LEVELS) { set_error("too many subtree levels; increase treelet_bytes"); return B2RT_ERR_INVALID; }
+  out->levels.assign(nl, LevelRange{0, 0});
+  for (size_t ti = 0; ti < tl.size(); ++ti) {
+    LevelRange& lr = out->levels[tl[ti].level];
+    if (lr.count == 0) lr.first = (uint32_t)ti;
+    lr.count++;
+    if (ti > 0 && tl[ti].level < tl[ti - 1].level) { set_error("internal: subtree levels not sorted"); return B2RT_ERR_INVALID; }
+  }
+  out->n_levels = nl;
+  out->build_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+  return B2RT_OK;
+}
+
+}  // namespace b2rt
+
+// ---- host-side structural validation of the serialised blob (no device needed) -----------------------
+// Walks every subtree blob exactly as the kernel decodes it and checks: each primitive is stored in
+// exactly one leaf, every child box contains the boxes of everything below it, EXIT children point
+// to subtrees of the next level, blob sizes respect the shared-memory budget, local stack bound holds.
+extern "C" int b2rt_bvh_validate_host(const b2rt_scene_desc* scene, uint32_t max_leaf, uint32_t width,
+                                      uint32_t treelet_bytes, uint64_t out[8]) {
+  using namespace b2rt;
+  HostScene hs;
+  int rc = make_host_scene(scene, &hs);
+  if (rc) return rc;
+  WideBVH wb;
+  rc = build_wide_bvh(hs, max_leaf, width, treelet_bytes, &wb);
+  if (rc) return rc;
+  const uint32_t W = wb.width, NB = node_bytes(W);
+  const uint32_t n = hs.n_prims();
+  std::vector<uint32_t> seen(n, 0);
+  std::vector<uint32_t> level_of(wb.treelets.size(), 0);
+  for (uint32_t L = 0; L < wb.n_levels; ++L)
+    for (uint32_t t = wb.levels[L].first; t < wb.levels[L].first + wb.levels[L].count; ++t) level_of[t] = L;
+  uint64_t n_nodes = 0, n_leaves = 0, max_stack = 0, n_exits = 0;
+  struct Bx { float mn[3], mx[3]; };
+  // bounds of each subtree root (filled bottom-up: children have larger ids)
+  std::vector<Bx> tl_box(wb.treelets.size());
+  std::string err;
+  for (int64_t t = (int64_t)wb.treelets.size() - 1; t >= 0 && err.empty(); --t) {
+    const TreeletDesc& td = wb.treelets[t];
+    if (td.bytes > std::max(treelet_bytes ? treelet_bytes : 48u * 1024u, NB + W * (max_leaf ? max_leaf : 4) * PRIM_BYTES)) err = "subtree exceeds byte budget";
+    if ((uint64_t)td.n_nodes * NB + (uint64_t)td.n_prims * PRIM_BYTES > td.bytes) err = "subtree size mismatch";
+    const uint8_t* base = wb.blob.data() + (size_t)td.offset16 * 16;
+    const uint8_t* prims = base + (size_t)td.n_nodes * NB;
+    // recursive bound computation over local nodes (children have larger local ids: BFS numbering)
+    std::vector<Bx> nb(td.n_nodes);
+    std::vector<uint32_t> depth(td.n_nodes, 1);
+    for (int64_t q = (int64_t)td.n_nodes - 1; q >= 0; --q) {
+      const float* f = reinterpret_cast<const float*>(base + (size_t)q * NB);
+      const uint32_t* refs = reinterpret_cast<const uint32_t*>(f + 6 * W);
+      Bx acc; for (int a = 0; a < 3; ++a) { acc.mn[a] = INFINITY; acc.mx[a] = -INFINITY; }
+      n_nodes++;
+      for (uint32_t k = 0; k < W; ++k) {
+        const uint32_t r = refs[k];
+        if (r == REF_EMPTY_WORD) continue;
+        Bx cb; for (int a = 0; a < 3; ++a) { cb.mn[a] = f[a * W + k]; cb.mx[a] = f[(3 + a) * W + k]; }
+        Bx inner; for (int a = 0; a < 3; ++a) { inner.mn[a] = INFINITY; inner.mx[a] = -INFINITY; }
+        const uint32_t tag = r >> 30;
+        if (tag == REF_LEAF) {
+          n_leaves++;
+          const uint32_t first = r & 0xFFFFFFu, cnt = ((r >> 24) & 63u) + 1;
+          if (first + cnt > td.n_prims) { err = "leaf range outside subtree"; break; }
+          for (uint32_t p = 0; p < cnt; ++p) {
+            const float* g = reinterpret_cast<const float*>(prims + (size_t)(first + p) * PRIM_BYTES);
+            uint32_t id, kind; memcpy(&id, &g[9], 4); memcpy(&kind, &g[10], 4);
+            if (id >= n) { err = "primitive id out of range"; break; }
+            seen[id]++;
+            if (memcmp(g, &hs.prim_geom[(size_t)id * 12], PRIM_BYTES) != 0) { err = "primitive record differs from scene"; break; }
+            if (kind == 0) {
+              for (int v = 0; v < 3; ++v)
+                for (int a = 0; a < 3; ++a) {
+                  float c = g[a] + (v == 1 ? g[3 + a] : (v == 2 ? g[6 + a] : 0.f));
+                  inner.mn[a] = std::min(inner.mn[a], c); inner.mx[a] = std::max(inner.mx[a], c);
+                }
+            } else {
+              for (int a = 0; a < 3; ++a) { inner.mn[a] = std::min(inner.mn[a], g[a] - g[3]); inner.mx[a] = std::max(inner.mx[a], g[a] + g[3]); }
+            }
+          }
+        } else if (tag == REF_INTERNAL) {
+          const uint32_t c = r & 0x3FFFFFFFu;
+          if (c >= td.n_nodes || c <= (uint32_t)q) { err = "bad local child index"; break; }
+          inner = nb[c];
+          depth[q] = std::max(depth[q], depth[c] + 1);
+        } else if (tag == REF_EXIT) {
+          const uint32_t c = r & 0x3FFFFFFFu;
+          n_exits++;
+          if (c >= wb.treelets.size() || level_of[c] != level_of[t] + 1) { err = "exit does not point to the next level"; break; }
+          inner = tl_box[c];
+        }
+        for (int a = 0; a < 3; ++a)
+          if (inner.mn[a] < cb.mn[a] || inner.mx[a] > cb.mx[a]) err = "child box does not contain its contents";
+        for (int a = 0; a < 3; ++a) { acc.mn[a] = std::min(acc.mn[a], cb.mn[a]); acc.mx[a] = std::max(acc.mx[a], cb.mx[a]); }
+      }
+      nb[q] = acc;
+    }
+    if (td.n_nodes) {
+      tl_box[t] = nb[0];
+      max_stack = std::max<uint64_t>(max_stack, 1 + (uint64_t)(W - 1) * depth[0]);
+    }
+  }
+  for (uint32_t i = 0; i < n && err.empty(); ++i)
+    if (seen[i] != 1) err = "primitive not stored exactly once";
+  if (max_stack > STACK_SIZE) err = "per-ray stack bound exceeded";
+  if (out) {
+    out[0] = wb.treelets.size(); out[1] = wb.n_levels; out[2] = n_nodes; out[3] = n_leaves; out[4] = wb.blob.size();
+    out[5] = wb.max_treelet_bytes; out[6] = max_stack; out[7] = n_exits;
+  }
+  if (!err.empty()) { set_error("bvh validation: " + err); return B2RT_ERR_INVALID; }
+  return B2RT_OK;
+}

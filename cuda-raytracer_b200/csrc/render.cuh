@@ -1,0 +1,57 @@
+// Renderer handle behind b2rt_renderer (see render.cu)
+#pragma once
+#include <cuda_runtime.h>
+
+#include "traverse.cuh"
+
+namespace b2rt {
+
+struct Renderer {
+  b2rt_config cfg{};
+  int device = -1;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev_start = nullptr, ev_done = nullptr;
+  // scene
+  DeviceBVH dbvh;
+  Tracer tracer;
+  void* d_prim_geom = nullptr; float* d_tri_normals = nullptr; uint32_t* d_prim_material = nullptr;
+  b2rt_material* d_materials = nullptr; b2rt_light* d_lights = nullptr; float* d_light_area = nullptr;
+  std::vector<b2rt_light> lights_host;
+  uint32_t n_tris = 0, n_lights = 0, n_wide_nodes = 0, shadow_per_hit = 0;
+  double build_ms = 0;
+  bool have_scene = false, have_camera = false, running = false;
+  b2rt_camera cam{};
+  // frame
+  uint32_t width = 0, height = 0;
+  void* accum = nullptr; void* img_a = nullptr; void* img_b = nullptr; uint32_t* ldr = nullptr;
+  void* resolved = nullptr;
+  uint64_t samples_done = 0, samples_pending = 0;
+  // wave buffers
+  uint64_t wave_cap = 0; uint32_t wave_S = 0;
+  void *ray_o = nullptr, *ray_d = nullptr, *thr = nullptr, *rad = nullptr, *s_o = nullptr, *s_d = nullptr, *s_contrib = nullptr;
+  unsigned long long *hits = nullptr, *s_hits = nullptr, *totals = nullptr;
+  uint32_t *ids_a = nullptr, *ids_b = nullptr, *s_ids = nullptr, *counts = nullptr;
+  // stats
+  b2rt_stats last{};
+  uint64_t launches = 0, cam_rays_enqueued = 0;
+  double ms_total = 0, ms_traverse_acc = 0;
+
+  int set_device();
+  int create(const b2rt_config* c);
+  void destroy();
+  void release_scene();
+  void release_wave();
+  int set_scene(const b2rt_scene_desc* d);
+  int set_camera(const b2rt_camera* c);
+  int set_frame_size(uint32_t w, uint32_t h);
+  int clear();
+  int ensure_wave();
+  int start();
+  int is_done();
+  int wait();
+  int stop();
+  int resolve(bool want_ldr);
+  void fill_stats(b2rt_stats* out) const;
+};
+
+}  // namespace b2rt

@@ -1,0 +1,541 @@
+// Breadth-first wide-BVH traversal with dynamic ray scheduling, sm_100a.
+//
+// Replaces the reference's per-level machinery:
+//   kernelScanCounts                      src/cudaRenderer.cu:1317-1431  -> k_schedule_level
+//   kernelRayIntersectSingle/Level        src/cudaRenderer.cu:1304-1310, 1435-1489, 846-1297 -> k_traverse
+//   sharedMemExclusiveScan                src/exclusiveScan.cu_inl:73-110 -> ballot/popc + shuffle scans
+//   kernelClearIntersections/Merge        src/cudaRenderer.cu:490-540    -> packed (t, prim) 64-bit atomicMin
+// Design (DESIGN.md "Traversal"): the BVH is cut into subtrees that fit in shared memory.  One pass
+// per subtree LEVEL: rays are grouped by the subtree they must visit; a CTA owns one subtree at a
+// time, stages its blob (SoA wide nodes + 48-byte primitive records) with ONE TMA bulk copy
+// (cp.async.bulk + mbarrier), and its warps pull 32-ray batches of that subtree's queue.  Rays that
+// leave through an EXIT child are pushed as (child subtree, ray id) pairs: warp ballot/popc exclusive
+// scan into a per-warp staging ring, one global atomicAdd per flush.  Between levels a single-CTA
+// scan turns per-subtree counts into segment offsets + a chunk work list and a scatter kernel
+// regroups the ray ids by subtree.  No host round trip anywhere: all counts live on the device and
+// every grid is persistent.
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <algorithm>
+
+#include "rt_device.cuh"
+#include "traverse.cuh"
+
+namespace b2rt {
+
+namespace {
+
+constexpr int TRAV_THREADS = 256;
+constexpr int TRAV_WARPS = TRAV_THREADS / 32;
+constexpr int STAGE_PAIRS = 96;   // per-warp staging ring (flush when > STAGE_PAIRS - 32)
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t done = 0;
+  const uint32_t addr = smem_u32(bar);
+  while (!done) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(done)
+        : "r"(addr), "r"(parity)
+        : "memory");
+  }
+}
+// TMA bulk copy global -> shared, completion signalled on the mbarrier (SASS: UBLKCP)
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// ---- k_trace_begin: reset queue counts; the root subtree receives every active ray ----------------
+__global__ void k_trace_begin(uint32_t* cnt, uint32_t n_treelets, uint32_t* ctrl, const uint32_t* n_active) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  uint32_t stride = gridDim.x * blockDim.x;
+  for (uint32_t t = i; t < n_treelets; t += stride) cnt[t] = (t == 0) ? *n_active : 0u;
+  if (i == 0) { ctrl[CTRL_PAIRS0] = 0; ctrl[CTRL_PAIRS1] = 0; ctrl[CTRL_NCHUNKS] = 0; ctrl[CTRL_NEXT] = 0; }
+}
+
+// ---- k_schedule_level: exclusive scan of per-subtree ray counts -> segment offsets + chunk list ----
+// One CTA of 1024 threads; warp-shuffle scans (no volatile-smem warp-synchronous code).
+__device__ __forceinline__ uint32_t warp_incl_scan(uint32_t v) {
+  const uint32_t lane = threadIdx.x & 31;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    uint32_t n = __shfl_up_sync(0xffffffffu, v, d);
+    if (lane >= (uint32_t)d) v += n;
+  }
+  return v;
+}
+// block-wide exclusive scan of two values at once; returns totals through tot_a/tot_b
+__device__ __forceinline__ void block_excl_scan2(uint32_t a, uint32_t b, uint32_t* ea, uint32_t* eb, uint32_t* tot_a,
+                                                 uint32_t* tot_b, uint32_t* sh /* 2*32+2 */) {
+  const uint32_t lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  uint32_t ia = warp_incl_scan(a), ib = warp_incl_scan(b);
+  if (lane == 31) { sh[w] = ia; sh[32 + w] = ib; }
+  __syncthreads();
+  if (w == 0) {
+    uint32_t xa = lane < nw ? sh[lane] : 0, xb = lane < nw ? sh[32 + lane] : 0;
+    uint32_t sa = warp_incl_scan(xa), sb = warp_incl_scan(xb);
+    sh[lane] = sa - xa; sh[32 + lane] = sb - xb;
+    if (lane == 31) { sh[64] = sa; sh[65] = sb; }
+  }
+  __syncthreads();
+  *ea = sh[w] + ia - a; *eb = sh[32 + w] + ib - b;
+  *tot_a = sh[64]; *tot_b = sh[65];
+  __syncthreads();
+}
+
+__global__ void __launch_bounds__(1024, 1)
+k_schedule_level(const uint32_t* __restrict__ cnt, uint32_t* __restrict__ seg_off, uint32_t* __restrict__ cursor,
+                 uint4* __restrict__ chunks, uint32_t* __restrict__ ctrl, uint32_t first, uint32_t n, uint32_t chunk_rays,
+                 uint32_t chunk_cap, uint32_t level) {
+  __shared__ uint32_t sh[66];
+  __shared__ uint4 big[1024];   // (subtree, seg offset, count, chunk base) of subtrees with many chunks
+  __shared__ uint32_t n_big;
+  if (threadIdx.x == 0) n_big = 0;
+  __syncthreads();
+  uint32_t run_off = 0, run_chunks = 0;
+  for (uint32_t base = 0; base < n; base += blockDim.x) {
+    uint32_t i = base + threadIdx.x;
+    uint32_t t = first + i;
+    uint32_t c = i < n ? cnt[t] : 0u;
+    uint32_t nch = (c + chunk_rays - 1) / chunk_rays;
+    uint32_t eo, ec, to, tc;
+    block_excl_scan2(c, nch, &eo, &ec, &to, &tc, sh);
+    if (i < n) {
+      uint32_t off = run_off + eo, cb = run_chunks + ec;
+      seg_off[t] = off; cursor[t] = 0;
+      if (nch <= 4) {
+        for (uint32_t k = 0; k < nch; ++k)
+          if (cb + k < chunk_cap) chunks[cb + k] = make_uint4(t, off + k * chunk_rays, min(chunk_rays, c - k * chunk_rays), 0);
+      } else {
+        uint32_t slot = atomicAdd(&n_big, 1u);
+        if (slot < 1024) big[slot] = make_uint4(t, off, c, cb);
+        else  // cannot happen for blockDim 1024 per tile, kept for safety: write serially
+          for (uint32_t k = 0; k < nch; ++k)
+            if (cb + k < chunk_cap) chunks[cb + k] = make_uint4(t, off + k * chunk_rays, min(chunk_rays, c - k * chunk_rays), 0);
+      }
+    }
+    __syncthreads();
+    uint32_t nb = min(n_big, 1024u);
+    for (uint32_t b = 0; b < nb; ++b) {
+      uint4 e = big[b];
+      uint32_t nch_b = (e.z + chunk_rays - 1) / chunk_rays;
+      for (uint32_t k = threadIdx.x; k < nch_b; k += blockDim.x)
+        if (e.w + k < chunk_cap) chunks[e.w + k] = make_uint4(e.x, e.y + k * chunk_rays, min(chunk_rays, e.z - k * chunk_rays), 0);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) n_big = 0;
+    run_off += to; run_chunks += tc;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    if (run_chunks > chunk_cap) { run_chunks = chunk_cap; ctrl[CTRL_OVERFLOW] = 1; }
+    ctrl[CTRL_NCHUNKS] = run_chunks;
+    ctrl[CTRL_NEXT] = 0;
+    ctrl[level & 1] = 0;   // pair counter the traversal of THIS level appends to
+  }
+}
+
+// ---- k_scatter: regroup ray ids by subtree (counting-sort scatter, warp-aggregated cursors) ---------
+__global__ void __launch_bounds__(256)
+k_scatter(const uint2* __restrict__ pairs, const uint32_t* __restrict__ pair_count, const uint32_t* __restrict__ seg_off,
+          uint32_t* __restrict__ cursor, uint32_t* __restrict__ ids_sorted, uint32_t pair_cap) {
+  const uint32_t n = min(*pair_count, pair_cap);
+  const uint32_t lane = threadIdx.x & 31;
+  const uint32_t stride = gridDim.x * blockDim.x;
+  // whole warps iterate together so the match/shuffle masks are well defined
+  for (uint32_t base = (blockIdx.x * blockDim.x + threadIdx.x) - lane; base < n; base += stride) {
+    uint32_t i = base + lane;
+    bool valid = i < n;
+    uint2 p = valid ? pairs[i] : make_uint2(0xFFFFFFFFu, 0u);
+    uint32_t active = __ballot_sync(0xffffffffu, valid);
+    if (!valid) continue;
+    uint32_t peers = __match_any_sync(active, p.x);
+    uint32_t leader = __ffs(peers) - 1;
+    uint32_t rank = __popc(peers & ((1u << lane) - 1u));
+    uint32_t basepos = 0;
+    if (lane == leader) basepos = atomicAdd(&cursor[p.x], (uint32_t)__popc(peers));
+    basepos = __shfl_sync(peers, basepos, leader);
+    ids_sorted[seg_off[p.x] + basepos + rank] = p.y;
+  }
+}
+
+// ---- k_traverse -----------------------------------------------------------------------------------
+struct TravParams {
+  const uint8_t* blob;
+  const TreeletDesc* treelets;
+  const float4* ray_o;
+  const float4* ray_d;
+  unsigned long long* hits;
+  const uint32_t* ids;        // ray ids grouped by subtree (nullptr => identity, level 0 only)
+  const uint4* chunks;
+  uint32_t* ctrl;
+  uint32_t* cnt;              // per-subtree counts for the NEXT level
+  uint2* pairs;               // (child subtree, ray id) output
+  uint32_t pair_cap;
+  uint32_t level;
+  TraceCounters* counters;
+};
+
+template <int W>
+struct NodeView;
+template <>
+struct NodeView<4> {
+  static constexpr int BYTES = 128;
+};
+template <>
+struct NodeView<8> {
+  static constexpr int BYTES = 256;
+};
+
+struct StackEntry { uint32_t ref; float tn; };
+
+// flush one warp's staged pairs: one global reservation, coalesced 8-byte stores, per-subtree counts
+__device__ __forceinline__ void flush_pairs(uint2* stage, uint32_t& n_staged, const TravParams& P, uint32_t lane) {
+  uint32_t n = n_staged;
+  uint32_t base = 0;
+  if (lane == 0) base = atomicAdd(&P.ctrl[P.level & 1], n);
+  base = __shfl_sync(0xffffffffu, base, 0);
+  for (uint32_t k = lane; k < n; k += 32) {
+    uint2 p = stage[k];
+    if (base + k < P.pair_cap) {
+      P.pairs[base + k] = p;
+      atomicAdd(&P.cnt[p.x], 1u);
+    } else {
+      P.ctrl[CTRL_OVERFLOW] = 1;
+    }
+  }
+  __syncwarp();
+  n_staged = 0;
+}
+
+template <int W, bool ANYHIT, bool STATS>
+__global__ void __launch_bounds__(TRAV_THREADS, (W == 4 ? 3 : 2))
+k_traverse(const TravParams P) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  __shared__ __align__(8) uint64_t s_bar;
+  __shared__ uint4 s_chunk;
+  __shared__ uint32_t s_next_batch;
+  __shared__ __align__(8) uint2 s_stage[TRAV_WARPS][STAGE_PAIRS];
+
+  const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  constexpr int NB = NodeView<W>::BYTES;
+  uint32_t cur_treelet = 0xFFFFFFFFu;
+  uint32_t phase = 0;
+  uint32_t n_staged = 0;   // warp-uniform
+  uint2* stage = s_stage[warp];
+  unsigned long long st_nodes = 0, st_prims = 0, st_visits = 0, st_push = 0;
+
+  if (threadIdx.x == 0) { mbar_init(&s_bar, 1); }
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  __syncthreads();
+
+  const uint32_t n_chunks = P.ctrl[CTRL_NCHUNKS];
+  for (;;) {
+    if (threadIdx.x == 0) {
+      uint32_t c = atomicAdd(&P.ctrl[CTRL_NEXT], 1u);
+      s_chunk = c < n_chunks ? P.chunks[c] : make_uint4(0xFFFFFFFFu, 0, 0, 0);
+      s_next_batch = 0;
+    }
+    __syncthreads();
+    const uint4 chunk = s_chunk;
+    if (chunk.x == 0xFFFFFFFFu) break;
+    const TreeletDesc td = P.treelets[chunk.x];
+    if (chunk.x != cur_treelet) {
+      if (threadIdx.x == 0) {
+        fence_proxy_async();
+        mbar_expect_tx(&s_bar, td.bytes);
+        bulk_g2s(smem, P.blob + (size_t)td.offset16 * 16, td.bytes, &s_bar);
+      }
+      mbar_wait(&s_bar, phase);
+      phase ^= 1;
+      cur_treelet = chunk.x;
+    }
+    const uint8_t* nodes = smem;
+    const uint8_t* prims = smem + (size_t)td.n_nodes * NB;
+
+    // warps pull 32-ray batches of this chunk
+    for (;;) {
+      uint32_t b = 0;
+      if (lane == 0) b = atomicAdd(&s_next_batch, 32u);
+      b = __shfl_sync(0xffffffffu, b, 0);
+      if (b >= chunk.z) break;
+      const uint32_t k = b + lane;
+      const bool have = k < chunk.z;
+      uint32_t rid = 0;
+      float best_t = 0.f; uint32_t best_id = 0xFFFFFFFFu;
+      f3 o = mk3(0, 0, 0), d = mk3(0, 0, 1), inv = mk3(0, 0, 0), noi = mk3(0, 0, 0);
+      float tmin = 0.f, tmax_user = 0.f;
+      StackEntry stack[STACK_SIZE];
+      int sp = 0;
+      bool improved = false;
+      if (have) {
+        rid = P.ids ? P.ids[chunk.y + k] : (chunk.y + k);
+        const float4 ro = P.ray_o[rid], rd = P.ray_d[rid];
+        const unsigned long long h = P.hits[rid];
+        o = mk3(ro.x, ro.y, ro.z); d = mk3(rd.x, rd.y, rd.z);
+        tmin = ro.w; tmax_user = rd.w;
+        best_t = __uint_as_float((uint32_t)(h >> 32));
+        best_id = (uint32_t)h;
+        inv = mk3(__frcp_rn(d.x), __frcp_rn(d.y), __frcp_rn(d.z));
+        noi = mk3(-(o.x * inv.x), -(o.y * inv.y), -(o.z * inv.z));
+        bool skip = ANYHIT && best_id != 0xFFFFFFFFu;
+        if (!skip) { stack[0].ref = 0u;  /* INTERNAL node 0 = subtree root */ stack[0].tn = tmin; sp = 1; }
+        if (STATS) st_visits++;
+      }
+      // warp-synchronous loop: one stack pop per lane per iteration
+      while (__any_sync(0xffffffffu, sp > 0)) {
+        bool do_push = false;
+        uint32_t push_treelet = 0;
+        if (sp > 0) {
+          const StackEntry e = stack[--sp];
+          if (e.tn <= best_t) {
+            const uint32_t tag = e.ref >> 30;
+            if (tag == REF_INTERNAL) {
+              if (STATS) st_nodes++;
+              const float4* nd = reinterpret_cast<const float4*>(nodes + (size_t)(e.ref & 0x3FFFFFFFu) * NB);
+              uint32_t keys[W];
+              uint32_t refs[W];
+#pragma unroll
+              for (int q = 0; q < W / 4; ++q) {
+                const float4 lx = nd[0 * (W / 4) + q], ly = nd[1 * (W / 4) + q], lz = nd[2 * (W / 4) + q];
+                const float4 hx = nd[3 * (W / 4) + q], hy = nd[4 * (W / 4) + q], hz = nd[5 * (W / 4) + q];
+                const uint4 rf = reinterpret_cast<const uint4*>(nd)[6 * (W / 4) + q];
+                const float lxa[4] = {lx.x, lx.y, lx.z, lx.w}, lya[4] = {ly.x, ly.y, ly.z, ly.w}, lza[4] = {lz.x, lz.y, lz.z, lz.w};
+                const float hxa[4] = {hx.x, hx.y, hx.z, hx.w}, hya[4] = {hy.x, hy.y, hy.z, hy.w}, hza[4] = {hz.x, hz.y, hz.z, hz.w};
+                const uint32_t rfa[4] = {rf.x, rf.y, rf.z, rf.w};
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                  float tx0 = __fmaf_rn(lxa[c], inv.x, noi.x), tx1 = __fmaf_rn(hxa[c], inv.x, noi.x);
+                  float ty0 = __fmaf_rn(lya[c], inv.y, noi.y), ty1 = __fmaf_rn(hya[c], inv.y, noi.y);
+                  float tz0 = __fmaf_rn(lza[c], inv.z, noi.z), tz1 = __fmaf_rn(hza[c], inv.z, noi.z);
+                  float tn = fmaxf(fmaxf(fminf(tx0, tx1), fminf(ty0, ty1)), fmaxf(fminf(tz0, tz1), tmin));
+                  float tf = fminf(fminf(fmaxf(tx0, tx1), fmaxf(ty0, ty1)), fminf(fmaxf(tz0, tz1), best_t));
+                  bool hit = (tn <= tf * 1.0000004f) && (rfa[c] != REF_EMPTY_WORD);
+                  // key: entry distance (rounded down, keeps order for t >= 0) | child slot
+                  keys[q * 4 + c] = hit ? ((__float_as_uint(tn) & ~(uint32_t)(W - 1)) | (uint32_t)(q * 4 + c)) : 0xFFFFFFFFu;
+                  refs[q * 4 + c] = rfa[c];
+                }
+              }
+              // sort keys ascending (small network), then push far-to-near
+              if (W == 4) {
+#define B2_CE(a, b) { uint32_t lo_ = min(keys[a], keys[b]), hi_ = max(keys[a], keys[b]); keys[a] = lo_; keys[b] = hi_; }
+                B2_CE(0, 1) B2_CE(2, 3) B2_CE(0, 2) B2_CE(1, 3) B2_CE(1, 2)
+              } else {
+                // 19-comparator network for 8 inputs
+                B2_CE(0, 1) B2_CE(2, 3) B2_CE(4, 5) B2_CE(6, 7)
+                B2_CE(0, 2) B2_CE(1, 3) B2_CE(4, 6) B2_CE(5, 7)
+                B2_CE(1, 2) B2_CE(5, 6) B2_CE(0, 4) B2_CE(3, 7)
+                B2_CE(1, 5) B2_CE(2, 6)
+                B2_CE(1, 4) B2_CE(3, 6)
+                B2_CE(2, 4) B2_CE(3, 5)
+                B2_CE(3, 4)
+#undef B2_CE
+              }
+#pragma unroll
+              for (int q = W - 1; q >= 0; --q) {
+                if (keys[q] != 0xFFFFFFFFu) {
+                  const uint32_t slot = keys[q] & (uint32_t)(W - 1);
+                  uint32_t r = refs[0];
+#pragma unroll
+                  for (int z = 1; z < W; ++z) r = (slot == (uint32_t)z) ? refs[z] : r;
+                  stack[sp].ref = r;
+                  stack[sp].tn = __uint_as_float(keys[q] & ~(uint32_t)(W - 1));
+                  ++sp;
+                }
+              }
+            } else if (tag == REF_LEAF) {
+              const uint32_t first = e.ref & 0x00FFFFFFu, count = ((e.ref >> 24) & 63u) + 1u;
+              const PrimRec* pr = reinterpret_cast<const PrimRec*>(prims) + first;
+              for (uint32_t q = 0; q < count; ++q) {
+                const PrimRec p = pr[q];
+                if (STATS) st_prims++;
+                float t, u, v;
+                const uint32_t pid = __float_as_uint(p.c.y);
+                const bool h = (__float_as_uint(p.c.z) != 0u) ? hit_sphere(p, o, d, tmin, tmax_user, &t)
+                                                              : hit_triangle(p, o, d, tmin, tmax_user, &t, &u, &v);
+                if (h && (t < best_t || (t == best_t && pid < best_id))) {
+                  best_t = t; best_id = pid; improved = true;
+                  if (ANYHIT) { best_t = 0.0f; sp = 0; break; }
+                }
+              }
+            } else if (tag == REF_EXIT) {
+              do_push = true;
+              push_treelet = e.ref & 0x3FFFFFFFu;
+            }
+          }
+        }
+        // scheduler push: ballot + popc = exclusive scan of the 0/1 flags inside the warp
+        const uint32_t m = __ballot_sync(0xffffffffu, do_push);
+        if (m) {
+          if (do_push) stage[n_staged + __popc(m & ((1u << lane) - 1u))] = make_uint2(push_treelet, rid);
+          n_staged += __popc(m);
+          if (STATS && do_push) st_push++;
+          __syncwarp();
+          if (n_staged > STAGE_PAIRS - 32) flush_pairs(stage, n_staged, P, lane);
+        }
+      }
+      if (have && improved) atomicMin(&P.hits[rid], pack_hit(best_t, best_id));
+    }
+    __syncthreads();   // every warp is done with this chunk (s_chunk / s_next_batch / subtree smem reusable)
+  }
+  if (n_staged) flush_pairs(stage, n_staged, P, lane);
+  if (STATS) {
+#pragma unroll
+    for (int dlt = 16; dlt > 0; dlt >>= 1) {
+      st_nodes += __shfl_xor_sync(0xffffffffu, st_nodes, dlt);
+      st_prims += __shfl_xor_sync(0xffffffffu, st_prims, dlt);
+      st_visits += __shfl_xor_sync(0xffffffffu, st_visits, dlt);
+      st_push += __shfl_xor_sync(0xffffffffu, st_push, dlt);
+    }
+    if (lane == 0) {
+      atomicAdd(&P.counters->node_visits, st_nodes);
+      atomicAdd(&P.counters->prim_tests, st_prims);
+      atomicAdd(&P.counters->subtree_visits, st_visits);
+      atomicAdd(&P.counters->pushes, st_push);
+    }
+  }
+}
+
+}  // namespace
+
+
+// ---- host side ---------------------------------------------------------------------------------------
+int upload_bvh(const WideBVH& h, DeviceBVH* d) {
+  *d = DeviceBVH();
+  d->n_treelets = (uint32_t)h.treelets.size();
+  d->n_levels = h.n_levels;
+  d->width = h.width;
+  d->max_treelet_bytes = h.max_treelet_bytes;
+  d->blob_bytes = h.blob.size();
+  for (uint32_t i = 0; i < h.n_levels; ++i) d->levels[i] = h.levels[i];
+  if (h.treelets.empty()) return B2RT_OK;
+  B2RT_CUDA_OK(cudaMalloc(&d->blob, h.blob.size()));
+  B2RT_CUDA_OK(cudaMalloc(&d->treelets, h.treelets.size() * sizeof(TreeletDesc)));
+  B2RT_CUDA_OK(cudaMemcpy(d->blob, h.blob.data(), h.blob.size(), cudaMemcpyHostToDevice));
+  B2RT_CUDA_OK(cudaMemcpy(d->treelets, h.treelets.data(), h.treelets.size() * sizeof(TreeletDesc), cudaMemcpyHostToDevice));
+  return B2RT_OK;
+}
+
+void free_bvh(DeviceBVH* d) {
+  if (d->blob) cudaFree(d->blob);
+  if (d->treelets) cudaFree(d->treelets);
+  *d = DeviceBVH();
+}
+
+template <int W, bool A, bool S>
+static int prep_kernel(size_t smem, int* occ) {
+  B2RT_CUDA_OK(cudaFuncSetAttribute(k_traverse<W, A, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  B2RT_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(occ, k_traverse<W, A, S>, TRAV_THREADS, smem));
+  return B2RT_OK;
+}
+
+int Tracer::init(const DeviceBVH& b, uint64_t max_rays_, uint32_t pair_factor) {
+  bvh = b;
+  max_rays = max_rays_;
+  if (pair_factor == 0) pair_factor = 4;
+  pair_cap = max_rays * pair_factor + 65536;
+  if (pair_cap > 0xFFFF0000ull) pair_cap = 0xFFFF0000ull;
+  chunk_cap = pair_cap / chunk_rays + (uint64_t)bvh.n_treelets + 1024;
+  int dev = 0;
+  B2RT_CUDA_OK(cudaGetDevice(&dev));
+  B2RT_CUDA_OK(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
+  smem_bytes = std::max<size_t>(bvh.max_treelet_bytes, 1024);
+  int occ = 1, o2 = 1;
+  int rc;
+  if (bvh.width == 8) {
+    if ((rc = prep_kernel<8, false, false>(smem_bytes, &occ))) return rc;
+    if ((rc = prep_kernel<8, true, false>(smem_bytes, &o2))) return rc;
+    if ((rc = prep_kernel<8, false, true>(smem_bytes, &o2))) return rc;
+    if ((rc = prep_kernel<8, true, true>(smem_bytes, &o2))) return rc;
+  } else {
+    if ((rc = prep_kernel<4, false, false>(smem_bytes, &occ))) return rc;
+    if ((rc = prep_kernel<4, true, false>(smem_bytes, &o2))) return rc;
+    if ((rc = prep_kernel<4, false, true>(smem_bytes, &o2))) return rc;
+    if ((rc = prep_kernel<4, true, true>(smem_bytes, &o2))) return rc;
+  }
+  ctas_per_sm = std::max(1, std::min(occ, o2));
+  const size_t nt = std::max<uint32_t>(1, bvh.n_treelets);
+  B2RT_CUDA_OK(cudaMalloc(&cnt, nt * 4));
+  B2RT_CUDA_OK(cudaMalloc(&seg_off, nt * 4));
+  B2RT_CUDA_OK(cudaMalloc(&cursor, nt * 4));
+  B2RT_CUDA_OK(cudaMalloc(&pairs, pair_cap * sizeof(uint2)));
+  B2RT_CUDA_OK(cudaMalloc(&ids_sorted, pair_cap * 4));
+  B2RT_CUDA_OK(cudaMalloc(&chunks, chunk_cap * sizeof(uint4)));
+  B2RT_CUDA_OK(cudaMalloc(&ctrl, 16 * 4));
+  B2RT_CUDA_OK(cudaMalloc(&counters, sizeof(TraceCounters)));
+  B2RT_CUDA_OK(cudaMemset(ctrl, 0, 16 * 4));
+  B2RT_CUDA_OK(cudaMemset(counters, 0, sizeof(TraceCounters)));
+  return B2RT_OK;
+}
+
+void Tracer::release() {
+  cudaFree(cnt); cudaFree(seg_off); cudaFree(cursor); cudaFree(pairs); cudaFree(ids_sorted); cudaFree(chunks);
+  cudaFree(ctrl); cudaFree(counters);
+  cnt = seg_off = cursor = ids_sorted = ctrl = nullptr; pairs = nullptr; chunks = nullptr; counters = nullptr;
+}
+
+template <int W>
+static void launch_traverse(const Tracer& T, cudaStream_t s, const TravParams& P, bool any_hit, bool stats) {
+  dim3 grid(T.num_sms * T.ctas_per_sm), block(TRAV_THREADS);
+  if (any_hit) {
+    if (stats) k_traverse<W, true, true><<<grid, block, T.smem_bytes, s>>>(P);
+    else k_traverse<W, true, false><<<grid, block, T.smem_bytes, s>>>(P);
+  } else {
+    if (stats) k_traverse<W, false, true><<<grid, block, T.smem_bytes, s>>>(P);
+    else k_traverse<W, false, false><<<grid, block, T.smem_bytes, s>>>(P);
+  }
+}
+
+int Tracer::trace(cudaStream_t s, const float4* ray_o, const float4* ray_d, unsigned long long* hits,
+                  const uint32_t* ids0, const uint32_t* n_active_dev, bool any_hit) {
+  if (bvh.n_levels == 0) return B2RT_OK;
+  k_trace_begin<<<std::max(1u, std::min(1024u, (bvh.n_treelets + 255) / 256)), 256, 0, s>>>(cnt, bvh.n_treelets, ctrl, n_active_dev);
+  launches++;
+  for (uint32_t L = 0; L < bvh.n_levels; ++L) {
+    const LevelRange lr = bvh.levels[L];
+    k_schedule_level<<<1, 1024, 0, s>>>(cnt, seg_off, cursor, chunks, ctrl, lr.first, lr.count, chunk_rays,
+                                        (uint32_t)chunk_cap, L);
+    launches++;
+    if (L > 0) {
+      k_scatter<<<num_sms * 8, 256, 0, s>>>(pairs, &ctrl[(L - 1) & 1], seg_off, cursor, ids_sorted, (uint32_t)pair_cap);
+      launches++;
+    }
+    TravParams P;
+    P.blob = bvh.blob; P.treelets = bvh.treelets; P.ray_o = ray_o; P.ray_d = ray_d; P.hits = hits;
+    P.ids = (L == 0) ? ids0 : ids_sorted;
+    P.chunks = chunks; P.ctrl = ctrl; P.cnt = cnt; P.pairs = pairs; P.pair_cap = (uint32_t)pair_cap; P.level = L;
+    P.counters = counters;
+    if (bvh.width == 8) launch_traverse<8>(*this, s, P, any_hit, collect_stats);
+    else launch_traverse<4>(*this, s, P, any_hit, collect_stats);
+    launches++;
+  }
+  B2RT_CUDA_OK(cudaGetLastError());
+  return B2RT_OK;
+}
+
+int Tracer::check_overflow(cudaStream_t s, bool* overflow) {
+  uint32_t v = 0;
+  B2RT_CUDA_OK(cudaMemcpyAsync(&v, ctrl + CTRL_OVERFLOW, 4, cudaMemcpyDeviceToHost, s));
+  B2RT_CUDA_OK(cudaStreamSynchronize(s));
+  *overflow = v != 0;
+  if (v) B2RT_CUDA_OK(cudaMemsetAsync(ctrl + CTRL_OVERFLOW, 0, 4, s));
+  return B2RT_OK;
+}
+
+}  // namespace b2rt

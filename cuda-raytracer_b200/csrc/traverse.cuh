@@ -1,0 +1,64 @@
+// Device-side traversal + ray scheduler interface (see traverse.cu).
+#pragma once
+#include <cuda_runtime.h>
+
+#include "b2rt_internal.h"
+
+namespace b2rt {
+
+struct DeviceBVH {
+  uint8_t* blob = nullptr;
+  TreeletDesc* treelets = nullptr;
+  uint32_t n_treelets = 0, n_levels = 0, width = 4, max_treelet_bytes = 0;
+  LevelRange levels[MAX_LEVELS];
+  uint64_t blob_bytes = 0;
+};
+
+// Device-resident statistics (all u64): see b2rt_stats
+struct TraceCounters {
+  unsigned long long node_visits, prim_tests, subtree_visits, pushes;
+};
+
+// Work buffers of the scheduler.  One Tracer serves one stream.
+struct Tracer {
+  DeviceBVH bvh;
+  uint64_t max_rays = 0, pair_cap = 0, chunk_cap = 0;
+  uint32_t chunk_rays = 1024;
+  int num_sms = 148, ctas_per_sm = 1;
+  size_t smem_bytes = 0;
+  // device buffers
+  uint32_t* cnt = nullptr;        // [n_treelets] rays queued per subtree
+  uint32_t* seg_off = nullptr;    // [n_treelets]
+  uint32_t* cursor = nullptr;     // [n_treelets]
+  uint2* pairs = nullptr;         // [pair_cap] (subtree id, ray id)
+  uint32_t* ids_sorted = nullptr; // [pair_cap]
+  uint4* chunks = nullptr;        // [chunk_cap] (subtree, first, count, -)
+  uint32_t* ctrl = nullptr;       // [16] pair_count[2], n_chunks, next_chunk, overflow, ...
+  TraceCounters* counters = nullptr;
+  bool collect_stats = false;
+  uint64_t launches = 0;
+
+  int init(const DeviceBVH& b, uint64_t max_rays_, uint32_t pair_factor);
+  void release();
+  // rays: o = (ox,oy,oz,tmin), d = (dx,dy,dz,tmax); hits must be initialised by the caller to
+  // pack(tmax, 0xFFFFFFFF).  ids0 == nullptr -> rays 0..n-1.  n_active_dev: device count of rays.
+  int trace(cudaStream_t s, const float4* ray_o, const float4* ray_d, unsigned long long* hits,
+            const uint32_t* ids0, const uint32_t* n_active_dev, bool any_hit);
+  int check_overflow(cudaStream_t s, bool* overflow);  // synchronises the stream
+};
+
+enum { CTRL_PAIRS0 = 0, CTRL_PAIRS1 = 1, CTRL_NCHUNKS = 2, CTRL_NEXT = 3, CTRL_OVERFLOW = 4 };
+
+int upload_bvh(const WideBVH& h, DeviceBVH* d);
+void free_bvh(DeviceBVH* d);
+
+#define B2RT_CUDA_OK(call)                                                                          \
+  do {                                                                                              \
+    cudaError_t e__ = (call);                                                                       \
+    if (e__ != cudaSuccess) {                                                                       \
+      ::b2rt::set_error(std::string(#call) + ": " + cudaGetErrorString(e__));                       \
+      return e__ == cudaErrorMemoryAllocation ? B2RT_ERR_OOM : B2RT_ERR_CUDA;                       \
+    }                                                                                               \
+  } while (0)
+
+}  // namespace b2rt

@@ -243,6 +243,12 @@ int b2rt_scene_load(const char* path, b2rt_scene_file** out);
 int b2rt_scene_save(const char* path, const b2rt_scene_file* scene);
 int b2rt_load_dae(const char* path, b2rt_scene_file** out);
 void b2rt_scene_free(b2rt_scene_file* s);
+/* Builds the wide BVH on the host and checks the serialised subtree blobs structurally (every primitive
+ * in exactly one leaf, child boxes contain their contents, exits point one level down, byte budget and
+ * per-ray stack bound respected).  out[8] = subtrees, levels, wide nodes, leaves, blob bytes, largest
+ * subtree bytes, stack bound, exits.  Test hook; no reference equivalent. */
+int b2rt_bvh_validate_host(const b2rt_scene_desc* scene, uint32_t max_leaf_size, uint32_t width,
+                           uint32_t treelet_bytes, uint64_t out[8]);
 int b2rt_camera_place(const float bbox[6], const float view_dir[3], float hfov_deg,
                       float vfov_deg, uint32_t width, uint32_t height, b2rt_camera* out);
 
