@@ -1,0 +1,311 @@
+#!/usr/bin/env python3
+"""Headline benchmark: Mrays/s (all bounces) and s/frame of the path-tracing hot path on B200.
+
+  python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path (one rank per GPU under torchrun)
+  python bench.py --impl reference --steps K --warmup W    # CPU arm: the oracle port on the box's host cores
+
+A "step" is one full frame of the workload (BASELINE.json configs[1]: CBbunny.dae, 1024x768, 64 spp,
+max depth 8, area light, 1 B200): ray generation, <= 8 closest-hit traversals and <= 8 shadow-ray
+traversals per path, shading, accumulation.  `value` counts every ray actually traced (camera + bounce +
+shadow) over all ranks / max-over-ranks device time of the K timed steps.  Multi-GPU: samples are
+sharded by index (rank r renders samples r, r+N, ...; per-GPU work fixed => weak scaling) with the scene
+replicated, and the per-GPU accumulation buffers are combined with ONE NCCL reduce per frame, inside the
+timed region.  Prints exactly one JSON line on rank 0.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(ROOT, "cuda-raytracer_b200"))
+
+import numpy as np  # noqa: E402
+
+WORKLOADS = {
+    # name: (scene file, width, height, spp, depth, ns_area_light)
+    "cfg1": ("CBspheres_lambertian", 480, 360, 16, 4, 1),
+    "cfg2": ("CBbunny", 1024, 768, 64, 8, 1),
+}
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
+    ap.add_argument("--spp", type=int, default=0, help="override samples per pixel (debug only; invalidates the number)")
+    ap.add_argument("--cpu-spp", type=int, default=0, help="spp of the bounded CPU sample (default: 4 main arm, 1 reference arm)")
+    ap.add_argument("--bvh-width", type=int, default=0)
+    ap.add_argument("--treelet-bytes", type=int, default=0)
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    return ap.parse_args()
+
+
+def load_workload(name, spp_override=0):
+    from b2rt.scene import Scene, place_camera
+    scene_name, w, h, spp, depth, nsl = WORKLOADS[name]
+    sc = Scene.load(os.path.join(ROOT, "scenes", scene_name + ".b2s"))
+    cam = place_camera(sc, w, h)
+    if spp_override:
+        spp = spp_override
+    return sc, cam, dict(scene=scene_name, width=w, height=h, spp=spp, depth=depth, ns_area_light=nsl)
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md clocks line)."""
+
+    def __init__(self, index):
+        self.rows = []
+        self.proc = None
+        self.index = index
+
+    def start(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            p = [x.strip() for x in r.split(",")]
+            if len(p) < 7:
+                continue
+            try:
+                sm.append(float(p[0])); mx.append(float(p[1]))
+            except ValueError:
+                continue
+            for n, v in zip(names, p[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def cpu_arm(args, sc, cam, wl, spp_sample, steps, warmup):
+    """The reference's CPU implementation of the path on the host cores: the oracle port (the checkout's own
+    CPU traversal / integrator bodies are stubs), all host threads, bounded sample."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import orc
+    from b2rt._abi import Config
+    threads = os.cpu_count() or 1
+    o = orc.OracleScene(sc, 4)
+    cfg = Config(ns_aa=spp_sample, max_ray_depth=wl["depth"], ns_area_light=wl["ns_area_light"], seed=1)
+    for _ in range(warmup):
+        o.render(cam, cfg, wl["width"], wl["height"], threads=threads, tile_stride=8)
+    rays = 0
+    secs = 0.0
+    for _ in range(steps):
+        o.render(cam, cfg, wl["width"], wl["height"], threads=threads)
+        st = o.last_stats
+        rays += st["rays_camera"] + st["rays_bounce"] + st["rays_shadow"]
+        secs += st["seconds"]
+    return dict(value=rays / secs / 1e6, unit="Mrays/s", cores=threads, kind="port",
+                sample=f"{wl['scene']} {wl['width']}x{wl['height']}, {spp_sample} of {wl['spp']} spp, depth {wl['depth']}, "
+                       f"{steps} frame(s), {threads} threads, oracle binary-SAH BVH (max_leaf 4)",
+                seconds=secs, rays=rays, s_per_frame_scaled=secs / steps * wl["spp"] / spp_sample)
+
+
+def main():
+    args = parse()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    sc, cam, wl = load_workload(args.workload, args.spp)
+    metric = "Mrays/s (all bounces)"
+    config = {"workload": f"{wl['scene']}.dae {wl['width']}x{wl['height']}, {wl['spp']} spp/GPU, max_ray_depth {wl['depth']}, "
+                          f"ns_area_light {wl['ns_area_light']} (BASELINE configs[1])",
+              "scene_tris": int(sc.n_tris), "parallelism": f"spp-sharded x{world}, scene replicated",
+              "l2": "per-wave ray/path state (4Mi paths x ~200 B) exceeds the 126 MB L2; no explicit flush"}
+
+    if args.impl == "reference":
+        if rank != 0:
+            return 0
+        spp_s = args.cpu_spp or 1
+        cb = cpu_arm(args, sc, cam, wl, spp_s, args.steps, args.warmup)
+        line = {"impl": "reference", "metric": metric, "value": cb["value"], "unit": "Mrays/s", "n_gpus": args.gpus,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": cb["seconds"] / args.steps * 1e3,
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": config,
+                "cpu_baseline": {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")},
+                "e2e": {"value": cb["value"], "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        print(json.dumps(line))
+        return 0
+
+    import torch
+    import b2rt
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the b200 arm has no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local_rank}"))
+    stream = torch.cuda.current_stream()
+
+    pt = b2rt.PathTracer(ns_aa=wl["spp"], max_ray_depth=wl["depth"], ns_area_light=wl["ns_area_light"], seed=1,
+                         device=local_rank, sample_first=rank, sample_stride=world, bvh_width=args.bvh_width,
+                         treelet_bytes=args.treelet_bytes)
+    pt.set_stream(stream.cuda_stream)
+    pt.set_scene(sc); pt.set_camera(cam); pt.set_frame_size(wl["width"], wl["height"])
+    accum = pt.accum_tensor() if world > 1 else None
+
+    def frame():
+        pt.clear()
+        pt.start_raytracing()
+        pt.wait()
+        if world > 1:
+            dist.reduce(accum, dst=0)     # ONE collective per frame: sum of the per-GPU accumulation buffers
+
+    # counters pass (untimed): algorithmic work of one frame
+    pt.set_profiling(counters=True, time_kernels=False)
+    frame()
+    cst = pt.stats()
+    pt.set_profiling(counters=False, time_kernels=True)
+    for _ in range(args.warmup):
+        frame()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    clocks = ClockSampler(local_rank)
+    if rank == 0:
+        clocks.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    rays = 0
+    ms_trav = 0.0
+    launches = 0
+    trav_launches = 0
+    ev0.record(stream)
+    for _ in range(args.steps):
+        frame()
+        st = pt.stats()
+        rays += st["rays_camera"] + st["rays_bounce"] + st["rays_shadow"]
+        ms_trav += st["ms_traverse"]
+        launches += st["kernel_launches"]
+        trav_launches += st["traverse_launches"]
+    ev1.record(stream)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    clk = clocks.stop() if rank == 0 else None
+    ms = ev0.elapsed_time(ev1)
+    if world > 1:
+        t = torch.tensor([ms], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+        r = torch.tensor([rays, launches], device="cuda", dtype=torch.float64)
+        dist.all_reduce(r, op=dist.ReduceOp.SUM)
+        rays_total, launches_total = int(r[0].item()), int(r[1].item())
+    else:
+        rays_total, launches_total = rays, launches
+    value = rays_total / (ms * 1e-3) / 1e6
+
+    # ---- end-to-end through the public API with HOST buffers: scene upload (+ host BVH build) + camera +
+    #      render + read-back of the HDR frame, every step ----
+    h2d = int(cst["bvh_bytes"] + sc.n_prims * (48 + 4) + (sc.n_tris * 36 if sc.tri_normals is not None else 0)
+              + len(sc.materials) * 48 + len(sc.lights) * 64)
+    d2h = wl["width"] * wl["height"] * 16
+    pt.set_profiling(counters=False, time_kernels=False)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    t0 = time.perf_counter()
+    rays_e = 0
+    for _ in range(args.steps):
+        pt.set_scene(sc); pt.set_camera(cam)
+        pt.start_raytracing(); pt.wait()
+        if world > 1:
+            dist.reduce(accum, dst=0)
+        img = pt.rgba32f()
+        st = pt.stats()
+        rays_e += st["rays_camera"] + st["rays_bounce"] + st["rays_shadow"]
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    if world > 1:
+        t = torch.tensor([e2e_s], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_s = float(t.item())
+        r = torch.tensor([rays_e], device="cuda", dtype=torch.float64)
+        dist.all_reduce(r, op=dist.ReduceOp.SUM)
+        rays_e = int(r.item())
+    e2e = {"value": rays_e / e2e_s / 1e6, "unit": "Mrays/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+           "s_per_frame": e2e_s / args.steps,
+           "what": "b2rt_set_scene (host BVH build + upload) + set_camera + start/wait + read_rgba32f to host, per step"}
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return 0
+
+    # ---- roofline of the dominant kernel (k_traverse) ----
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(peaks_path):
+        peaks = json.load(open(peaks_path)); hbm = float(peaks["hbm_gbs"]); peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)"
+    else:
+        hbm = 6650.0; peak_src = "fallback (B200_PROFILING.md 6.65 TB/s)"
+    W = cst["bvh_width"]
+    alg_bytes = (40 * cst["subtree_visits"] + 24 * cst["queue_pushes"] + 8 * cst["hit_updates"] + cst["staged_bytes"])
+    alg_flops = 24 * W * cst["node_visits"] + 55 * cst["leaf_prim_tests"]
+    trav_ms_frame = ms_trav / args.steps
+    tl = max(1, trav_launches // args.steps)
+    achieved = alg_bytes / (trav_ms_frame * 1e-3) / 1e9
+    sm_mhz = (clk or {}).get("sm_mhz") or 1965.0
+    fp32_peak = 148 * 128 * 2 * sm_mhz * 1e6 / 1e12
+    fp32_ach = alg_flops / (trav_ms_frame * 1e-3) / 1e12
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "traverse_traffic.json")
+    if os.path.exists(tpath):
+        traffic = json.load(open(tpath)).get("dram_bytes_per_launch")
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": hbm, "unit": "GB/s", "frac": achieved / hbm, "traffic": traffic,
+                "kernel": "k_traverse", "peak_source": peak_src, "launches_per_step": tl,
+                "avg_launch_ms": trav_ms_frame / tl, "alg_bytes_per_launch": alg_bytes / tl,
+                "alg_bytes_per_ray": alg_bytes / max(1, cst["rays_camera"] + cst["rays_bounce"] + cst["rays_shadow"]),
+                "kernel_share_of_step": trav_ms_frame / (ms / args.steps),
+                "fp32": {"achieved_tflops": fp32_ach, "peak_tflops": fp32_peak, "frac": fp32_ach / fp32_peak,
+                         "peak_source": f"148 SMs x 128 lanes x 2 x {sm_mhz:.0f} MHz (clock observed under load)"},
+                "binding_term": "hbm" if achieved / hbm >= fp32_ach / fp32_peak else "fp32",
+                "counters_per_frame": {k: cst[k] for k in ("subtree_visits", "queue_pushes", "hit_updates", "staged_bytes",
+                                                           "node_visits", "leaf_prim_tests")}}
+
+    cpu_baseline = None
+    if world == 1 and not args.no_cpu:
+        cb = cpu_arm(args, sc, cam, wl, args.cpu_spp or 4, 1, 1)
+        cpu_baseline = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample", "s_per_frame_scaled")}
+
+    line = {"metric": metric, "value": value, "unit": "Mrays/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms / args.steps, "s_per_frame": ms / args.steps / 1e3, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config, "clocks": clk, "e2e": e2e,
+            "gpu_launches": launches_total, "roofline": roofline, "cpu_baseline": cpu_baseline,
+            "rays_per_step": rays_total // args.steps, "bvh": {k: cst[k] for k in ("bvh_nodes", "bvh_subtrees", "bvh_levels",
+                                                                                   "bvh_width", "bvh_bytes", "ms_build")}}
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

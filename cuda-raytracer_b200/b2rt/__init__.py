@@ -25,7 +25,8 @@ EXPORTS = [
     "b2rt_bvh_occluded", "b2rt_bvh_bench_rays", "b2rt_bvh_get_stats", "b2rt_bvh_get_bbox", "b2rt_bvh_destroy",
     "b2rt_create", "b2rt_set_config", "b2rt_set_scene", "b2rt_set_camera", "b2rt_set_frame_size", "b2rt_start",
     "b2rt_is_done", "b2rt_wait", "b2rt_stop", "b2rt_clear", "b2rt_render", "b2rt_read_hdr", "b2rt_read_ldr",
-    "b2rt_read_rgba32f", "b2rt_get_stats", "b2rt_accum_device_ptr", "b2rt_stream_handle", "b2rt_destroy",
+    "b2rt_read_rgba32f", "b2rt_get_stats", "b2rt_accum_device_ptr", "b2rt_stream_handle", "b2rt_set_stream",
+    "b2rt_set_profiling", "b2rt_destroy", "b2rt_bvh_validate_host",
     "b2rt_scene_load", "b2rt_scene_save", "b2rt_load_dae", "b2rt_scene_free", "b2rt_camera_place",
 ]
 
@@ -69,6 +70,9 @@ def lib():
         L.b2rt_get_stats.argtypes = [vp, C.POINTER(Stats)]
         L.b2rt_accum_device_ptr.argtypes = [vp, C.POINTER(vp), C.POINTER(C.c_size_t)]
         L.b2rt_stream_handle.argtypes = [vp, C.POINTER(vp)]
+        L.b2rt_set_stream.argtypes = [vp, vp]
+        L.b2rt_set_profiling.argtypes = [vp, C.c_int, C.c_int]
+        L.b2rt_bvh_validate_host.argtypes = [C.POINTER(SceneDesc), u32, u32, u32, vp]
         L.b2rt_destroy.argtypes = [vp]; L.b2rt_destroy.restype = None
         L.b2rt_camera_place.argtypes = [vp, vp, C.c_float, C.c_float, u32, u32, C.POINTER(Camera)]
         _lib = L
@@ -88,6 +92,15 @@ def device_count():
 def _f32(a, shape=None):
     a = np.ascontiguousarray(a, np.float32)
     return a if shape is None else a.reshape(shape)
+
+
+def validate_bvh_host(scene, max_leaf_size=4, width=4, treelet_bytes=0):
+    """Host-only structural check of the serialised BVH (no GPU)."""
+    d, keep = scene.desc()
+    out = np.zeros(8, np.uint64)
+    _check(lib().b2rt_bvh_validate_host(C.byref(d), max_leaf_size, width, treelet_bytes, out.ctypes.data))
+    keys = ("subtrees", "levels", "wide_nodes", "leaves", "blob_bytes", "max_subtree_bytes", "stack_bound", "exits")
+    return dict(zip(keys, out.tolist()))
 
 
 class BVHAccel:
@@ -268,6 +281,12 @@ class PathTracer:
         s = Stats()
         _check(lib().b2rt_get_stats(self._h, C.byref(s)))
         return s.as_dict()
+
+    def set_stream(self, cuda_stream_ptr):
+        _check(lib().b2rt_set_stream(self._h, C.c_void_p(cuda_stream_ptr)))
+
+    def set_profiling(self, counters=False, time_kernels=False):
+        _check(lib().b2rt_set_profiling(self._h, int(counters), int(time_kernels)))
 
     def accum_device_ptr(self):
         p = C.c_void_p(); n = C.c_size_t(0)

@@ -36,7 +36,8 @@ class Config(C.Structure):
 class Stats(C.Structure):
     _fields_ = [("rays_camera", C.c_uint64), ("rays_bounce", C.c_uint64), ("rays_shadow", C.c_uint64),
                 ("node_visits", C.c_uint64), ("leaf_prim_tests", C.c_uint64), ("subtree_visits", C.c_uint64),
-                ("queue_pushes", C.c_uint64), ("kernel_launches", C.c_uint64), ("ms_total", C.c_double),
+                ("queue_pushes", C.c_uint64), ("staged_bytes", C.c_uint64), ("hit_updates", C.c_uint64),
+                ("kernel_launches", C.c_uint64), ("traverse_launches", C.c_uint64), ("ms_total", C.c_double),
                 ("ms_traverse", C.c_double), ("ms_build", C.c_double), ("bvh_nodes", C.c_uint32),
                 ("bvh_subtrees", C.c_uint32), ("bvh_levels", C.c_uint32), ("bvh_width", C.c_uint32),
                 ("bvh_bytes", C.c_uint64)]

@@ -173,7 +173,8 @@ int intersect_host(b2rt_bvh* b, const float* org, const float* dir, const float*
   TraceCounters tc;
   cudaMemcpy(&tc, b->tracer.counters, sizeof tc, cudaMemcpyDeviceToHost);
   b->last.node_visits = tc.node_visits; b->last.leaf_prim_tests = tc.prim_tests; b->last.subtree_visits = tc.subtree_visits;
-  b->last.queue_pushes = tc.pushes; b->last.kernel_launches = b->tracer.launches; b->last.ms_total = ms_sum; b->last.ms_traverse = ms_sum;
+  b->last.queue_pushes = tc.pushes; b->last.staged_bytes = tc.staged_bytes; b->last.hit_updates = tc.hit_updates;
+  b->last.kernel_launches = b->tracer.launches; b->last.ms_total = ms_sum; b->last.ms_traverse = ms_sum;
   cudaMemset(b->tracer.counters, 0, sizeof tc);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) { set_error(std::string("intersect: ") + cudaGetErrorString(e)); return B2RT_ERR_CUDA; }
@@ -274,7 +275,8 @@ int b2rt_bvh_bench_rays(b2rt_bvh* b, uint64_t n, int mode, uint64_t seed, int re
   cudaFree(d_cnt);
   if (hits_out) *hits_out = hc;
   b->last.node_visits = tc.node_visits; b->last.leaf_prim_tests = tc.prim_tests; b->last.subtree_visits = tc.subtree_visits;
-  b->last.queue_pushes = tc.pushes; b->last.ms_total = total / repeats; b->last.ms_traverse = total / repeats;
+  b->last.queue_pushes = tc.pushes; b->last.staged_bytes = tc.staged_bytes; b->last.hit_updates = tc.hit_updates;
+  b->last.ms_total = total / repeats; b->last.ms_traverse = total / repeats;
   b->last.kernel_launches = b->tracer.launches / (uint64_t)(repeats + 1);
   b->last.rays_camera = n;
   return B2RT_OK;
@@ -385,6 +387,17 @@ int b2rt_accum_device_ptr(b2rt_renderer* h, void** dev_ptr, size_t* n_floats) {
 int b2rt_stream_handle(b2rt_renderer* h, void** s) {
   if (!h || !s) { set_error("null argument"); return B2RT_ERR_INVALID; }
   *s = (void*)h->r.stream;
+  return B2RT_OK;
+}
+int b2rt_set_stream(b2rt_renderer* h, void* s) {
+  if (!h) { set_error("null handle"); return B2RT_ERR_INVALID; }
+  return h->r.set_stream((cudaStream_t)s);
+}
+int b2rt_set_profiling(b2rt_renderer* h, int collect_counters, int time_kernels) {
+  if (!h) { set_error("null handle"); return B2RT_ERR_INVALID; }
+  if (h->r.running) { int rc = h->r.wait(); if (rc) return rc; }
+  h->r.tracer.collect_stats = collect_counters != 0;
+  h->r.tracer.time_kernels = time_kernels != 0;
   return B2RT_OK;
 }
 void b2rt_destroy(b2rt_renderer* h) {

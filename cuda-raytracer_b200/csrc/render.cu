@@ -410,7 +410,8 @@ int Renderer::create(const b2rt_config* c) {
   device = cfg.device;
   if (device < 0) B2RT_CUDA_OK(cudaGetDevice(&device));
   RCHECK(set_device());
-  B2RT_CUDA_OK(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+  B2RT_CUDA_OK(cudaStreamCreateWithFlags(&own_stream, cudaStreamNonBlocking));
+  stream = own_stream;
   B2RT_CUDA_OK(cudaEventCreate(&ev_start));
   B2RT_CUDA_OK(cudaEventCreate(&ev_done));
   return B2RT_OK;
@@ -441,7 +442,14 @@ void Renderer::destroy() {
   free_ptr(accum); free_ptr(img_a); free_ptr(img_b); free_ptr(ldr);
   if (ev_start) cudaEventDestroy(ev_start);
   if (ev_done) cudaEventDestroy(ev_done);
-  if (stream) cudaStreamDestroy(stream);
+  if (own_stream) cudaStreamDestroy(own_stream);
+}
+
+int Renderer::set_stream(cudaStream_t s) {
+  if (running) RCHECK(wait());
+  if (stream) cudaStreamSynchronize(stream);
+  stream = s ? s : own_stream;
+  return B2RT_OK;
 }
 
 int Renderer::set_scene(const b2rt_scene_desc* d) {
@@ -585,7 +593,7 @@ int Renderer::start() {
   pb.s_o = (float4*)s_o; pb.s_d = (float4*)s_d; pb.s_hits = s_hits; pb.s_contrib = (float4*)s_contrib;
   pb.ids_a = ids_a; pb.ids_b = ids_b; pb.s_ids = s_ids; pb.counts = counts;
 
-  tracer.launches = 0;
+  tracer.launches = 0; tracer.traverse_launches = 0; tracer.ev_used = 0;
   launches = 0;
   B2RT_CUDA_OK(cudaMemsetAsync(totals, 0, 8 * 8, stream));
   B2RT_CUDA_OK(cudaMemsetAsync(tracer.counters, 0, sizeof(TraceCounters), stream));
@@ -666,8 +674,10 @@ int Renderer::wait() {
   last.rays_camera = cancelled ? 0 : cam_rays_enqueued;
   last.rays_bounce = t[0]; last.rays_shadow = t[1];
   last.node_visits = tc.node_visits; last.leaf_prim_tests = tc.prim_tests; last.subtree_visits = tc.subtree_visits;
-  last.queue_pushes = tc.pushes;
+  last.queue_pushes = tc.pushes; last.staged_bytes = tc.staged_bytes; last.hit_updates = tc.hit_updates;
   last.kernel_launches = launches + tracer.launches;
+  last.traverse_launches = tracer.traverse_launches;
+  last.ms_traverse = tracer.harvest_traverse_ms();
   last.ms_total = ms_total;
   bool ovf = false;
   RCHECK(tracer.check_overflow(stream, &ovf));

@@ -9,7 +9,7 @@ namespace b2rt {
 struct Renderer {
   b2rt_config cfg{};
   int device = -1;
-  cudaStream_t stream = nullptr;
+  cudaStream_t stream = nullptr, own_stream = nullptr;
   cudaEvent_t ev_start = nullptr, ev_done = nullptr;
   // scene
   DeviceBVH dbvh;
@@ -37,6 +37,7 @@ struct Renderer {
   double ms_total = 0, ms_traverse_acc = 0;
 
   int set_device();
+  int set_stream(cudaStream_t s);
   int create(const b2rt_config* c);
   void destroy();
   void release_scene();

@@ -239,7 +239,7 @@ k_traverse(const TravParams P) {
   uint32_t phase = 0;
   uint32_t n_staged = 0;   // warp-uniform
   uint2* stage = s_stage[warp];
-  unsigned long long st_nodes = 0, st_prims = 0, st_visits = 0, st_push = 0;
+  unsigned long long st_nodes = 0, st_prims = 0, st_visits = 0, st_push = 0, st_upd = 0;
 
   if (threadIdx.x == 0) { mbar_init(&s_bar, 1); }
   asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -265,6 +265,7 @@ k_traverse(const TravParams P) {
       mbar_wait(&s_bar, phase);
       phase ^= 1;
       cur_treelet = chunk.x;
+      if (STATS && threadIdx.x == 0) atomicAdd(&P.counters->staged_bytes, (unsigned long long)td.bytes);
     }
     const uint8_t* nodes = smem;
     const uint8_t* prims = smem + (size_t)td.n_nodes * NB;
@@ -390,7 +391,7 @@ k_traverse(const TravParams P) {
           if (n_staged > STAGE_PAIRS - 32) flush_pairs(stage, n_staged, P, lane);
         }
       }
-      if (have && improved) atomicMin(&P.hits[rid], pack_hit(best_t, best_id));
+      if (have && improved) { atomicMin(&P.hits[rid], pack_hit(best_t, best_id)); if (STATS) st_upd++; }
     }
     __syncthreads();   // every warp is done with this chunk (s_chunk / s_next_batch / subtree smem reusable)
   }
@@ -402,12 +403,14 @@ k_traverse(const TravParams P) {
       st_prims += __shfl_xor_sync(0xffffffffu, st_prims, dlt);
       st_visits += __shfl_xor_sync(0xffffffffu, st_visits, dlt);
       st_push += __shfl_xor_sync(0xffffffffu, st_push, dlt);
+      st_upd += __shfl_xor_sync(0xffffffffu, st_upd, dlt);
     }
     if (lane == 0) {
       atomicAdd(&P.counters->node_visits, st_nodes);
       atomicAdd(&P.counters->prim_tests, st_prims);
       atomicAdd(&P.counters->subtree_visits, st_visits);
       atomicAdd(&P.counters->pushes, st_push);
+      atomicAdd(&P.counters->hit_updates, st_upd);
     }
   }
 }
@@ -484,6 +487,16 @@ int Tracer::init(const DeviceBVH& b, uint64_t max_rays_, uint32_t pair_factor) {
   return B2RT_OK;
 }
 
+double Tracer::harvest_traverse_ms() {
+  double total = 0;
+  for (size_t i = 0; i + 1 < ev_used; i += 2) {
+    float ms = 0;
+    if (cudaEventElapsedTime(&ms, ev_pool[i], ev_pool[i + 1]) == cudaSuccess) total += ms;
+  }
+  ev_used = 0;
+  return total;
+}
+
 void Tracer::release() {
   cudaFree(cnt); cudaFree(seg_off); cudaFree(cursor); cudaFree(pairs); cudaFree(ids_sorted); cudaFree(chunks);
   cudaFree(ctrl); cudaFree(counters);
@@ -521,9 +534,18 @@ int Tracer::trace(cudaStream_t s, const float4* ray_o, const float4* ray_d, unsi
     P.ids = (L == 0) ? ids0 : ids_sorted;
     P.chunks = chunks; P.ctrl = ctrl; P.cnt = cnt; P.pairs = pairs; P.pair_cap = (uint32_t)pair_cap; P.level = L;
     P.counters = counters;
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    if (time_kernels) {
+      if (ev_used + 2 > ev_pool.size()) {
+        for (int k = 0; k < 64; ++k) { cudaEvent_t e; B2RT_CUDA_OK(cudaEventCreate(&e)); ev_pool.push_back(e); }
+      }
+      e0 = ev_pool[ev_used++]; e1 = ev_pool[ev_used++];
+      cudaEventRecord(e0, s);
+    }
     if (bvh.width == 8) launch_traverse<8>(*this, s, P, any_hit, collect_stats);
     else launch_traverse<4>(*this, s, P, any_hit, collect_stats);
-    launches++;
+    if (time_kernels) cudaEventRecord(e1, s);
+    launches++; traverse_launches++;
   }
   B2RT_CUDA_OK(cudaGetLastError());
   return B2RT_OK;

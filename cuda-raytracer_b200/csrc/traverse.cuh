@@ -17,6 +17,8 @@ struct DeviceBVH {
 // Device-resident statistics (all u64): see b2rt_stats
 struct TraceCounters {
   unsigned long long node_visits, prim_tests, subtree_visits, pushes;
+  unsigned long long staged_bytes;   // subtree bytes moved global -> shared by the TMA bulk copies
+  unsigned long long hit_updates;    // 64-bit atomicMin operations issued
 };
 
 // Work buffers of the scheduler.  One Tracer serves one stream.
@@ -37,6 +39,12 @@ struct Tracer {
   TraceCounters* counters = nullptr;
   bool collect_stats = false;
   uint64_t launches = 0;
+  // per-launch CUDA-event timing of k_traverse (the dominant kernel), on the launching stream
+  bool time_kernels = false;
+  std::vector<cudaEvent_t> ev_pool;
+  size_t ev_used = 0;
+  uint64_t traverse_launches = 0;
+  double harvest_traverse_ms();      // call after the stream is synchronised; resets the pool cursor
 
   int init(const DeviceBVH& b, uint64_t max_rays_, uint32_t pair_factor);
   void release();

@@ -132,7 +132,10 @@ typedef struct b2rt_stats {
   uint64_t leaf_prim_tests;  /* ray-primitive tests */
   uint64_t subtree_visits;   /* (ray, subtree) queue entries processed */
   uint64_t queue_pushes;     /* ray ids pushed to child-subtree queues */
+  uint64_t staged_bytes;     /* subtree bytes staged global->shared by TMA bulk copies */
+  uint64_t hit_updates;      /* packed (t, prim) 64-bit atomicMin operations */
   uint64_t kernel_launches;  /* kernels launched by the last render/intersect call */
+  uint64_t traverse_launches;/* of which launches of the traversal kernel */
   double ms_total;           /* device time of the last render/intersect call (CUDA events) */
   double ms_traverse;        /* device time inside traversal + scheduling kernels */
   double ms_build;           /* host BVH build + upload of the current scene */
@@ -219,6 +222,12 @@ int b2rt_get_stats(b2rt_renderer* r, b2rt_stats* out);
  * pointer is device memory owned by the handle, valid until set_frame_size/destroy. */
 int b2rt_accum_device_ptr(b2rt_renderer* r, void** dev_ptr, size_t* n_floats);
 int b2rt_stream_handle(b2rt_renderer* r, void** cuda_stream);
+/* Run on a caller-owned CUDA stream (e.g. the framework stream that also carries the NCCL reduce).
+ * cuda_stream = NULL restores the handle's own stream. */
+int b2rt_set_stream(b2rt_renderer* r, void* cuda_stream);
+/* collect_counters: traversal statistics (node visits, pushes, ...) cost a few percent; off by default.
+ * time_kernels: CUDA-event pair around every traversal-kernel launch -> b2rt_stats.ms_traverse. */
+int b2rt_set_profiling(b2rt_renderer* r, int collect_counters, int time_kernels);
 void b2rt_destroy(b2rt_renderer* r);
 
 /* ---- host helpers (no device needed) -----------------------------------------------------------

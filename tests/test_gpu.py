@@ -1,0 +1,295 @@
+"""GPU parity tests (run on the B200 box: pytest -m gpu).  Everything goes through the C ABI (libb2rt.so via the
+ctypes binding) and is compared with the CPU oracle on the same seeded inputs.
+
+Bars: closest-hit primitive ids and distances, any-hit flags: BIT-EXACT.  Radiance: the integrator's fp32
+arithmetic is restated identically in the oracle and in the kernels (explicit fma contract, -fmad=false), so the
+HDR frame is expected to be bit-identical; the asserted tolerance is per-pixel RMSE <= 1e-6 and max abs diff <= 1e-5
+(north_star: "within a stated per-pixel RMSE tolerance at equal spp").  8-bit tone-mapped output: +-1 LSB (powf)."""
+import numpy as np
+import pytest
+
+import b2rt
+import orc
+from b2rt._abi import Config
+from b2rt.scene import Scene, camera_rays, place_camera, random_soup, subdivide
+from conftest import scene_path
+
+pytestmark = pytest.mark.gpu
+
+MISS = 0xFFFFFFFF
+
+
+def _rays(sc, n, seed):
+    rng = np.random.default_rng(seed)
+    lo, hi = sc.bbox[:3], sc.bbox[3:]
+    o = (lo + (hi - lo) * rng.random((n, 3))).astype(np.float32)
+    d = rng.normal(size=(n, 3)); d /= np.linalg.norm(d, axis=1, keepdims=True)
+    return o, d.astype(np.float32)
+
+
+def _mixed_rays(sc, n_random, seed, w=160, h=120):
+    cam = place_camera(sc, w, h)
+    ro, rd = camera_rays(cam, w, h)
+    r2o, r2d = _rays(sc, n_random, seed)
+    return np.concatenate([ro, r2o]), np.concatenate([rd, r2d])
+
+
+@pytest.mark.parametrize("name", ["CBbunny", "CBcoil", "CBgems", "CBspheres_lambertian", "CBspheres", "CBempty", "trigs10",
+                                  "sphere_diffuse", "plane1024", "floating"])
+@pytest.mark.parametrize("width,treelet_bytes,max_leaf", [(4, 0, 4), (8, 0, 4), (4, 8192, 2), (8, 100000, 8)])
+def test_closest_hit_bit_exact(name, width, treelet_bytes, max_leaf):
+    sc = Scene.load(scene_path(name))
+    o = orc.OracleScene(sc, 4)
+    bvh = b2rt.BVHAccel(sc, max_leaf_size=max_leaf, width=width, treelet_bytes=treelet_bytes)
+    org, dirs = _mixed_rays(sc, 40000, 3)
+    t, p = bvh.intersect(org, dirs)
+    tr, pr = o.intersect(org, dirs, mode="bvh")
+    assert np.array_equal(p, pr), f"{np.sum(p != pr)} primitive ids differ"
+    assert np.array_equal(t, tr)
+    st = bvh.stats()
+    assert st["kernel_launches"] >= 3 and st["subtree_visits"] >= len(org)
+    bvh.close()
+
+
+def test_closest_hit_vs_exhaustive_search():
+    """Against the argmin over ALL primitives (what an exact closest hit is, independent of any BVH)."""
+    sc = Scene.load(scene_path("CBcoil"))
+    o = orc.OracleScene(sc, 4)
+    bvh = b2rt.BVHAccel(sc)
+    org, dirs = _mixed_rays(sc, 4000, 5, 64, 48)
+    t, p = bvh.intersect(org, dirs)
+    tr, pr = o.intersect(org, dirs, mode="brute")
+    assert np.array_equal(p, pr) and np.array_equal(t, tr)
+
+
+def test_tmin_tmax_windows_and_any_hit():
+    sc = Scene.load(scene_path("CBbunny"))
+    o = orc.OracleScene(sc, 4)
+    bvh = b2rt.BVHAccel(sc)
+    org, dirs = _mixed_rays(sc, 30000, 8)
+    rng = np.random.default_rng(1)
+    tmin = (rng.random(len(org)) * 0.5).astype(np.float32)
+    tmax = (tmin + rng.random(len(org)) * 3).astype(np.float32)
+    t, p = bvh.intersect(org, dirs, tmin, tmax)
+    tr, pr = o.intersect(org, dirs, tmin, tmax)
+    assert np.array_equal(p, pr) and np.array_equal(t, tr)
+    hit = p != MISS
+    assert np.all((t[hit] >= tmin[hit]) & (t[hit] <= tmax[hit]))
+    occ = bvh.occluded(org, dirs, tmin, tmax)
+    assert np.array_equal(occ, pr != MISS)       # any hit inside the window <=> a closest hit exists
+
+
+def test_edge_cases():
+    sc = Scene.load(scene_path("CBspheres_lambertian"))
+    o = orc.OracleScene(sc, 4)
+    bvh = b2rt.BVHAccel(sc)
+    # empty batch
+    t, p = bvh.intersect(np.zeros((0, 3), np.float32), np.zeros((0, 3), np.float32))
+    assert len(t) == 0 and len(p) == 0
+    # axis-aligned directions (zero components), rays starting on surfaces, rays leaving the scene
+    org = np.array([[0, 0.75, 3], [0, 0.75, 0], [0, 0, 0], [0.5, 1.0, 0.2], [0, 5, 0], [0, 0.75, 0]], np.float32)
+    dirs = np.array([[0, 0, -1], [0, -1, 0], [0, 1, 0], [1, 0, 0], [0, 1, 0], [0, 0, 1]], np.float32)
+    t, p = bvh.intersect(org, dirs)
+    tr, pr = o.intersect(org, dirs)
+    assert np.array_equal(p, pr) and np.array_equal(t, tr)
+    assert p[4] == MISS and np.isinf(t[4])
+    # ragged batch sizes around warp / chunk boundaries
+    for n in (1, 31, 33, 1023, 1025, 4097):
+        ro, rd = _rays(sc, n, n)
+        t, p = bvh.intersect(ro, rd)
+        tr, pr = o.intersect(ro, rd)
+        assert np.array_equal(p, pr) and np.array_equal(t, tr)
+
+
+def test_tie_rule_lowest_prim_id():
+    tri = np.array([[0, 0, 0, 1, 0, 0, 0, 1, 0]], np.float32)
+    quad2 = np.array([[1, 0, 0, 1, 1, 0, 0, 1, 0]], np.float32)     # shares the diagonal edge
+    sc = Scene(np.concatenate([tri, tri, quad2, tri]))
+    o = orc.OracleScene(sc, 4)
+    bvh = b2rt.BVHAccel(sc, max_leaf_size=1)
+    n = 2000
+    s = np.linspace(0.001, 0.999, n, dtype=np.float32)
+    org = np.stack([s, 1 - s, np.ones(n, np.float32)], 1)   # along the shared diagonal
+    dirs = np.tile(np.array([[0, 0, -1]], np.float32), (n, 1))
+    t, p = bvh.intersect(org, dirs)
+    tr, pr = o.intersect(org, dirs, mode="brute")
+    assert np.array_equal(p, pr) and np.array_equal(t, tr)
+    assert set(np.unique(p)) <= {0, 2}
+
+
+def test_soup_parity_and_multilevel():
+    sc = random_soup(300000, size=0.02)
+    o = orc.OracleScene(sc, 4)
+    bvh = b2rt.BVHAccel(sc, treelet_bytes=16384)
+    assert bvh.stats()["bvh_levels"] >= 3
+    org, dirs = _rays(sc, 60000, 21)
+    t, p = bvh.intersect(org, dirs)
+    tr, pr = o.intersect(org, dirs)
+    assert np.array_equal(p, pr) and np.array_equal(t, tr)
+    assert (p != MISS).mean() > 0.5
+
+
+RENDER_CASES = [
+    # scene, w, h, spp, depth, ns_area_light
+    ("CBspheres_lambertian", 480, 360, 16, 4, 1),   # BASELINE configs[0] at full size
+    ("CBbunny", 256, 192, 4, 8, 1),                 # configs[1] knobs at reduced size (full size below, via properties)
+    ("CBgems", 160, 120, 8, 6, 2),                  # glass
+    ("CBcoil", 160, 120, 4, 5, 1),                  # mirror
+    ("CBspheres", 160, 120, 8, 6, 1),               # glass + mirror spheres
+    ("CBempty", 96, 72, 3, 2, 4),
+    ("floating", 96, 72, 2, 3, 1),
+]
+
+
+@pytest.mark.parametrize("name,w,h,spp,depth,nsl", RENDER_CASES)
+def test_radiance_parity(name, w, h, spp, depth, nsl):
+    sc = Scene.load(scene_path(name))
+    cam = place_camera(sc, w, h)
+    pt = b2rt.PathTracer(ns_aa=spp, max_ray_depth=depth, ns_area_light=nsl, seed=11)
+    pt.set_scene(sc); pt.set_camera(cam); pt.set_frame_size(w, h)
+    assert pt.start_raytracing()
+    pt.wait()
+    assert pt.is_done()
+    img = pt.hdr()
+    o = orc.OracleScene(sc, 4)
+    ref = o.render(cam, Config(ns_aa=spp, max_ray_depth=depth, ns_area_light=nsl, seed=11), w, h)
+    rmse = float(np.sqrt(np.mean((img - ref) ** 2)))
+    assert rmse <= 1e-6, rmse
+    assert float(np.abs(img - ref).max()) <= 1e-5
+    st = pt.stats()
+    cs = o.last_stats
+    assert (st["rays_camera"], st["rays_bounce"], st["rays_shadow"]) == (cs["rays_camera"], cs["rays_bounce"], cs["rays_shadow"])
+    # tone-mapped 8-bit output: toColor formula, +-1 LSB
+    ldr = pt.ldr()
+    ref_ldr = orc.tonemap(ref)
+    for s in (0, 8, 16, 24):
+        d = np.abs(((ldr >> s) & 255).astype(np.int32) - ((ref_ldr >> s) & 255).astype(np.int32))
+        assert d.max() <= 1
+    pt.close()
+
+
+def test_waves_and_width_do_not_change_the_image():
+    sc = Scene.load(scene_path("CBbunny"))
+    w, h = 128, 96
+    cam = place_camera(sc, w, h)
+    imgs = []
+    for kw in (dict(), dict(max_wave_paths=5000), dict(bvh_width=8, treelet_bytes=20000), dict(max_leaf_size=8, max_wave_paths=40000)):
+        pt = b2rt.PathTracer(ns_aa=6, max_ray_depth=4, ns_area_light=1, seed=2, **kw)
+        pt.set_scene(sc); pt.set_camera(cam); pt.set_frame_size(w, h)
+        pt.render()
+        imgs.append(pt.hdr())
+        pt.close()
+    for im in imgs[1:]:
+        assert np.array_equal(im, imgs[0])
+
+
+def test_full_size_properties_cfg2():
+    """BASELINE configs[1] at full size (CBbunny 1024x768, 64 spp, depth 8): too slow for the oracle, so checked through
+    size-independent properties: determinism, sample-shard linearity (the multi-GPU decomposition), agreement of a
+    sub-window of samples with the oracle, ray-count conservation."""
+    sc = Scene.load(scene_path("CBbunny"))
+    w, h, spp, depth = 1024, 768, 64, 8
+    cam = place_camera(sc, w, h)
+    pt = b2rt.PathTracer(ns_aa=spp, max_ray_depth=depth, ns_area_light=1, seed=1)
+    pt.set_scene(sc); pt.set_camera(cam); pt.set_frame_size(w, h)
+    pt.render(); full = pt.hdr(); st = pt.stats()
+    assert st["rays_camera"] == w * h * spp
+    assert st["rays_bounce"] < st["rays_camera"] * (depth - 1) and st["rays_shadow"] < st["rays_camera"] * depth
+    pt.clear(); pt.render()
+    assert np.array_equal(pt.hdr(), full)                                  # deterministic
+    halves = []
+    for r in range(2):
+        pt.set_config(ns_aa=spp // 2, sample_first=r, sample_stride=2)
+        pt.clear(); pt.render(); halves.append(pt.hdr())
+    np.testing.assert_allclose(0.5 * (halves[0] + halves[1]), full, rtol=1e-4, atol=1e-5)   # linearity over sample shards
+    # oracle on a 1-sample shard (sample index 37 of the same global stream)
+    pt.set_config(ns_aa=1, sample_first=37, sample_stride=64)
+    pt.clear(); pt.render(); one = pt.hdr()
+    ref = orc.OracleScene(sc, 4).render(cam, Config(ns_aa=1, max_ray_depth=depth, ns_area_light=1, seed=1, sample_first=37,
+                                                    sample_stride=64), w, h)
+    assert float(np.sqrt(np.mean((one - ref) ** 2))) <= 1e-6
+    assert 0.05 < full.mean() < 0.3
+    pt.close()
+
+
+def test_dragon_class_standin_parity():
+    """cfg3 stand-in: CBbunny with the bunny mesh subdivided once, 114,316 triangles."""
+    base = Scene.load(scene_path("CBbunny"))
+    sc = subdivide(base, 1, select=lambda tv, tm: tm == tm[np.argmax(np.bincount(tm))])
+    o = orc.OracleScene(sc, 4)
+    bvh = b2rt.BVHAccel(sc)
+    org, dirs = _mixed_rays(sc, 50000, 4, 320, 240)
+    t, p = bvh.intersect(org, dirs)
+    tr, pr = o.intersect(org, dirs)
+    assert np.array_equal(p, pr) and np.array_equal(t, tr)
+    bvh.close()
+    w, h = 192, 108
+    cam = place_camera(sc, w, h)
+    pt = b2rt.PathTracer(ns_aa=2, max_ray_depth=8, ns_area_light=1, seed=4)
+    pt.set_scene(sc); pt.set_camera(cam); pt.set_frame_size(w, h); pt.render()
+    ref = o.render(cam, Config(ns_aa=2, max_ray_depth=8, ns_area_light=1, seed=4), w, h)
+    assert float(np.sqrt(np.mean((pt.hdr() - ref) ** 2))) <= 1e-6
+
+
+def test_median_filter_and_progressive_renderer():
+    sc = Scene.load(scene_path("CBspheres_lambertian"))
+    w, h = 100, 75
+    r = b2rt.CudaRenderer(samples_per_frame=2, max_ray_depth=3, ns_area_light=2, median_threshold=32, seed=6)
+    r.allocOutputImage(w, h); r.loadScene(sc); r.setup()
+    r.render()
+    img1 = r.getImage()
+    o = orc.OracleScene(sc, 4)
+    cam = place_camera(sc, w, h)
+    ref1 = o.render(cam, Config(ns_aa=2, max_ray_depth=3, ns_area_light=2, seed=6), w, h)
+    np.testing.assert_array_equal(img1[..., :3], orc.median3x3(ref1))       # below the threshold: 3x3 median, border 1.0
+    assert np.all(img1[..., 3] == 1.0)
+    r.render()                                                              # second frame: samples 2,3 accumulate
+    ref2 = o.render(cam, Config(ns_aa=4, max_ray_depth=3, ns_area_light=2, seed=6), w, h)
+    np.testing.assert_allclose(r.getImage()[..., :3], orc.median3x3(ref2), rtol=1e-5, atol=1e-6)
+    r.setViewpoint(cam)                                                     # resets accumulation
+    r.render()
+    np.testing.assert_array_equal(r.getImage()[..., :3], orc.median3x3(ref1))
+
+
+def test_state_machine_and_errors():
+    sc = Scene.load(scene_path("CBempty"))
+    pt = b2rt.PathTracer(ns_aa=1)
+    assert pt.state == pt.INIT and not pt.start_raytracing()               # only from READY (pathtracer.cpp:184)
+    with pytest.raises(b2rt.B2rtError):
+        b2rt._check(b2rt.lib().b2rt_start(pt._h))                          # C ABI: error code instead of a silent no-op
+    pt.set_scene(sc); pt.set_camera(place_camera(sc, 64, 48)); pt.set_frame_size(64, 48)
+    assert pt.state == pt.READY
+    pt.set_config(ns_aa=64, max_ray_depth=8)
+    assert pt.start_raytracing() and pt.state == pt.RENDERING
+    pt.stop()
+    assert pt.state == pt.READY
+    pt.set_config(ns_aa=1)
+    pt.set_frame_size(32, 24)                                              # resize invalidates the frame
+    assert pt.start_raytracing(); pt.wait(); assert pt.is_done()
+    assert pt.hdr().shape == (24, 32, 3)
+    pt.increase_area_light_sample_count(); assert pt.cfg.ns_area_light == 2
+    pt.decrease_area_light_sample_count(); assert pt.cfg.ns_area_light == 1
+    with pytest.raises(b2rt.B2rtError):
+        pt.set_frame_size(0, 10)
+    pt.close()
+
+
+def test_two_gpu_style_sharding_on_one_device():
+    """The multi-GPU decomposition emulated on one GPU: two handles render disjoint sample shards, their accumulation
+    buffers are summed (what the NCCL reduce does) and resolved."""
+    import torch
+    from b2rt.dist import resolve_mean, shard_samples
+    sc = Scene.load(scene_path("CBcoil"))
+    w, h, spp = 96, 72, 8
+    cam = place_camera(sc, w, h)
+    total = None
+    for r in range(2):
+        first, stride, cnt = shard_samples(spp, r, 2)
+        pt = b2rt.PathTracer(ns_aa=cnt, max_ray_depth=4, seed=13, sample_first=first, sample_stride=stride)
+        pt.set_scene(sc); pt.set_camera(cam); pt.set_frame_size(w, h); pt.render()
+        acc = pt.accum_tensor().clone()
+        total = acc if total is None else total + acc
+        pt.close()
+    got = resolve_mean(total).cpu().numpy().reshape(h, w, 3)
+    ref = orc.OracleScene(sc, 4).render(cam, Config(ns_aa=spp, max_ray_depth=4, ns_area_light=1, seed=13), w, h)
+    np.testing.assert_allclose(got, ref, rtol=2e-5, atol=1e-6)

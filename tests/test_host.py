@@ -1,0 +1,175 @@
+"""CPU tests of the product's host side: the C-ABI library loads and exports every symbol of include/b2rt.h,
+fails loudly without a device, the host BVH builder produces structurally valid subtree blobs, scene IO and
+camera placement agree with the Python mirror, and the multi-GPU plumbing (sample sharding + one reduce)
+works with world_size 2 over gloo."""
+import ctypes as C
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+import b2rt
+from b2rt._abi import Camera, Config
+from b2rt.scene import Scene, place_camera, random_soup, subdivide
+from conftest import ROOT, scene_path
+
+
+def test_header_symbols_exported():
+    hdr = open(os.path.join(ROOT, "include", "b2rt.h")).read()
+    declared = set(re.findall(r"\b(b2rt_[a-z0-9_]+)\s*\(", hdr))
+    declared -= {"b2rt_status"}
+    lib = b2rt.lib()
+    missing = [s for s in sorted(declared) if not hasattr(lib, s)]
+    assert not missing, missing
+    assert set(b2rt.EXPORTS) <= declared
+    assert lib.b2rt_abi_version() == 1
+
+
+def test_fails_loudly_without_device():
+    if b2rt.device_count() > 0:
+        pytest.skip("a CUDA device is visible")
+    sc = Scene.load(scene_path("trigs1"))
+    with pytest.raises(b2rt.B2rtError) as e:
+        b2rt.BVHAccel(sc)
+    assert e.value.code == -2 and "no CPU fallback" in str(e.value)
+    with pytest.raises(b2rt.B2rtError) as e:
+        b2rt.PathTracer()
+    assert e.value.code == -2
+
+
+def test_product_does_not_link_oracle():
+    out = subprocess.check_output(["ldd", b2rt.LIB_PATH], text=True)
+    assert "oracle" not in out
+    for root, _, files in os.walk(os.path.join(ROOT, "cuda-raytracer_b200")):
+        for f in files:
+            if f.endswith((".cu", ".cuh", ".cpp", ".h", ".py")):
+                src = open(os.path.join(root, f)).read()
+                assert "liboracle" not in src and "import orc" not in src, f
+
+
+@pytest.mark.parametrize("name", ["CBbunny", "CBcoil", "CBgems", "CBspheres_lambertian", "CBempty", "trigs1", "sphere_diffuse",
+                                  "plane1024"])
+@pytest.mark.parametrize("width", [4, 8])
+def test_bvh_blob_structure(name, width):
+    sc = Scene.load(scene_path(name))
+    for tb in (0, 8192, 150000):
+        for ml in (2, 4, 8):
+            st = b2rt.validate_bvh_host(sc, ml, width, tb)
+            assert st["stack_bound"] <= 64
+            assert st["subtrees"] >= 1 and st["levels"] >= 1
+
+
+def test_bvh_blob_structure_soup_and_degenerate():
+    st = b2rt.validate_bvh_host(random_soup(200000), 4, 4, 0)
+    assert st["levels"] >= 2 and st["exits"] == st["subtrees"] - 1
+    # all-coincident triangles (degenerate centroids) and a single triangle
+    tri = np.tile(np.array([[0, 0, 0, 1, 0, 0, 0, 1, 0]], np.float32), (1000, 1))
+    st = b2rt.validate_bvh_host(Scene(tri), 4, 4, 0)
+    assert st["leaves"] >= 250
+    st = b2rt.validate_bvh_host(Scene(tri[:1]), 4, 8, 0)
+    assert st["wide_nodes"] == 1 and st["leaves"] == 1
+
+
+def test_invalid_arguments():
+    sc = Scene.load(scene_path("trigs1"))
+    with pytest.raises(b2rt.B2rtError):
+        b2rt.validate_bvh_host(sc, 4, 5, 0)          # width must be 4 or 8
+    with pytest.raises(b2rt.B2rtError):
+        b2rt.validate_bvh_host(sc, 100, 4, 0)        # leaf size limit
+    bad = Scene(sc.tri_verts, None, np.array([7], np.uint32))
+    with pytest.raises(b2rt.B2rtError):
+        b2rt.validate_bvh_host(bad, 4, 4, 0)         # material index out of range
+
+
+def test_scene_file_roundtrip_and_camera(tmp_path):
+    lib = b2rt.lib()
+
+    class SceneFile(C.Structure):
+        _fields_ = [("desc", b2rt._abi.SceneDesc), ("camera", Camera), ("cam_dir", C.c_float * 3), ("cam_hfov_deg", C.c_float),
+                    ("cam_vfov_deg", C.c_float), ("bbox", C.c_float * 6), ("storage", C.c_void_p)]
+    lib.b2rt_scene_load.argtypes = [C.c_char_p, C.POINTER(C.POINTER(SceneFile))]
+    lib.b2rt_scene_save.argtypes = [C.c_char_p, C.POINTER(SceneFile)]
+    lib.b2rt_scene_free.argtypes = [C.POINTER(SceneFile)]
+    for name in ("CBspheres_lambertian", "CBcoil"):
+        sc = Scene.load(scene_path(name))
+        p = C.POINTER(SceneFile)()
+        assert lib.b2rt_scene_load(scene_path(name).encode(), C.byref(p)) == 0
+        f = p.contents
+        assert f.desc.n_tris == sc.n_tris and f.desc.n_spheres == len(sc.spheres) and f.desc.n_lights == len(sc.lights)
+        tv = np.ctypeslib.as_array(f.desc.tri_verts, shape=(sc.n_tris * 9,))
+        assert np.array_equal(tv, sc.tri_verts.reshape(-1))
+        out = tmp_path / (name + ".b2s")
+        assert lib.b2rt_scene_save(str(out).encode(), p) == 0
+        assert open(out, "rb").read() == open(scene_path(name), "rb").read()
+        for (w, h) in ((640, 480), (1920, 1080), (100, 300)):
+            cam_c = Camera()
+            bbox = (C.c_float * 6)(*[float(x) for x in sc.bbox]); vd = (C.c_float * 3)(*[float(x) for x in sc.cam_dir])
+            assert lib.b2rt_camera_place(bbox, vd, sc.hfov, sc.vfov, w, h, C.byref(cam_c)) == 0
+            cam_p = place_camera(sc, w, h)
+            np.testing.assert_allclose(cam_c.pos[:], cam_p.pos[:], rtol=1e-6, atol=1e-6)
+            np.testing.assert_allclose(cam_c.c2w[:], cam_p.c2w[:], rtol=1e-6, atol=1e-6)
+            assert abs(cam_c.hfov_deg - cam_p.hfov_deg) < 1e-4 and abs(cam_c.vfov_deg - cam_p.vfov_deg) < 1e-4
+        lib.b2rt_scene_free(p)
+    p = C.POINTER(SceneFile)()
+    assert lib.b2rt_scene_load(b"/nonexistent.b2s", C.byref(p)) == -5
+
+
+def test_subdivide_standin():
+    sc = Scene.load(scene_path("CBbunny"))
+    big = subdivide(sc, 1, select=lambda tv, tm: tm == tm[np.argmax(np.bincount(tm))])
+    assert big.n_tris == 12 + 28576 * 4     # "CBdragon_standin" = 114,316 triangles
+    st = b2rt.validate_bvh_host(big, 4, 4, 0)
+    assert st["leaves"] > 20000
+
+
+def test_shard_samples():
+    from b2rt.dist import shard_samples
+    for total in (1, 7, 64, 256):
+        for world in (1, 2, 3, 8):
+            got = []
+            for r in range(world):
+                first, stride, cnt = shard_samples(total, r, world)
+                got += [first + k * stride for k in range(cnt)]
+            assert sorted(got) == list(range(total))
+
+
+_WORKER = r'''
+import os, sys
+sys.path.insert(0, os.path.join(sys.argv[1], "cuda-raytracer_b200")); sys.path.insert(0, os.path.join(sys.argv[1], "oracle"))
+import numpy as np, torch, torch.distributed as dist
+from b2rt._abi import Config
+from b2rt.scene import Scene, place_camera
+from b2rt.dist import shard_samples, reduce_accum, resolve_mean
+import orc   # the CPU oracle stands in for the device renderer in this gloo test of the host plumbing
+dist.init_process_group("gloo")
+rank, world = dist.get_rank(), dist.get_world_size()
+sc = Scene.load(os.path.join(sys.argv[1], "scenes", "CBspheres_lambertian.b2s"))
+w, h, spp = 32, 24, 6
+cam = place_camera(sc, w, h)
+first, stride, cnt = shard_samples(spp, rank, world)
+o = orc.OracleScene(sc, 4)
+img = o.render(cam, Config(ns_aa=cnt, max_ray_depth=3, ns_area_light=1, seed=9, sample_first=first, sample_stride=stride), w, h, threads=1)
+accum = torch.zeros(h * w * 4)
+a = accum.view(-1, 4); a[:, :3] = torch.from_numpy(img.reshape(-1, 3)) * cnt; a[:, 3] = cnt
+reduce_accum(accum, dst=0)
+if rank == 0:
+    full = o.render(cam, Config(ns_aa=spp, max_ray_depth=3, ns_area_light=1, seed=9), w, h, threads=1)
+    got = resolve_mean(accum).numpy().reshape(h, w, 3)
+    assert float(accum.view(-1, 4)[:, 3].min()) == spp
+    np.testing.assert_allclose(got, full, rtol=2e-5, atol=1e-6)
+    print("DIST_OK")
+dist.destroy_process_group()
+'''
+
+
+def test_two_rank_gloo_reduce(tmp_path):
+    script = tmp_path / "worker.py"
+    script.write_text(_WORKER)
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1")
+    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+                          "--master-port", "29541", str(script), ROOT], capture_output=True, text=True, env=env, timeout=300)
+    assert out.returncode == 0, out.stderr[-2000:]
+    assert "DIST_OK" in out.stdout
