@@ -293,7 +293,11 @@ k_traverse(const TravParams P) {
         tmin = ro.w; tmax_user = rd.w;
         best_t = __uint_as_float((uint32_t)(h >> 32));
         best_id = (uint32_t)h;
-        inv = mk3(__frcp_rn(d.x), __frcp_rn(d.y), __frcp_rn(d.z));
+        // reciprocal direction for the slab test; |d_k| < 1e-18 (incl. +-0) is clamped so that o_k * inv_k
+        // stays finite: the ray is then parallel to the slab and the test reduces to lo_k <= o_k <= hi_k
+        inv = mk3(fabsf(d.x) > 1e-18f ? __frcp_rn(d.x) : copysignf(1e18f, d.x),
+                  fabsf(d.y) > 1e-18f ? __frcp_rn(d.y) : copysignf(1e18f, d.y),
+                  fabsf(d.z) > 1e-18f ? __frcp_rn(d.z) : copysignf(1e18f, d.z));
         noi = mk3(-(o.x * inv.x), -(o.y * inv.y), -(o.z * inv.z));
         bool skip = ANYHIT && best_id != 0xFFFFFFFFu;
         if (!skip) { stack[0].ref = 0u;  /* INTERNAL node 0 = subtree root */ stack[0].tn = tmin; sp = 1; }
