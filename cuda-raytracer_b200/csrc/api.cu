@@ -175,7 +175,8 @@ int intersect_host(b2rt_bvh* b, const float* org, const float* dir, const float*
   b->last.node_visits = tc.node_visits; b->last.leaf_prim_tests = tc.prim_tests; b->last.subtree_visits = tc.subtree_visits;
   b->last.queue_pushes = tc.pushes; b->last.staged_bytes = tc.staged_bytes; b->last.hit_updates = tc.hit_updates;
   b->last.kernel_launches = b->tracer.launches; b->last.ms_total = ms_sum; b->last.ms_traverse = ms_sum;
-  cudaMemset(b->tracer.counters, 0, sizeof tc);
+  cudaMemsetAsync(b->tracer.counters, 0, sizeof tc, b->stream);
+  cudaStreamSynchronize(b->stream);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) { set_error(std::string("intersect: ") + cudaGetErrorString(e)); return B2RT_ERR_CUDA; }
   return B2RT_OK;

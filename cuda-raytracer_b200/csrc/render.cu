@@ -497,6 +497,7 @@ int Renderer::set_scene(const b2rt_scene_desc* d) {
   for (auto& l : hs.lights) shadow_per_hit += l.kind == B2RT_LIGHT_AREA ? std::max(1u, cfg.ns_area_light) : 1u;
   lights_host = hs.lights;
   have_scene = true;
+  B2RT_CUDA_OK(cudaDeviceSynchronize());   // uploads above used the legacy stream; work runs on `stream`
   return B2RT_OK;
 }
 

@@ -16,6 +16,7 @@
 // every grid is persistent.
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdio.h>
 
 #include <algorithm>
 
@@ -189,6 +190,7 @@ struct TravParams {
   uint2* pairs;               // (child subtree, ray id) output
   uint32_t pair_cap;
   uint32_t level;
+  uint32_t n_treelets, n_rays_cap;
   TraceCounters* counters;
 };
 
@@ -224,16 +226,25 @@ __device__ __forceinline__ void flush_pairs(uint2* stage, uint32_t& n_staged, co
   n_staged = 0;
 }
 
+#ifdef B2RT_CHECKS
+#define B2_CHECK(cond, code, info) do { if (!(cond)) { atomicExch(&P.ctrl[6], (uint32_t)(code)); atomicExch(&P.ctrl[7], (uint32_t)(info)); } } while (0)
+#else
+#define B2_CHECK(cond, code, info) do { } while (0)
+#endif
+constexpr uint32_t REF_NONE = 0xFFFFFFFEu;   // "no current node" marker of the traversal loop (tag EMPTY)
+constexpr int REFILL_MIN_IDLE = 8;            // refill a warp's idle lanes once this many are idle
+
 template <int W, bool ANYHIT, bool STATS>
 __global__ void __launch_bounds__(TRAV_THREADS, (W == 4 ? 3 : 2))
 k_traverse(const TravParams P) {
   extern __shared__ __align__(128) uint8_t smem[];
   __shared__ __align__(8) uint64_t s_bar;
   __shared__ uint4 s_chunk;
-  __shared__ uint32_t s_next_batch;
+  __shared__ uint32_t s_next_ray;
   __shared__ __align__(8) uint2 s_stage[TRAV_WARPS][STAGE_PAIRS];
 
   const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const uint32_t lane_lt = (1u << lane) - 1u;
   constexpr int NB = NodeView<W>::BYTES;
   uint32_t cur_treelet = 0xFFFFFFFFu;
   uint32_t phase = 0;
@@ -250,7 +261,7 @@ k_traverse(const TravParams P) {
     if (threadIdx.x == 0) {
       uint32_t c = atomicAdd(&P.ctrl[CTRL_NEXT], 1u);
       s_chunk = c < n_chunks ? P.chunks[c] : make_uint4(0xFFFFFFFFu, 0, 0, 0);
-      s_next_batch = 0;
+      s_next_ray = 0;
     }
     __syncthreads();
     const uint4 chunk = s_chunk;
@@ -270,134 +281,168 @@ k_traverse(const TravParams P) {
     const uint8_t* nodes = smem;
     const uint8_t* prims = smem + (size_t)td.n_nodes * NB;
 
-    // warps pull 32-ray batches of this chunk
+    // ---- per-lane ray state; lanes are refilled from the chunk as their rays finish -------------------
+    uint32_t rid = 0;
+    float best_t = 0.f; uint32_t best_id = 0xFFFFFFFFu;
+    f3 o = mk3(0, 0, 0), d = mk3(0, 0, 1), inv = mk3(0, 0, 0), noi = mk3(0, 0, 0);
+    float tmin = 0.f, tmax_user = 0.f;
+    uint32_t nx = 0, ny = 0, nz = 0, fx = 0, fy = 0, fz = 0;   // byte offsets of the near / far plane rows
+    StackEntry stack[STACK_SIZE];
+    int sp = 0;
+    uint32_t cur = REF_NONE;
+    bool have = false, improved = false;
+    bool exhausted = false;   // warp-uniform: the chunk has no more rays to hand out
+
+    // One convergence point per iteration: the ballot at the top.  The loop is left only there (all lanes idle
+    // and the chunk handed out); there is no other warp-level primitive on a conditional path except the
+    // warp-uniform refill / push blocks, each closed by __syncwarp().
     for (;;) {
-      uint32_t b = 0;
-      if (lane == 0) b = atomicAdd(&s_next_batch, 32u);
-      b = __shfl_sync(0xffffffffu, b, 0);
-      if (b >= chunk.z) break;
-      const uint32_t k = b + lane;
-      const bool have = k < chunk.z;
-      uint32_t rid = 0;
-      float best_t = 0.f; uint32_t best_id = 0xFFFFFFFFu;
-      f3 o = mk3(0, 0, 0), d = mk3(0, 0, 1), inv = mk3(0, 0, 0), noi = mk3(0, 0, 0);
-      float tmin = 0.f, tmax_user = 0.f;
-      StackEntry stack[STACK_SIZE];
-      int sp = 0;
-      bool improved = false;
-      if (have) {
-        rid = P.ids ? P.ids[chunk.y + k] : (chunk.y + k);
-        const float4 ro = P.ray_o[rid], rd = P.ray_d[rid];
-        const unsigned long long h = P.hits[rid];
-        o = mk3(ro.x, ro.y, ro.z); d = mk3(rd.x, rd.y, rd.z);
-        tmin = ro.w; tmax_user = rd.w;
-        best_t = __uint_as_float((uint32_t)(h >> 32));
-        best_id = (uint32_t)h;
-        // reciprocal direction for the slab test; |d_k| < 1e-18 (incl. +-0) is clamped so that o_k * inv_k
-        // stays finite: the ray is then parallel to the slab and the test reduces to lo_k <= o_k <= hi_k
-        inv = mk3(fabsf(d.x) > 1e-18f ? __frcp_rn(d.x) : copysignf(1e18f, d.x),
-                  fabsf(d.y) > 1e-18f ? __frcp_rn(d.y) : copysignf(1e18f, d.y),
-                  fabsf(d.z) > 1e-18f ? __frcp_rn(d.z) : copysignf(1e18f, d.z));
-        noi = mk3(-(o.x * inv.x), -(o.y * inv.y), -(o.z * inv.z));
-        bool skip = ANYHIT && best_id != 0xFFFFFFFFu;
-        if (!skip) { stack[0].ref = 0u;  /* INTERNAL node 0 = subtree root */ stack[0].tn = tmin; sp = 1; }
-        if (STATS) st_visits++;
+      __syncwarp();
+      const uint32_t m_idle = __ballot_sync(0xffffffffu, cur == REF_NONE);
+      if (m_idle == 0xffffffffu && exhausted) break;
+      if (m_idle && !exhausted && (__popc(m_idle) >= REFILL_MIN_IDLE || m_idle == 0xffffffffu)) {
+        // retire finished rays, then hand new rays to the idle lanes
+        const bool idle = cur == REF_NONE;
+        if (idle && have) {
+          if (improved) { atomicMin(&P.hits[rid], pack_hit(best_t, best_id)); if (STATS) st_upd++; }
+          have = false;
+        }
+        const uint32_t n_idle = __popc(m_idle);
+        uint32_t base = 0;
+        if (lane == 0) base = atomicAdd(&s_next_ray, n_idle);
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (base + n_idle >= chunk.z) exhausted = true;
+        const uint32_t k = base + __popc(m_idle & lane_lt);
+        if (idle && k < chunk.z) {
+          rid = P.ids ? P.ids[chunk.y + k] : (chunk.y + k);
+          B2_CHECK(rid < P.n_rays_cap, 1, rid);
+          if (rid >= P.n_rays_cap) rid = 0;
+          const float4 ro = P.ray_o[rid], rd = P.ray_d[rid];
+          const unsigned long long h = P.hits[rid];
+          o = mk3(ro.x, ro.y, ro.z); d = mk3(rd.x, rd.y, rd.z);
+          tmin = ro.w; tmax_user = rd.w;
+          best_t = __uint_as_float((uint32_t)(h >> 32));
+          best_id = (uint32_t)h;
+          // reciprocal direction for the slab test; |d_k| < 1e-18 (incl. +-0) is clamped so that o_k * inv_k
+          // stays finite: the ray is then parallel to the slab and the test reduces to lo_k <= o_k <= hi_k
+          inv = mk3(fabsf(d.x) > 1e-18f ? __frcp_rn(d.x) : copysignf(1e18f, d.x),
+                    fabsf(d.y) > 1e-18f ? __frcp_rn(d.y) : copysignf(1e18f, d.y),
+                    fabsf(d.z) > 1e-18f ? __frcp_rn(d.z) : copysignf(1e18f, d.z));
+          noi = mk3(-(o.x * inv.x), -(o.y * inv.y), -(o.z * inv.z));
+          nx = inv.x >= 0.f ? 0u : 12u * W; fx = 12u * W - nx;
+          ny = inv.y >= 0.f ? 4u * W : 16u * W; fy = 20u * W - ny;
+          nz = inv.z >= 0.f ? 8u * W : 20u * W; fz = 28u * W - nz;
+          have = true; improved = false; sp = 0;
+          const bool skip = ANYHIT && best_id != 0xFFFFFFFFu;
+          cur = skip ? REF_NONE : 0u;   // INTERNAL node 0 = subtree root
+          if (STATS) st_visits++;
+        }
+        __syncwarp();
       }
-      // warp-synchronous loop: one stack pop per lane per iteration
-      while (__any_sync(0xffffffffu, sp > 0)) {
-        bool do_push = false;
-        uint32_t push_treelet = 0;
-        if (sp > 0) {
-          const StackEntry e = stack[--sp];
-          if (e.tn <= best_t) {
-            const uint32_t tag = e.ref >> 30;
-            if (tag == REF_INTERNAL) {
-              if (STATS) st_nodes++;
-              const float4* nd = reinterpret_cast<const float4*>(nodes + (size_t)(e.ref & 0x3FFFFFFFu) * NB);
-              uint32_t keys[W];
-              uint32_t refs[W];
+
+      // ---- one traversal step per lane -----------------------------------------------------------------
+      bool do_push = false;
+      uint32_t push_treelet = 0;
+      bool need_pop = false;
+      if (cur != REF_NONE) {
+        const uint32_t tag = cur >> 30;
+        if (tag == REF_INTERNAL) {
+          if (STATS) st_nodes++;
+          B2_CHECK((cur & 0x3FFFFFFFu) < td.n_nodes, 2, cur);
+          const uint8_t* nbase = nodes + (size_t)(cur & 0x3FFFFFFFu) * NB;
+          const uint32_t* nrefs = reinterpret_cast<const uint32_t*>(nbase + 24 * W);
+          uint32_t keys[W];
+          // sign-ordered slab test: per axis the near plane row is lo (inv >= 0) or hi (inv < 0), chosen once
+          // per ray (row offsets nx/ny/nz, fx/fy/fz), so a box costs 6 fma + 3 max + 3 min.  Empty slots hold
+          // inverted infinite boxes (lo = +inf, hi = -inf) => t_near = +inf, t_far = -inf => never hit.
 #pragma unroll
-              for (int q = 0; q < W / 4; ++q) {
-                const float4 lx = nd[0 * (W / 4) + q], ly = nd[1 * (W / 4) + q], lz = nd[2 * (W / 4) + q];
-                const float4 hx = nd[3 * (W / 4) + q], hy = nd[4 * (W / 4) + q], hz = nd[5 * (W / 4) + q];
-                const uint4 rf = reinterpret_cast<const uint4*>(nd)[6 * (W / 4) + q];
-                const float lxa[4] = {lx.x, lx.y, lx.z, lx.w}, lya[4] = {ly.x, ly.y, ly.z, ly.w}, lza[4] = {lz.x, lz.y, lz.z, lz.w};
-                const float hxa[4] = {hx.x, hx.y, hx.z, hx.w}, hya[4] = {hy.x, hy.y, hy.z, hy.w}, hza[4] = {hz.x, hz.y, hz.z, hz.w};
-                const uint32_t rfa[4] = {rf.x, rf.y, rf.z, rf.w};
+          for (int q = 0; q < W / 4; ++q) {
+            const float4 ax = *reinterpret_cast<const float4*>(nbase + nx + 16 * q), bx = *reinterpret_cast<const float4*>(nbase + fx + 16 * q);
+            const float4 ay = *reinterpret_cast<const float4*>(nbase + ny + 16 * q), by = *reinterpret_cast<const float4*>(nbase + fy + 16 * q);
+            const float4 az = *reinterpret_cast<const float4*>(nbase + nz + 16 * q), bz = *reinterpret_cast<const float4*>(nbase + fz + 16 * q);
+            const float axa[4] = {ax.x, ax.y, ax.z, ax.w}, aya[4] = {ay.x, ay.y, ay.z, ay.w}, aza[4] = {az.x, az.y, az.z, az.w};
+            const float bxa[4] = {bx.x, bx.y, bx.z, bx.w}, bya[4] = {by.x, by.y, by.z, by.w}, bza[4] = {bz.x, bz.y, bz.z, bz.w};
 #pragma unroll
-                for (int c = 0; c < 4; ++c) {
-                  float tx0 = __fmaf_rn(lxa[c], inv.x, noi.x), tx1 = __fmaf_rn(hxa[c], inv.x, noi.x);
-                  float ty0 = __fmaf_rn(lya[c], inv.y, noi.y), ty1 = __fmaf_rn(hya[c], inv.y, noi.y);
-                  float tz0 = __fmaf_rn(lza[c], inv.z, noi.z), tz1 = __fmaf_rn(hza[c], inv.z, noi.z);
-                  float tn = fmaxf(fmaxf(fminf(tx0, tx1), fminf(ty0, ty1)), fmaxf(fminf(tz0, tz1), tmin));
-                  float tf = fminf(fminf(fmaxf(tx0, tx1), fmaxf(ty0, ty1)), fminf(fmaxf(tz0, tz1), best_t));
-                  bool hit = (tn <= tf * 1.0000004f) && (rfa[c] != REF_EMPTY_WORD);
-                  // key: entry distance (rounded down, keeps order for t >= 0) | child slot
-                  keys[q * 4 + c] = hit ? ((__float_as_uint(tn) & ~(uint32_t)(W - 1)) | (uint32_t)(q * 4 + c)) : 0xFFFFFFFFu;
-                  refs[q * 4 + c] = rfa[c];
-                }
-              }
-              // sort keys ascending (small network), then push far-to-near
-              if (W == 4) {
-#define B2_CE(a, b) { uint32_t lo_ = min(keys[a], keys[b]), hi_ = max(keys[a], keys[b]); keys[a] = lo_; keys[b] = hi_; }
-                B2_CE(0, 1) B2_CE(2, 3) B2_CE(0, 2) B2_CE(1, 3) B2_CE(1, 2)
-              } else {
-                // 19-comparator network for 8 inputs
-                B2_CE(0, 1) B2_CE(2, 3) B2_CE(4, 5) B2_CE(6, 7)
-                B2_CE(0, 2) B2_CE(1, 3) B2_CE(4, 6) B2_CE(5, 7)
-                B2_CE(1, 2) B2_CE(5, 6) B2_CE(0, 4) B2_CE(3, 7)
-                B2_CE(1, 5) B2_CE(2, 6)
-                B2_CE(1, 4) B2_CE(3, 6)
-                B2_CE(2, 4) B2_CE(3, 5)
-                B2_CE(3, 4)
-#undef B2_CE
-              }
-#pragma unroll
-              for (int q = W - 1; q >= 0; --q) {
-                if (keys[q] != 0xFFFFFFFFu) {
-                  const uint32_t slot = keys[q] & (uint32_t)(W - 1);
-                  uint32_t r = refs[0];
-#pragma unroll
-                  for (int z = 1; z < W; ++z) r = (slot == (uint32_t)z) ? refs[z] : r;
-                  stack[sp].ref = r;
-                  stack[sp].tn = __uint_as_float(keys[q] & ~(uint32_t)(W - 1));
-                  ++sp;
-                }
-              }
-            } else if (tag == REF_LEAF) {
-              const uint32_t first = e.ref & 0x00FFFFFFu, count = ((e.ref >> 24) & 63u) + 1u;
-              const PrimRec* pr = reinterpret_cast<const PrimRec*>(prims) + first;
-              for (uint32_t q = 0; q < count; ++q) {
-                const PrimRec p = pr[q];
-                if (STATS) st_prims++;
-                float t, u, v;
-                const uint32_t pid = __float_as_uint(p.c.y);
-                const bool h = (__float_as_uint(p.c.z) != 0u) ? hit_sphere(p, o, d, tmin, tmax_user, &t)
-                                                              : hit_triangle(p, o, d, tmin, tmax_user, &t, &u, &v);
-                if (h && (t < best_t || (t == best_t && pid < best_id))) {
-                  best_t = t; best_id = pid; improved = true;
-                  if (ANYHIT) { best_t = 0.0f; sp = 0; break; }
-                }
-              }
-            } else if (tag == REF_EXIT) {
-              do_push = true;
-              push_treelet = e.ref & 0x3FFFFFFFu;
+            for (int c = 0; c < 4; ++c) {
+              const float tn = fmaxf(fmaxf(__fmaf_rn(axa[c], inv.x, noi.x), __fmaf_rn(aya[c], inv.y, noi.y)),
+                                     fmaxf(__fmaf_rn(aza[c], inv.z, noi.z), tmin));
+              const float tf = fminf(fminf(__fmaf_rn(bxa[c], inv.x, noi.x), __fmaf_rn(bya[c], inv.y, noi.y)),
+                                     fminf(__fmaf_rn(bza[c], inv.z, noi.z), best_t));
+              const bool hit = tn <= tf * 1.0000004f;
+              // key: entry distance (rounded down, keeps order for t >= 0) | child slot
+              keys[q * 4 + c] = hit ? ((__float_as_uint(tn) & ~(uint32_t)(W - 1)) | (uint32_t)(q * 4 + c)) : 0xFFFFFFFFu;
             }
           }
+#define B2_CE(a, b) { const uint32_t lo_ = min(keys[a], keys[b]), hi_ = max(keys[a], keys[b]); keys[a] = lo_; keys[b] = hi_; }
+          if (W == 4) {
+            B2_CE(0, 1) B2_CE(2, 3) B2_CE(0, 2) B2_CE(1, 3) B2_CE(1, 2)
+          } else {
+            B2_CE(0, 1) B2_CE(2, 3) B2_CE(4, 5) B2_CE(6, 7)
+            B2_CE(0, 2) B2_CE(1, 3) B2_CE(4, 6) B2_CE(5, 7)
+            B2_CE(1, 2) B2_CE(5, 6) B2_CE(0, 4) B2_CE(3, 7)
+            B2_CE(1, 5) B2_CE(2, 6)
+            B2_CE(1, 4) B2_CE(3, 6)
+            B2_CE(2, 4) B2_CE(3, 5)
+            B2_CE(3, 4)
+          }
+#undef B2_CE
+          // far-to-near onto the stack; the nearest child becomes the current node without a stack round trip
+#pragma unroll
+          for (int q = W - 1; q >= 1; --q) {
+            if (keys[q] != 0xFFFFFFFFu) {
+              B2_CHECK(sp < (int)STACK_SIZE, 3, sp);
+              stack[sp].ref = nrefs[keys[q] & (uint32_t)(W - 1)];
+              stack[sp].tn = __uint_as_float(keys[q] & ~(uint32_t)(W - 1));
+              ++sp;
+            }
+          }
+          if (keys[0] != 0xFFFFFFFFu) cur = nrefs[keys[0] & (uint32_t)(W - 1)];
+          else need_pop = true;
+        } else if (tag == REF_LEAF) {
+          const uint32_t first = cur & 0x00FFFFFFu, count = ((cur >> 24) & 63u) + 1u;
+          const PrimRec* pr = reinterpret_cast<const PrimRec*>(prims) + first;
+          B2_CHECK(first + count <= td.n_prims, 4, cur);
+          need_pop = true;
+          for (uint32_t q = 0; q < count; ++q) {
+            const PrimRec p = pr[q];
+            if (STATS) st_prims++;
+            float t, u, v;
+            const uint32_t pid = __float_as_uint(p.c.y);
+            const bool h = (__float_as_uint(p.c.z) != 0u) ? hit_sphere(p, o, d, tmin, tmax_user, &t)
+                                                          : hit_triangle(p, o, d, tmin, tmax_user, &t, &u, &v);
+            if (h && (t < best_t || (t == best_t && pid < best_id))) {
+              best_t = t; best_id = pid; improved = true;
+              if (ANYHIT) { best_t = 0.0f; sp = 0; break; }
+            }
+          }
+        } else {   // EXIT
+          B2_CHECK(tag == REF_EXIT && (cur & 0x3FFFFFFFu) < P.n_treelets, 5, cur);
+          do_push = true;
+          push_treelet = cur & 0x3FFFFFFFu;
+          need_pop = true;
         }
-        // scheduler push: ballot + popc = exclusive scan of the 0/1 flags inside the warp
-        const uint32_t m = __ballot_sync(0xffffffffu, do_push);
-        if (m) {
-          if (do_push) stage[n_staged + __popc(m & ((1u << lane) - 1u))] = make_uint2(push_treelet, rid);
-          n_staged += __popc(m);
-          if (STATS && do_push) st_push++;
-          __syncwarp();
-          if (n_staged > STAGE_PAIRS - 32) flush_pairs(stage, n_staged, P, lane);
+        if (need_pop) {
+          cur = REF_NONE;
+          while (sp > 0) {
+            const StackEntry e = stack[--sp];
+            if (e.tn <= best_t) { cur = e.ref; break; }
+          }
         }
       }
-      if (have && improved) { atomicMin(&P.hits[rid], pack_hit(best_t, best_id)); if (STATS) st_upd++; }
+      // scheduler push: ballot + popc = exclusive scan of the 0/1 flags inside the warp
+      const uint32_t m = __ballot_sync(0xffffffffu, do_push);
+      if (m) {
+        B2_CHECK(n_staged + 32 <= STAGE_PAIRS, 6, n_staged);
+        if (do_push) stage[n_staged + __popc(m & lane_lt)] = make_uint2(push_treelet, rid);
+        n_staged += __popc(m);
+        if (STATS && do_push) st_push++;
+        __syncwarp();
+        if (n_staged > STAGE_PAIRS - 32) flush_pairs(stage, n_staged, P, lane);
+      }
     }
-    __syncthreads();   // every warp is done with this chunk (s_chunk / s_next_batch / subtree smem reusable)
+    // retire the rays still held by the lanes
+    if (have && improved) { atomicMin(&P.hits[rid], pack_hit(best_t, best_id)); if (STATS) st_upd++; }
+    __syncthreads();   // every warp is done with this chunk (s_chunk / s_next_ray / subtree smem reusable)
   }
   if (n_staged) flush_pairs(stage, n_staged, P, lane);
   if (STATS) {
@@ -436,6 +481,9 @@ int upload_bvh(const WideBVH& h, DeviceBVH* d) {
   B2RT_CUDA_OK(cudaMalloc(&d->treelets, h.treelets.size() * sizeof(TreeletDesc)));
   B2RT_CUDA_OK(cudaMemcpy(d->blob, h.blob.data(), h.blob.size(), cudaMemcpyHostToDevice));
   B2RT_CUDA_OK(cudaMemcpy(d->treelets, h.treelets.data(), h.treelets.size() * sizeof(TreeletDesc), cudaMemcpyHostToDevice));
+  // cudaMemcpy from pageable memory may return before the DMA has landed, and the non-blocking work streams do
+  // not order against the legacy stream: make the upload visible to every stream before anything traverses it
+  B2RT_CUDA_OK(cudaDeviceSynchronize());
   return B2RT_OK;
 }
 
@@ -488,6 +536,7 @@ int Tracer::init(const DeviceBVH& b, uint64_t max_rays_, uint32_t pair_factor) {
   B2RT_CUDA_OK(cudaMalloc(&counters, sizeof(TraceCounters)));
   B2RT_CUDA_OK(cudaMemset(ctrl, 0, 16 * 4));
   B2RT_CUDA_OK(cudaMemset(counters, 0, sizeof(TraceCounters)));
+  B2RT_CUDA_OK(cudaDeviceSynchronize());   // legacy-stream memsets vs the non-blocking work stream
   return B2RT_OK;
 }
 
@@ -537,7 +586,7 @@ int Tracer::trace(cudaStream_t s, const float4* ray_o, const float4* ray_d, unsi
     P.blob = bvh.blob; P.treelets = bvh.treelets; P.ray_o = ray_o; P.ray_d = ray_d; P.hits = hits;
     P.ids = (L == 0) ? ids0 : ids_sorted;
     P.chunks = chunks; P.ctrl = ctrl; P.cnt = cnt; P.pairs = pairs; P.pair_cap = (uint32_t)pair_cap; P.level = L;
-    P.counters = counters;
+    P.counters = counters; P.n_treelets = bvh.n_treelets; P.n_rays_cap = (uint32_t)std::min<uint64_t>(max_rays, 0xFFFFFFFFull);
     cudaEvent_t e0 = nullptr, e1 = nullptr;
     if (time_kernels) {
       if (ev_used + 2 > ev_pool.size()) {
@@ -560,6 +609,11 @@ int Tracer::check_overflow(cudaStream_t s, bool* overflow) {
   B2RT_CUDA_OK(cudaMemcpyAsync(&v, ctrl + CTRL_OVERFLOW, 4, cudaMemcpyDeviceToHost, s));
   B2RT_CUDA_OK(cudaStreamSynchronize(s));
   *overflow = v != 0;
+#ifdef B2RT_CHECKS
+  uint32_t dbg[2] = {0, 0};
+  cudaMemcpy(dbg, ctrl + 6, 8, cudaMemcpyDeviceToHost);
+  if (dbg[0]) { fprintf(stderr, "B2RT_CHECKS: code %u info %u (0x%08x)\n", dbg[0], dbg[1], dbg[1]); cudaMemset(ctrl + 6, 0, 8); }
+#endif
   if (v) B2RT_CUDA_OK(cudaMemsetAsync(ctrl + CTRL_OVERFLOW, 0, 4, s));
   return B2RT_OK;
 }
