@@ -26,6 +26,7 @@ namespace b2rt {
 namespace {
 
 constexpr float INF_F = __builtin_huge_valf();
+constexpr uint32_t MAX_DEPTH = 96, ACT0 = 8, SH0 = 8 + MAX_DEPTH + 8, N_COUNTS = 256;
 
 struct WaveParams {
   // wave geometry
@@ -58,16 +59,16 @@ struct PathBufs {
   float4* rad;     // rgb radiance of the path
   float4* s_o; float4* s_d; unsigned long long* s_hits; float4* s_contrib;  // shadow rays [slot*S + j]
   uint32_t* ids_a; uint32_t* ids_b; uint32_t* s_ids;
-  uint32_t* counts;  // [0]=n_active(cur) [1]=n_active(next) [2]=n_shadow [3]=cancel, [8+b] per-bounce stats
+  uint32_t* counts;  // [3] = cancel flag; [ACT0 + b] = active paths at bounce b; [SH0 + b] = shadow rays of bounce b
 };
 
 __global__ void __launch_bounds__(256)
 k_raygen(WaveParams wp, CamDev cam, PathBufs pb) {
   const uint32_t n = wp.n_pix * wp.spp;
   const uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x;
-  if (slot == 0) {
-    pb.counts[0] = pb.counts[3] ? 0u : n;
-    pb.counts[1] = 0; pb.counts[2] = 0;
+  if (blockIdx.x == 0 && threadIdx.x < MAX_DEPTH + 1) {   // per-bounce list counters of this wave
+    pb.counts[ACT0 + threadIdx.x] = (threadIdx.x == 0) ? (pb.counts[3] ? 0u : n) : 0u;
+    pb.counts[SH0 + threadIdx.x] = 0u;
   }
   if (slot >= n) return;
   const uint32_t pix = wp.pix0 + slot / wp.spp;
@@ -116,7 +117,7 @@ __device__ __forceinline__ void append_id(uint32_t* list, uint32_t* counter, boo
 __global__ void __launch_bounds__(256)
 k_shade(WaveParams wp, SceneDev sc, PathBufs pb, const uint32_t* __restrict__ ids, uint32_t* __restrict__ ids_next,
         uint32_t b, uint32_t identity_ids) {
-  const uint32_t n = pb.counts[0];
+  const uint32_t n = pb.counts[ACT0 + b];
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   bool cont = false;
   uint32_t slot = 0;
@@ -272,30 +273,20 @@ k_shade(WaveParams wp, SceneDev sc, PathBufs pb, const uint32_t* __restrict__ id
       }
     }
   }
-  append_id(ids_next, &pb.counts[1], cont, slot);
-}
-
-// shadow-ray id list for the any-hit trace: every valid (slot, j)
-__global__ void __launch_bounds__(256)
-k_collect_shadow(WaveParams wp, PathBufs pb, const uint32_t* __restrict__ ids, uint32_t identity_ids) {
-  const uint32_t n = pb.counts[0];
-  const uint32_t S = wp.S;
-  const unsigned long long total = (unsigned long long)n * S;
-  const unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
-  bool valid = false;
-  uint32_t sid = 0;
-  if (i < total) {
-    const uint32_t slot = identity_ids ? (uint32_t)(i / S) : ids[i / S];
-    sid = slot * S + (uint32_t)(i % S);
-    valid = pb.s_contrib[sid].w != 0.f;
+  append_id(ids_next, &pb.counts[ACT0 + b + 1], cont, slot);
+  // shadow-ray id list for the any-hit trace: every valid (slot, j); the loop is uniform across the warp
+  for (uint32_t j = 0; j < wp.S; ++j) {
+    bool valid = false;
+    uint32_t sid = 0;
+    if (i < n) { sid = slot * wp.S + j; valid = pb.s_contrib[sid].w != 0.f; }
+    append_id(pb.s_ids, &pb.counts[SH0 + b], valid, sid);
   }
-  append_id(pb.s_ids, &pb.counts[2], valid, sid);
 }
 
 // add the unoccluded light samples in sample order (deterministic), then advance the lists
 __global__ void __launch_bounds__(256)
-k_resolve_shadow(WaveParams wp, PathBufs pb, const uint32_t* __restrict__ ids, uint32_t identity_ids) {
-  const uint32_t n = pb.counts[0];
+k_resolve_shadow(WaveParams wp, PathBufs pb, const uint32_t* __restrict__ ids, uint32_t identity_ids, uint32_t b) {
+  const uint32_t n = pb.counts[ACT0 + b];
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const uint32_t slot = identity_ids ? i : ids[i];
@@ -313,11 +304,11 @@ k_resolve_shadow(WaveParams wp, PathBufs pb, const uint32_t* __restrict__ ids, u
   if (any) pb.rad[slot] = L;
 }
 
-__global__ void k_next_bounce(PathBufs pb, uint32_t b, unsigned long long* totals) {
+__global__ void k_wave_end(PathBufs pb, uint32_t max_depth, unsigned long long* totals) {
   // totals: [0] bounce rays, [1] shadow rays
-  const uint32_t next = pb.counts[1], sh = pb.counts[2];
-  totals[0] += next; totals[1] += sh;
-  pb.counts[0] = next; pb.counts[1] = 0; pb.counts[2] = 0;
+  unsigned long long nb = 0, ns = 0;
+  for (uint32_t b = 0; b < max_depth; ++b) { if (b) nb += pb.counts[ACT0 + b]; ns += pb.counts[SH0 + b]; }
+  totals[0] += nb; totals[1] += ns;
 }
 
 // per-pixel accumulation in sample order (deterministic): accum.rgb += L_s, accum.w += 1
@@ -538,7 +529,7 @@ int Renderer::ensure_wave() {
   for (auto& l : lights_host) S += l.kind == B2RT_LIGHT_AREA ? std::max(1u, cfg.ns_area_light) : 1u;
   shadow_per_hit = S;
   const uint64_t n_pix = (uint64_t)width * height;
-  uint64_t cap = cfg.max_wave_paths ? cfg.max_wave_paths : (4u << 20);
+  uint64_t cap = cfg.max_wave_paths ? cfg.max_wave_paths : (32u << 20);   // ~200 B of state per path: 6.4 GB of the 180 GB
   cap = std::max<uint64_t>(cap, 1024);
   const uint64_t want = std::min<uint64_t>(cap, n_pix * std::max(1u, cfg.ns_aa));
   const uint32_t Salloc = std::max(1u, S);
@@ -558,9 +549,9 @@ int Renderer::ensure_wave() {
   B2RT_CUDA_OK(cudaMalloc(&ids_a, wave_cap * 4));
   B2RT_CUDA_OK(cudaMalloc(&ids_b, wave_cap * 4));
   B2RT_CUDA_OK(cudaMalloc(&s_ids, wave_cap * Salloc * 4));
-  B2RT_CUDA_OK(cudaMalloc(&counts, 64 * 4));
+  B2RT_CUDA_OK(cudaMalloc(&counts, N_COUNTS * 4));
   B2RT_CUDA_OK(cudaMalloc(&totals, 8 * 8));
-  B2RT_CUDA_OK(cudaMemset(counts, 0, 64 * 4));
+  B2RT_CUDA_OK(cudaMemset(counts, 0, N_COUNTS * 4));
   B2RT_CUDA_OK(cudaMemset(totals, 0, 8 * 8));
   RCHECK(tracer.init(dbvh, wave_cap * Salloc, 4));
   return B2RT_OK;
@@ -573,7 +564,7 @@ int Renderer::start() {
   if (running) RCHECK(wait());
   RCHECK(ensure_wave());
   const uint32_t S = shadow_per_hit;
-  const uint32_t max_depth = std::max(1u, cfg.max_ray_depth);
+  const uint32_t max_depth = std::min(MAX_DEPTH, std::max(1u, cfg.max_ray_depth));
   const uint32_t stride = cfg.sample_stride ? cfg.sample_stride : 1;
   const uint64_t n_pix = (uint64_t)width * height;
 
@@ -625,17 +616,15 @@ int Renderer::start() {
       uint32_t* cur = ids_a; uint32_t* nxt = ids_b;
       for (uint32_t b = 0; b < max_depth; ++b) {
         const uint32_t identity = b == 0 ? 1u : 0u;
-        RCHECK(tracer.trace(stream, pb.ray_o, pb.ray_d, pb.hits, identity ? nullptr : cur, counts + 0, false));
+        RCHECK(tracer.trace(stream, pb.ray_o, pb.ray_d, pb.hits, identity ? nullptr : cur, counts + ACT0 + b, false));
         k_shade<<<g, 256, 0, stream>>>(wp, sd, pb, cur, nxt, b, identity); launches++;
         if (S > 0) {
-          const uint64_t tot = (uint64_t)n * S;
-          k_collect_shadow<<<(uint32_t)((tot + 255) / 256), 256, 0, stream>>>(wp, pb, cur, identity); launches++;
-          RCHECK(tracer.trace(stream, pb.s_o, pb.s_d, pb.s_hits, pb.s_ids, counts + 2, true));
-          k_resolve_shadow<<<g, 256, 0, stream>>>(wp, pb, cur, identity); launches++;
+          RCHECK(tracer.trace(stream, pb.s_o, pb.s_d, pb.s_hits, pb.s_ids, counts + SH0 + b, true));
+          k_resolve_shadow<<<g, 256, 0, stream>>>(wp, pb, cur, identity, b); launches++;
         }
-        k_next_bounce<<<1, 1, 0, stream>>>(pb, b, totals); launches++;
         std::swap(cur, nxt);
       }
+      k_wave_end<<<1, 1, 0, stream>>>(pb, max_depth, totals); launches++;
       k_accumulate<<<(wp.n_pix + 255) / 256, 256, 0, stream>>>(wp, pb, (float4*)accum); launches++;
     }
   }

@@ -27,6 +27,9 @@ namespace b2rt {
 
 namespace {
 
+#ifndef B2RT_OCC4
+#define B2RT_OCC4 3
+#endif
 constexpr int TRAV_THREADS = 256;
 constexpr int TRAV_WARPS = TRAV_THREADS / 32;
 constexpr int STAGE_PAIRS = 96;   // per-warp staging ring (flush when > STAGE_PAIRS - 32)
@@ -62,14 +65,6 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
 }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
-// ---- k_trace_begin: reset queue counts; the root subtree receives every active ray ----------------
-__global__ void k_trace_begin(uint32_t* cnt, uint32_t n_treelets, uint32_t* ctrl, const uint32_t* n_active) {
-  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-  uint32_t stride = gridDim.x * blockDim.x;
-  for (uint32_t t = i; t < n_treelets; t += stride) cnt[t] = (t == 0) ? *n_active : 0u;
-  if (i == 0) { ctrl[CTRL_PAIRS0] = 0; ctrl[CTRL_PAIRS1] = 0; ctrl[CTRL_NCHUNKS] = 0; ctrl[CTRL_NEXT] = 0; }
-}
-
 // ---- k_schedule_level: exclusive scan of per-subtree ray counts -> segment offsets + chunk list ----
 // One CTA of 1024 threads; warp-shuffle scans (no volatile-smem warp-synchronous code).
 __device__ __forceinline__ uint32_t warp_incl_scan(uint32_t v) {
@@ -101,7 +96,7 @@ __device__ __forceinline__ void block_excl_scan2(uint32_t a, uint32_t b, uint32_
 }
 
 __global__ void __launch_bounds__(1024, 1)
-k_schedule_level(const uint32_t* __restrict__ cnt, uint32_t* __restrict__ seg_off, uint32_t* __restrict__ cursor,
+k_schedule_level(uint32_t* __restrict__ cnt, uint32_t* __restrict__ seg_off, uint32_t* __restrict__ cursor,
                  uint4* __restrict__ chunks, uint32_t* __restrict__ ctrl, uint32_t first, uint32_t n, uint32_t chunk_rays,
                  uint32_t chunk_cap, uint32_t level) {
   __shared__ uint32_t sh[66];
@@ -114,6 +109,7 @@ k_schedule_level(const uint32_t* __restrict__ cnt, uint32_t* __restrict__ seg_of
     uint32_t i = base + threadIdx.x;
     uint32_t t = first + i;
     uint32_t c = i < n ? cnt[t] : 0u;
+    if (i < n) cnt[t] = 0;   // self-cleaning: every level >= 1 is scheduled exactly once per trace
     uint32_t nch = (c + chunk_rays - 1) / chunk_rays;
     uint32_t eo, ec, to, tc;
     block_excl_scan2(c, nch, &eo, &ec, &to, &tc, sh);
@@ -147,8 +143,8 @@ k_schedule_level(const uint32_t* __restrict__ cnt, uint32_t* __restrict__ seg_of
   if (threadIdx.x == 0) {
     if (run_chunks > chunk_cap) { run_chunks = chunk_cap; ctrl[CTRL_OVERFLOW] = 1; }
     ctrl[CTRL_NCHUNKS] = run_chunks;
-    ctrl[CTRL_NEXT] = 0;
-    ctrl[level & 1] = 0;   // pair counter the traversal of THIS level appends to
+    ctrl[CTRL_NEXT0 + (level & 1)] = 0;   // chunk cursor of THIS level's traversal
+    ctrl[level & 1] = 0;                  // pair counter the traversal of THIS level appends to
   }
 }
 
@@ -191,6 +187,8 @@ struct TravParams {
   uint32_t pair_cap;
   uint32_t level;
   uint32_t n_treelets, n_rays_cap;
+  uint32_t chunk_rays;
+  const uint32_t* n_active;
   TraceCounters* counters;
 };
 
@@ -235,7 +233,7 @@ constexpr uint32_t REF_NONE = 0xFFFFFFFEu;   // "no current node" marker of the 
 constexpr int REFILL_MIN_IDLE = 8;            // refill a warp's idle lanes once this many are idle
 
 template <int W, bool ANYHIT, bool STATS>
-__global__ void __launch_bounds__(TRAV_THREADS, (W == 4 ? 3 : 2))
+__global__ void __launch_bounds__(TRAV_THREADS, (W == 4 ? B2RT_OCC4 : 2))
 k_traverse(const TravParams P) {
   extern __shared__ __align__(128) uint8_t smem[];
   __shared__ __align__(8) uint64_t s_bar;
@@ -256,11 +254,15 @@ k_traverse(const TravParams P) {
   asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   __syncthreads();
 
-  const uint32_t n_chunks = P.ctrl[CTRL_NCHUNKS];
+  // level 0: every active ray visits the root subtree; its chunk list is implicit (no scheduling kernel)
+  const uint32_t n_root = P.level == 0 ? *P.n_active : 0u;
+  const uint32_t n_chunks = P.level == 0 ? (n_root + P.chunk_rays - 1) / P.chunk_rays : P.ctrl[CTRL_NCHUNKS];
   for (;;) {
     if (threadIdx.x == 0) {
-      uint32_t c = atomicAdd(&P.ctrl[CTRL_NEXT], 1u);
-      s_chunk = c < n_chunks ? P.chunks[c] : make_uint4(0xFFFFFFFFu, 0, 0, 0);
+      uint32_t c = atomicAdd(&P.ctrl[CTRL_NEXT0 + (P.level & 1)], 1u);
+      uint4 ch = make_uint4(0xFFFFFFFFu, 0, 0, 0);
+      if (c < n_chunks) ch = P.level == 0 ? make_uint4(0u, c * P.chunk_rays, min(P.chunk_rays, n_root - c * P.chunk_rays), 0u) : P.chunks[c];
+      s_chunk = ch;
       s_next_ray = 0;
     }
     __syncthreads();
@@ -534,6 +536,7 @@ int Tracer::init(const DeviceBVH& b, uint64_t max_rays_, uint32_t pair_factor) {
   B2RT_CUDA_OK(cudaMalloc(&chunks, chunk_cap * sizeof(uint4)));
   B2RT_CUDA_OK(cudaMalloc(&ctrl, 16 * 4));
   B2RT_CUDA_OK(cudaMalloc(&counters, sizeof(TraceCounters)));
+  B2RT_CUDA_OK(cudaMemset(cnt, 0, nt * 4));
   B2RT_CUDA_OK(cudaMemset(ctrl, 0, 16 * 4));
   B2RT_CUDA_OK(cudaMemset(counters, 0, sizeof(TraceCounters)));
   B2RT_CUDA_OK(cudaDeviceSynchronize());   // legacy-stream memsets vs the non-blocking work stream
@@ -571,13 +574,16 @@ static void launch_traverse(const Tracer& T, cudaStream_t s, const TravParams& P
 int Tracer::trace(cudaStream_t s, const float4* ray_o, const float4* ray_d, unsigned long long* hits,
                   const uint32_t* ids0, const uint32_t* n_active_dev, bool any_hit) {
   if (bvh.n_levels == 0) return B2RT_OK;
-  k_trace_begin<<<std::max(1u, std::min(1024u, (bvh.n_treelets + 255) / 256)), 256, 0, s>>>(cnt, bvh.n_treelets, ctrl, n_active_dev);
-  launches++;
+  // control words: pair counters, chunk cursors (level 0 uses PAIRS0 / NEXT0; higher levels are reset by their
+  // scheduling kernel).  Per-subtree counts are left at zero by the previous trace (self-cleaning scheduler).
+  B2RT_CUDA_OK(cudaMemsetAsync(ctrl, 0, 4 * 4, s));
   for (uint32_t L = 0; L < bvh.n_levels; ++L) {
     const LevelRange lr = bvh.levels[L];
-    k_schedule_level<<<1, 1024, 0, s>>>(cnt, seg_off, cursor, chunks, ctrl, lr.first, lr.count, chunk_rays,
-                                        (uint32_t)chunk_cap, L);
-    launches++;
+    if (L > 0) {
+      k_schedule_level<<<1, 1024, 0, s>>>(cnt, seg_off, cursor, chunks, ctrl, lr.first, lr.count, chunk_rays,
+                                          (uint32_t)chunk_cap, L);
+      launches++;
+    }
     if (L > 0) {
       k_scatter<<<num_sms * 8, 256, 0, s>>>(pairs, &ctrl[(L - 1) & 1], seg_off, cursor, ids_sorted, (uint32_t)pair_cap);
       launches++;
@@ -586,7 +592,7 @@ int Tracer::trace(cudaStream_t s, const float4* ray_o, const float4* ray_d, unsi
     P.blob = bvh.blob; P.treelets = bvh.treelets; P.ray_o = ray_o; P.ray_d = ray_d; P.hits = hits;
     P.ids = (L == 0) ? ids0 : ids_sorted;
     P.chunks = chunks; P.ctrl = ctrl; P.cnt = cnt; P.pairs = pairs; P.pair_cap = (uint32_t)pair_cap; P.level = L;
-    P.counters = counters; P.n_treelets = bvh.n_treelets; P.n_rays_cap = (uint32_t)std::min<uint64_t>(max_rays, 0xFFFFFFFFull);
+    P.counters = counters; P.n_treelets = bvh.n_treelets; P.chunk_rays = chunk_rays; P.n_active = n_active_dev; P.n_rays_cap = (uint32_t)std::min<uint64_t>(max_rays, 0xFFFFFFFFull);
     cudaEvent_t e0 = nullptr, e1 = nullptr;
     if (time_kernels) {
       if (ev_used + 2 > ev_pool.size()) {

@@ -55,7 +55,7 @@ struct Tracer {
   int check_overflow(cudaStream_t s, bool* overflow);  // synchronises the stream
 };
 
-enum { CTRL_PAIRS0 = 0, CTRL_PAIRS1 = 1, CTRL_NCHUNKS = 2, CTRL_NEXT = 3, CTRL_OVERFLOW = 4 };
+enum { CTRL_PAIRS0 = 0, CTRL_PAIRS1 = 1, CTRL_NEXT0 = 2, CTRL_NEXT1 = 3, CTRL_OVERFLOW = 4, CTRL_NCHUNKS = 5 };
 
 int upload_bvh(const WideBVH& h, DeviceBVH* d);
 void free_bvh(DeviceBVH* d);

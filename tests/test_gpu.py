@@ -47,7 +47,7 @@ def test_closest_hit_bit_exact(name, width, treelet_bytes, max_leaf):
     assert np.array_equal(p, pr), f"{np.sum(p != pr)} primitive ids differ"
     assert np.array_equal(t, tr)
     st = bvh.stats()
-    assert st["kernel_launches"] >= 3 and st["subtree_visits"] >= len(org)
+    assert st["kernel_launches"] >= 1 and st["subtree_visits"] >= len(org)
     bvh.close()
 
 
