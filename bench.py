@@ -40,7 +40,7 @@ def parse():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
     ap.add_argument("--spp", type=int, default=0, help="override samples per pixel (debug only; invalidates the number)")
-    ap.add_argument("--cpu-spp", type=int, default=0, help="spp of the bounded CPU sample (default: 4 main arm, 1 reference arm)")
+    ap.add_argument("--cpu-spp", type=int, default=0, help="spp of the bounded CPU sample (default 4 of 64)")
     ap.add_argument("--bvh-width", type=int, default=0)
     ap.add_argument("--treelet-bytes", type=int, default=0)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
@@ -139,12 +139,12 @@ def main():
     config = {"workload": f"{wl['scene']}.dae {wl['width']}x{wl['height']}, {wl['spp']} spp/GPU, max_ray_depth {wl['depth']}, "
                           f"ns_area_light {wl['ns_area_light']} (BASELINE configs[1])",
               "scene_tris": int(sc.n_tris), "parallelism": f"spp-sharded x{world}, scene replicated",
-              "l2": "per-wave ray/path state (4Mi paths x ~200 B) exceeds the 126 MB L2; no explicit flush"}
+              "l2": "per-wave ray/path state (<= 32Mi paths x ~200 B = GBs) exceeds the 126 MB L2; no explicit flush"}
 
     if args.impl == "reference":
         if rank != 0:
             return 0
-        spp_s = args.cpu_spp or 1
+        spp_s = args.cpu_spp or 4
         cb = cpu_arm(args, sc, cam, wl, spp_s, args.steps, args.warmup)
         line = {"impl": "reference", "metric": metric, "value": cb["value"], "unit": "Mrays/s", "n_gpus": args.gpus,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": cb["seconds"] / args.steps * 1e3,

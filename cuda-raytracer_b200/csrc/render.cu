@@ -409,7 +409,6 @@ int Renderer::create(const b2rt_config* c) {
 }
 
 void Renderer::release_scene() {
-  tracer.release();
   free_bvh(&dbvh);
   free_ptr(d_prim_geom); free_ptr(d_tri_normals); free_ptr(d_prim_material); free_ptr(d_materials); free_ptr(d_lights);
   free_ptr(d_light_area);
@@ -429,6 +428,7 @@ void Renderer::release_wave() {
 void Renderer::destroy() {
   if (stream) cudaStreamSynchronize(stream);
   release_wave();
+  tracer.release();
   release_scene();
   free_ptr(accum); free_ptr(img_a); free_ptr(img_b); free_ptr(ldr);
   if (ev_start) cudaEventDestroy(ev_start);
@@ -451,8 +451,8 @@ int Renderer::set_scene(const b2rt_scene_desc* d) {
   WideBVH wb;
   RCHECK(build_wide_bvh(hs, cfg.max_leaf_size, cfg.bvh_width, cfg.treelet_bytes, &wb));
   release_scene();
-  release_wave();
   RCHECK(upload_bvh(wb, &dbvh));
+  bvh_stale = true;   // wave buffers are kept; the tracer re-binds its (small) per-subtree arrays
   n_wide_nodes = wb.n_wide_nodes;
   build_ms = wb.build_ms;
   n_tris = hs.n_tris;
@@ -533,7 +533,10 @@ int Renderer::ensure_wave() {
   cap = std::max<uint64_t>(cap, 1024);
   const uint64_t want = std::min<uint64_t>(cap, n_pix * std::max(1u, cfg.ns_aa));
   const uint32_t Salloc = std::max(1u, S);
-  if (wave_cap >= want && wave_S >= Salloc && tracer.max_rays >= want * Salloc) return B2RT_OK;
+  if (wave_cap >= want && wave_S >= Salloc && tracer.max_rays >= want * Salloc) {
+    if (bvh_stale) { RCHECK(tracer.init(dbvh, tracer.max_rays, 4)); bvh_stale = false; }
+    return B2RT_OK;
+  }
   release_wave();
   tracer.release();
   wave_cap = want; wave_S = Salloc;

@@ -19,7 +19,7 @@ struct Renderer {
   std::vector<b2rt_light> lights_host;
   uint32_t n_tris = 0, n_lights = 0, n_wide_nodes = 0, shadow_per_hit = 0;
   double build_ms = 0;
-  bool have_scene = false, have_camera = false, running = false;
+  bool have_scene = false, have_camera = false, running = false, bvh_stale = false;
   b2rt_camera cam{};
   // frame
   uint32_t width = 0, height = 0;

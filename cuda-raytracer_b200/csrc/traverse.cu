@@ -503,42 +503,52 @@ static int prep_kernel(size_t smem, int* occ) {
 }
 
 int Tracer::init(const DeviceBVH& b, uint64_t max_rays_, uint32_t pair_factor) {
-  bvh = b;
-  max_rays = max_rays_;
+  // ray-count dependent buffers (large) are kept when only the BVH changes
   if (pair_factor == 0) pair_factor = 4;
-  pair_cap = max_rays * pair_factor + 65536;
-  if (pair_cap > 0xFFFF0000ull) pair_cap = 0xFFFF0000ull;
-  chunk_cap = pair_cap / chunk_rays + (uint64_t)bvh.n_treelets + 1024;
+  uint64_t want_pairs = max_rays_ * pair_factor + 65536;
+  if (want_pairs > 0xFFFF0000ull) want_pairs = 0xFFFF0000ull;
   int dev = 0;
   B2RT_CUDA_OK(cudaGetDevice(&dev));
   B2RT_CUDA_OK(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
+  if (!pairs || want_pairs != pair_cap) {
+    cudaFree(pairs); cudaFree(ids_sorted); pairs = nullptr; ids_sorted = nullptr;
+    pair_cap = want_pairs;
+    B2RT_CUDA_OK(cudaMalloc(&pairs, pair_cap * sizeof(uint2)));
+    B2RT_CUDA_OK(cudaMalloc(&ids_sorted, pair_cap * 4));
+  }
+  max_rays = max_rays_;
+  if (!ctrl) {
+    B2RT_CUDA_OK(cudaMalloc(&ctrl, 16 * 4));
+    B2RT_CUDA_OK(cudaMalloc(&counters, sizeof(TraceCounters)));
+    B2RT_CUDA_OK(cudaMemset(ctrl, 0, 16 * 4));
+    B2RT_CUDA_OK(cudaMemset(counters, 0, sizeof(TraceCounters)));
+  }
+  // BVH dependent part (small)
+  bvh = b;
+  cudaFree(cnt); cudaFree(seg_off); cudaFree(cursor); cudaFree(chunks);
+  cnt = seg_off = cursor = nullptr; chunks = nullptr;
+  chunk_cap = pair_cap / chunk_rays + (uint64_t)bvh.n_treelets + 1024;
   smem_bytes = std::max<size_t>(bvh.max_treelet_bytes, 1024);
-  int occ = 1, o2 = 1;
+  int occ = 1, o2 = 1, o3 = 1, o4 = 1;
   int rc;
   if (bvh.width == 8) {
     if ((rc = prep_kernel<8, false, false>(smem_bytes, &occ))) return rc;
     if ((rc = prep_kernel<8, true, false>(smem_bytes, &o2))) return rc;
-    if ((rc = prep_kernel<8, false, true>(smem_bytes, &o2))) return rc;
-    if ((rc = prep_kernel<8, true, true>(smem_bytes, &o2))) return rc;
+    if ((rc = prep_kernel<8, false, true>(smem_bytes, &o3))) return rc;
+    if ((rc = prep_kernel<8, true, true>(smem_bytes, &o4))) return rc;
   } else {
     if ((rc = prep_kernel<4, false, false>(smem_bytes, &occ))) return rc;
     if ((rc = prep_kernel<4, true, false>(smem_bytes, &o2))) return rc;
-    if ((rc = prep_kernel<4, false, true>(smem_bytes, &o2))) return rc;
-    if ((rc = prep_kernel<4, true, true>(smem_bytes, &o2))) return rc;
+    if ((rc = prep_kernel<4, false, true>(smem_bytes, &o3))) return rc;
+    if ((rc = prep_kernel<4, true, true>(smem_bytes, &o4))) return rc;
   }
-  ctas_per_sm = std::max(1, std::min(occ, o2));
+  ctas_per_sm = std::max(1, std::min(std::min(occ, o2), std::min(o3, o4)));
   const size_t nt = std::max<uint32_t>(1, bvh.n_treelets);
   B2RT_CUDA_OK(cudaMalloc(&cnt, nt * 4));
   B2RT_CUDA_OK(cudaMalloc(&seg_off, nt * 4));
   B2RT_CUDA_OK(cudaMalloc(&cursor, nt * 4));
-  B2RT_CUDA_OK(cudaMalloc(&pairs, pair_cap * sizeof(uint2)));
-  B2RT_CUDA_OK(cudaMalloc(&ids_sorted, pair_cap * 4));
   B2RT_CUDA_OK(cudaMalloc(&chunks, chunk_cap * sizeof(uint4)));
-  B2RT_CUDA_OK(cudaMalloc(&ctrl, 16 * 4));
-  B2RT_CUDA_OK(cudaMalloc(&counters, sizeof(TraceCounters)));
   B2RT_CUDA_OK(cudaMemset(cnt, 0, nt * 4));
-  B2RT_CUDA_OK(cudaMemset(ctrl, 0, 16 * 4));
-  B2RT_CUDA_OK(cudaMemset(counters, 0, sizeof(TraceCounters)));
   B2RT_CUDA_OK(cudaDeviceSynchronize());   // legacy-stream memsets vs the non-blocking work stream
   return B2RT_OK;
 }
@@ -557,6 +567,7 @@ void Tracer::release() {
   cudaFree(cnt); cudaFree(seg_off); cudaFree(cursor); cudaFree(pairs); cudaFree(ids_sorted); cudaFree(chunks);
   cudaFree(ctrl); cudaFree(counters);
   cnt = seg_off = cursor = ids_sorted = ctrl = nullptr; pairs = nullptr; chunks = nullptr; counters = nullptr;
+  pair_cap = 0; max_rays = 0;
 }
 
 template <int W>

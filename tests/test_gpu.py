@@ -293,3 +293,24 @@ def test_two_gpu_style_sharding_on_one_device():
     got = resolve_mean(total).cpu().numpy().reshape(h, w, 3)
     ref = orc.OracleScene(sc, 4).render(cam, Config(ns_aa=spp, max_ray_depth=4, ns_area_light=1, seed=13), w, h)
     np.testing.assert_allclose(got, ref, rtol=2e-5, atol=1e-6)
+
+
+def test_cpp_host_example(tmp_path):
+    """The C++ host program (shim classes over the C ABI) renders the same RGBA8 frame as the Python binding."""
+    import os
+    import subprocess
+    from PIL import Image
+    from conftest import ROOT
+    exe = os.path.join(ROOT, "cuda-raytracer_b200", "examples", "render_scene")
+    out = tmp_path / "cpp.png"
+    r = subprocess.run([exe, "-s", "4", "-m", "3", "-l", "1", "-r", "96x72", "-w", str(out), scene_path("CBspheres_lambertian")],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    sc = Scene.load(scene_path("CBspheres_lambertian"))
+    pt = b2rt.PathTracer(ns_aa=4, max_ray_depth=3, ns_area_light=1)
+    pt.set_scene(sc); pt.set_camera(place_camera(sc, 96, 72)); pt.set_frame_size(96, 72); pt.render()
+    ldr = pt.ldr()[::-1]
+    ref = np.stack([(ldr >> s) & 255 for s in (0, 8, 16, 24)], -1).astype(np.uint8)
+    got = np.asarray(Image.open(out).convert("RGBA"))
+    assert got.shape == ref.shape
+    assert np.abs(got.astype(np.int32) - ref.astype(np.int32)).max() <= 1     # double vs float camera placement: <= 1 LSB

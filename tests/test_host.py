@@ -173,3 +173,13 @@ def test_two_rank_gloo_reduce(tmp_path):
                           "--master-port", "29541", str(script), ROOT], capture_output=True, text=True, env=env, timeout=300)
     assert out.returncode == 0, out.stderr[-2000:]
     assert "DIST_OK" in out.stdout
+
+
+def test_cpp_example_fails_loudly_without_device():
+    exe = os.path.join(ROOT, "cuda-raytracer_b200", "examples", "render_scene")
+    if not os.path.exists(exe):
+        pytest.skip("C++ example not built")
+    if b2rt.device_count() > 0:
+        pytest.skip("a CUDA device is visible")
+    out = subprocess.run([exe, scene_path("CBempty")], capture_output=True, text=True)
+    assert out.returncode == 1 and "no CPU fallback" in out.stderr
