@@ -410,10 +410,11 @@ int Renderer::create(const b2rt_config* c) {
 
 void Renderer::release_scene() {
   free_bvh(&dbvh);
-  free_ptr(d_prim_geom); free_ptr(d_tri_normals); free_ptr(d_prim_material); free_ptr(d_materials); free_ptr(d_lights);
+  free_ptr(d_prim_geom); free_ptr(d_tri_normals_buf); free_ptr(d_prim_material); free_ptr(d_materials); free_ptr(d_lights);
   free_ptr(d_light_area);
-  d_prim_geom = nullptr; d_tri_normals = nullptr; d_prim_material = nullptr; d_materials = nullptr; d_lights = nullptr;
-  d_light_area = nullptr;
+  d_prim_geom = nullptr; d_tri_normals = nullptr; d_tri_normals_buf = nullptr; d_prim_material = nullptr; d_materials = nullptr;
+  d_lights = nullptr; d_light_area = nullptr;
+  cap_prims = cap_normals = cap_mats = cap_lights = 0;
   have_scene = false;
 }
 
@@ -450,27 +451,45 @@ int Renderer::set_scene(const b2rt_scene_desc* d) {
   RCHECK(make_host_scene(d, &hs));
   WideBVH wb;
   RCHECK(build_wide_bvh(hs, cfg.max_leaf_size, cfg.bvh_width, cfg.treelet_bytes, &wb));
-  release_scene();
-  RCHECK(upload_bvh(wb, &dbvh));
-  bvh_stale = true;   // wave buffers are kept; the tracer re-binds its (small) per-subtree arrays
+  RCHECK(upload_bvh(wb, &dbvh));   // grow-only device buffers: no cudaMalloc/cudaFree when the scene fits
+  bvh_stale = true;                // wave buffers are kept; the tracer re-binds its (small) per-subtree arrays
   n_wide_nodes = wb.n_wide_nodes;
   build_ms = wb.build_ms;
   n_tris = hs.n_tris;
   n_lights = (uint32_t)hs.lights.size();
   const size_t np = std::max<size_t>(1, hs.n_prims());
-  B2RT_CUDA_OK(cudaMalloc(&d_prim_geom, np * PRIM_BYTES));
-  B2RT_CUDA_OK(cudaMalloc(&d_prim_material, np * 4));
-  B2RT_CUDA_OK(cudaMalloc(&d_materials, hs.materials.size() * sizeof(b2rt_material)));
-  B2RT_CUDA_OK(cudaMalloc(&d_lights, std::max<size_t>(1, hs.lights.size()) * sizeof(b2rt_light)));
-  B2RT_CUDA_OK(cudaMalloc(&d_light_area, std::max<size_t>(1, hs.lights.size()) * 4));
+  if (cap_prims < np) {
+    free_ptr(d_prim_geom); free_ptr(d_prim_material); d_prim_geom = nullptr; d_prim_material = nullptr;
+    cap_prims = np + np / 4;
+    B2RT_CUDA_OK(cudaMalloc(&d_prim_geom, cap_prims * PRIM_BYTES));
+    B2RT_CUDA_OK(cudaMalloc(&d_prim_material, cap_prims * 4));
+  }
+  if (cap_mats < hs.materials.size()) {
+    free_ptr(d_materials); d_materials = nullptr;
+    cap_mats = hs.materials.size() + 16;
+    B2RT_CUDA_OK(cudaMalloc(&d_materials, cap_mats * sizeof(b2rt_material)));
+  }
+  if (cap_lights < std::max<size_t>(1, hs.lights.size())) {
+    free_ptr(d_lights); free_ptr(d_light_area); d_lights = nullptr; d_light_area = nullptr;
+    cap_lights = hs.lights.size() + 8;
+    B2RT_CUDA_OK(cudaMalloc(&d_lights, cap_lights * sizeof(b2rt_light)));
+    B2RT_CUDA_OK(cudaMalloc(&d_light_area, cap_lights * 4));
+  }
   if (hs.n_prims()) {
     B2RT_CUDA_OK(cudaMemcpy(d_prim_geom, hs.prim_geom.data(), (size_t)hs.n_prims() * PRIM_BYTES, cudaMemcpyHostToDevice));
     B2RT_CUDA_OK(cudaMemcpy(d_prim_material, hs.prim_material.data(), (size_t)hs.n_prims() * 4, cudaMemcpyHostToDevice));
   }
   B2RT_CUDA_OK(cudaMemcpy(d_materials, hs.materials.data(), hs.materials.size() * sizeof(b2rt_material), cudaMemcpyHostToDevice));
   if (!hs.tri_normals.empty()) {
-    B2RT_CUDA_OK(cudaMalloc(&d_tri_normals, hs.tri_normals.size() * 4));
+    if (cap_normals < hs.tri_normals.size()) {
+      free_ptr(d_tri_normals_buf); d_tri_normals_buf = nullptr;
+      cap_normals = hs.tri_normals.size() + hs.tri_normals.size() / 4;
+      B2RT_CUDA_OK(cudaMalloc(&d_tri_normals_buf, cap_normals * 4));
+    }
+    d_tri_normals = d_tri_normals_buf;
     B2RT_CUDA_OK(cudaMemcpy(d_tri_normals, hs.tri_normals.data(), hs.tri_normals.size() * 4, cudaMemcpyHostToDevice));
+  } else {
+    d_tri_normals = nullptr;
   }
   if (!hs.lights.empty()) {
     std::vector<float> area(hs.lights.size());

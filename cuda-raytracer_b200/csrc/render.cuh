@@ -14,9 +14,10 @@ struct Renderer {
   // scene
   DeviceBVH dbvh;
   Tracer tracer;
-  void* d_prim_geom = nullptr; float* d_tri_normals = nullptr; uint32_t* d_prim_material = nullptr;
+  void* d_prim_geom = nullptr; float* d_tri_normals = nullptr; float* d_tri_normals_buf = nullptr; uint32_t* d_prim_material = nullptr;
   b2rt_material* d_materials = nullptr; b2rt_light* d_lights = nullptr; float* d_light_area = nullptr;
   std::vector<b2rt_light> lights_host;
+  size_t cap_prims = 0, cap_normals = 0, cap_mats = 0, cap_lights = 0;   // grow-only device array capacities (elements)
   uint32_t n_tris = 0, n_lights = 0, n_wide_nodes = 0, shadow_per_hit = 0;
   double build_ms = 0;
   bool have_scene = false, have_camera = false, running = false, bvh_stale = false;

@@ -471,7 +471,11 @@ k_traverse(const TravParams P) {
 
 // ---- host side ---------------------------------------------------------------------------------------
 int upload_bvh(const WideBVH& h, DeviceBVH* d) {
+  // grow-only: a re-upload of a scene of similar size costs two copies, no cudaMalloc / cudaFree
+  uint8_t* blob = d->blob; TreeletDesc* tl = d->treelets;
+  uint64_t blob_cap = d->blob_cap, tl_cap = d->treelet_cap;
   *d = DeviceBVH();
+  d->blob = blob; d->treelets = tl; d->blob_cap = blob_cap; d->treelet_cap = tl_cap;
   d->n_treelets = (uint32_t)h.treelets.size();
   d->n_levels = h.n_levels;
   d->width = h.width;
@@ -479,8 +483,18 @@ int upload_bvh(const WideBVH& h, DeviceBVH* d) {
   d->blob_bytes = h.blob.size();
   for (uint32_t i = 0; i < h.n_levels; ++i) d->levels[i] = h.levels[i];
   if (h.treelets.empty()) return B2RT_OK;
-  B2RT_CUDA_OK(cudaMalloc(&d->blob, h.blob.size()));
-  B2RT_CUDA_OK(cudaMalloc(&d->treelets, h.treelets.size() * sizeof(TreeletDesc)));
+  if (d->blob_cap < h.blob.size()) {
+    cudaFree(d->blob); d->blob = nullptr; d->blob_cap = 0;
+    const size_t cap = h.blob.size() + h.blob.size() / 4;
+    B2RT_CUDA_OK(cudaMalloc(&d->blob, cap));
+    d->blob_cap = cap;
+  }
+  if (d->treelet_cap < h.treelets.size()) {
+    cudaFree(d->treelets); d->treelets = nullptr; d->treelet_cap = 0;
+    const size_t cap = h.treelets.size() + h.treelets.size() / 4 + 16;
+    B2RT_CUDA_OK(cudaMalloc(&d->treelets, cap * sizeof(TreeletDesc)));
+    d->treelet_cap = cap;
+  }
   B2RT_CUDA_OK(cudaMemcpy(d->blob, h.blob.data(), h.blob.size(), cudaMemcpyHostToDevice));
   B2RT_CUDA_OK(cudaMemcpy(d->treelets, h.treelets.data(), h.treelets.size() * sizeof(TreeletDesc), cudaMemcpyHostToDevice));
   // cudaMemcpy from pageable memory may return before the DMA has landed, and the non-blocking work streams do
@@ -523,10 +537,8 @@ int Tracer::init(const DeviceBVH& b, uint64_t max_rays_, uint32_t pair_factor) {
     B2RT_CUDA_OK(cudaMemset(ctrl, 0, 16 * 4));
     B2RT_CUDA_OK(cudaMemset(counters, 0, sizeof(TraceCounters)));
   }
-  // BVH dependent part (small)
+  // BVH dependent part (small, grow-only)
   bvh = b;
-  cudaFree(cnt); cudaFree(seg_off); cudaFree(cursor); cudaFree(chunks);
-  cnt = seg_off = cursor = nullptr; chunks = nullptr;
   chunk_cap = pair_cap / chunk_rays + (uint64_t)bvh.n_treelets + 1024;
   smem_bytes = std::max<size_t>(bvh.max_treelet_bytes, 1024);
   int occ = 1, o2 = 1, o3 = 1, o4 = 1;
@@ -544,11 +556,19 @@ int Tracer::init(const DeviceBVH& b, uint64_t max_rays_, uint32_t pair_factor) {
   }
   ctas_per_sm = std::max(1, std::min(std::min(occ, o2), std::min(o3, o4)));
   const size_t nt = std::max<uint32_t>(1, bvh.n_treelets);
-  B2RT_CUDA_OK(cudaMalloc(&cnt, nt * 4));
-  B2RT_CUDA_OK(cudaMalloc(&seg_off, nt * 4));
-  B2RT_CUDA_OK(cudaMalloc(&cursor, nt * 4));
-  B2RT_CUDA_OK(cudaMalloc(&chunks, chunk_cap * sizeof(uint4)));
-  B2RT_CUDA_OK(cudaMemset(cnt, 0, nt * 4));
+  if (nt_cap < nt) {
+    cudaFree(cnt); cudaFree(seg_off); cudaFree(cursor); cnt = seg_off = cursor = nullptr;
+    nt_cap = nt + nt / 4 + 16;
+    B2RT_CUDA_OK(cudaMalloc(&cnt, nt_cap * 4));
+    B2RT_CUDA_OK(cudaMalloc(&seg_off, nt_cap * 4));
+    B2RT_CUDA_OK(cudaMalloc(&cursor, nt_cap * 4));
+  }
+  if (chunk_alloc < chunk_cap) {
+    cudaFree(chunks); chunks = nullptr;
+    chunk_alloc = chunk_cap + chunk_cap / 4;
+    B2RT_CUDA_OK(cudaMalloc(&chunks, chunk_alloc * sizeof(uint4)));
+  }
+  B2RT_CUDA_OK(cudaMemset(cnt, 0, nt_cap * 4));
   B2RT_CUDA_OK(cudaDeviceSynchronize());   // legacy-stream memsets vs the non-blocking work stream
   return B2RT_OK;
 }
@@ -567,7 +587,7 @@ void Tracer::release() {
   cudaFree(cnt); cudaFree(seg_off); cudaFree(cursor); cudaFree(pairs); cudaFree(ids_sorted); cudaFree(chunks);
   cudaFree(ctrl); cudaFree(counters);
   cnt = seg_off = cursor = ids_sorted = ctrl = nullptr; pairs = nullptr; chunks = nullptr; counters = nullptr;
-  pair_cap = 0; max_rays = 0;
+  pair_cap = 0; max_rays = 0; nt_cap = 0; chunk_alloc = 0;
 }
 
 template <int W>

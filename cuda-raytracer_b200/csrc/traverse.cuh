@@ -12,6 +12,7 @@ struct DeviceBVH {
   uint32_t n_treelets = 0, n_levels = 0, width = 4, max_treelet_bytes = 0;
   LevelRange levels[MAX_LEVELS];
   uint64_t blob_bytes = 0;
+  uint64_t blob_cap = 0, treelet_cap = 0;   // grow-only device allocations (re-upload without cudaMalloc/cudaFree)
 };
 
 // Device-resident statistics (all u64): see b2rt_stats
@@ -25,6 +26,7 @@ struct TraceCounters {
 struct Tracer {
   DeviceBVH bvh;
   uint64_t max_rays = 0, pair_cap = 0, chunk_cap = 0;
+  uint64_t nt_cap = 0, chunk_alloc = 0;     // grow-only capacities of the per-subtree arrays / chunk list
   uint32_t chunk_rays = 1024;
   int num_sms = 148, ctas_per_sm = 1;
   size_t smem_bytes = 0;
