@@ -26,6 +26,7 @@ struct b2rt_bvh {
   WideBVH host_meta;     // blob released after upload; keeps levels / counts
   cudaStream_t stream = nullptr;
   uint64_t ray_cap = 0;
+  uint32_t pair_factor = 0;
   float4 *ray_o = nullptr, *ray_d = nullptr;
   unsigned long long* hits = nullptr;
   uint32_t* n_dev = nullptr;
@@ -96,17 +97,17 @@ __global__ void k_count_hits(uint32_t n, const unsigned long long* hits, unsigne
   if ((threadIdx.x & 31) == 0 && m) atomicAdd(out, (unsigned long long)__popc(m));
 }
 
-int ensure_rays(b2rt_bvh* b, uint64_t n) {
-  if (b->ray_cap >= n) return B2RT_OK;
+int ensure_rays(b2rt_bvh* b, uint64_t n, uint32_t pair_factor = 6) {
+  if (b->ray_cap >= n && b->pair_factor >= pair_factor) return B2RT_OK;
   if (b->ray_o) { cudaFree(b->ray_o); cudaFree(b->ray_d); cudaFree(b->hits); b->ray_o = b->ray_d = nullptr; b->hits = nullptr; }
   b->tracer.release();
   b->ray_cap = 0;
   B2RT_CUDA_OK(cudaMalloc(&b->ray_o, n * sizeof(float4)));
   B2RT_CUDA_OK(cudaMalloc(&b->ray_d, n * sizeof(float4)));
   B2RT_CUDA_OK(cudaMalloc(&b->hits, n * 8));
-  int rc = b->tracer.init(b->dbvh, n, 6);
+  int rc = b->tracer.init(b->dbvh, n, pair_factor);
   if (rc) return rc;
-  b->ray_cap = n;
+  b->ray_cap = n; b->pair_factor = pair_factor;
   return B2RT_OK;
 }
 
@@ -230,7 +231,7 @@ int b2rt_bvh_bench_rays(b2rt_bvh* b, uint64_t n, int mode, uint64_t seed, int re
   if (!b || n == 0 || n > 0x7FFFFFFFull || repeats < 1) { set_error("bad argument"); return B2RT_ERR_INVALID; }
   B2RT_CUDA_OK(cudaSetDevice(b->device));
   const bool keep_stats = b->tracer.collect_stats;
-  int rc = ensure_rays(b, n);
+  int rc = ensure_rays(b, n, 48);
   if (rc) return rc;
   cudaStream_t s = b->stream;
   const uint32_t n32 = (uint32_t)n;

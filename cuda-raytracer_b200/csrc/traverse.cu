@@ -172,6 +172,41 @@ k_scatter(const uint2* __restrict__ pairs, const uint32_t* __restrict__ pair_cou
   }
 }
 
+// Tiled variant: a CTA ranks a tile of pairs in a shared-memory histogram over the level's subtrees and then
+// reserves ONE global cursor range per (tile, subtree) instead of one per warp-group -- the global atomics on the
+// few hot cursors of a small level (CBbunny: 119 subtrees) were the cost of the plain kernel.
+constexpr int SCATTER_TILE = 2048;   // pairs per CTA iteration (8 per thread)
+__global__ void __launch_bounds__(256)
+k_scatter_tiled(const uint2* __restrict__ pairs, const uint32_t* __restrict__ pair_count, const uint32_t* __restrict__ seg_off,
+                uint32_t* __restrict__ cursor, uint32_t* __restrict__ ids_sorted, uint32_t pair_cap, uint32_t first, uint32_t K) {
+  extern __shared__ uint32_t s_hist[];   // [K] counts, then [K] bases
+  uint32_t* s_cnt = s_hist;
+  uint32_t* s_base = s_hist + K;
+  const uint32_t n = min(*pair_count, pair_cap);
+  for (uint32_t tile = blockIdx.x * SCATTER_TILE; tile < n; tile += gridDim.x * SCATTER_TILE) {
+    for (uint32_t i = threadIdx.x; i < K; i += 256) s_cnt[i] = 0;
+    __syncthreads();
+    uint2 p[SCATTER_TILE / 256];
+    uint32_t r[SCATTER_TILE / 256];
+#pragma unroll
+    for (int j = 0; j < SCATTER_TILE / 256; ++j) {
+      const uint32_t idx = tile + j * 256 + threadIdx.x;
+      p[j] = idx < n ? pairs[idx] : make_uint2(0xFFFFFFFFu, 0u);
+      if (idx < n) r[j] = atomicAdd(&s_cnt[p[j].x - first], 1u);
+    }
+    __syncthreads();
+    for (uint32_t i = threadIdx.x; i < K; i += 256) {
+      const uint32_t c = s_cnt[i];
+      if (c) s_base[i] = seg_off[first + i] + atomicAdd(&cursor[first + i], c);
+    }
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < SCATTER_TILE / 256; ++j)
+      if (p[j].x != 0xFFFFFFFFu) ids_sorted[s_base[p[j].x - first] + r[j]] = p[j].y;
+    __syncthreads();
+  }
+}
+
 // ---- k_traverse -----------------------------------------------------------------------------------
 struct TravParams {
   const uint8_t* blob;
@@ -342,13 +377,21 @@ k_traverse(const TravParams P) {
         __syncwarp();
       }
 
-      // ---- one traversal step per lane -----------------------------------------------------------------
+      // ---- one phase per iteration --------------------------------------------------------------------
+      // Lanes are INTERNAL (wide node to test), LEAF (primitives to test), EXIT (push to a child subtree) or idle.
+      // Exits are cheap and handled every iteration.  Of the two expensive phases only the one the majority of
+      // lanes needs is executed; the minority keeps its state and waits, so each phase runs with fuller warps
+      // instead of the warp executing node code and primitive code back to back for a few lanes each.
+      const uint32_t tag = cur >> 30;
+      const uint32_t m_node = __ballot_sync(0xffffffffu, tag == REF_INTERNAL);
+      const uint32_t m_leaf = __ballot_sync(0xffffffffu, tag == REF_LEAF);
+      const bool node_phase = __popc(m_node) >= __popc(m_leaf);
       bool do_push = false;
       uint32_t push_treelet = 0;
       bool need_pop = false;
       if (cur != REF_NONE) {
-        const uint32_t tag = cur >> 30;
         if (tag == REF_INTERNAL) {
+         if (node_phase) {
           if (STATS) st_nodes++;
           B2_CHECK((cur & 0x3FFFFFFFu) < td.n_nodes, 2, cur);
           const uint8_t* nbase = nodes + (size_t)(cur & 0x3FFFFFFFu) * NB;
@@ -400,11 +443,13 @@ k_traverse(const TravParams P) {
           }
           if (keys[0] != 0xFFFFFFFFu) cur = nrefs[keys[0] & (uint32_t)(W - 1)];
           else need_pop = true;
+         }
         } else if (tag == REF_LEAF) {
+         if (!node_phase) {
+          need_pop = true;
           const uint32_t first = cur & 0x00FFFFFFu, count = ((cur >> 24) & 63u) + 1u;
           const PrimRec* pr = reinterpret_cast<const PrimRec*>(prims) + first;
           B2_CHECK(first + count <= td.n_prims, 4, cur);
-          need_pop = true;
           for (uint32_t q = 0; q < count; ++q) {
             const PrimRec p = pr[q];
             if (STATS) st_prims++;
@@ -417,6 +462,7 @@ k_traverse(const TravParams P) {
               if (ANYHIT) { best_t = 0.0f; sp = 0; break; }
             }
           }
+         }
         } else {   // EXIT
           B2_CHECK(tag == REF_EXIT && (cur & 0x3FFFFFFFu) < P.n_treelets, 5, cur);
           do_push = true;
@@ -555,6 +601,7 @@ int Tracer::init(const DeviceBVH& b, uint64_t max_rays_, uint32_t pair_factor) {
     if ((rc = prep_kernel<4, true, true>(smem_bytes, &o4))) return rc;
   }
   ctas_per_sm = std::max(1, std::min(std::min(occ, o2), std::min(o3, o4)));
+  B2RT_CUDA_OK(cudaFuncSetAttribute(k_scatter_tiled, cudaFuncAttributeMaxDynamicSharedMemorySize, 12288 * 8));
   const size_t nt = std::max<uint32_t>(1, bvh.n_treelets);
   if (nt_cap < nt) {
     cudaFree(cnt); cudaFree(seg_off); cudaFree(cursor); cnt = seg_off = cursor = nullptr;
@@ -616,7 +663,12 @@ int Tracer::trace(cudaStream_t s, const float4* ray_o, const float4* ray_d, unsi
       launches++;
     }
     if (L > 0) {
-      k_scatter<<<num_sms * 8, 256, 0, s>>>(pairs, &ctrl[(L - 1) & 1], seg_off, cursor, ids_sorted, (uint32_t)pair_cap);
+      if (lr.count <= 12288) {
+        k_scatter_tiled<<<num_sms * 4, 256, (size_t)lr.count * 8, s>>>(pairs, &ctrl[(L - 1) & 1], seg_off, cursor, ids_sorted,
+                                                                        (uint32_t)pair_cap, lr.first, lr.count);
+      } else {
+        k_scatter<<<num_sms * 8, 256, 0, s>>>(pairs, &ctrl[(L - 1) & 1], seg_off, cursor, ids_sorted, (uint32_t)pair_cap);
+      }
       launches++;
     }
     TravParams P;
