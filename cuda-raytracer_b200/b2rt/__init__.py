@@ -14,7 +14,7 @@ import os
 
 import numpy as np
 
-from ._abi import Camera, Config, Light, Material, SceneDesc, Stats
+from ._abi import Camera, Config, Light, Material, SceneDesc, SceneFile, Stats
 from .scene import Scene, camera_rays, place_camera, random_soup, subdivide  # noqa: F401
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
@@ -75,6 +75,10 @@ def lib():
         L.b2rt_bvh_validate_host.argtypes = [C.POINTER(SceneDesc), u32, u32, u32, vp]
         L.b2rt_destroy.argtypes = [vp]; L.b2rt_destroy.restype = None
         L.b2rt_camera_place.argtypes = [vp, vp, C.c_float, C.c_float, u32, u32, C.POINTER(Camera)]
+        for f in ("b2rt_scene_load", "b2rt_load_dae"):
+            getattr(L, f).argtypes = [C.c_char_p, C.POINTER(C.POINTER(SceneFile))]
+        L.b2rt_scene_save.argtypes = [C.c_char_p, C.POINTER(SceneFile)]
+        L.b2rt_scene_free.argtypes = [C.POINTER(SceneFile)]; L.b2rt_scene_free.restype = None
         _lib = L
     return _lib
 
@@ -87,6 +91,39 @@ def _check(rc):
 
 def device_count():
     return lib().b2rt_device_count()
+
+
+def _scene_from_file(entry, path):
+    """Run b2rt_scene_load / b2rt_load_dae and copy the result into a host Scene (the library frees its copy)."""
+    pf = C.POINTER(SceneFile)()
+    _check(getattr(lib(), entry)(os.fsencode(path), C.byref(pf)))
+    try:
+        f = pf.contents
+        d = f.desc
+        def arr(ptr, n, dt):
+            return np.ctypeslib.as_array(ptr, shape=(n,)).astype(dt, copy=True) if n and ptr else np.zeros(0, dt)
+        mats = [dict(kind=m.kind, albedo=tuple(m.albedo), transmittance=tuple(m.transmittance), emission=tuple(m.emission),
+                     ior=m.ior, roughness=m.roughness) for m in (d.materials[i] for i in range(d.n_materials))]
+        lights = [dict(kind=l.kind, radiance=tuple(l.radiance), position=tuple(l.position), direction=tuple(l.direction),
+                       dim_x=tuple(l.dim_x), dim_y=tuple(l.dim_y)) for l in (d.lights[i] for i in range(d.n_lights))]
+        return Scene(arr(d.tri_verts, d.n_tris * 9, np.float32),
+                     arr(d.tri_normals, d.n_tris * 9, np.float32) if d.tri_normals else None,
+                     arr(d.tri_material, d.n_tris, np.uint32), arr(d.spheres, d.n_spheres * 4, np.float32),
+                     arr(d.sphere_material, d.n_spheres, np.uint32), mats, lights, cam_dir=tuple(f.cam_dir),
+                     hfov=f.cam_hfov_deg, vfov=f.cam_vfov_deg, bbox=np.array(tuple(f.bbox), np.float64))
+    finally:
+        lib().b2rt_scene_free(pf)
+
+
+def load_dae(path):
+    """Collada::ColladaParser::load + Application::load flattening (src/collada/collada.cpp:117-214,
+    src/application.cpp:347-435) through the C ABI's b2rt_load_dae -> Scene."""
+    return _scene_from_file("b2rt_load_dae", path)
+
+
+def load_scene(path):
+    """.dae through b2rt_load_dae, anything else as a .b2s file through b2rt_scene_load."""
+    return _scene_from_file("b2rt_load_dae" if str(path).lower().endswith(".dae") else "b2rt_scene_load", path)
 
 
 def _f32(a, shape=None):
@@ -320,7 +357,7 @@ class CudaRenderer:
         self.pt.set_frame_size(width, height)
 
     def loadScene(self, scene_or_path):
-        self.scene = Scene.load(scene_or_path) if isinstance(scene_or_path, str) else scene_or_path
+        self.scene = load_scene(scene_or_path) if isinstance(scene_or_path, str) else scene_or_path
         self.pt.set_scene(self.scene)
 
     def setup(self):

@@ -25,6 +25,12 @@ class Camera(C.Structure):
     _fields_ = [("pos", C.c_float * 3), ("c2w", C.c_float * 9), ("hfov_deg", C.c_float), ("vfov_deg", C.c_float)]
 
 
+class SceneFile(C.Structure):
+    """b2rt_scene_file: what b2rt_scene_load / b2rt_load_dae return (storage owned by the library)."""
+    _fields_ = [("desc", SceneDesc), ("camera", Camera), ("cam_dir", C.c_float * 3), ("cam_hfov_deg", C.c_float),
+                ("cam_vfov_deg", C.c_float), ("bbox", C.c_float * 6), ("storage", C.c_void_p)]
+
+
 class Config(C.Structure):
     _fields_ = [("ns_aa", C.c_uint32), ("max_ray_depth", C.c_uint32), ("ns_area_light", C.c_uint32),
                 ("seed", C.c_uint64), ("ray_eps", C.c_float), ("bvh_width", C.c_uint32),

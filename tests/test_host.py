@@ -183,3 +183,86 @@ def test_cpp_example_fails_loudly_without_device():
         pytest.skip("a CUDA device is visible")
     out = subprocess.run([exe, scene_path("CBempty")], capture_output=True, text=True)
     assert out.returncode == 1 and "no CPU fallback" in out.stderr
+
+
+# ---- b2rt_load_dae: the C++ COLLADA loader ---------------------------------------------
+def _same_scene(a, b):
+    assert np.array_equal(a.tri_verts, b.tri_verts)
+    if a.n_tris:
+        assert np.array_equal(a.tri_normals, b.tri_normals)
+    assert np.array_equal(a.tri_material, b.tri_material)
+    assert np.array_equal(a.spheres, b.spheres) and np.array_equal(a.sphere_material, b.sphere_material)
+    assert a.materials == b.materials and a.lights == b.lights
+    assert np.array_equal(a.cam_dir.astype(np.float32), b.cam_dir.astype(np.float32))
+    assert a.hfov == b.hfov and a.vfov == b.vfov and np.array_equal(a.bbox, b.bbox)
+
+
+def test_load_dae_fixture_matches_converter():
+    """tests/golden/mini_scene.dae (hand-written) through the C++ loader == the .b2s the independent Python
+    converter (tools/dae2scene.py) produced from the same file, bit for bit; also checks the loader's semantics."""
+    a = b2rt.load_dae(os.path.join(ROOT, "tests", "golden", "mini_scene.dae"))
+    b = Scene.load(os.path.join(ROOT, "tests", "golden", "mini_scene.b2s"))
+    _same_scene(a, b)
+    assert a.n_tris == 7 and len(a.spheres) == 1
+    # Z_UP -> Y_UP fix-up (collada.cpp:171-183): the floor's z = 0.125 corner became y = 0.125; quad -> first 3 vertices
+    assert a.tri_verts[2].tolist() == [2, 0, -2, -2, 0, -2, -2, 0.125, 2]
+    kinds = [m["kind"] for m in a.materials]
+    assert kinds == [3, 0, 1, 2, 0]            # emission, phong diffuse, mirror, glass, default white
+    assert a.materials[4]["albedo"] == (1.0, 1.0, 1.0)
+    assert [l["kind"] for l in a.lights] == [0, 2]     # CMU462 <area> wins over the common <point>; directional
+    assert a.lights[0]["position"] == (-0.125, 2.0, -0.25)      # parent <translate> applied
+    assert a.spheres[0].tolist() == [-0.25, 0.25, -0.5, 0.25]    # radius scaled by |M e_x|
+    assert abs(a.vfov - 29.068184) < 1e-5                       # derived from xfov + aspect_ratio
+
+
+def test_load_dae_roundtrip_save(tmp_path):
+    lib = b2rt.lib()
+    from b2rt._abi import SceneFile
+    pf = C.POINTER(SceneFile)()
+    assert lib.b2rt_load_dae(os.path.join(ROOT, "tests", "golden", "mini_scene.dae").encode(), C.byref(pf)) == 0
+    out = str(tmp_path / "mini.b2s")
+    assert lib.b2rt_scene_save(out.encode(), pf) == 0
+    lib.b2rt_scene_free(pf)
+    assert open(out, "rb").read() == open(os.path.join(ROOT, "tests", "golden", "mini_scene.b2s"), "rb").read()
+    _same_scene(b2rt.load_scene(out), b2rt.load_scene(os.path.join(ROOT, "tests", "golden", "mini_scene.dae")))
+
+
+@pytest.mark.parametrize("text,needle", [
+    ("", "no root element"),
+    ("<COLLADA><asset><up_axis>Y_UP</up_axis></asset>", "unterminated"),
+    ("<COLLADA><asset></wrong></COLLADA>", "mismatched end tag"),
+    ("<scene/>", "not <COLLADA>"),
+    ("<COLLADA><asset><up_axis>Y_UP</up_axis></asset></COLLADA>", "instance_visual_scene"),
+    ("<COLLADA><asset><up_axis>Y_UP</up_axis></asset><library_visual_scenes><visual_scene id='s'/></library_visual_scenes>"
+     "<scene><instance_visual_scene url='#s'/></scene></COLLADA>", "no geometry"),
+    ("<COLLADA><asset><up_axis>Y_UP</up_axis></asset><scene><instance_visual_scene url='#nope'/></scene></COLLADA>",
+     "unresolved reference"),
+])
+def test_load_dae_errors(tmp_path, text, needle):
+    """Malformed input is an error code + message (the reference exit()s, collada.cpp:117-214)."""
+    p = tmp_path / "bad.dae"
+    p.write_text(text)
+    with pytest.raises(b2rt.B2rtError) as e:
+        b2rt.load_dae(str(p))
+    assert e.value.code == -5 and needle in str(e.value)
+
+
+def test_load_dae_missing_file():
+    with pytest.raises(b2rt.B2rtError) as e:
+        b2rt.load_dae("/nonexistent/scene.dae")
+    assert e.value.code == -5 and "cannot open" in str(e.value)
+
+
+REF_MEDIA = "/root/reference/media/pathtracer"
+REF_SCENES = {"CBbunny": "advanced/CBbunny.dae", "CBcoil": "advanced/CBcoil.dae", "CBempty": "advanced/CBempty.dae",
+              "CBgems": "advanced/CBgems.dae", "CBspheres": "advanced/CBspheres.dae",
+              "CBspheres_lambertian": "advanced/CBspheres_lambertian.dae", "floating": "basic/floating.dae",
+              "plane1024": "basic/plane1024.dae", "sphere_diffuse": "basic/sphere_diffuse.dae", "trigs1": "basic/trigs1.dae",
+              "trigs5": "basic/trigs5.dae", "trigs10": "basic/trigs10.dae"}
+
+
+@pytest.mark.skipif(not os.path.isdir(REF_MEDIA), reason="reference media only exists in the build container")
+@pytest.mark.parametrize("name", sorted(REF_SCENES))
+def test_load_dae_reference_media(name):
+    """Every bundled scene under scenes/ is what the C++ loader makes of the reference's own .dae."""
+    _same_scene(b2rt.load_dae(os.path.join(REF_MEDIA, REF_SCENES[name])), Scene.load(scene_path(name)))
