@@ -76,9 +76,9 @@ def lib():
         L.b2rt_destroy.argtypes = [vp]; L.b2rt_destroy.restype = None
         L.b2rt_camera_place.argtypes = [vp, vp, C.c_float, C.c_float, u32, u32, C.POINTER(Camera)]
         for f in ("b2rt_scene_load", "b2rt_load_dae"):
-            getattr(L, f).argtypes = [C.c_char_p, C.POINTER(C.POINTER(SceneFile))]
-        L.b2rt_scene_save.argtypes = [C.c_char_p, C.POINTER(SceneFile)]
-        L.b2rt_scene_free.argtypes = [C.POINTER(SceneFile)]; L.b2rt_scene_free.restype = None
+            getattr(L, f).argtypes = [C.c_char_p, C.POINTER(vp)]
+        L.b2rt_scene_save.argtypes = [C.c_char_p, vp]
+        L.b2rt_scene_free.argtypes = [vp]; L.b2rt_scene_free.restype = None
         _lib = L
     return _lib
 
@@ -95,10 +95,10 @@ def device_count():
 
 def _scene_from_file(entry, path):
     """Run b2rt_scene_load / b2rt_load_dae and copy the result into a host Scene (the library frees its copy)."""
-    pf = C.POINTER(SceneFile)()
+    pf = C.c_void_p()
     _check(getattr(lib(), entry)(os.fsencode(path), C.byref(pf)))
     try:
-        f = pf.contents
+        f = C.cast(pf, C.POINTER(SceneFile)).contents
         d = f.desc
         def arr(ptr, n, dt):
             return np.ctypeslib.as_array(ptr, shape=(n,)).astype(dt, copy=True) if n and ptr else np.zeros(0, dt)

@@ -217,8 +217,7 @@ def test_load_dae_fixture_matches_converter():
 
 def test_load_dae_roundtrip_save(tmp_path):
     lib = b2rt.lib()
-    from b2rt._abi import SceneFile
-    pf = C.POINTER(SceneFile)()
+    pf = C.c_void_p()
     assert lib.b2rt_load_dae(os.path.join(ROOT, "tests", "golden", "mini_scene.dae").encode(), C.byref(pf)) == 0
     out = str(tmp_path / "mini.b2s")
     assert lib.b2rt_scene_save(out.encode(), pf) == 0
