@@ -86,18 +86,12 @@ def test_invalid_arguments():
 
 def test_scene_file_roundtrip_and_camera(tmp_path):
     lib = b2rt.lib()
-
-    class SceneFile(C.Structure):
-        _fields_ = [("desc", b2rt._abi.SceneDesc), ("camera", Camera), ("cam_dir", C.c_float * 3), ("cam_hfov_deg", C.c_float),
-                    ("cam_vfov_deg", C.c_float), ("bbox", C.c_float * 6), ("storage", C.c_void_p)]
-    lib.b2rt_scene_load.argtypes = [C.c_char_p, C.POINTER(C.POINTER(SceneFile))]
-    lib.b2rt_scene_save.argtypes = [C.c_char_p, C.POINTER(SceneFile)]
-    lib.b2rt_scene_free.argtypes = [C.POINTER(SceneFile)]
+    SceneFile = b2rt._abi.SceneFile
     for name in ("CBspheres_lambertian", "CBcoil"):
         sc = Scene.load(scene_path(name))
-        p = C.POINTER(SceneFile)()
+        p = C.c_void_p()
         assert lib.b2rt_scene_load(scene_path(name).encode(), C.byref(p)) == 0
-        f = p.contents
+        f = C.cast(p, C.POINTER(SceneFile)).contents
         assert f.desc.n_tris == sc.n_tris and f.desc.n_spheres == len(sc.spheres) and f.desc.n_lights == len(sc.lights)
         tv = np.ctypeslib.as_array(f.desc.tri_verts, shape=(sc.n_tris * 9,))
         assert np.array_equal(tv, sc.tri_verts.reshape(-1))
@@ -113,7 +107,7 @@ def test_scene_file_roundtrip_and_camera(tmp_path):
             np.testing.assert_allclose(cam_c.c2w[:], cam_p.c2w[:], rtol=1e-6, atol=1e-6)
             assert abs(cam_c.hfov_deg - cam_p.hfov_deg) < 1e-4 and abs(cam_c.vfov_deg - cam_p.vfov_deg) < 1e-4
         lib.b2rt_scene_free(p)
-    p = C.POINTER(SceneFile)()
+    p = C.c_void_p()
     assert lib.b2rt_scene_load(b"/nonexistent.b2s", C.byref(p)) == -5
 
 
