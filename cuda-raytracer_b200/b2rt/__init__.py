@@ -18,7 +18,8 @@ from ._abi import Camera, Config, Light, Material, SceneDesc, SceneFile, Stats
 from .scene import Scene, camera_rays, place_camera, random_soup, subdivide  # noqa: F401
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(os.path.dirname(_HERE), "libb2rt.so")
+# B2RT_LIB selects another build of the same library (A/B runs of kernel variants, tools/build_variant.sh)
+LIB_PATH = os.environ.get("B2RT_LIB") or os.path.join(os.path.dirname(_HERE), "libb2rt.so")
 
 EXPORTS = [
     "b2rt_last_error", "b2rt_abi_version", "b2rt_device_count", "b2rt_bvh_build", "b2rt_bvh_intersect",

@@ -21,7 +21,18 @@ inline uint32_t make_ref(uint32_t tag, uint32_t payload) { return (tag << 30) | 
 
 constexpr uint32_t PRIM_BYTES = 48;   // float4 x3: v0.xyz e1.x | e1.yz e2.xy | e2.z id kind pad
 constexpr uint32_t MAX_LEVELS = 32;
-constexpr uint32_t STACK_SIZE = 64;   // per-ray stack inside one subtree (bounded by the builder)
+// Per-ray traversal stack inside one subtree: 32-bit entries in shared memory, [31:12] = entry distance (fp32
+// bits truncated = rounded down, so culling against it is conservative), [11:0] = local node index << log2(W) | child
+// slot.  The builder bounds the subtree depth so that (W-1) * depth <= stack_entries(W), and the node count so that
+// the index fits.
+#ifndef B2RT_STACK4
+#define B2RT_STACK4 16
+#endif
+#ifndef B2RT_STACK8
+#define B2RT_STACK8 35
+#endif
+constexpr uint32_t stack_entries(uint32_t width) { return width == 8 ? (uint32_t)B2RT_STACK8 : (uint32_t)B2RT_STACK4; }
+constexpr uint32_t max_treelet_nodes(uint32_t width) { return width == 8 ? 512u : 1024u; }
 
 inline uint32_t node_bytes(uint32_t width) { return width == 8 ? 256u : 128u; }
 

@@ -149,6 +149,7 @@ struct WNode {
   uint64_t subtree_bytes = 0;   // this node + everything below
   uint32_t height = 1;          // levels of wide nodes below and including this one
   uint64_t own_bytes = 0;       // node record + its leaf primitives
+  uint64_t subtree_nodes = 1;   // wide nodes below and including this one
 };
 
 }  // namespace
@@ -203,10 +204,14 @@ int build_wide_bvh(const HostScene& sc, uint32_t max_leaf, uint32_t width, uint3
   if (max_leaf > 64) { set_error("max_leaf_size must be <= 64"); return B2RT_ERR_INVALID; }
   const uint32_t NB = node_bytes(width);
   const uint32_t min_budget = NB + width * max_leaf * PRIM_BYTES;
-  if (treelet_bytes == 0) treelet_bytes = 48 * 1024;
+  if (treelet_bytes == 0) treelet_bytes = 24 * 1024;
   treelet_bytes = std::max(treelet_bytes, min_budget) & ~15u;
-  if (treelet_bytes > 200 * 1024) { set_error("treelet_bytes exceeds the shared-memory budget (200 KiB)"); return B2RT_ERR_INVALID; }
-  const uint32_t depth_limit = (STACK_SIZE - 1) / (width - 1);
+  // 227 KiB per CTA = subtree blob + per-thread stacks (<= 35 KiB) + the push staging rings
+  if (treelet_bytes > 160 * 1024) { set_error("treelet_bytes exceeds the shared-memory budget (160 KiB)"); return B2RT_ERR_INVALID; }
+  // a ray pushes at most width-1 children per wide node it descends through, so a subtree of at most depth_limit
+  // node levels never needs more than stack_entries(width) stack slots (the kernel's shared-memory stack)
+  const uint32_t depth_limit = stack_entries(width) / (width - 1);
+  const uint64_t node_limit = max_treelet_nodes(width);
 
   const uint32_t n = sc.n_prims();
   out->width = width;
@@ -287,11 +292,11 @@ int build_wide_bvh(const HostScene& sc, uint32_t max_leaf, uint32_t width, uint3
     // bottom-up sizes (children have larger indices than parents => reverse order works)
     for (int64_t i = (int64_t)wn.size() - 1; i >= 0; --i) {
       WNode& w = wn[i];
-      w.own_bytes = NB; w.height = 1;
+      w.own_bytes = NB; w.height = 1; w.subtree_nodes = 1;
       uint64_t sub = 0;
       for (auto& c : w.ch) {
         if (c.node < 0) w.own_bytes += (uint64_t)c.count * PRIM_BYTES;
-        else { sub += wn[c.node].subtree_bytes; w.height = std::max(w.height, wn[c.node].height + 1); }
+        else { sub += wn[c.node].subtree_bytes; w.height = std::max(w.height, wn[c.node].height + 1); w.subtree_nodes += wn[c.node].subtree_nodes; }
       }
       w.subtree_bytes = w.own_bytes + sub;
     }
@@ -325,7 +330,8 @@ int build_wide_bvh(const HostScene& sc, uint32_t max_leaf, uint32_t width, uint3
         Cand c = pq.top(); pq.pop();
         const WNode& w = wn[c.node];
         // whole subtree fits (bytes and stack depth): take all of it
-        if (used + w.subtree_bytes <= treelet_bytes && c.depth + w.height - 1 <= depth_limit) {
+        if (used + w.subtree_bytes <= treelet_bytes && c.depth + w.height - 1 <= depth_limit &&
+            members.size() + w.subtree_nodes <= node_limit) {
           std::vector<int32_t> st{c.node};
           while (!st.empty()) {
             int32_t x = st.back(); st.pop_back();
@@ -334,7 +340,7 @@ int build_wide_bvh(const HostScene& sc, uint32_t max_leaf, uint32_t width, uint3
           }
           continue;
         }
-        if (used + w.own_bytes <= treelet_bytes && c.depth <= depth_limit) {
+        if (used + w.own_bytes <= treelet_bytes && c.depth <= depth_limit && members.size() < node_limit) {
           include(c.node, c.depth, include);
           for (auto& cc : w.ch) if (cc.node >= 0) pq.push({wn[cc.node].area, cc.node, c.depth + 1});
           continue;
@@ -454,7 +460,7 @@ extern "C" int b2rt_bvh_validate_host(const b2rt_scene_desc* scene, uint32_t max
   std::string err;
   for (int64_t t = (int64_t)wb.treelets.size() - 1; t >= 0 && err.empty(); --t) {
     const TreeletDesc& td = wb.treelets[t];
-    if (td.bytes > std::max(treelet_bytes ? treelet_bytes : 48u * 1024u, NB + W * (max_leaf ? max_leaf : 4) * PRIM_BYTES)) err = "subtree exceeds byte budget";
+    if (td.bytes > std::max(treelet_bytes ? treelet_bytes : 24u * 1024u, NB + W * (max_leaf ? max_leaf : 4) * PRIM_BYTES)) err = "subtree exceeds byte budget";
     if ((uint64_t)td.n_nodes * NB + (uint64_t)td.n_prims * PRIM_BYTES > td.bytes) err = "subtree size mismatch";
     const uint8_t* base = wb.blob.data() + (size_t)td.offset16 * 16;
     const uint8_t* prims = base + (size_t)td.n_nodes * NB;
@@ -511,12 +517,13 @@ extern "C" int b2rt_bvh_validate_host(const b2rt_scene_desc* scene, uint32_t max
     }
     if (td.n_nodes) {
       tl_box[t] = nb[0];
-      max_stack = std::max<uint64_t>(max_stack, 1 + (uint64_t)(W - 1) * depth[0]);
+      max_stack = std::max<uint64_t>(max_stack, (uint64_t)(W - 1) * depth[0]);
+      if (td.n_nodes > max_treelet_nodes(W)) err = "subtree has more nodes than a stack entry can address";
     }
   }
   for (uint32_t i = 0; i < n && err.empty(); ++i)
     if (seen[i] != 1) err = "primitive not stored exactly once";
-  if (max_stack > STACK_SIZE) err = "per-ray stack bound exceeded";
+  if (max_stack > stack_entries(W)) err = "per-ray stack bound exceeded";
   if (out) {
     out[0] = wb.treelets.size(); out[1] = wb.n_levels; out[2] = n_nodes; out[3] = n_leaves; out[4] = wb.blob.size();
     out[5] = wb.max_treelet_bytes; out[6] = max_stack; out[7] = n_exits;

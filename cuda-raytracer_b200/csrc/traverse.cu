@@ -17,6 +17,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
 
 #include <algorithm>
 
@@ -28,9 +29,12 @@ namespace b2rt {
 namespace {
 
 #ifndef B2RT_OCC4
-#define B2RT_OCC4 3
+#define B2RT_OCC4 4
 #endif
-constexpr int TRAV_THREADS = 256;
+#ifndef B2RT_TRAV_THREADS
+#define B2RT_TRAV_THREADS 256
+#endif
+constexpr int TRAV_THREADS = B2RT_TRAV_THREADS;
 constexpr int TRAV_WARPS = TRAV_THREADS / 32;
 constexpr int STAGE_PAIRS = 96;   // per-warp staging ring (flush when > STAGE_PAIRS - 32)
 
@@ -223,6 +227,8 @@ struct TravParams {
   uint32_t level;
   uint32_t n_treelets, n_rays_cap;
   uint32_t chunk_rays;
+  uint32_t chunk0_max;        // upper bound of the level-0 chunk size
+  uint32_t stack_off;         // byte offset of the per-thread traversal stacks inside dynamic shared memory
   const uint32_t* n_active;
   TraceCounters* counters;
 };
@@ -232,13 +238,14 @@ struct NodeView;
 template <>
 struct NodeView<4> {
   static constexpr int BYTES = 128;
+  static constexpr int SLOT_BITS = 2;
 };
 template <>
 struct NodeView<8> {
   static constexpr int BYTES = 256;
+  static constexpr int SLOT_BITS = 3;
 };
-
-struct StackEntry { uint32_t ref; float tn; };
+constexpr uint32_t STACK_TN_MASK = 0xFFFFF000u;   // stack entry: [31:12] entry distance bits, [11:0] node << SLOT_BITS | slot
 
 // flush one warp's staged pairs: one global reservation, coalesced 8-byte stores, per-subtree counts
 __device__ __forceinline__ void flush_pairs(uint2* stage, uint32_t& n_staged, const TravParams& P, uint32_t lane) {
@@ -265,7 +272,22 @@ __device__ __forceinline__ void flush_pairs(uint2* stage, uint32_t& n_staged, co
 #define B2_CHECK(cond, code, info) do { } while (0)
 #endif
 constexpr uint32_t REF_NONE = 0xFFFFFFFEu;   // "no current node" marker of the traversal loop (tag EMPTY)
-constexpr int REFILL_MIN_IDLE = 8;            // refill a warp's idle lanes once this many are idle
+#ifndef B2RT_MIN_IDLE
+#define B2RT_MIN_IDLE 12
+#endif
+constexpr int REFILL_MIN_IDLE = B2RT_MIN_IDLE;   // refill a warp's idle lanes once this many are idle
+
+// three-input fp32 min / max (sm_100: one FMNMX3 instead of two FMNMX)
+__device__ __forceinline__ float fmax3(float a, float b, float c) {
+  float r;
+  asm("max.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));
+  return r;
+}
+__device__ __forceinline__ float fmin3(float a, float b, float c) {
+  float r;
+  asm("min.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));
+  return r;
+}
 
 template <int W, bool ANYHIT, bool STATS>
 __global__ void __launch_bounds__(TRAV_THREADS, (W == 4 ? B2RT_OCC4 : 2))
@@ -279,6 +301,9 @@ k_traverse(const TravParams P) {
   const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const uint32_t lane_lt = (1u << lane) - 1u;
   constexpr int NB = NodeView<W>::BYTES;
+  constexpr int SLOT_BITS = NodeView<W>::SLOT_BITS;
+  // per-thread stack in shared memory, entry k of thread t at word k * TRAV_THREADS + t (conflict-free)
+  uint32_t* const stack = reinterpret_cast<uint32_t*>(smem + P.stack_off) + threadIdx.x;
   uint32_t cur_treelet = 0xFFFFFFFFu;
   uint32_t phase = 0;
   uint32_t n_staged = 0;   // warp-uniform
@@ -290,13 +315,15 @@ k_traverse(const TravParams P) {
   __syncthreads();
 
   // level 0: every active ray visits the root subtree; its chunk list is implicit (no scheduling kernel)
+  // (large chunks there: one subtree, so the only cost of a chunk boundary is the CTA-wide barrier)
   const uint32_t n_root = P.level == 0 ? *P.n_active : 0u;
-  const uint32_t n_chunks = P.level == 0 ? (n_root + P.chunk_rays - 1) / P.chunk_rays : P.ctrl[CTRL_NCHUNKS];
+  const uint32_t chunk0 = min(P.chunk0_max, max(P.chunk_rays, (n_root / (gridDim.x * 8u) + 1023u) & ~1023u));
+  const uint32_t n_chunks = P.level == 0 ? (n_root + chunk0 - 1) / chunk0 : P.ctrl[CTRL_NCHUNKS];
   for (;;) {
     if (threadIdx.x == 0) {
       uint32_t c = atomicAdd(&P.ctrl[CTRL_NEXT0 + (P.level & 1)], 1u);
       uint4 ch = make_uint4(0xFFFFFFFFu, 0, 0, 0);
-      if (c < n_chunks) ch = P.level == 0 ? make_uint4(0u, c * P.chunk_rays, min(P.chunk_rays, n_root - c * P.chunk_rays), 0u) : P.chunks[c];
+      if (c < n_chunks) ch = P.level == 0 ? make_uint4(0u, c * chunk0, min(chunk0, n_root - c * chunk0), 0u) : P.chunks[c];
       s_chunk = ch;
       s_next_ray = 0;
     }
@@ -324,7 +351,6 @@ k_traverse(const TravParams P) {
     f3 o = mk3(0, 0, 0), d = mk3(0, 0, 1), inv = mk3(0, 0, 0), noi = mk3(0, 0, 0);
     float tmin = 0.f, tmax_user = 0.f;
     uint32_t nx = 0, ny = 0, nz = 0, fx = 0, fy = 0, fz = 0;   // byte offsets of the near / far plane rows
-    StackEntry stack[STACK_SIZE];
     int sp = 0;
     uint32_t cur = REF_NONE;
     bool have = false, improved = false;
@@ -409,10 +435,10 @@ k_traverse(const TravParams P) {
             const float bxa[4] = {bx.x, bx.y, bx.z, bx.w}, bya[4] = {by.x, by.y, by.z, by.w}, bza[4] = {bz.x, bz.y, bz.z, bz.w};
 #pragma unroll
             for (int c = 0; c < 4; ++c) {
-              const float tn = fmaxf(fmaxf(__fmaf_rn(axa[c], inv.x, noi.x), __fmaf_rn(aya[c], inv.y, noi.y)),
-                                     fmaxf(__fmaf_rn(aza[c], inv.z, noi.z), tmin));
-              const float tf = fminf(fminf(__fmaf_rn(bxa[c], inv.x, noi.x), __fmaf_rn(bya[c], inv.y, noi.y)),
-                                     fminf(__fmaf_rn(bza[c], inv.z, noi.z), best_t));
+              const float tn = fmaxf(fmax3(__fmaf_rn(axa[c], inv.x, noi.x), __fmaf_rn(aya[c], inv.y, noi.y),
+                                           __fmaf_rn(aza[c], inv.z, noi.z)), tmin);
+              const float tf = fminf(fmin3(__fmaf_rn(bxa[c], inv.x, noi.x), __fmaf_rn(bya[c], inv.y, noi.y),
+                                           __fmaf_rn(bza[c], inv.z, noi.z)), best_t);
               const bool hit = tn <= tf * 1.0000004f;
               // key: entry distance (rounded down, keeps order for t >= 0) | child slot
               keys[q * 4 + c] = hit ? ((__float_as_uint(tn) & ~(uint32_t)(W - 1)) | (uint32_t)(q * 4 + c)) : 0xFFFFFFFFu;
@@ -431,13 +457,14 @@ k_traverse(const TravParams P) {
             B2_CE(3, 4)
           }
 #undef B2_CE
-          // far-to-near onto the stack; the nearest child becomes the current node without a stack round trip
+          // far-to-near onto the stack; the nearest child becomes the current node without a stack round trip.
+          // An entry names the child by (node, slot); its reference is read from the node when it is popped.
+          const uint32_t node_tag = (cur & 0x3FFFFFFFu) << SLOT_BITS;
 #pragma unroll
           for (int q = W - 1; q >= 1; --q) {
             if (keys[q] != 0xFFFFFFFFu) {
-              B2_CHECK(sp < (int)STACK_SIZE, 3, sp);
-              stack[sp].ref = nrefs[keys[q] & (uint32_t)(W - 1)];
-              stack[sp].tn = __uint_as_float(keys[q] & ~(uint32_t)(W - 1));
+              B2_CHECK(sp < (int)stack_entries(W), 3, sp);
+              stack[sp * TRAV_THREADS] = (keys[q] & (STACK_TN_MASK | (uint32_t)(W - 1))) | node_tag;
               ++sp;
             }
           }
@@ -472,8 +499,11 @@ k_traverse(const TravParams P) {
         if (need_pop) {
           cur = REF_NONE;
           while (sp > 0) {
-            const StackEntry e = stack[--sp];
-            if (e.tn <= best_t) { cur = e.ref; break; }
+            const uint32_t e = stack[--sp * TRAV_THREADS];
+            if (__uint_as_float(e & STACK_TN_MASK) <= best_t) {
+              cur = *reinterpret_cast<const uint32_t*>(nodes + (size_t)((e & 0xFFFu) >> SLOT_BITS) * NB + 24 * W + (e & (uint32_t)(W - 1)) * 4u);
+              break;
+            }
           }
         }
       }
@@ -555,6 +585,8 @@ void free_bvh(DeviceBVH* d) {
   *d = DeviceBVH();
 }
 
+static size_t stack_bytes(uint32_t width) { return (size_t)stack_entries(width) * TRAV_THREADS * 4; }
+
 template <int W, bool A, bool S>
 static int prep_kernel(size_t smem, int* occ) {
   B2RT_CUDA_OK(cudaFuncSetAttribute(k_traverse<W, A, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -586,7 +618,11 @@ int Tracer::init(const DeviceBVH& b, uint64_t max_rays_, uint32_t pair_factor) {
   // BVH dependent part (small, grow-only)
   bvh = b;
   chunk_cap = pair_cap / chunk_rays + (uint64_t)bvh.n_treelets + 1024;
-  smem_bytes = std::max<size_t>(bvh.max_treelet_bytes, 1024);
+  // dynamic shared memory: the staged subtree blob, then the per-thread traversal stacks
+  stack_off = (std::max<size_t>(bvh.max_treelet_bytes, 1024) + 127) & ~(size_t)127;
+  smem_bytes = stack_off + stack_bytes(bvh.width);
+  if (const char* e = getenv("B2RT_CHUNK_RAYS")) { int v = atoi(e); if (v >= 32 && v <= (1 << 20)) chunk_rays = (uint32_t)v; }
+  if (const char* e = getenv("B2RT_CHUNK0_MAX")) { int v = atoi(e); if (v >= 32 && v <= (1 << 24)) chunk0_max = (uint32_t)v; }
   int occ = 1, o2 = 1, o3 = 1, o4 = 1;
   int rc;
   if (bvh.width == 8) {
@@ -675,7 +711,7 @@ int Tracer::trace(cudaStream_t s, const float4* ray_o, const float4* ray_d, unsi
     P.blob = bvh.blob; P.treelets = bvh.treelets; P.ray_o = ray_o; P.ray_d = ray_d; P.hits = hits;
     P.ids = (L == 0) ? ids0 : ids_sorted;
     P.chunks = chunks; P.ctrl = ctrl; P.cnt = cnt; P.pairs = pairs; P.pair_cap = (uint32_t)pair_cap; P.level = L;
-    P.counters = counters; P.n_treelets = bvh.n_treelets; P.chunk_rays = chunk_rays; P.n_active = n_active_dev; P.n_rays_cap = (uint32_t)std::min<uint64_t>(max_rays, 0xFFFFFFFFull);
+    P.counters = counters; P.n_treelets = bvh.n_treelets; P.chunk_rays = chunk_rays; P.chunk0_max = std::max(chunk0_max, chunk_rays); P.stack_off = (uint32_t)stack_off; P.n_active = n_active_dev; P.n_rays_cap = (uint32_t)std::min<uint64_t>(max_rays, 0xFFFFFFFFull);
     cudaEvent_t e0 = nullptr, e1 = nullptr;
     if (time_kernels) {
       if (ev_used + 2 > ev_pool.size()) {
