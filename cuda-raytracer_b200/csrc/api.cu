@@ -102,9 +102,9 @@ int ensure_rays(b2rt_bvh* b, uint64_t n, uint32_t pair_factor = 6) {
   if (b->ray_o) { cudaFree(b->ray_o); cudaFree(b->ray_d); cudaFree(b->hits); b->ray_o = b->ray_d = nullptr; b->hits = nullptr; }
   b->tracer.release();
   b->ray_cap = 0;
-  B2RT_CUDA_OK(cudaMalloc(&b->ray_o, n * sizeof(float4)));
-  B2RT_CUDA_OK(cudaMalloc(&b->ray_d, n * sizeof(float4)));
-  B2RT_CUDA_OK(cudaMalloc(&b->hits, n * 8));
+  B2RT_CUDA_OK(cudaMalloc(&b->ray_o, (n + 16) * sizeof(float4)));
+  B2RT_CUDA_OK(cudaMalloc(&b->ray_d, (n + 16) * sizeof(float4)));
+  B2RT_CUDA_OK(cudaMalloc(&b->hits, (n + 16) * 8));
   int rc = b->tracer.init(b->dbvh, n, pair_factor);
   if (rc) return rc;
   b->ray_cap = n; b->pair_factor = pair_factor;
@@ -150,7 +150,7 @@ int intersect_host(b2rt_bvh* b, const float* org, const float* dir, const float*
       cudaMemcpyAsync(b->n_dev, &m32, 4, cudaMemcpyHostToDevice, s);
       cudaEventRecord(e0, s);
       k_pack_rays<<<(m32 + 255) / 256, 256, 0, s>>>(d_org, d_dir, d_tmin, d_tmax, m32, b->ray_o, b->ray_d, b->hits);
-      rc = b->tracer.trace(s, b->ray_o, b->ray_d, b->hits, nullptr, b->n_dev, any_hit);
+      rc = b->tracer.trace(s, b->ray_o, b->ray_d, b->hits, b->n_dev, any_hit);
       if (rc) { cleanup(); return rc; }
       k_unpack_hits<<<(m32 + 255) / 256, 256, 0, s>>>(b->hits, m32, d_t, d_prim, d_occ);
       cudaEventRecord(e1, s);
@@ -243,7 +243,7 @@ int b2rt_bvh_bench_rays(b2rt_bvh* b, uint64_t n, int mode, uint64_t seed, int re
   B2RT_CUDA_OK(cudaMemsetAsync(b->tracer.counters, 0, sizeof(TraceCounters), s));
   // one untimed pass with statistics, then `repeats` timed passes without
   b->tracer.collect_stats = true;
-  rc = b->tracer.trace(s, b->ray_o, b->ray_d, b->hits, nullptr, b->n_dev, any_hit != 0);
+  rc = b->tracer.trace(s, b->ray_o, b->ray_d, b->hits, b->n_dev, any_hit != 0);
   if (rc) return rc;
   bool ovf = false;
   rc = b->tracer.check_overflow(s, &ovf);
@@ -258,7 +258,7 @@ int b2rt_bvh_bench_rays(b2rt_bvh* b, uint64_t n, int mode, uint64_t seed, int re
   for (int r = 0; r < repeats; ++r) {
     k_reset_hits<<<(n32 + 255) / 256, 256, 0, s>>>(n32, b->ray_d, b->hits);
     cudaEventRecord(e0, s);
-    rc = b->tracer.trace(s, b->ray_o, b->ray_d, b->hits, nullptr, b->n_dev, any_hit != 0);
+    rc = b->tracer.trace(s, b->ray_o, b->ray_d, b->hits, b->n_dev, any_hit != 0);
     cudaEventRecord(e1, s);
     if (rc) return rc;
     B2RT_CUDA_OK(cudaEventSynchronize(e1));

@@ -26,7 +26,7 @@ namespace b2rt {
 namespace {
 
 constexpr float INF_F = __builtin_huge_valf();
-constexpr uint32_t MAX_DEPTH = 96, ACT0 = 8, SH0 = 8 + MAX_DEPTH + 8, N_COUNTS = 256;
+constexpr uint32_t MAX_DEPTH = 96, ACT0 = 8, SH0 = ACT0 + MAX_DEPTH + 8, SHV0 = SH0 + MAX_DEPTH + 8, N_COUNTS = 512;
 
 struct WaveParams {
   // wave geometry
@@ -53,13 +53,23 @@ struct SceneDev {
   uint32_t n_tris, n_lights;
 };
 
+// Rays live in DENSE lists (what the traversal streams with TMA): entry i of the bounce-b list is the ray of path
+// `lslot[i]`; shading appends the continuing paths to the other list, so no list ever has holes.  Per-path state
+// (throughput, radiance) is indexed by the path's slot.
 struct PathBufs {
-  float4* ray_o; float4* ray_d; unsigned long long* hits;
-  float4* thr;     // rgb throughput, w = count_emission flag
-  float4* rad;     // rgb radiance of the path
-  float4* s_o; float4* s_d; unsigned long long* s_hits; float4* s_contrib;  // shadow rays [slot*S + j]
-  uint32_t* ids_a; uint32_t* ids_b; uint32_t* s_ids;
-  uint32_t* counts;  // [3] = cancel flag; [ACT0 + b] = active paths at bounce b; [SH0 + b] = shadow rays of bounce b
+  // current bounce's list (read) and the next bounce's (appended to); the host swaps them per bounce -- plain
+  // pointers, not an indexed array: a dynamically indexed kernel parameter would be copied to local memory
+  float4* lo; float4* ld; unsigned long long* lh; uint32_t* lslot;
+  float4* no; float4* nd; unsigned long long* nh; uint32_t* nslot;
+  float4* thr;     // [slot] rgb throughput, w = count_emission flag
+  float4* rad;     // [slot] rgb radiance of the path
+  // dense shadow-ray list of the current bounce: a path that hit a diffuse surface owns S consecutive entries
+  // (one per light sample; samples that cannot contribute are null rays the any-hit traversal skips)
+  float4* s_o; float4* s_d; unsigned long long* s_hits; float4* s_contrib;
+  uint32_t* s_q0;    // [slot] first shadow-list entry of the path's block, 0xFFFFFFFF = none
+  // [3] = cancel flag; [ACT0 + b] = active paths at bounce b; [SH0 + b] = shadow-list entries of bounce b;
+  // [SHV0 + b] = of which real shadow rays
+  uint32_t* counts;
 };
 
 __global__ void __launch_bounds__(256)
@@ -69,6 +79,7 @@ k_raygen(WaveParams wp, CamDev cam, PathBufs pb) {
   if (blockIdx.x == 0 && threadIdx.x < MAX_DEPTH + 1) {   // per-bounce list counters of this wave
     pb.counts[ACT0 + threadIdx.x] = (threadIdx.x == 0) ? (pb.counts[3] ? 0u : n) : 0u;
     pb.counts[SH0 + threadIdx.x] = 0u;
+    pb.counts[SHV0 + threadIdx.x] = 0u;
   }
   if (slot >= n) return;
   const uint32_t pix = wp.pix0 + slot / wp.spp;
@@ -83,9 +94,10 @@ k_raygen(WaveParams wp, CamDev cam, PathBufs pb) {
   const float py = (2.0f * sy - 1.0f) * cam.tan_v;
   const f3 w = cam.cx * px + cam.cy * py - cam.cz;
   const f3 d = normalize3(w);
-  pb.ray_o[slot] = make_float4(cam.pos.x, cam.pos.y, cam.pos.z, 0.0f);
-  pb.ray_d[slot] = make_float4(d.x, d.y, d.z, INF_F);
-  pb.hits[slot] = pack_hit(INF_F, 0xFFFFFFFFu);
+  pb.lo[slot] = make_float4(cam.pos.x, cam.pos.y, cam.pos.z, 0.0f);
+  pb.ld[slot] = make_float4(d.x, d.y, d.z, INF_F);
+  pb.lh[slot] = pack_hit(INF_F, 0xFFFFFFFFu);
+  pb.lslot[slot] = slot;
   pb.thr[slot] = make_float4(1.f, 1.f, 1.f, 1.f);
   pb.rad[slot] = make_float4(0.f, 0.f, 0.f, 0.f);
 }
@@ -102,35 +114,72 @@ __device__ __forceinline__ void make_coord_space(f3 n, f3* X, f3* Y, f3* Z) {
   *X = x; *Y = y; *Z = z;
 }
 
-__device__ __forceinline__ void append_id(uint32_t* list, uint32_t* counter, bool pred, uint32_t value) {
+// warp-aggregated append: position of this thread's element in a dense list (callers with pred == false get
+// garbage).  Works on whatever subset of the warp is converged at the call site.
+__device__ __forceinline__ uint32_t append_pos(uint32_t* counter, bool pred) {
   const uint32_t m = __ballot_sync(__activemask(), pred);
-  if (!pred) return;
+  if (!pred) return 0xFFFFFFFFu;
   const uint32_t lane = threadIdx.x & 31;
   const uint32_t leader = __ffs(m) - 1;
   uint32_t base = 0;
   if (lane == leader) base = atomicAdd(counter, (uint32_t)__popc(m));
   base = __shfl_sync(m, base, leader);
-  list[base + __popc(m & ((1u << lane) - 1u))] = value;
+  return base + __popc(m & ((1u << lane) - 1u));
+}
+
+// CTA-aggregated append: position of this thread's run of `per_item` consecutive elements in a dense list (garbage
+// when pred == false).  One global atomic per CTA -- the per-bounce list counters are single addresses, and L2
+// serialises same-address atomics, so one atomic per warp made the shading kernel atomic-bound.  Must be called by
+// every thread of a 256-thread CTA.  `extra` is a second per-thread value summed over the CTA into *extra_counter.
+__device__ __forceinline__ uint32_t block_append(uint32_t* counter, bool pred, uint32_t per_item, uint32_t* sh /* 10 words */,
+                                                 uint32_t extra = 0, uint32_t* extra_counter = nullptr) {
+  const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const uint32_t m = __ballot_sync(0xffffffffu, pred);
+  const uint32_t ex = extra_counter ? __reduce_add_sync(0xffffffffu, extra) : 0u;
+  if (lane == 0) sh[warp] = (uint32_t)__popc(m) | (ex << 8);   // <= 32 items, extra < 2^24 per warp
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    uint32_t tot = 0, tex = 0;
+    for (int w = 0; w < 8; ++w) { const uint32_t v = sh[w]; sh[w] = tot; tot += v & 0xFFu; tex += v >> 8; }
+    sh[8] = tot ? atomicAdd(counter, tot * per_item) : 0u;
+    if (tex) atomicAdd(extra_counter, tex);
+  }
+  __syncthreads();
+  const uint32_t pos = sh[8] + (sh[warp] + (uint32_t)__popc(m & ((1u << lane) - 1u))) * per_item;
+  __syncthreads();   // sh is reused by the next call
+  return pos;
 }
 
 // One surface interaction for every active path (bounce index b).
 __global__ void __launch_bounds__(256)
-k_shade(WaveParams wp, SceneDev sc, PathBufs pb, const uint32_t* __restrict__ ids, uint32_t* __restrict__ ids_next,
-        uint32_t b, uint32_t identity_ids) {
+k_shade(WaveParams wp, SceneDev sc, PathBufs pb, uint32_t b) {
   const uint32_t n = pb.counts[ACT0 + b];
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   bool cont = false;
   uint32_t slot = 0;
+  float4 next_o = make_float4(0.f, 0.f, 0.f, 0.f), next_d = make_float4(0.f, 0.f, 1.f, 0.f);
+  const uint32_t S = wp.S;
+  unsigned long long h = 0;
+  uint32_t prim = 0xFFFFFFFFu;
+  b2rt_material m;
+  m.kind = -1;
   if (i < n) {
-    slot = identity_ids ? i : ids[i];
-    const unsigned long long h = pb.hits[slot];
-    const uint32_t prim = (uint32_t)h;
-    const uint32_t S = wp.S;
-    // default: no shadow rays
-    for (uint32_t j = 0; j < S; ++j) pb.s_contrib[(size_t)slot * S + j].w = 0.f;
+    slot = pb.lslot[i];
+    h = pb.lh[i];
+    prim = (uint32_t)h;
+    if (prim != 0xFFFFFFFFu) m = sc.materials[sc.prim_material[prim]];
+  }
+  // every diffuse hit reserves S consecutive entries of the bounce's shadow-ray list: one atomic per warp, blocks in
+  // lane order, so the list stays coalesced against the path list
+  const bool wants_shadow = prim != 0xFFFFFFFFu && m.kind == B2RT_MAT_DIFFUSE && S > 0;
+  __shared__ uint32_t s_app[10];
+  uint32_t q0 = block_append(&pb.counts[SH0 + b], wants_shadow, S, s_app);
+  if (!wants_shadow) q0 = 0xFFFFFFFFu;
+  uint32_t n_valid = 0;
+  if (i < n) {
+    pb.s_q0[slot] = q0;
     if (prim != 0xFFFFFFFFu) {
       const float t = __uint_as_float((uint32_t)(h >> 32));
-      const b2rt_material m = sc.materials[sc.prim_material[prim]];
       const float4 thr4 = pb.thr[slot];
       f3 thr = mk3(thr4.x, thr4.y, thr4.z);
       const bool count_emission = thr4.w != 0.f;
@@ -142,7 +191,7 @@ k_shade(WaveParams wp, SceneDev sc, PathBufs pb, const uint32_t* __restrict__ id
           pb.rad[slot] = L;
         }
       } else {
-        const float4 ro = pb.ray_o[slot], rd = pb.ray_d[slot];
+        const float4 ro = pb.lo[i], rd = pb.ld[i];
         const f3 o = mk3(ro.x, ro.y, ro.z), d = mk3(rd.x, rd.y, rd.z);
         const f3 P = o + d * t;
         PrimRec pr;
@@ -204,18 +253,25 @@ k_shade(WaveParams wp, SceneDev sc, PathBufs pb, const uint32_t* __restrict__ id
                 wi = neg3(ld); dist = INF_F; pdf = 1.0f; Lr = radc;
               }
               const float cos_in = dot3(wi, Z);
-              if (!(cos_in >= 0.0f)) continue;
-              if (!(Lr.x > 0.0f || Lr.y > 0.0f || Lr.z > 0.0f)) continue;
-              if (!(pdf > 0.0f)) continue;
-              const float wgt = __fdiv_rn(cos_in, (float)ns * pdf);
-              const f3 f = mk3(m.albedo[0], m.albedo[1], m.albedo[2]) * 0.318309886183790672f;
-              const f3 c = thr * f * Lr * wgt;
-              const size_t sid = (size_t)slot * S + j;
-              const float tmx = dist - wp.eps;
-              pb.s_o[sid] = make_float4(P.x, P.y, P.z, wp.eps);
-              pb.s_d[sid] = make_float4(wi.x, wi.y, wi.z, tmx);
-              pb.s_hits[sid] = pack_hit(tmx, 0xFFFFFFFFu);
-              pb.s_contrib[sid] = make_float4(c.x, c.y, c.z, 1.f);
+              const bool valid = cos_in >= 0.0f && (Lr.x > 0.0f || Lr.y > 0.0f || Lr.z > 0.0f) && pdf > 0.0f;
+              const uint32_t q = q0 + j;
+              if (valid) {
+                const float wgt = __fdiv_rn(cos_in, (float)ns * pdf);
+                const f3 f = mk3(m.albedo[0], m.albedo[1], m.albedo[2]) * 0.318309886183790672f;
+                const f3 c = thr * f * Lr * wgt;
+                const float tmx = dist - wp.eps;
+                pb.s_o[q] = make_float4(P.x, P.y, P.z, wp.eps);
+                pb.s_d[q] = make_float4(wi.x, wi.y, wi.z, tmx);
+                pb.s_hits[q] = pack_hit(tmx, 0xFFFFFFFFu);
+                pb.s_contrib[q] = make_float4(c.x, c.y, c.z, 1.f);
+                n_valid++;
+              } else {
+                // null entry: hit word already "occluded", so the any-hit traversal retires it without a node visit
+                pb.s_o[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+                pb.s_d[q] = make_float4(0.f, 0.f, 1.f, -1.f);
+                pb.s_hits[q] = pack_hit(0.f, 0u);
+                pb.s_contrib[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+              }
             }
           }
         }
@@ -263,9 +319,8 @@ k_shade(WaveParams wp, SceneDev sc, PathBufs pb, const uint32_t* __restrict__ id
           if (weight.x > 0.0f || weight.y > 0.0f || weight.z > 0.0f) {
             thr = thr * weight;
             const f3 nd = normalize3(X * wi_l.x + Y * wi_l.y + Z * wi_l.z);
-            pb.ray_o[slot] = make_float4(P.x, P.y, P.z, wp.eps);
-            pb.ray_d[slot] = make_float4(nd.x, nd.y, nd.z, INF_F);
-            pb.hits[slot] = pack_hit(INF_F, 0xFFFFFFFFu);
+            next_o = make_float4(P.x, P.y, P.z, wp.eps);
+            next_d = make_float4(nd.x, nd.y, nd.z, INF_F);
             pb.thr[slot] = make_float4(thr.x, thr.y, thr.z, delta ? 1.f : 0.f);
             cont = true;
           }
@@ -273,30 +328,28 @@ k_shade(WaveParams wp, SceneDev sc, PathBufs pb, const uint32_t* __restrict__ id
       }
     }
   }
-  append_id(ids_next, &pb.counts[ACT0 + b + 1], cont, slot);
-  // shadow-ray id list for the any-hit trace: every valid (slot, j); the loop is uniform across the warp
-  for (uint32_t j = 0; j < wp.S; ++j) {
-    bool valid = false;
-    uint32_t sid = 0;
-    if (i < n) { sid = slot * wp.S + j; valid = pb.s_contrib[sid].w != 0.f; }
-    append_id(pb.s_ids, &pb.counts[SH0 + b], valid, sid);
+  // the continuing paths form the next bounce's dense ray list
+  const uint32_t p = block_append(&pb.counts[ACT0 + b + 1], cont, 1, s_app, n_valid, &pb.counts[SHV0 + b]);
+  if (cont) {
+    pb.no[p] = next_o; pb.nd[p] = next_d; pb.nh[p] = pack_hit(INF_F, 0xFFFFFFFFu); pb.nslot[p] = slot;
   }
 }
 
 // add the unoccluded light samples in sample order (deterministic), then advance the lists
 __global__ void __launch_bounds__(256)
-k_resolve_shadow(WaveParams wp, PathBufs pb, const uint32_t* __restrict__ ids, uint32_t identity_ids, uint32_t b) {
+k_resolve_shadow(WaveParams wp, PathBufs pb, uint32_t b) {
   const uint32_t n = pb.counts[ACT0 + b];
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
-  const uint32_t slot = identity_ids ? i : ids[i];
+  const uint32_t slot = pb.lslot[i];
   const uint32_t S = wp.S;
+  const uint32_t q0 = pb.s_q0[slot];
+  if (q0 == 0xFFFFFFFFu) return;
   float4 L = pb.rad[slot];
   bool any = false;
   for (uint32_t j = 0; j < S; ++j) {
-    const size_t sid = (size_t)slot * S + j;
-    const float4 c = pb.s_contrib[sid];
-    if (c.w != 0.f && (uint32_t)pb.s_hits[sid] == 0xFFFFFFFFu) {
+    const float4 c = pb.s_contrib[q0 + j];
+    if (c.w != 0.f && (uint32_t)pb.s_hits[q0 + j] == 0xFFFFFFFFu) {
       L.x = L.x + c.x; L.y = L.y + c.y; L.z = L.z + c.z;
       any = true;
     }
@@ -307,7 +360,7 @@ k_resolve_shadow(WaveParams wp, PathBufs pb, const uint32_t* __restrict__ ids, u
 __global__ void k_wave_end(PathBufs pb, uint32_t max_depth, unsigned long long* totals) {
   // totals: [0] bounce rays, [1] shadow rays
   unsigned long long nb = 0, ns = 0;
-  for (uint32_t b = 0; b < max_depth; ++b) { if (b) nb += pb.counts[ACT0 + b]; ns += pb.counts[SH0 + b]; }
+  for (uint32_t b = 0; b < max_depth; ++b) { if (b) nb += pb.counts[ACT0 + b]; ns += pb.counts[SHV0 + b]; }
   totals[0] += nb; totals[1] += ns;
 }
 
@@ -419,10 +472,12 @@ void Renderer::release_scene() {
 }
 
 void Renderer::release_wave() {
-  void* ptrs[] = {ray_o, ray_d, hits, thr, rad, s_o, s_d, s_hits, s_contrib, ids_a, ids_b, s_ids, counts, totals};
+  void* ptrs[] = {l_o[0], l_o[1], l_d[0], l_d[1], l_h[0], l_h[1], l_slot[0], l_slot[1], thr, rad, s_o, s_d, s_hits, s_contrib,
+                  s_q0, counts, totals};
   for (void* p : ptrs) free_ptr(p);
-  ray_o = ray_d = thr = rad = s_o = s_d = s_contrib = nullptr; hits = s_hits = nullptr;
-  ids_a = ids_b = s_ids = counts = nullptr; totals = nullptr;
+  for (int k = 0; k < 2; ++k) { l_o[k] = l_d[k] = nullptr; l_h[k] = nullptr; l_slot[k] = nullptr; }
+  thr = rad = s_o = s_d = s_contrib = nullptr; s_hits = nullptr;
+  s_q0 = counts = nullptr; totals = nullptr;
   wave_cap = 0;
 }
 
@@ -559,18 +614,20 @@ int Renderer::ensure_wave() {
   release_wave();
   tracer.release();
   wave_cap = want; wave_S = Salloc;
-  B2RT_CUDA_OK(cudaMalloc(&ray_o, wave_cap * sizeof(float4)));
-  B2RT_CUDA_OK(cudaMalloc(&ray_d, wave_cap * sizeof(float4)));
-  B2RT_CUDA_OK(cudaMalloc(&hits, wave_cap * 8));
+  // (+16 entries: the traversal copies ray tiles in 16-byte units and may read up to 3 entries past a list's end)
+  for (int k = 0; k < 2; ++k) {
+    B2RT_CUDA_OK(cudaMalloc(&l_o[k], (wave_cap + 16) * sizeof(float4)));
+    B2RT_CUDA_OK(cudaMalloc(&l_d[k], (wave_cap + 16) * sizeof(float4)));
+    B2RT_CUDA_OK(cudaMalloc(&l_h[k], (wave_cap + 16) * 8));
+    B2RT_CUDA_OK(cudaMalloc(&l_slot[k], (wave_cap + 16) * 4));
+  }
   B2RT_CUDA_OK(cudaMalloc(&thr, wave_cap * sizeof(float4)));
   B2RT_CUDA_OK(cudaMalloc(&rad, wave_cap * sizeof(float4)));
-  B2RT_CUDA_OK(cudaMalloc(&s_o, wave_cap * Salloc * sizeof(float4)));
-  B2RT_CUDA_OK(cudaMalloc(&s_d, wave_cap * Salloc * sizeof(float4)));
-  B2RT_CUDA_OK(cudaMalloc(&s_hits, wave_cap * Salloc * 8));
+  B2RT_CUDA_OK(cudaMalloc(&s_o, (wave_cap * Salloc + 16) * sizeof(float4)));
+  B2RT_CUDA_OK(cudaMalloc(&s_d, (wave_cap * Salloc + 16) * sizeof(float4)));
+  B2RT_CUDA_OK(cudaMalloc(&s_hits, (wave_cap * Salloc + 16) * 8));
   B2RT_CUDA_OK(cudaMalloc(&s_contrib, wave_cap * Salloc * sizeof(float4)));
-  B2RT_CUDA_OK(cudaMalloc(&ids_a, wave_cap * 4));
-  B2RT_CUDA_OK(cudaMalloc(&ids_b, wave_cap * 4));
-  B2RT_CUDA_OK(cudaMalloc(&s_ids, wave_cap * Salloc * 4));
+  B2RT_CUDA_OK(cudaMalloc(&s_q0, wave_cap * 4));
   B2RT_CUDA_OK(cudaMalloc(&counts, N_COUNTS * 4));
   B2RT_CUDA_OK(cudaMalloc(&totals, 8 * 8));
   B2RT_CUDA_OK(cudaMemset(counts, 0, N_COUNTS * 4));
@@ -603,9 +660,15 @@ int Renderer::start() {
   sd.materials = d_materials; sd.lights = d_lights; sd.light_area = d_light_area; sd.n_tris = n_tris; sd.n_lights = n_lights;
 
   PathBufs pb;
-  pb.ray_o = (float4*)ray_o; pb.ray_d = (float4*)ray_d; pb.hits = hits; pb.thr = (float4*)thr; pb.rad = (float4*)rad;
+  auto bind_lists = [&](uint32_t cur) {   // list `cur` is read, the other one is appended to
+    const uint32_t nxt = cur ^ 1u;
+    pb.lo = (float4*)l_o[cur]; pb.ld = (float4*)l_d[cur]; pb.lh = l_h[cur]; pb.lslot = l_slot[cur];
+    pb.no = (float4*)l_o[nxt]; pb.nd = (float4*)l_d[nxt]; pb.nh = l_h[nxt]; pb.nslot = l_slot[nxt];
+  };
+  bind_lists(0);
+  pb.thr = (float4*)thr; pb.rad = (float4*)rad;
   pb.s_o = (float4*)s_o; pb.s_d = (float4*)s_d; pb.s_hits = s_hits; pb.s_contrib = (float4*)s_contrib;
-  pb.ids_a = ids_a; pb.ids_b = ids_b; pb.s_ids = s_ids; pb.counts = counts;
+  pb.s_q0 = s_q0; pb.counts = counts;
 
   tracer.launches = 0; tracer.traverse_launches = 0; tracer.ev_used = 0;
   launches = 0;
@@ -633,18 +696,17 @@ int Renderer::start() {
       wp.max_depth = max_depth; wp.ns_area_light = cfg.ns_area_light; wp.S = S;
       const uint32_t n = wp.n_pix * wp.spp;
       const uint32_t g = (n + 255) / 256;
+      bind_lists(0);   // k_raygen fills list 0; k_shade(b) appends the continuing paths to list (b+1)&1
       k_raygen<<<g, 256, 0, stream>>>(wp, cd, pb); launches++;
       cam_rays_enqueued += n;
-      uint32_t* cur = ids_a; uint32_t* nxt = ids_b;
       for (uint32_t b = 0; b < max_depth; ++b) {
-        const uint32_t identity = b == 0 ? 1u : 0u;
-        RCHECK(tracer.trace(stream, pb.ray_o, pb.ray_d, pb.hits, identity ? nullptr : cur, counts + ACT0 + b, false));
-        k_shade<<<g, 256, 0, stream>>>(wp, sd, pb, cur, nxt, b, identity); launches++;
+        bind_lists(b & 1u);
+        RCHECK(tracer.trace(stream, pb.lo, pb.ld, pb.lh, counts + ACT0 + b, false));
+        k_shade<<<g, 256, 0, stream>>>(wp, sd, pb, b); launches++;
         if (S > 0) {
-          RCHECK(tracer.trace(stream, pb.s_o, pb.s_d, pb.s_hits, pb.s_ids, counts + SH0 + b, true));
-          k_resolve_shadow<<<g, 256, 0, stream>>>(wp, pb, cur, identity, b); launches++;
+          RCHECK(tracer.trace(stream, pb.s_o, pb.s_d, pb.s_hits, counts + SH0 + b, true));
+          k_resolve_shadow<<<g, 256, 0, stream>>>(wp, pb, b); launches++;
         }
-        std::swap(cur, nxt);
       }
       k_wave_end<<<1, 1, 0, stream>>>(pb, max_depth, totals); launches++;
       k_accumulate<<<(wp.n_pix + 255) / 256, 256, 0, stream>>>(wp, pb, (float4*)accum); launches++;

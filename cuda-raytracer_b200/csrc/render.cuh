@@ -29,9 +29,12 @@ struct Renderer {
   uint64_t samples_done = 0, samples_pending = 0;
   // wave buffers
   uint64_t wave_cap = 0; uint32_t wave_S = 0;
-  void *ray_o = nullptr, *ray_d = nullptr, *thr = nullptr, *rad = nullptr, *s_o = nullptr, *s_d = nullptr, *s_contrib = nullptr;
-  unsigned long long *hits = nullptr, *s_hits = nullptr, *totals = nullptr;
-  uint32_t *ids_a = nullptr, *ids_b = nullptr, *s_ids = nullptr, *counts = nullptr;
+  void *l_o[2] = {nullptr, nullptr}, *l_d[2] = {nullptr, nullptr};           // dense ray lists (double-buffered by bounce)
+  unsigned long long *l_h[2] = {nullptr, nullptr};
+  uint32_t *l_slot[2] = {nullptr, nullptr};
+  void *thr = nullptr, *rad = nullptr, *s_o = nullptr, *s_d = nullptr, *s_contrib = nullptr;
+  unsigned long long *s_hits = nullptr, *totals = nullptr;
+  uint32_t *s_q0 = nullptr, *counts = nullptr;
   // stats
   b2rt_stats last{};
   uint64_t launches = 0, cam_rays_enqueued = 0;

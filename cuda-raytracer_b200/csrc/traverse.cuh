@@ -30,6 +30,7 @@ struct Tracer {
   uint32_t chunk_rays = 1024;      // rays per work item of a level >= 1 subtree queue
   uint32_t chunk0_max = 8192;      // level 0 (one subtree, every ray): chunks grow up to this
   size_t stack_off = 0;            // offset of the traversal stacks in dynamic shared memory
+  size_t ring_off = 0;             // offset of the ray ring
   int num_sms = 148, ctas_per_sm = 1;
   size_t smem_bytes = 0;
   // device buffers
@@ -37,7 +38,9 @@ struct Tracer {
   uint32_t* seg_off = nullptr;    // [n_treelets]
   uint32_t* cursor = nullptr;     // [n_treelets]
   uint2* pairs = nullptr;         // [pair_cap] (subtree id, ray id)
-  uint32_t* ids_sorted = nullptr; // [pair_cap]
+  // dense SoA ray stream of the levels >= 1, grouped by subtree (written by the scatter kernel)
+  float4* q_o = nullptr; float4* q_d = nullptr; unsigned long long* q_h = nullptr; uint32_t* q_rid = nullptr;
+  uint64_t q_cap = 0;
   uint4* chunks = nullptr;        // [chunk_cap] (subtree, first, count, -)
   uint32_t* ctrl = nullptr;       // [16] pair_count[2], n_chunks, next_chunk, overflow, ...
   TraceCounters* counters = nullptr;
@@ -52,10 +55,11 @@ struct Tracer {
 
   int init(const DeviceBVH& b, uint64_t max_rays_, uint32_t pair_factor);
   void release();
-  // rays: o = (ox,oy,oz,tmin), d = (dx,dy,dz,tmax); hits must be initialised by the caller to
-  // pack(tmax, 0xFFFFFFFF).  ids0 == nullptr -> rays 0..n-1.  n_active_dev: device count of rays.
+  // rays 0..n-1 (a dense list): o = (ox,oy,oz,tmin), d = (dx,dy,dz,tmax); hits must be initialised by the
+  // caller to pack(tmax, 0xFFFFFFFF).  n_active_dev: device count of rays.  The arrays must be readable up to the
+  // next multiple of 4 entries (TMA tiles are copied in 16-byte units).
   int trace(cudaStream_t s, const float4* ray_o, const float4* ray_d, unsigned long long* hits,
-            const uint32_t* ids0, const uint32_t* n_active_dev, bool any_hit);
+            const uint32_t* n_active_dev, bool any_hit);
   int check_overflow(cudaStream_t s, bool* overflow);  // synchronises the stream
 };
 

@@ -6,12 +6,10 @@ run() { # name lib treelet [env...]
   env B2RT_LIB=$lib "$@" timeout 120 python tools/profile_frame.py --spp 32 --frames 3 --treelet-bytes $tb 2>&1 | tail -1
 }
 B=cuda-raytracer_b200/libb2rt.so
-run base $B 40960
-run base $B 32768
-run mi4 build/mi4/libb2rt.so 32768
-run mi16 build/mi16/libb2rt.so 32768
-run occ4s16 build/occ4s16/libb2rt.so 24576
-run occ4s16 build/occ4s16/libb2rt.so 20480
-run occ4s16 build/occ4s16/libb2rt.so 16384
-run occ4s16mi4 build/occ4s16mi4/libb2rt.so 24576
-run occ4s16mi12 build/occ4s16mi12/libb2rt.so 24576
+B2RT_VERBOSE=1 python tools/profile_frame.py --spp 8 2>&1 | grep "b2rt:" | head -2
+run base_mi12 $B 24576
+run base_mi12 $B 20480
+run mi1 build/mi1/libb2rt.so 24576
+run mi4 build/mi4/libb2rt.so 24576
+run mi8 build/mi8/libb2rt.so 24576
+run mi16 build/mi16/libb2rt.so 24576
