@@ -151,7 +151,10 @@ __device__ __forceinline__ uint32_t block_append(uint32_t* counter, bool pred, u
 }
 
 // One surface interaction for every active path (bounce index b).
-__global__ void __launch_bounds__(256)
+#ifndef B2RT_SHADE_OCC
+#define B2RT_SHADE_OCC 4
+#endif
+__global__ void __launch_bounds__(256, B2RT_SHADE_OCC)
 k_shade(WaveParams wp, SceneDev sc, PathBufs pb, uint32_t b) {
   const uint32_t n = pb.counts[ACT0 + b];
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;

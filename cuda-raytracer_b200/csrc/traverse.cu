@@ -8,15 +8,16 @@
 // Design (DESIGN.md "Traversal"): the BVH is cut into subtrees that fit in shared memory.  One pass
 // per subtree LEVEL: rays are grouped by the subtree they must visit; a CTA owns one subtree at a
 // time, stages its blob (SoA wide nodes + 48-byte primitive records) with ONE TMA bulk copy
-// (cp.async.bulk + mbarrier).  The rays of a subtree's queue are a DENSE SoA stream in HBM (origin, direction,
-// current hit word, ray id); the CTA streams it through a double-buffered shared-memory ring with TMA bulk copies
-// (128-ray tiles, one mbarrier per buffer) and the lanes of its warps pull rays from the ring as they go idle, so a
-// refill never waits on a global gather.  Rays that
+// (cp.async.bulk + mbarrier).  Level 0 (the root subtree, visited by every ray) reads the caller's DENSE SoA ray list
+// (origin, direction, hit word): the CTA streams its chunk through a double-buffered shared-memory ring with TMA
+// bulk copies (128-ray tiles, one mbarrier per buffer) and the lanes of its warps pull rays from the ring as they go
+// idle.  Deeper levels read ray ids grouped by subtree and gather the three 8/16-byte records.  Rays that
 // leave through an EXIT child are pushed as (child subtree, ray id) pairs: warp ballot/popc exclusive
 // scan into a per-warp staging ring, one global atomicAdd per flush.  Between levels a single-CTA
 // scan turns per-subtree counts into segment offsets + a chunk work list and a scatter kernel
-// regroups the rays by subtree, writing the next level's dense stream (gathering origin / direction / hit word
-// once per push).  No host round trip anywhere: all counts live on the device and every grid is persistent.
+// regroups the ray ids by subtree.  (Scattering whole 44-byte ray records so that deeper levels could stream too
+// was measured: the gather moved into the scatter kernel and cost more than it saved.)  No host round trip
+// anywhere: all counts live on the device and every grid is persistent.
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
@@ -119,8 +120,7 @@ k_schedule_level(uint32_t* __restrict__ cnt, uint32_t* __restrict__ seg_off, uin
     if (i < n) cnt[t] = 0;   // self-cleaning: every level >= 1 is scheduled exactly once per trace
     uint32_t nch = (c + chunk_rays - 1) / chunk_rays;
     uint32_t eo, ec, to, tc;
-    // segments start at multiples of 4 rays so that every tile of the dense stream is 16-byte aligned for TMA
-    block_excl_scan2((c + 3u) & ~3u, nch, &eo, &ec, &to, &tc, sh);
+    block_excl_scan2(c, nch, &eo, &ec, &to, &tc, sh);
     if (i < n) {
       uint32_t off = run_off + eo, cb = run_chunks + ec;
       seg_off[t] = off; cursor[t] = 0;
@@ -137,10 +137,10 @@ k_schedule_level(uint32_t* __restrict__ cnt, uint32_t* __restrict__ seg_off, uin
     }
     __syncthreads();
     uint32_t nb = min(n_big, 1024u);
-    for (uint32_t b = 0; b < nb; ++b) {
+    for (uint32_t b = threadIdx.x >> 5; b < nb; b += blockDim.x >> 5) {   // one warp per subtree with many chunks
       uint4 e = big[b];
       uint32_t nch_b = (e.z + chunk_rays - 1) / chunk_rays;
-      for (uint32_t k = threadIdx.x; k < nch_b; k += blockDim.x)
+      for (uint32_t k = threadIdx.x & 31; k < nch_b; k += 32)
         if (e.w + k < chunk_cap) chunks[e.w + k] = make_uint4(e.x, e.y + k * chunk_rays, min(chunk_rays, e.z - k * chunk_rays), 0);
     }
     __syncthreads();
@@ -157,19 +157,9 @@ k_schedule_level(uint32_t* __restrict__ cnt, uint32_t* __restrict__ seg_off, uin
 }
 
 // ---- k_scatter: regroup ray ids by subtree (counting-sort scatter, warp-aggregated cursors) ---------
-// source = the level-0 dense ray list (+ its hit words, already improved by the levels above); destination = the
-// dense stream of the next level
-struct ScatterIO {
-  const float4* src_o; const float4* src_d; const unsigned long long* src_h;
-  float4* q_o; float4* q_d; unsigned long long* q_h; uint32_t* q_rid;
-};
-__device__ __forceinline__ void scatter_ray(const ScatterIO& io, uint32_t pos, uint32_t rid) {
-  io.q_o[pos] = io.src_o[rid]; io.q_d[pos] = io.src_d[rid]; io.q_h[pos] = io.src_h[rid]; io.q_rid[pos] = rid;
-}
-
 __global__ void __launch_bounds__(256)
 k_scatter(const uint2* __restrict__ pairs, const uint32_t* __restrict__ pair_count, const uint32_t* __restrict__ seg_off,
-          uint32_t* __restrict__ cursor, const ScatterIO io, uint32_t pair_cap) {
+          uint32_t* __restrict__ cursor, uint32_t* __restrict__ ids_sorted, uint32_t pair_cap) {
   const uint32_t n = min(*pair_count, pair_cap);
   const uint32_t lane = threadIdx.x & 31;
   const uint32_t stride = gridDim.x * blockDim.x;
@@ -186,7 +176,7 @@ k_scatter(const uint2* __restrict__ pairs, const uint32_t* __restrict__ pair_cou
     uint32_t basepos = 0;
     if (lane == leader) basepos = atomicAdd(&cursor[p.x], (uint32_t)__popc(peers));
     basepos = __shfl_sync(peers, basepos, leader);
-    scatter_ray(io, seg_off[p.x] + basepos + rank, p.y);
+    ids_sorted[seg_off[p.x] + basepos + rank] = p.y;
   }
 }
 
@@ -196,7 +186,7 @@ k_scatter(const uint2* __restrict__ pairs, const uint32_t* __restrict__ pair_cou
 constexpr int SCATTER_TILE = 2048;   // pairs per CTA iteration (8 per thread)
 __global__ void __launch_bounds__(256)
 k_scatter_tiled(const uint2* __restrict__ pairs, const uint32_t* __restrict__ pair_count, const uint32_t* __restrict__ seg_off,
-                uint32_t* __restrict__ cursor, const ScatterIO io, uint32_t pair_cap, uint32_t first, uint32_t K) {
+                uint32_t* __restrict__ cursor, uint32_t* __restrict__ ids_sorted, uint32_t pair_cap, uint32_t first, uint32_t K) {
   extern __shared__ uint32_t s_hist[];   // [K] counts, then [K] bases
   uint32_t* s_cnt = s_hist;
   uint32_t* s_base = s_hist + K;
@@ -220,7 +210,7 @@ k_scatter_tiled(const uint2* __restrict__ pairs, const uint32_t* __restrict__ pa
     __syncthreads();
 #pragma unroll
     for (int j = 0; j < SCATTER_TILE / 256; ++j)
-      if (p[j].x != 0xFFFFFFFFu) scatter_ray(io, s_base[p[j].x - first] + r[j], p[j].y);
+      if (p[j].x != 0xFFFFFFFFu) ids_sorted[s_base[p[j].x - first] + r[j]] = p[j].y;
     __syncthreads();
   }
 }
@@ -229,12 +219,11 @@ k_scatter_tiled(const uint2* __restrict__ pairs, const uint32_t* __restrict__ pa
 struct TravParams {
   const uint8_t* blob;
   const TreeletDesc* treelets;
-  // dense ray stream of this level: entry i of a chunk's range = (origin|tmin, direction|tmax, hit word, ray id)
-  const float4* q_o;
-  const float4* q_d;
-  const unsigned long long* q_h;
-  const uint32_t* q_rid;      // nullptr => identity (level 0: the stream IS the ray list)
-  unsigned long long* hits;   // closest-hit words by ray id
+  // the dense ray list: (origin | tmin), (direction | tmax), packed hit word, indexed by ray id
+  const float4* ray_o;
+  const float4* ray_d;
+  unsigned long long* hits;
+  const uint32_t* ids;        // levels >= 1: ray ids grouped by subtree; nullptr at level 0 (chunk ranges ARE ray ids)
   const uint4* chunks;
   uint32_t* ctrl;
   uint32_t* cnt;              // per-subtree counts for the NEXT level
@@ -266,8 +255,8 @@ constexpr uint32_t STACK_TN_MASK = 0xFFFFF000u;   // stack entry: [31:12] entry 
 
 // ray ring: RING_BUFS buffers of RING_TILE rays, SoA inside a buffer
 constexpr uint32_t RING_TILE = 128, RING_BUFS = 2;
-constexpr uint32_t RING_O = 0, RING_D = RING_TILE * 16, RING_H = RING_TILE * 32, RING_RID = RING_TILE * 40;
-constexpr uint32_t RING_BUF_BYTES = RING_TILE * 44;
+constexpr uint32_t RING_O = 0, RING_D = RING_TILE * 16, RING_H = RING_TILE * 32;
+constexpr uint32_t RING_BUF_BYTES = RING_TILE * 40;
 
 // flush one warp's staged pairs: one global reservation, coalesced 8-byte stores, per-subtree counts
 __device__ __forceinline__ void flush_pairs(uint2* stage, uint32_t& n_staged, const TravParams& P, uint32_t lane) {
@@ -353,11 +342,10 @@ k_traverse(const TravParams P) {
     const size_t at = (size_t)first + (size_t)tile * RING_TILE;
     uint8_t* dst = ring + b * RING_BUF_BYTES;
     fence_proxy_async();
-    mbar_expect_tx(&s_ring_bar[b], n4 * (P.q_rid ? 44u : 40u));
-    bulk_g2s(dst + RING_O, P.q_o + at, n4 * 16u, &s_ring_bar[b]);
-    bulk_g2s(dst + RING_D, P.q_d + at, n4 * 16u, &s_ring_bar[b]);
-    bulk_g2s(dst + RING_H, P.q_h + at, n4 * 8u, &s_ring_bar[b]);
-    if (P.q_rid) bulk_g2s(dst + RING_RID, P.q_rid + at, n4 * 4u, &s_ring_bar[b]);
+    mbar_expect_tx(&s_ring_bar[b], n4 * 40u);
+    bulk_g2s(dst + RING_O, P.ray_o + at, n4 * 16u, &s_ring_bar[b]);
+    bulk_g2s(dst + RING_D, P.ray_d + at, n4 * 16u, &s_ring_bar[b]);
+    bulk_g2s(dst + RING_H, P.hits + at, n4 * 8u, &s_ring_bar[b]);
     __threadfence_block();
     atomicAdd(&s_ring_issued[b], 1u);
   };
@@ -380,7 +368,7 @@ k_traverse(const TravParams P) {
         s_ring_cons[b] = 0;
       }
       prev_tiles = 0;
-      if (ch.x != 0xFFFFFFFFu) {
+      if (ch.x != 0xFFFFFFFFu && !P.ids) {
         prev_tiles = (ch.z + RING_TILE - 1) / RING_TILE;
         for (uint32_t t = 0; t < RING_BUFS && t < prev_tiles; ++t) ring_issue(ch.y, ch.z, t);
       }
@@ -436,8 +424,20 @@ k_traverse(const TravParams P) {
         if (lane == 0) base = atomicAdd(&s_next_ray, n_idle);
         base = __shfl_sync(0xffffffffu, base, 0);
         if (base + n_idle >= chunk.z) exhausted = true;
-        if (base < chunk.z) {
-          // the warp takes rays base .. base + n_take - 1 of the chunk; they lie in at most two ring tiles
+        const uint32_t k = base + __popc(m_idle & lane_lt);
+        const bool take = idle && k < chunk.z;
+        float4 ro = make_float4(0.f, 0.f, 0.f, 0.f), rd = make_float4(0.f, 0.f, 1.f, 0.f);
+        unsigned long long h = 0;
+        if (P.ids) {
+          // levels >= 1: ray ids grouped by subtree, gather the records
+          if (take) {
+            rid = P.ids[chunk.y + k];
+            B2_CHECK(rid < P.n_rays_cap, 1, rid);
+            if (rid >= P.n_rays_cap) rid = 0;
+            ro = P.ray_o[rid]; rd = P.ray_d[rid]; h = P.hits[rid];
+          }
+        } else if (base < chunk.z) {
+          // level 0: the warp takes rays base .. base + n_take - 1 of the chunk out of the ring (at most two tiles)
           const uint32_t n_take = min(n_idle, chunk.z - base);
           const uint32_t tA = base / RING_TILE;
           const uint32_t nA = min(n_take, (tA + 1) * RING_TILE - base), nB = n_take - nA;
@@ -450,32 +450,12 @@ k_traverse(const TravParams P) {
             while ((int32_t)(*(volatile uint32_t*)&s_ring_issued[b] - load) <= 0) { }
             mbar_wait(&s_ring_bar[b], load & 1u);
           }
-          const uint32_t k = base + __popc(m_idle & lane_lt);
-          if (idle && k < chunk.z) {
+          if (take) {
             const uint32_t t = k / RING_TILE, e = k % RING_TILE;
             const uint8_t* rb = ring + (t % RING_BUFS) * RING_BUF_BYTES;
-            const float4 ro = reinterpret_cast<const float4*>(rb + RING_O)[e], rd = reinterpret_cast<const float4*>(rb + RING_D)[e];
-            const unsigned long long h = reinterpret_cast<const unsigned long long*>(rb + RING_H)[e];
-            rid = P.q_rid ? reinterpret_cast<const uint32_t*>(rb + RING_RID)[e] : (chunk.y + k);
-            B2_CHECK(rid < P.n_rays_cap, 1, rid);
-            if (rid >= P.n_rays_cap) rid = 0;
-            o = mk3(ro.x, ro.y, ro.z); d = mk3(rd.x, rd.y, rd.z);
-            tmin = ro.w; tmax_user = rd.w;
-            best_t = __uint_as_float((uint32_t)(h >> 32));
-            best_id = (uint32_t)h;
-            // reciprocal direction for the slab test; |d_k| < 1e-18 (incl. +-0) is clamped so that o_k * inv_k
-            // stays finite: the ray is then parallel to the slab and the test reduces to lo_k <= o_k <= hi_k
-            inv = mk3(fabsf(d.x) > 1e-18f ? __frcp_rn(d.x) : copysignf(1e18f, d.x),
-                      fabsf(d.y) > 1e-18f ? __frcp_rn(d.y) : copysignf(1e18f, d.y),
-                      fabsf(d.z) > 1e-18f ? __frcp_rn(d.z) : copysignf(1e18f, d.z));
-            noi = mk3(-(o.x * inv.x), -(o.y * inv.y), -(o.z * inv.z));
-            nx = inv.x >= 0.f ? 0u : 12u * W; fx = 12u * W - nx;
-            ny = inv.y >= 0.f ? 4u * W : 16u * W; fy = 20u * W - ny;
-            nz = inv.z >= 0.f ? 8u * W : 20u * W; fz = 28u * W - nz;
-            have = true; improved = false; sp = 0;
-            const bool skip = ANYHIT && best_id != 0xFFFFFFFFu;
-            cur = skip ? REF_NONE : 0u;   // INTERNAL node 0 = subtree root
-            if (STATS) st_visits++;
+            ro = reinterpret_cast<const float4*>(rb + RING_O)[e]; rd = reinterpret_cast<const float4*>(rb + RING_D)[e];
+            h = reinterpret_cast<const unsigned long long*>(rb + RING_H)[e];
+            rid = chunk.y + k;
           }
           __syncwarp();   // every lane's ring reads are done
           if (lane == 0) {
@@ -486,15 +466,34 @@ k_traverse(const TravParams P) {
               const uint32_t t = tA + j, n = j ? nB : nA;
               if (n == 0) continue;
               const uint32_t b = t % RING_BUFS;
-              const uint32_t size_t_ = min(RING_TILE, chunk.z - t * RING_TILE);
+              const uint32_t tile_rays = min(RING_TILE, chunk.z - t * RING_TILE);
               const uint32_t old = atomicAdd(&s_ring_cons[b], n);
-              if (old + n == size_t_) {
+              if (old + n == tile_rays) {
                 s_ring_cons[b] = 0;
                 __threadfence_block();
                 if ((t + RING_BUFS) * RING_TILE < chunk.z) ring_issue(chunk.y, chunk.z, t + RING_BUFS);
               }
             }
           }
+        }
+        if (take) {
+          o = mk3(ro.x, ro.y, ro.z); d = mk3(rd.x, rd.y, rd.z);
+          tmin = ro.w; tmax_user = rd.w;
+          best_t = __uint_as_float((uint32_t)(h >> 32));
+          best_id = (uint32_t)h;
+          // reciprocal direction for the slab test; |d_k| < 1e-18 (incl. +-0) is clamped so that o_k * inv_k
+          // stays finite: the ray is then parallel to the slab and the test reduces to lo_k <= o_k <= hi_k
+          inv = mk3(fabsf(d.x) > 1e-18f ? __frcp_rn(d.x) : copysignf(1e18f, d.x),
+                    fabsf(d.y) > 1e-18f ? __frcp_rn(d.y) : copysignf(1e18f, d.y),
+                    fabsf(d.z) > 1e-18f ? __frcp_rn(d.z) : copysignf(1e18f, d.z));
+          noi = mk3(-(o.x * inv.x), -(o.y * inv.y), -(o.z * inv.z));
+          nx = inv.x >= 0.f ? 0u : 12u * W; fx = 12u * W - nx;
+          ny = inv.y >= 0.f ? 4u * W : 16u * W; fy = 20u * W - ny;
+          nz = inv.z >= 0.f ? 8u * W : 20u * W; fz = 28u * W - nz;
+          have = true; improved = false; sp = 0;
+          const bool skip = ANYHIT && best_id != 0xFFFFFFFFu;
+          cur = skip ? REF_NONE : 0u;   // INTERNAL node 0 = subtree root
+          if (STATS) st_visits++;
         }
         __syncwarp();
       }
@@ -699,19 +698,10 @@ int Tracer::init(const DeviceBVH& b, uint64_t max_rays_, uint32_t pair_factor) {
   B2RT_CUDA_OK(cudaGetDevice(&dev));
   B2RT_CUDA_OK(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
   if (!pairs || want_pairs != pair_cap) {
-    cudaFree(pairs); pairs = nullptr;
+    cudaFree(pairs); cudaFree(ids_sorted); pairs = nullptr; ids_sorted = nullptr;
     pair_cap = want_pairs;
     B2RT_CUDA_OK(cudaMalloc(&pairs, pair_cap * sizeof(uint2)));
-  }
-  // dense ray stream of the levels >= 1: one entry per push, segments padded to multiples of 4 rays
-  const uint64_t want_q = pair_cap + 4ull * b.n_treelets + 64;
-  if (q_cap < want_q) {
-    cudaFree(q_o); cudaFree(q_d); cudaFree(q_h); cudaFree(q_rid); q_o = q_d = nullptr; q_h = nullptr; q_rid = nullptr;
-    q_cap = want_q + want_q / 16;
-    B2RT_CUDA_OK(cudaMalloc(&q_o, q_cap * sizeof(float4)));
-    B2RT_CUDA_OK(cudaMalloc(&q_d, q_cap * sizeof(float4)));
-    B2RT_CUDA_OK(cudaMalloc(&q_h, q_cap * 8));
-    B2RT_CUDA_OK(cudaMalloc(&q_rid, q_cap * 4));
+    B2RT_CUDA_OK(cudaMalloc(&ids_sorted, pair_cap * 4));
   }
   max_rays = max_rays_;
   if (!ctrl) {
@@ -777,12 +767,10 @@ double Tracer::harvest_traverse_ms() {
 }
 
 void Tracer::release() {
-  cudaFree(cnt); cudaFree(seg_off); cudaFree(cursor); cudaFree(pairs); cudaFree(chunks);
-  cudaFree(q_o); cudaFree(q_d); cudaFree(q_h); cudaFree(q_rid);
+  cudaFree(cnt); cudaFree(seg_off); cudaFree(cursor); cudaFree(pairs); cudaFree(ids_sorted); cudaFree(chunks);
   cudaFree(ctrl); cudaFree(counters);
-  cnt = seg_off = cursor = ctrl = nullptr; pairs = nullptr; chunks = nullptr; counters = nullptr;
-  q_o = q_d = nullptr; q_h = nullptr; q_rid = nullptr;
-  pair_cap = 0; max_rays = 0; nt_cap = 0; chunk_alloc = 0; q_cap = 0;
+  cnt = seg_off = cursor = ids_sorted = ctrl = nullptr; pairs = nullptr; chunks = nullptr; counters = nullptr;
+  pair_cap = 0; max_rays = 0; nt_cap = 0; chunk_alloc = 0;
 }
 
 template <int W>
@@ -811,21 +799,17 @@ int Tracer::trace(cudaStream_t s, const float4* ray_o, const float4* ray_d, unsi
       launches++;
     }
     if (L > 0) {
-      ScatterIO io;
-      io.src_o = ray_o; io.src_d = ray_d; io.src_h = hits;
-      io.q_o = q_o; io.q_d = q_d; io.q_h = q_h; io.q_rid = q_rid;
       if (lr.count <= 12288) {
-        k_scatter_tiled<<<num_sms * 4, 256, (size_t)lr.count * 8, s>>>(pairs, &ctrl[(L - 1) & 1], seg_off, cursor, io,
+        k_scatter_tiled<<<num_sms * 4, 256, (size_t)lr.count * 8, s>>>(pairs, &ctrl[(L - 1) & 1], seg_off, cursor, ids_sorted,
                                                                         (uint32_t)pair_cap, lr.first, lr.count);
       } else {
-        k_scatter<<<num_sms * 8, 256, 0, s>>>(pairs, &ctrl[(L - 1) & 1], seg_off, cursor, io, (uint32_t)pair_cap);
+        k_scatter<<<num_sms * 8, 256, 0, s>>>(pairs, &ctrl[(L - 1) & 1], seg_off, cursor, ids_sorted, (uint32_t)pair_cap);
       }
       launches++;
     }
     TravParams P;
-    P.blob = bvh.blob; P.treelets = bvh.treelets; P.hits = hits;
-    if (L == 0) { P.q_o = ray_o; P.q_d = ray_d; P.q_h = hits; P.q_rid = nullptr; }
-    else { P.q_o = q_o; P.q_d = q_d; P.q_h = q_h; P.q_rid = q_rid; }
+    P.blob = bvh.blob; P.treelets = bvh.treelets; P.ray_o = ray_o; P.ray_d = ray_d; P.hits = hits;
+    P.ids = (L == 0) ? nullptr : ids_sorted;
     P.chunks = chunks; P.ctrl = ctrl; P.cnt = cnt; P.pairs = pairs; P.pair_cap = (uint32_t)pair_cap; P.level = L;
     P.counters = counters; P.n_treelets = bvh.n_treelets; P.chunk_rays = chunk_rays; P.chunk0_max = std::max(chunk0_max, chunk_rays); P.stack_off = (uint32_t)stack_off; P.ring_off = (uint32_t)ring_off; P.n_active = n_active_dev; P.n_rays_cap = (uint32_t)std::min<uint64_t>(max_rays, 0xFFFFFFFFull);
     cudaEvent_t e0 = nullptr, e1 = nullptr;

@@ -38,9 +38,7 @@ struct Tracer {
   uint32_t* seg_off = nullptr;    // [n_treelets]
   uint32_t* cursor = nullptr;     // [n_treelets]
   uint2* pairs = nullptr;         // [pair_cap] (subtree id, ray id)
-  // dense SoA ray stream of the levels >= 1, grouped by subtree (written by the scatter kernel)
-  float4* q_o = nullptr; float4* q_d = nullptr; unsigned long long* q_h = nullptr; uint32_t* q_rid = nullptr;
-  uint64_t q_cap = 0;
+  uint32_t* ids_sorted = nullptr; // [pair_cap] ray ids grouped by subtree (levels >= 1)
   uint4* chunks = nullptr;        // [chunk_cap] (subtree, first, count, -)
   uint32_t* ctrl = nullptr;       // [16] pair_count[2], n_chunks, next_chunk, overflow, ...
   TraceCounters* counters = nullptr;
