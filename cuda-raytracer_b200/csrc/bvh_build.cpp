@@ -10,10 +10,14 @@
 // one position-independent blob per subtree: SoA wide nodes (128-bit aligned rows) followed by the
 // 48-byte primitive records of its leaves.  Closest-hit results do not depend on the tree shape, so
 // this builder does not have to reproduce the reference's tree (the oracle's builder does).
+#include <emmintrin.h>
+
 #include <algorithm>
 #include <atomic>
 #include <chrono>
 #include <cmath>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <limits>
 #include <queue>
@@ -49,72 +53,123 @@ struct BinNode {
   uint32_t start = 0, count = 0;  // primitive range in the index array
 };
 
+// Binned-SAH binary builder.  The per-primitive passes (bounds, 3-axis binning) run on SSE registers: a box is two
+// __m128 (min xyz_, max xyz_), the centroid is recomputed instead of stored, and all three axes are binned in the
+// same pass over the primitives.
 struct BinaryBuilder {
-  const std::vector<Box>& pbox;
-  std::vector<float> cen;          // 3 per prim
-  std::vector<uint32_t> idx;
+  std::vector<__m128> pmn, pmx;    // primitive boxes, lane 3 unused
+  std::vector<uint32_t> idx, scratch_l, scratch_r;
   std::vector<BinNode> nodes;
   std::atomic<uint32_t> next_node{0};
   std::atomic<int> live_threads{0};
   uint32_t max_leaf;
   int max_threads;
+  uint32_t par_threshold = 8192;   // subtrees above this size are built by their own thread (up to max_threads)
 
-  BinaryBuilder(const std::vector<Box>& pb, uint32_t ml) : pbox(pb), max_leaf(ml) {
+  BinaryBuilder(const std::vector<Box>& pb, uint32_t ml) : max_leaf(ml) {
     size_t n = pb.size();
-    cen.resize(n * 3);
-    idx.resize(n);
+    pmn.resize(n); pmx.resize(n);
+    idx.resize(n); scratch_l.resize(n + 1); scratch_r.resize(n + 1);
     for (size_t i = 0; i < n; ++i) {
       idx[i] = (uint32_t)i;
-      for (int a = 0; a < 3; ++a) cen[i * 3 + a] = 0.5f * (pb[i].mn[a] + pb[i].mx[a]);
+      pmn[i] = _mm_set_ps(0.f, pb[i].mn[2], pb[i].mn[1], pb[i].mn[0]);
+      pmx[i] = _mm_set_ps(0.f, pb[i].mx[2], pb[i].mx[1], pb[i].mx[0]);
     }
     nodes.resize(std::max<size_t>(1, 2 * n));
     max_threads = (int)std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
+    if (const char* e = getenv("B2RT_BUILD_PAR")) par_threshold = (uint32_t)std::max(64, atoi(e));
+  }
+
+  static float area_of(__m128 mn, __m128 mx) {
+    alignas(16) float e[4];
+    _mm_store_ps(e, _mm_sub_ps(mx, mn));
+    if (e[0] < 0 || e[1] < 0 || e[2] < 0) return 0.f;
+    return 2.f * (e[0] * e[1] + e[1] * e[2] + e[2] * e[0]);
   }
 
   uint32_t build(uint32_t b, uint32_t e) {
     uint32_t me = next_node.fetch_add(1);
     BinNode& nd = nodes[me];
-    nd.box.reset();
-    Box cb; cb.reset();
-    for (uint32_t i = b; i < e; ++i) { nd.box.grow(pbox[idx[i]]); cb.grow(&cen[(size_t)idx[i] * 3]); }
+    const __m128 pinf = _mm_set1_ps(std::numeric_limits<float>::infinity()), ninf = _mm_set1_ps(-std::numeric_limits<float>::infinity());
+    const __m128 half = _mm_set1_ps(0.5f);
+    __m128 nmn = pinf, nmx = ninf, cmn = pinf, cmx = ninf;
+    for (uint32_t i = b; i < e; ++i) {
+      const uint32_t p = idx[i];
+      const __m128 mn = pmn[p], mx = pmx[p], c = _mm_mul_ps(half, _mm_add_ps(mn, mx));
+      nmn = _mm_min_ps(nmn, mn); nmx = _mm_max_ps(nmx, mx);
+      cmn = _mm_min_ps(cmn, c); cmx = _mm_max_ps(cmx, c);
+    }
+    alignas(16) float t4[4];
+    _mm_store_ps(t4, nmn); nd.box.mn[0] = t4[0]; nd.box.mn[1] = t4[1]; nd.box.mn[2] = t4[2];
+    _mm_store_ps(t4, nmx); nd.box.mx[0] = t4[0]; nd.box.mx[1] = t4[1]; nd.box.mx[2] = t4[2];
     nd.start = b; nd.count = e - b; nd.left = nd.right = 0;
     if (e - b <= max_leaf) return me;
 
-    constexpr int NB = 16;
+    // bins: 16 for big nodes, fewer for small ones (most nodes are small; resetting and sweeping 3 x 16 bins
+    // would dominate the build)
+    constexpr int NBMAX = 16;
+    const int NB = (e - b) >= 64 ? 16 : ((e - b) >= 16 ? 8 : 4);
+    alignas(16) float lo3[4], hi3[4], scale3[4];
+    _mm_store_ps(lo3, cmn); _mm_store_ps(hi3, cmx);
+    bool use[3];
+    for (int a = 0; a < 3; ++a) {
+      const float ext = hi3[a] - lo3[a];
+      use[a] = ext > 0.f;
+      scale3[a] = use[a] ? (float)NB / ext : 0.f;
+    }
+    scale3[3] = 0.f;
+    const __m128 scale = _mm_load_ps(scale3), kmax = _mm_set1_ps((float)(NB - 1)), zero = _mm_setzero_ps();
+    __m128 bmn[3][NBMAX], bmx[3][NBMAX]; uint32_t bc[3][NBMAX];
+    for (int a = 0; a < 3; ++a)
+      for (int k = 0; k < NB; ++k) { bmn[a][k] = pinf; bmx[a][k] = ninf; bc[a][k] = 0; }
+    for (uint32_t i = b; i < e; ++i) {
+      const uint32_t p = idx[i];
+      const __m128 mn = pmn[p], mx = pmx[p], c = _mm_mul_ps(half, _mm_add_ps(mn, mx));
+      const __m128 kf = _mm_min_ps(_mm_max_ps(_mm_mul_ps(_mm_sub_ps(c, cmn), scale), zero), kmax);
+      alignas(16) int k4[4];
+      _mm_store_si128(reinterpret_cast<__m128i*>(k4), _mm_cvttps_epi32(kf));
+      for (int a = 0; a < 3; ++a) {
+        if (!use[a]) continue;
+        const int k = k4[a];
+        bmn[a][k] = _mm_min_ps(bmn[a][k], mn); bmx[a][k] = _mm_max_ps(bmx[a][k], mx); bc[a][k]++;
+      }
+    }
     float best_cost = std::numeric_limits<float>::infinity();
     int best_axis = -1, best_bin = -1;
     for (int a = 0; a < 3; ++a) {
-      float lo = cb.mn[a], ext = cb.mx[a] - cb.mn[a];
-      if (!(ext > 0.f)) continue;
-      float scale = (float)NB / ext;
-      Box bb[NB]; uint32_t bc[NB];
-      for (int k = 0; k < NB; ++k) { bb[k].reset(); bc[k] = 0; }
-      for (uint32_t i = b; i < e; ++i) {
-        uint32_t p = idx[i];
-        int k = (int)((cen[(size_t)p * 3 + a] - lo) * scale);
-        k = k < 0 ? 0 : (k >= NB ? NB - 1 : k);
-        bb[k].grow(pbox[p]); bc[k]++;
-      }
-      float ra[NB]; uint32_t rc[NB];
-      Box acc; acc.reset(); uint32_t c = 0;
-      for (int k = NB - 1; k > 0; --k) { acc.grow(bb[k]); c += bc[k]; ra[k] = acc.area(); rc[k] = c; }
-      acc.reset(); c = 0;
+      if (!use[a]) continue;
+      float ra[NBMAX]; uint32_t rc[NBMAX];
+      __m128 amn = pinf, amx = ninf; uint32_t c = 0;
+      for (int k = NB - 1; k > 0; --k) { amn = _mm_min_ps(amn, bmn[a][k]); amx = _mm_max_ps(amx, bmx[a][k]); c += bc[a][k]; ra[k] = area_of(amn, amx); rc[k] = c; }
+      amn = pinf; amx = ninf; c = 0;
       for (int k = 0; k < NB - 1; ++k) {
-        acc.grow(bb[k]); c += bc[k];
+        amn = _mm_min_ps(amn, bmn[a][k]); amx = _mm_max_ps(amx, bmx[a][k]); c += bc[a][k];
         if (c == 0 || rc[k + 1] == 0) continue;
-        float cost = acc.area() * (float)c + ra[k + 1] * (float)rc[k + 1];
+        float cost = area_of(amn, amx) * (float)c + ra[k + 1] * (float)rc[k + 1];
         if (cost < best_cost) { best_cost = cost; best_axis = a; best_bin = k; }
       }
     }
     uint32_t mid;
     if (best_axis >= 0) {
-      float lo = cb.mn[best_axis], scale = (float)NB / (cb.mx[best_axis] - cb.mn[best_axis]);
-      auto it = std::partition(idx.begin() + b, idx.begin() + e, [&](uint32_t p) {
-        int k = (int)((cen[(size_t)p * 3 + best_axis] - lo) * scale);
-        k = k < 0 ? 0 : (k >= NB ? NB - 1 : k);
-        return k <= best_bin;
-      });
-      mid = (uint32_t)(it - idx.begin());
+      const float lo = lo3[best_axis], sc = scale3[best_axis];
+      const int ax = best_axis;
+      // branch-free stable partition through two scratch ranges (the side of a primitive is a coin flip for the
+      // branch predictor; std::partition spent a third of the build in mispredictions)
+      uint32_t nl = 0, nr = 0;
+      uint32_t* L = scratch_l.data() + b; uint32_t* R = scratch_r.data() + b;
+      const float kmaxf = (float)(NB - 1);
+      for (uint32_t i = b; i < e; ++i) {
+        const uint32_t p = idx[i];
+        const float* mn = reinterpret_cast<const float*>(&pmn[p]); const float* mx = reinterpret_cast<const float*>(&pmx[p]);
+        float kf = (0.5f * (mn[ax] + mx[ax]) - lo) * sc;
+        kf = std::min(std::max(kf, 0.f), kmaxf);
+        const uint32_t left = (int)kf <= best_bin ? 1u : 0u;
+        L[nl] = p; R[nr] = p;
+        nl += left; nr += 1u - left;
+      }
+      memcpy(idx.data() + b, L, (size_t)nl * 4);
+      memcpy(idx.data() + b + nl, R, (size_t)nr * 4);
+      mid = b + nl;
     } else {
       mid = b;
     }
@@ -122,7 +177,7 @@ struct BinaryBuilder {
       mid = b + (e - b) / 2;
     }
     uint32_t l, r;
-    if (e - b > 200000 && live_threads.load() < max_threads) {
+    if (e - b > par_threshold && live_threads.load() < max_threads) {
       live_threads.fetch_add(1);
       uint32_t lres = 0;
       std::thread t([&]() { lres = build(b, mid); live_threads.fetch_sub(1); });
@@ -243,9 +298,15 @@ int build_wide_bvh(const HostScene& sc, uint32_t max_leaf, uint32_t width, uint3
     for (int a = 0; a < 3; ++a) { b.mn[a] -= pad; b.mx[a] += pad; }
   for (int a = 0; a < 3; ++a) { out->bbox[a] = n ? scene_box.mn[a] : 0.f; out->bbox[3 + a] = n ? scene_box.mx[a] : 0.f; }
 
+  const bool verbose = getenv("B2RT_VERBOSE") != nullptr;
+  auto lap = [&](const char* what) {
+    if (verbose) fprintf(stderr, "b2rt: build %-10s %8.3f ms\n", what, std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count());
+  };
+  lap("boxes");
   // ---- binary build ----
   BinaryBuilder bb(pbox, max_leaf);
   if (n) bb.build(0, n);
+  lap("binary");
 
   // ---- collapse to W-wide ----
   std::vector<WNode> wn;
@@ -302,6 +363,7 @@ int build_wide_bvh(const HostScene& sc, uint32_t max_leaf, uint32_t width, uint3
     }
   }
   out->n_wide_nodes = (uint32_t)wn.size();
+  lap("collapse");
 
   // ---- partition into treelets (BFS over treelet roots => level-contiguous ids) ----
   struct TreeletBuild { int32_t root; uint32_t level; std::vector<int32_t> nodes; };
@@ -365,6 +427,7 @@ int build_wide_bvh(const HostScene& sc, uint32_t max_leaf, uint32_t width, uint3
   std::vector<int32_t> root_treelet(wn.size(), -1);
   for (size_t ti = 0; ti < tl.size(); ++ti) root_treelet[tl[ti].root] = (int32_t)ti;
 
+  lap("treelets");
   // ---- serialise ----
   uint64_t total = 0;
   out->treelets.resize(tl.size());
@@ -428,6 +491,7 @@ int build_wide_bvh(const HostScene& sc, uint32_t max_leaf, uint32_t width, uint3
     if (ti > 0 && tl[ti].level < tl[ti - 1].level) { set_error("internal: subtree levels not sorted"); return B2RT_ERR_INVALID; }
   }
   out->n_levels = nl;
+  lap("serialise");
   out->build_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
   return B2RT_OK;
 }
