@@ -239,26 +239,43 @@ int b2rt_bvh_bench_rays(b2rt_bvh* b, uint64_t n, int mode, uint64_t seed, int re
   const float* bb = b->host_meta.bbox;
   k_gen_rays<<<(n32 + 255) / 256, 256, 0, s>>>(n32, mode, (uint32_t)seed, (uint32_t)(seed >> 32), make_float3(bb[0], bb[1], bb[2]),
                                                make_float3(bb[3], bb[4], bb[5]), b->ray_o, b->ray_d, b->hits);
-  b->tracer.launches = 0;
-  B2RT_CUDA_OK(cudaMemsetAsync(b->tracer.counters, 0, sizeof(TraceCounters), s));
+  // The batch is traced in sub-batches of `sub` rays; a queue overflow (very incoherent rays on a deep subtree
+  // graph push one ray to dozens of subtrees per level) halves `sub` and starts over.
+  uint32_t sub = n32;
+  auto trace_all = [&]() -> int {
+    for (uint32_t first = 0; first < n32; first += sub) {
+      const uint32_t m = std::min(sub, n32 - first);
+      B2RT_CUDA_OK(cudaMemcpyAsync(b->n_dev, &m, 4, cudaMemcpyHostToDevice, s));
+      int r2 = b->tracer.trace(s, b->ray_o + first, b->ray_d + first, b->hits + first, b->n_dev, any_hit != 0);
+      if (r2) return r2;
+    }
+    return B2RT_OK;
+  };
   // one untimed pass with statistics, then `repeats` timed passes without
-  b->tracer.collect_stats = true;
-  rc = b->tracer.trace(s, b->ray_o, b->ray_d, b->hits, b->n_dev, any_hit != 0);
-  if (rc) return rc;
-  bool ovf = false;
-  rc = b->tracer.check_overflow(s, &ovf);
-  if (rc) return rc;
-  if (ovf) { b->tracer.collect_stats = keep_stats; set_error("ray queue overflow: use fewer rays per batch"); return B2RT_ERR_OVERFLOW; }
   TraceCounters tc;
+  for (;;) {
+    b->tracer.launches = 0;
+    B2RT_CUDA_OK(cudaMemsetAsync(b->tracer.counters, 0, sizeof(TraceCounters), s));
+    b->tracer.collect_stats = true;
+    rc = trace_all();
+    b->tracer.collect_stats = false;
+    if (rc) { b->tracer.collect_stats = keep_stats; return rc; }
+    bool ovf = false;
+    rc = b->tracer.check_overflow(s, &ovf);
+    if (rc) { b->tracer.collect_stats = keep_stats; return rc; }
+    if (!ovf) break;
+    if (sub <= 65536) { b->tracer.collect_stats = keep_stats; set_error("ray queue overflow on a 64 Ki-ray batch"); return B2RT_ERR_OVERFLOW; }
+    sub = ((sub / 2) + 3u) & ~3u;   // sub-batch starts stay 16-byte aligned for the TMA tiles
+    k_reset_hits<<<(n32 + 255) / 256, 256, 0, s>>>(n32, b->ray_d, b->hits);
+  }
   B2RT_CUDA_OK(cudaMemcpy(&tc, b->tracer.counters, sizeof tc, cudaMemcpyDeviceToHost));
-  b->tracer.collect_stats = false;
   cudaEvent_t e0, e1;
   cudaEventCreate(&e0); cudaEventCreate(&e1);
   double total = 0;
   for (int r = 0; r < repeats; ++r) {
     k_reset_hits<<<(n32 + 255) / 256, 256, 0, s>>>(n32, b->ray_d, b->hits);
     cudaEventRecord(e0, s);
-    rc = b->tracer.trace(s, b->ray_o, b->ray_d, b->hits, b->n_dev, any_hit != 0);
+    rc = trace_all();
     cudaEventRecord(e1, s);
     if (rc) return rc;
     B2RT_CUDA_OK(cudaEventSynchronize(e1));
