@@ -129,7 +129,20 @@ def cpu_arm(args, sc, cam, wl, spp_sample, steps, warmup):
                 seconds=secs, rays=rays, s_per_frame_scaled=secs / steps * wl["spp"] / spp_sample)
 
 
+def emit(line):
+    """The ONE JSON line goes to the process's original stdout (fd 1 is pointed at stderr while the bench runs, so
+    that library chatter such as NCCL's version banner cannot pollute it)."""
+    os.write(_REAL_STDOUT, (json.dumps(line) + "\n").encode())
+
+
+_REAL_STDOUT = 1
+
+
 def main():
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     args = parse()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -152,7 +165,7 @@ def main():
                 "config": config,
                 "cpu_baseline": {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")},
                 "e2e": {"value": cb["value"], "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-        print(json.dumps(line))
+        emit(line)
         return 0
 
     import torch
@@ -301,7 +314,7 @@ def main():
             "gpu_launches": launches_total, "roofline": roofline, "cpu_baseline": cpu_baseline,
             "rays_per_step": rays_total // args.steps, "bvh": {k: cst[k] for k in ("bvh_nodes", "bvh_subtrees", "bvh_levels",
                                                                                    "bvh_width", "bvh_bytes", "ms_build")}}
-    print(json.dumps(line))
+    emit(line)
     if world > 1:
         dist.destroy_process_group()
     return 0
