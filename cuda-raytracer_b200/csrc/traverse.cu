@@ -71,6 +71,25 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
                "l"(src), "r"(bytes), "r"(smem_u32(bar))
                : "memory");
 }
+// explicit shared-state-space accesses by 32-bit address: the per-thread stacks and the ray ring live at run-time
+// offsets of dynamic shared memory, and through generic pointers every access paid for rebuilding the generic
+// address (S2R SR_CgaCtaId + LEA), about 4 % of the kernel's issue slots
+__device__ __forceinline__ uint32_t lds_u32(uint32_t a) {
+  uint32_t v;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a) : "memory");
+  return v;
+}
+__device__ __forceinline__ void sts_u32(uint32_t a, uint32_t v) { asm volatile("st.shared.u32 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
+__device__ __forceinline__ float4 lds_f4(uint32_t a) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a) : "memory");
+  return v;
+}
+__device__ __forceinline__ unsigned long long lds_u64(uint32_t a) {
+  unsigned long long v;
+  asm volatile("ld.shared.u64 %0, [%1];" : "=l"(v) : "r"(a) : "memory");
+  return v;
+}
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
 // ---- k_schedule_level: exclusive scan of per-subtree ray counts -> segment offsets + chunk list ----
@@ -318,8 +337,9 @@ k_traverse(const TravParams P) {
   constexpr int NB = NodeView<W>::BYTES;
   constexpr int SLOT_BITS = NodeView<W>::SLOT_BITS;
   // per-thread stack in shared memory, entry k of thread t at word k * TRAV_THREADS + t (conflict-free)
-  uint32_t* const stack = reinterpret_cast<uint32_t*>(smem + P.stack_off) + threadIdx.x;
-  uint8_t* const ring = smem + P.ring_off;
+  const uint32_t stack = smem_u32(smem) + P.stack_off + threadIdx.x * 4u;   // shared-space byte address
+  const uint32_t ring = smem_u32(smem) + P.ring_off;
+  uint8_t* const ring_generic = smem + P.ring_off;
   uint32_t cur_treelet = 0xFFFFFFFFu;
   uint32_t phase = 0;
   uint32_t n_staged = 0;   // warp-uniform
@@ -340,7 +360,7 @@ k_traverse(const TravParams P) {
     const uint32_t b = tile % RING_BUFS;
     const uint32_t n = min(RING_TILE, count - tile * RING_TILE), n4 = (n + 3u) & ~3u;
     const size_t at = (size_t)first + (size_t)tile * RING_TILE;
-    uint8_t* dst = ring + b * RING_BUF_BYTES;
+    uint8_t* dst = ring_generic + b * RING_BUF_BYTES;
     fence_proxy_async();
     mbar_expect_tx(&s_ring_bar[b], n4 * 40u);
     bulk_g2s(dst + RING_O, P.ray_o + at, n4 * 16u, &s_ring_bar[b]);
@@ -388,9 +408,6 @@ k_traverse(const TravParams P) {
       cur_treelet = chunk.x;
       if (STATS && threadIdx.x == 0) atomicAdd(&P.counters->staged_bytes, (unsigned long long)td.bytes);
     }
-    uint32_t ring_gen[RING_BUFS];
-#pragma unroll
-    for (uint32_t b = 0; b < RING_BUFS; ++b) ring_gen[b] = s_ring_gen[b];
     const uint8_t* nodes = smem;
     const uint8_t* prims = smem + (size_t)td.n_nodes * NB;
 
@@ -399,7 +416,7 @@ k_traverse(const TravParams P) {
     float best_t = 0.f; uint32_t best_id = 0xFFFFFFFFu;
     f3 o = mk3(0, 0, 0), d = mk3(0, 0, 1), inv = mk3(0, 0, 0), noi = mk3(0, 0, 0);
     float tmin = 0.f, tmax_user = 0.f;
-    uint32_t nx = 0, ny = 0, nz = 0, fx = 0, fy = 0, fz = 0;   // byte offsets of the near / far plane rows
+    uint32_t nx = 0, ny = 0, nz = 0;   // byte offsets of the near plane rows (far rows: 12W - nx, 20W - ny, 28W - nz)
     int sp = 0;
     uint32_t cur = REF_NONE;
     bool have = false, improved = false;
@@ -423,28 +440,31 @@ k_traverse(const TravParams P) {
         uint32_t base = 0;
         if (lane == 0) base = atomicAdd(&s_next_ray, n_idle);
         base = __shfl_sync(0xffffffffu, base, 0);
-        if (base + n_idle >= chunk.z) exhausted = true;
+        // (chunk range and ring bookkeeping are re-read from shared memory here rather than held in registers
+        //  across the traversal loop: the kernel runs at 64 registers for 4 CTAs per SM)
+        const uint32_t chunk_first = s_chunk.y, chunk_count = s_chunk.z;
+        if (base + n_idle >= chunk_count) exhausted = true;
         const uint32_t k = base + __popc(m_idle & lane_lt);
-        const bool take = idle && k < chunk.z;
+        const bool take = idle && k < chunk_count;
         float4 ro = make_float4(0.f, 0.f, 0.f, 0.f), rd = make_float4(0.f, 0.f, 1.f, 0.f);
         unsigned long long h = 0;
         if (P.ids) {
           // levels >= 1: ray ids grouped by subtree, gather the records
           if (take) {
-            rid = P.ids[chunk.y + k];
+            rid = P.ids[chunk_first + k];
             B2_CHECK(rid < P.n_rays_cap, 1, rid);
             if (rid >= P.n_rays_cap) rid = 0;
             ro = P.ray_o[rid]; rd = P.ray_d[rid]; h = P.hits[rid];
           }
-        } else if (base < chunk.z) {
+        } else if (base < chunk_count) {
           // level 0: the warp takes rays base .. base + n_take - 1 of the chunk out of the ring (at most two tiles)
-          const uint32_t n_take = min(n_idle, chunk.z - base);
+          const uint32_t n_take = min(n_idle, chunk_count - base);
           const uint32_t tA = base / RING_TILE;
           const uint32_t nA = min(n_take, (tA + 1) * RING_TILE - base), nB = n_take - nA;
 #pragma unroll
           for (uint32_t j = 0; j < 2; ++j) {
             if (j == 1 && nB == 0) break;
-            const uint32_t t = tA + j, b = t % RING_BUFS, load = ring_gen[b] + t / RING_BUFS;
+            const uint32_t t = tA + j, b = t % RING_BUFS, load = s_ring_gen[b] + t / RING_BUFS;
             // the load must have been issued before its mbarrier phase can be waited for (a parity wait cannot tell
             // "not started" from "completed" two phases apart)
             while ((int32_t)(*(volatile uint32_t*)&s_ring_issued[b] - load) <= 0) { }
@@ -452,10 +472,10 @@ k_traverse(const TravParams P) {
           }
           if (take) {
             const uint32_t t = k / RING_TILE, e = k % RING_TILE;
-            const uint8_t* rb = ring + (t % RING_BUFS) * RING_BUF_BYTES;
-            ro = reinterpret_cast<const float4*>(rb + RING_O)[e]; rd = reinterpret_cast<const float4*>(rb + RING_D)[e];
-            h = reinterpret_cast<const unsigned long long*>(rb + RING_H)[e];
-            rid = chunk.y + k;
+            const uint32_t rb = ring + (t % RING_BUFS) * RING_BUF_BYTES;
+            ro = lds_f4(rb + RING_O + e * 16u); rd = lds_f4(rb + RING_D + e * 16u);
+            h = lds_u64(rb + RING_H + e * 8u);
+            rid = chunk_first + k;
           }
           __syncwarp();   // every lane's ring reads are done
           if (lane == 0) {
@@ -466,12 +486,12 @@ k_traverse(const TravParams P) {
               const uint32_t t = tA + j, n = j ? nB : nA;
               if (n == 0) continue;
               const uint32_t b = t % RING_BUFS;
-              const uint32_t tile_rays = min(RING_TILE, chunk.z - t * RING_TILE);
+              const uint32_t tile_rays = min(RING_TILE, chunk_count - t * RING_TILE);
               const uint32_t old = atomicAdd(&s_ring_cons[b], n);
               if (old + n == tile_rays) {
                 s_ring_cons[b] = 0;
                 __threadfence_block();
-                if ((t + RING_BUFS) * RING_TILE < chunk.z) ring_issue(chunk.y, chunk.z, t + RING_BUFS);
+                if ((t + RING_BUFS) * RING_TILE < chunk_count) ring_issue(chunk_first, chunk_count, t + RING_BUFS);
               }
             }
           }
@@ -487,9 +507,9 @@ k_traverse(const TravParams P) {
                     fabsf(d.y) > 1e-18f ? __frcp_rn(d.y) : copysignf(1e18f, d.y),
                     fabsf(d.z) > 1e-18f ? __frcp_rn(d.z) : copysignf(1e18f, d.z));
           noi = mk3(-(o.x * inv.x), -(o.y * inv.y), -(o.z * inv.z));
-          nx = inv.x >= 0.f ? 0u : 12u * W; fx = 12u * W - nx;
-          ny = inv.y >= 0.f ? 4u * W : 16u * W; fy = 20u * W - ny;
-          nz = inv.z >= 0.f ? 8u * W : 20u * W; fz = 28u * W - nz;
+          nx = inv.x >= 0.f ? 0u : 12u * W;
+          ny = inv.y >= 0.f ? 4u * W : 16u * W;
+          nz = inv.z >= 0.f ? 8u * W : 20u * W;
           have = true; improved = false; sp = 0;
           const bool skip = ANYHIT && best_id != 0xFFFFFFFFu;
           cur = skip ? REF_NONE : 0u;   // INTERNAL node 0 = subtree root
@@ -517,6 +537,7 @@ k_traverse(const TravParams P) {
           B2_CHECK((cur & 0x3FFFFFFFu) < td.n_nodes, 2, cur);
           const uint8_t* nbase = nodes + (size_t)(cur & 0x3FFFFFFFu) * NB;
           const uint32_t* nrefs = reinterpret_cast<const uint32_t*>(nbase + 24 * W);
+          const uint32_t fx = 12u * W - nx, fy = 20u * W - ny, fz = 28u * W - nz;
           uint32_t keys[W];
           // sign-ordered slab test: per axis the near plane row is lo (inv >= 0) or hi (inv < 0), chosen once
           // per ray (row offsets nx/ny/nz, fx/fy/fz), so a box costs 6 fma + 3 max + 3 min.  Empty slots hold
@@ -559,7 +580,7 @@ k_traverse(const TravParams P) {
           for (int q = W - 1; q >= 1; --q) {
             if (keys[q] != 0xFFFFFFFFu) {
               B2_CHECK(sp < (int)stack_entries(W), 3, sp);
-              stack[sp * TRAV_THREADS] = (keys[q] & (STACK_TN_MASK | (uint32_t)(W - 1))) | node_tag;
+              sts_u32(stack + (uint32_t)sp * (TRAV_THREADS * 4u), (keys[q] & (STACK_TN_MASK | (uint32_t)(W - 1))) | node_tag);
               ++sp;
             }
           }
@@ -594,7 +615,7 @@ k_traverse(const TravParams P) {
         if (need_pop) {
           cur = REF_NONE;
           while (sp > 0) {
-            const uint32_t e = stack[--sp * TRAV_THREADS];
+            const uint32_t e = lds_u32(stack + (uint32_t)(--sp) * (TRAV_THREADS * 4u));
             if (__uint_as_float(e & STACK_TN_MASK) <= best_t) {
               cur = *reinterpret_cast<const uint32_t*>(nodes + (size_t)((e & 0xFFFu) >> SLOT_BITS) * NB + 24 * W + (e & (uint32_t)(W - 1)) * 4u);
               break;

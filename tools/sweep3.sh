@@ -6,7 +6,5 @@ run() { # name lib treelet [env...]
   env B2RT_LIB=$lib "$@" timeout 120 python tools/profile_frame.py --spp 32 --frames 3 --treelet-bytes $tb 2>&1 | tail -1
 }
 B=cuda-raytracer_b200/libb2rt.so
-run nosplit $B 24576
-run nosplit $B 20480
-run nosplit $B 16384
-run greedy build/greedy/libb2rt.so 24576
+run base $B 24576
+run base $B 16384
