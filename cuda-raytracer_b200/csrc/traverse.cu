@@ -50,6 +50,9 @@ __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
 __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   uint32_t done = 0;
   const uint32_t addr = smem_u32(bar);
@@ -327,7 +330,7 @@ k_traverse(const TravParams P) {
   __shared__ __align__(8) uint64_t s_ring_bar[RING_BUFS];
   __shared__ uint32_t s_ring_cons[RING_BUFS];     // rays of the buffer's current tile already taken
   __shared__ uint32_t s_ring_issued[RING_BUFS];   // tile loads issued on the buffer since the kernel started
-  __shared__ uint32_t s_ring_gen[RING_BUFS];      // ... of which before the current chunk
+  __shared__ uint32_t s_ring_tile[RING_BUFS];     // global index of the tile the buffer holds, 0xFFFFFFFF = stream ended
   __shared__ uint4 s_chunk;
   __shared__ uint32_t s_next_ray;
   __shared__ __align__(8) uint2 s_stage[TRAV_WARPS][STAGE_PAIRS];
@@ -348,51 +351,54 @@ k_traverse(const TravParams P) {
 
   if (threadIdx.x == 0) {
     mbar_init(&s_bar, 1);
-    for (uint32_t b = 0; b < RING_BUFS; ++b) { mbar_init(&s_ring_bar[b], 1); s_ring_issued[b] = 0; s_ring_cons[b] = 0; s_ring_gen[b] = 0; }
+    for (uint32_t b = 0; b < RING_BUFS; ++b) { mbar_init(&s_ring_bar[b], 1); s_ring_issued[b] = 0; s_ring_cons[b] = 0; s_ring_tile[b] = 0xFFFFFFFFu; }
   }
   asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   __syncthreads();
-  uint32_t prev_tiles = 0;   // thread 0: tiles of the previous chunk (to advance s_ring_gen)
-
-  // TMA load of tile `tile` of the chunk (first ray `first`, `count` rays) into ring buffer tile % RING_BUFS.
-  // Called by ONE thread, after every ray of the buffer's previous tile has been taken (or at chunk start).
-  auto ring_issue = [&](uint32_t first, uint32_t count, uint32_t tile) {
-    const uint32_t b = tile % RING_BUFS;
-    const uint32_t n = min(RING_TILE, count - tile * RING_TILE), n4 = (n + 3u) & ~3u;
-    const size_t at = (size_t)first + (size_t)tile * RING_TILE;
-    uint8_t* dst = ring_generic + b * RING_BUF_BYTES;
-    fence_proxy_async();
-    mbar_expect_tx(&s_ring_bar[b], n4 * 40u);
-    bulk_g2s(dst + RING_O, P.ray_o + at, n4 * 16u, &s_ring_bar[b]);
-    bulk_g2s(dst + RING_D, P.ray_d + at, n4 * 16u, &s_ring_bar[b]);
-    bulk_g2s(dst + RING_H, P.hits + at, n4 * 8u, &s_ring_bar[b]);
+  // ---- level 0: every active ray visits the root subtree.  No chunks: the ray list is cut into 128-ray tiles and a
+  // CTA claims the next tile from a global cursor whenever one of its ring buffers runs empty, so the CTAs stay
+  // balanced at tile granularity and the only barrier (and the only drain of half-empty warps) is at the kernel's end.
+  const uint32_t n_root = P.level == 0 ? *P.n_active : 0u;
+  // TMA load of the next unclaimed tile into ring buffer b.  Called by ONE thread, after every ray of the buffer's
+  // previous tile has been taken (or at the start).  Past the end of the list the buffer is marked "stream ended".
+  auto ring_issue = [&](uint32_t b) {
+    const uint32_t g = atomicAdd(&P.ctrl[CTRL_NEXT0], 1u);
+    const size_t at = (size_t)g * RING_TILE;
+    if (at < n_root) {
+      const uint32_t n = min(RING_TILE, n_root - (uint32_t)at), n4 = (n + 3u) & ~3u;
+      uint8_t* dst = ring_generic + b * RING_BUF_BYTES;
+      s_ring_tile[b] = g;
+      fence_proxy_async();
+      mbar_expect_tx(&s_ring_bar[b], n4 * 40u);
+      bulk_g2s(dst + RING_O, P.ray_o + at, n4 * 16u, &s_ring_bar[b]);
+      bulk_g2s(dst + RING_D, P.ray_d + at, n4 * 16u, &s_ring_bar[b]);
+      bulk_g2s(dst + RING_H, P.hits + at, n4 * 8u, &s_ring_bar[b]);
+    } else {
+      s_ring_tile[b] = 0xFFFFFFFFu;
+      __threadfence_block();
+      mbar_arrive(&s_ring_bar[b]);   // completes the phase without a copy, so waiters see the end marker
+    }
     __threadfence_block();
     atomicAdd(&s_ring_issued[b], 1u);
   };
-
-  // level 0: every active ray visits the root subtree; its chunk list is implicit (no scheduling kernel)
-  // (large chunks there: one subtree, so the only cost of a chunk boundary is the CTA-wide barrier)
-  const uint32_t n_root = P.level == 0 ? *P.n_active : 0u;
-  const uint32_t chunk0 = min(P.chunk0_max, max(P.chunk_rays, (n_root / (gridDim.x * 8u) + 1023u) & ~1023u));
-  const uint32_t n_chunks = P.level == 0 ? (n_root + chunk0 - 1) / chunk0 : P.ctrl[CTRL_NCHUNKS];
+  const uint32_t n_chunks = P.level == 0 ? 1u : P.ctrl[CTRL_NCHUNKS];
+  bool stream_started = false;
   for (;;) {
     if (threadIdx.x == 0) {
-      uint32_t c = atomicAdd(&P.ctrl[CTRL_NEXT0 + (P.level & 1)], 1u);
       uint4 ch = make_uint4(0xFFFFFFFFu, 0, 0, 0);
-      if (c < n_chunks) ch = P.level == 0 ? make_uint4(0u, c * chunk0, min(chunk0, n_root - c * chunk0), 0u) : P.chunks[c];
+      if (P.level == 0) {
+        if (!stream_started) {   // the one pseudo-chunk of level 0: the whole ray list, as a tile stream
+          ch = make_uint4(0u, 0u, 0xFFFFFFFFu, 0u);
+          for (uint32_t b = 0; b < RING_BUFS; ++b) ring_issue(b);
+        }
+      } else {
+        const uint32_t c = atomicAdd(&P.ctrl[CTRL_NEXT0 + (P.level & 1)], 1u);
+        if (c < n_chunks) ch = P.chunks[c];
+      }
       s_chunk = ch;
       s_next_ray = 0;
-      // every tile of the previous chunk was consumed (all warps passed the barrier below): start this chunk's stream
-      for (uint32_t b = 0; b < RING_BUFS; ++b) {
-        s_ring_gen[b] += b < prev_tiles ? (prev_tiles - b + RING_BUFS - 1) / RING_BUFS : 0u;
-        s_ring_cons[b] = 0;
-      }
-      prev_tiles = 0;
-      if (ch.x != 0xFFFFFFFFu && !P.ids) {
-        prev_tiles = (ch.z + RING_TILE - 1) / RING_TILE;
-        for (uint32_t t = 0; t < RING_BUFS && t < prev_tiles; ++t) ring_issue(ch.y, ch.z, t);
-      }
     }
+    stream_started = true;
     __syncthreads();
     const uint4 chunk = s_chunk;
     if (chunk.x == 0xFFFFFFFFu) break;
@@ -421,6 +427,7 @@ k_traverse(const TravParams P) {
     uint32_t cur = REF_NONE;
     bool have = false, improved = false;
     bool exhausted = false;   // warp-uniform: the chunk has no more rays to hand out
+    uint32_t ring_ended = 0;  // warp-uniform: ring buffers on which this warp has seen the end-of-stream marker
 
     // One convergence point per iteration: the ballot at the top.  The loop is left only there (all lanes idle
     // and the chunk handed out); there is no other warp-level primitive on a conditional path except the
@@ -443,9 +450,9 @@ k_traverse(const TravParams P) {
         // (chunk range and ring bookkeeping are re-read from shared memory here rather than held in registers
         //  across the traversal loop: the kernel runs at 64 registers for 4 CTAs per SM)
         const uint32_t chunk_first = s_chunk.y, chunk_count = s_chunk.z;
-        if (base + n_idle >= chunk_count) exhausted = true;
+        if (P.ids && base + n_idle >= chunk_count) exhausted = true;
         const uint32_t k = base + __popc(m_idle & lane_lt);
-        const bool take = idle && k < chunk_count;
+        bool take = idle && k < chunk_count;
         float4 ro = make_float4(0.f, 0.f, 0.f, 0.f), rd = make_float4(0.f, 0.f, 1.f, 0.f);
         unsigned long long h = 0;
         if (P.ids) {
@@ -456,42 +463,65 @@ k_traverse(const TravParams P) {
             if (rid >= P.n_rays_cap) rid = 0;
             ro = P.ray_o[rid]; rd = P.ray_d[rid]; h = P.hits[rid];
           }
-        } else if (base < chunk_count) {
-          // level 0: the warp takes rays base .. base + n_take - 1 of the chunk out of the ring (at most two tiles)
-          const uint32_t n_take = min(n_idle, chunk_count - base);
+        } else {
+          // level 0: the warp takes slots base .. base + n_idle - 1 of the CTA's tile stream (at most two tiles)
           const uint32_t tA = base / RING_TILE;
-          const uint32_t nA = min(n_take, (tA + 1) * RING_TILE - base), nB = n_take - nA;
+          const uint32_t nA = min(n_idle, (tA + 1) * RING_TILE - base), nB = n_idle - nA;
+          uint32_t gA = 0xFFFFFFFFu, gB = 0xFFFFFFFFu;
 #pragma unroll
           for (uint32_t j = 0; j < 2; ++j) {
             if (j == 1 && nB == 0) break;
-            const uint32_t t = tA + j, b = t % RING_BUFS, load = s_ring_gen[b] + t / RING_BUFS;
+            const uint32_t t = tA + j, b = t % RING_BUFS, load = t / RING_BUFS;
             // the load must have been issued before its mbarrier phase can be waited for (a parity wait cannot tell
             // "not started" from "completed" two phases apart)
-            while ((int32_t)(*(volatile uint32_t*)&s_ring_issued[b] - load) <= 0) { }
-            mbar_wait(&s_ring_bar[b], load & 1u);
+            uint32_t spins = 0;
+            bool stuck = false;
+            while ((int32_t)(*(volatile uint32_t*)&s_ring_issued[b] - load) <= 0) {
+              if (++spins == (1u << 24)) {   // watchdog: give up on the stream and report instead of hanging the device
+                if (lane == 0 && atomicCAS(&P.ctrl[8], 0u, 1u) == 0u) {
+                  P.ctrl[9] = blockIdx.x; P.ctrl[10] = warp | (j << 8) | (n_idle << 16); P.ctrl[11] = t; P.ctrl[12] = load;
+                  P.ctrl[13] = s_ring_issued[0] | (s_ring_issued[1] << 16); P.ctrl[14] = base;
+                  P.ctrl[15] = s_ring_cons[0] | (s_ring_cons[1] << 16);
+                  P.ctrl[CTRL_OVERFLOW] = 1;
+                }
+                stuck = true;
+                break;
+              }
+            }
+            if (!stuck) mbar_wait(&s_ring_bar[b], load & 1u);
+            const uint32_t g = stuck ? 0xFFFFFFFFu : *(volatile uint32_t*)&s_ring_tile[b];
+            if (j == 0) gA = g; else gB = g;
           }
+          // The ray list is handed out once BOTH buffers have shown the end marker: the buffers claim global tiles
+          // independently, so the last real tile can sit (in the CTA's slot order) behind the first end marker.
+          if (gA == 0xFFFFFFFFu) ring_ended |= 1u << (tA % RING_BUFS);
+          if (nB && gB == 0xFFFFFFFFu) ring_ended |= 1u << ((tA + 1) % RING_BUFS);
+          if (ring_ended == (1u << RING_BUFS) - 1u) exhausted = true;
+          const uint32_t t = k / RING_TILE, e = k % RING_TILE;
+          const uint32_t g = t == tA ? gA : gB;
+          take = idle && g != 0xFFFFFFFFu && g * RING_TILE + e < n_root;
           if (take) {
-            const uint32_t t = k / RING_TILE, e = k % RING_TILE;
             const uint32_t rb = ring + (t % RING_BUFS) * RING_BUF_BYTES;
             ro = lds_f4(rb + RING_O + e * 16u); rd = lds_f4(rb + RING_D + e * 16u);
             h = lds_u64(rb + RING_H + e * 8u);
-            rid = chunk_first + k;
+            rid = g * RING_TILE + e;
           }
           __syncwarp();   // every lane's ring reads are done
           if (lane == 0) {
-            // hand the tiles back; whoever takes the last ray of a tile re-arms its buffer with the tile after next
+            // hand the slots back; whoever takes the last slot of a tile re-arms its buffer with the next unclaimed tile
             __threadfence_block();
 #pragma unroll
             for (uint32_t j = 0; j < 2; ++j) {
-              const uint32_t t = tA + j, n = j ? nB : nA;
+              const uint32_t n = j ? nB : nA;
               if (n == 0) continue;
-              const uint32_t b = t % RING_BUFS;
-              const uint32_t tile_rays = min(RING_TILE, chunk_count - t * RING_TILE);
+              const uint32_t b = (tA + j) % RING_BUFS;
               const uint32_t old = atomicAdd(&s_ring_cons[b], n);
-              if (old + n == tile_rays) {
+              if (old + n == RING_TILE) {
                 s_ring_cons[b] = 0;
                 __threadfence_block();
-                if ((t + RING_BUFS) * RING_TILE < chunk_count) ring_issue(chunk_first, chunk_count, t + RING_BUFS);
+                // always, even after an end marker: the two buffers claim global tiles independently, so a buffer
+                // can hold the end marker while the other still gets a real tile and warps move on past both
+                ring_issue(b);
               }
             }
           }
@@ -860,6 +890,13 @@ int Tracer::check_overflow(cudaStream_t s, bool* overflow) {
   cudaMemcpy(dbg, ctrl + 6, 8, cudaMemcpyDeviceToHost);
   if (dbg[0]) { fprintf(stderr, "B2RT_CHECKS: code %u info %u (0x%08x)\n", dbg[0], dbg[1], dbg[1]); cudaMemset(ctrl + 6, 0, 8); }
 #endif
+  uint32_t wd[8] = {0};
+  cudaMemcpy(wd, ctrl + 8, 32, cudaMemcpyDeviceToHost);
+  if (wd[0]) {
+    fprintf(stderr, "b2rt: ray-ring watchdog: cta %u warp %u j %u n_idle %u tile %u load %u issued %u/%u base %u cons %u/%u\n", wd[1],
+            wd[2] & 255, (wd[2] >> 8) & 255, wd[2] >> 16, wd[3], wd[4], wd[5] & 0xFFFF, wd[5] >> 16, wd[6], wd[7] & 0xFFFF, wd[7] >> 16);
+    cudaMemset(ctrl + 8, 0, 32);
+  }
   if (v) B2RT_CUDA_OK(cudaMemsetAsync(ctrl + CTRL_OVERFLOW, 0, 4, s));
   return B2RT_OK;
 }

@@ -34,6 +34,28 @@ def _mixed_rays(sc, n_random, seed, w=160, h=120):
     return np.concatenate([ro, r2o]), np.concatenate([rd, r2d])
 
 
+@pytest.mark.parametrize("n_random,w,h", [(0, 1024, 768), (123457, 640, 480), (700001, 1024, 768), (3000077, 160, 120)])
+def test_closest_hit_bit_exact_mid_sized_batches(n_random, w, h):
+    """Ray counts between 'a tile or two per CTA' and 'thousands of tiles per CTA': the end of the level-0 tile stream,
+    where the ring buffers of a CTA claim global tiles out of order (regression: a warp that saw the end marker on one
+    buffer stopped while the other buffer still held the last real tile -> lost rays; before that, a hang).  Counts
+    that are not multiples of 128 / 4 exercise the partial last tile."""
+    sc = Scene.load(scene_path("CBbunny"))
+    o = orc.OracleScene(sc, 4)
+    bvh = b2rt.BVHAccel(sc)
+    org, dirs = _mixed_rays(sc, n_random, 11, w, h)
+    for rep in range(2):
+        t, p = bvh.intersect(org, dirs)
+        tr, pr = o.intersect(org, dirs, mode="bvh")
+        assert np.array_equal(p, pr), f"{np.sum(p != pr)} primitive ids differ of {len(org)}"
+        assert np.array_equal(t, tr)
+    tmax = np.full(len(org), 2.5, np.float32)
+    occ = bvh.occluded(org, dirs, None, tmax)
+    _, pw = o.intersect(org, dirs, None, tmax)
+    assert np.array_equal(occ, pw != MISS)       # any hit inside the window <=> a closest hit exists
+    bvh.close()
+
+
 @pytest.mark.parametrize("name", ["CBbunny", "CBcoil", "CBgems", "CBspheres_lambertian", "CBspheres", "CBempty", "trigs10",
                                   "sphere_diffuse", "plane1024", "floating"])
 @pytest.mark.parametrize("width,treelet_bytes,max_leaf", [(4, 0, 4), (8, 0, 4), (4, 8192, 2), (8, 100000, 8)])
