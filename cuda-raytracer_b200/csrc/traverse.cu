@@ -306,10 +306,15 @@ __device__ __forceinline__ void flush_pairs(uint2* stage, uint32_t& n_staged, co
 #endif
 constexpr uint32_t REF_NONE = 0xFFFFFFFEu;   // "no current node" marker of the traversal loop (tag EMPTY)
 #ifndef B2RT_MIN_IDLE
-#define B2RT_MIN_IDLE 12
+#define B2RT_MIN_IDLE 20
 #endif
 constexpr int REFILL_MIN_IDLE = B2RT_MIN_IDLE;   // refill a warp's idle lanes once this many are idle
 
+__device__ __forceinline__ float fast_rcp(float x) {
+  float r;
+  asm("rcp.approx.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
 // three-input fp32 min / max (sm_100: one FMNMX3 instead of two FMNMX)
 __device__ __forceinline__ float fmax3(float a, float b, float c) {
   float r;
@@ -533,9 +538,11 @@ k_traverse(const TravParams P) {
           best_id = (uint32_t)h;
           // reciprocal direction for the slab test; |d_k| < 1e-18 (incl. +-0) is clamped so that o_k * inv_k
           // stays finite: the ray is then parallel to the slab and the test reduces to lo_k <= o_k <= hi_k
-          inv = mk3(fabsf(d.x) > 1e-18f ? __frcp_rn(d.x) : copysignf(1e18f, d.x),
-                    fabsf(d.y) > 1e-18f ? __frcp_rn(d.y) : copysignf(1e18f, d.y),
-                    fabsf(d.z) > 1e-18f ? __frcp_rn(d.z) : copysignf(1e18f, d.z));
+          // (MUFU.RCP, 1 ulp: the slab test only has to be conservative, and the box padding + the 4-ulp slack on
+          //  t_far cover it; the IEEE-rounded reciprocal cost 3 x 8 instructions per ray)
+          inv = mk3(fabsf(d.x) > 1e-18f ? fast_rcp(d.x) : copysignf(1e18f, d.x),
+                    fabsf(d.y) > 1e-18f ? fast_rcp(d.y) : copysignf(1e18f, d.y),
+                    fabsf(d.z) > 1e-18f ? fast_rcp(d.z) : copysignf(1e18f, d.z));
           noi = mk3(-(o.x * inv.x), -(o.y * inv.y), -(o.z * inv.z));
           nx = inv.x >= 0.f ? 0u : 12u * W;
           ny = inv.y >= 0.f ? 4u * W : 16u * W;

@@ -8,7 +8,8 @@ import sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, os.path.join(ROOT, "cuda-raytracer_b200"))
 import b2rt  # noqa: E402
-from b2rt.scene import Scene, place_camera  # noqa: E402
+import numpy as np  # noqa: E402
+from b2rt.scene import Scene, place_camera, subdivide  # noqa: E402
 
 ap = argparse.ArgumentParser()
 ap.add_argument("--spp", type=int, default=8)
@@ -20,8 +21,11 @@ ap.add_argument("--bvh-width", type=int, default=0)
 ap.add_argument("--treelet-bytes", type=int, default=0)
 ap.add_argument("--wave", type=int, default=0)
 ap.add_argument("--frames", type=int, default=1)
+ap.add_argument("--subdivide", type=int, default=0, help="subdivide the scene's largest mesh n times (cfg3 stand-in: CBbunny, 1)")
 a = ap.parse_args()
 sc = Scene.load(os.path.join(ROOT, "scenes", a.scene + ".b2s"))
+if a.subdivide:
+    sc = subdivide(sc, a.subdivide, select=lambda tv, tm: tm == tm[np.argmax(np.bincount(tm))])
 cam = place_camera(sc, a.width, a.height)
 pt = b2rt.PathTracer(ns_aa=a.spp, max_ray_depth=a.depth, ns_area_light=1, seed=1, bvh_width=a.bvh_width,
                      treelet_bytes=a.treelet_bytes, max_wave_paths=a.wave)

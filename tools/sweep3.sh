@@ -1,10 +1,11 @@
 #!/bin/sh
-# A/B sweep of build variants (tools/build_variant.sh) on cfg2 at 32 spp.
-run() { # name lib treelet [env...]
-  name=$1; lib=$2; tb=$3; shift 3
-  printf "%-28s treelet=%-6s %s : " "$name" "$tb" "$*"
-  env B2RT_LIB=$lib "$@" timeout 120 python tools/profile_frame.py --spp 32 --frames 3 --treelet-bytes $tb 2>&1 | tail -1
+# A/B sweep of build variants (tools/build_variant.sh) and subtree budgets on cfg2 (32 spp) and the cfg3 stand-in (16 spp).
+run() { # name lib treelet extra-args [env...]
+  name=$1; lib=$2; tb=$3; extra=$4; shift 4
+  printf "%-14s treelet=%-6s %-34s %s : " "$name" "$tb" "$extra" "$*"
+  env B2RT_LIB=$lib "$@" timeout 120 python tools/profile_frame.py --frames 3 --treelet-bytes $tb $extra 2>&1 | tail -1
 }
 B=cuda-raytracer_b200/libb2rt.so
-run base $B 24576
-run base $B 16384
+run mi20 $B 0 "--spp 32"
+for v in mi24 mi28 mi32; do run $v build/$v/libb2rt.so 0 "--spp 32"; done
+run mi20 $B 0 "--spp 16 --subdivide 1 --width 1920 --height 1080"
