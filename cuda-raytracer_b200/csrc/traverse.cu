@@ -616,7 +616,7 @@ k_traverse(const TravParams P) {
 #pragma unroll
           for (int q = W - 1; q >= 1; --q) {
             if (keys[q] != 0xFFFFFFFFu) {
-              B2_CHECK(sp < (int)stack_entries(W), 3, sp);
+              B2_CHECK(sp < (W == 8 ? B2RT_STACK8 : B2RT_STACK4), 3, sp);
               sts_u32(stack + (uint32_t)sp * (TRAV_THREADS * 4u), (keys[q] & (STACK_TN_MASK | (uint32_t)(W - 1))) | node_tag);
               ++sp;
             }
@@ -895,7 +895,12 @@ int Tracer::check_overflow(cudaStream_t s, bool* overflow) {
 #ifdef B2RT_CHECKS
   uint32_t dbg[2] = {0, 0};
   cudaMemcpy(dbg, ctrl + 6, 8, cudaMemcpyDeviceToHost);
-  if (dbg[0]) { fprintf(stderr, "B2RT_CHECKS: code %u info %u (0x%08x)\n", dbg[0], dbg[1], dbg[1]); cudaMemset(ctrl + 6, 0, 8); }
+  if (dbg[0]) {
+    fprintf(stderr, "B2RT_CHECKS: code %u info %u (0x%08x)\n", dbg[0], dbg[1], dbg[1]);
+    cudaMemset(ctrl + 6, 0, 8);
+    set_error("B2RT_CHECKS: device invariant " + std::to_string(dbg[0]) + " violated (info " + std::to_string(dbg[1]) + ")");
+    return B2RT_ERR_CUDA;
+  }
 #endif
   uint32_t wd[8] = {0};
   cudaMemcpy(wd, ctrl + 8, 32, cudaMemcpyDeviceToHost);

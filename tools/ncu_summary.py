@@ -11,7 +11,7 @@ import subprocess
 import sys
 
 METRICS = [
-    ("gpu__time_duration.sum", "time us", 1.0),
+    ("gpu__time_duration.sum", "time us", "time"),
     ("launch__grid_size", "grid", 1.0),
     ("launch__registers_per_thread", "regs", 1.0),
     ("sm__warps_active.avg.pct_of_peak_sustained_active", "occupancy % (achieved)", 1.0),
@@ -56,7 +56,10 @@ def main():
             except ValueError:
                 vals.append("-")
                 continue
-            sc = UNIT_SCALE.get(units[ci[key]], 1.0) if scale is None else scale
+            if scale == "time":
+                sc = {"ns": 1e-3, "us": 1.0, "ms": 1e3, "s": 1e6}.get(units[ci[key]], 1.0)
+            else:
+                sc = UNIT_SCALE.get(units[ci[key]], 1.0) if scale is None else scale
             v *= sc
             vals.append(f"{v:.2f}" if abs(v) < 100 else f"{v:.0f}")
         print(f"| {label} | " + " | ".join(vals) + " |")
