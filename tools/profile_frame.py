@@ -21,6 +21,7 @@ ap.add_argument("--bvh-width", type=int, default=0)
 ap.add_argument("--treelet-bytes", type=int, default=0)
 ap.add_argument("--wave", type=int, default=0)
 ap.add_argument("--frames", type=int, default=1)
+ap.add_argument("--max-leaf", type=int, default=0)
 ap.add_argument("--subdivide", type=int, default=0, help="subdivide the scene's largest mesh n times (cfg3 stand-in: CBbunny, 1)")
 a = ap.parse_args()
 sc = Scene.load(os.path.join(ROOT, "scenes", a.scene + ".b2s"))
@@ -28,7 +29,7 @@ if a.subdivide:
     sc = subdivide(sc, a.subdivide, select=lambda tv, tm: tm == tm[np.argmax(np.bincount(tm))])
 cam = place_camera(sc, a.width, a.height)
 pt = b2rt.PathTracer(ns_aa=a.spp, max_ray_depth=a.depth, ns_area_light=1, seed=1, bvh_width=a.bvh_width,
-                     treelet_bytes=a.treelet_bytes, max_wave_paths=a.wave)
+                     treelet_bytes=a.treelet_bytes, max_wave_paths=a.wave, max_leaf_size=a.max_leaf)
 pt.set_scene(sc); pt.set_camera(cam); pt.set_frame_size(a.width, a.height)
 pt.set_profiling(counters=False, time_kernels=True)
 for _ in range(a.frames):
