@@ -140,7 +140,8 @@ __device__ __forceinline__ uint32_t block_append(uint32_t* counter, bool pred, u
   __syncthreads();
   if (threadIdx.x == 0) {
     uint32_t tot = 0, tex = 0;
-    for (int w = 0; w < 8; ++w) { const uint32_t v = sh[w]; sh[w] = tot; tot += v & 0xFFu; tex += v >> 8; }
+    const uint32_t nw = blockDim.x >> 5;
+    for (uint32_t w = 0; w < nw; ++w) { const uint32_t v = sh[w]; sh[w] = tot; tot += v & 0xFFu; tex += v >> 8; }
     sh[8] = tot ? atomicAdd(counter, tot * per_item) : 0u;
     if (tex) atomicAdd(extra_counter, tex);
   }
@@ -154,7 +155,11 @@ __device__ __forceinline__ uint32_t block_append(uint32_t* counter, bool pred, u
 #ifndef B2RT_SHADE_OCC
 #define B2RT_SHADE_OCC 4
 #endif
-__global__ void __launch_bounds__(256, B2RT_SHADE_OCC)
+#ifndef B2RT_SHADE_THREADS
+#define B2RT_SHADE_THREADS 256
+#endif
+constexpr int SHADE_THREADS = B2RT_SHADE_THREADS;   // <= 256 (block_append's scratch holds 8 warp counts)
+__global__ void __launch_bounds__(SHADE_THREADS, B2RT_SHADE_OCC)
 k_shade(WaveParams wp, SceneDev sc, PathBufs pb, uint32_t b) {
   const uint32_t n = pb.counts[ACT0 + b];
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -705,7 +710,7 @@ int Renderer::start() {
       for (uint32_t b = 0; b < max_depth; ++b) {
         bind_lists(b & 1u);
         RCHECK(tracer.trace(stream, pb.lo, pb.ld, pb.lh, counts + ACT0 + b, false));
-        k_shade<<<g, 256, 0, stream>>>(wp, sd, pb, b); launches++;
+        k_shade<<<(n + SHADE_THREADS - 1) / SHADE_THREADS, SHADE_THREADS, 0, stream>>>(wp, sd, pb, b); launches++;
         if (S > 0) {
           RCHECK(tracer.trace(stream, pb.s_o, pb.s_d, pb.s_hits, counts + SH0 + b, true));
           k_resolve_shadow<<<g, 256, 0, stream>>>(wp, pb, b); launches++;
