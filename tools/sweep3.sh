@@ -5,5 +5,5 @@ run() { # name lib treelet extra-args [env...]
   env B2RT_LIB=$lib "$@" timeout 120 python tools/profile_frame.py --frames 3 --treelet-bytes $tb $extra 2>&1 | tail -1
 }
 B=cuda-raytracer_b200/libb2rt.so
-run base256 $B 0 "--spp 32"
-for v in st128 st64; do run $v build/$v/libb2rt.so 0 "--spp 32"; done
+run count $B 0 "--spp 32"
+run count $B 0 "--spp 16 --subdivide 1 --width 1920 --height 1080"
