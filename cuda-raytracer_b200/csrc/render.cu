@@ -169,17 +169,19 @@ k_shade(WaveParams wp, SceneDev sc, PathBufs pb, uint32_t b) {
   const uint32_t S = wp.S;
   unsigned long long h = 0;
   uint32_t prim = 0xFFFFFFFFu;
-  b2rt_material m;
-  m.kind = -1;
+  // the material is read field by field where it is used (the table is a few cache lines); holding the 48-byte record
+  // and the 64-byte light record in registers across the kernel was the main source of spills at 64 registers
+  const b2rt_material* mp = sc.materials;
+  int32_t m_kind = -1;
   if (i < n) {
     slot = pb.lslot[i];
     h = pb.lh[i];
     prim = (uint32_t)h;
-    if (prim != 0xFFFFFFFFu) m = sc.materials[sc.prim_material[prim]];
+    if (prim != 0xFFFFFFFFu) { mp = sc.materials + sc.prim_material[prim]; m_kind = __ldg(&mp->kind); }
   }
   // every diffuse hit reserves S consecutive entries of the bounce's shadow-ray list: one atomic per warp, blocks in
   // lane order, so the list stays coalesced against the path list
-  const bool wants_shadow = prim != 0xFFFFFFFFu && m.kind == B2RT_MAT_DIFFUSE && S > 0;
+  const bool wants_shadow = prim != 0xFFFFFFFFu && m_kind == B2RT_MAT_DIFFUSE && S > 0;
   __shared__ uint32_t s_app[10];
   uint32_t q0 = block_append(&pb.counts[SH0 + b], wants_shadow, S, s_app);
   if (!wants_shadow) q0 = 0xFFFFFFFFu;
@@ -191,10 +193,10 @@ k_shade(WaveParams wp, SceneDev sc, PathBufs pb, uint32_t b) {
       const float4 thr4 = pb.thr[slot];
       f3 thr = mk3(thr4.x, thr4.y, thr4.z);
       const bool count_emission = thr4.w != 0.f;
-      if (m.kind == B2RT_MAT_EMISSION) {
+      if (m_kind == B2RT_MAT_EMISSION) {
         if (count_emission) {
           float4 L = pb.rad[slot];
-          const f3 add = thr * mk3(m.emission[0], m.emission[1], m.emission[2]);
+          const f3 add = thr * mk3(__ldg(&mp->emission[0]), __ldg(&mp->emission[1]), __ldg(&mp->emission[2]));
           L.x = L.x + add.x; L.y = L.y + add.y; L.z = L.z + add.z;
           pb.rad[slot] = L;
         }
@@ -228,22 +230,23 @@ k_shade(WaveParams wp, SceneDev sc, PathBufs pb, uint32_t b) {
         const uint32_t pix = wp.pix0 + slot / wp.spp;
         const uint32_t sample = wp.sample0 + (slot % wp.spp) * wp.sample_stride;
 
-        if (m.kind == B2RT_MAT_DIFFUSE) {
+        if (m_kind == B2RT_MAT_DIFFUSE) {
           // direct lighting: src/pathtracer.cpp:439-478 + shadow ray (Task 4)
           uint32_t j = 0;
           for (uint32_t li = 0; li < sc.n_lights; ++li) {
-            const b2rt_light lt = sc.lights[li];
-            const uint32_t ns = lt.kind == B2RT_LIGHT_AREA ? max(1u, wp.ns_area_light) : 1u;
+            const b2rt_light* lt = sc.lights + li;
+            const int32_t lt_kind = __ldg(&lt->kind);
+            const uint32_t ns = lt_kind == B2RT_LIGHT_AREA ? max(1u, wp.ns_area_light) : 1u;
             for (uint32_t k = 0; k < ns; ++k, ++j) {
               f3 wi; float dist, pdf; f3 Lr;
-              const f3 lp = mk3(lt.position[0], lt.position[1], lt.position[2]);
-              const f3 ld = mk3(lt.direction[0], lt.direction[1], lt.direction[2]);
-              const f3 radc = mk3(lt.radiance[0], lt.radiance[1], lt.radiance[2]);
-              if (lt.kind == B2RT_LIGHT_AREA) {
+              const f3 lp = mk3(__ldg(&lt->position[0]), __ldg(&lt->position[1]), __ldg(&lt->position[2]));
+              const f3 ld = mk3(__ldg(&lt->direction[0]), __ldg(&lt->direction[1]), __ldg(&lt->direction[2]));
+              const f3 radc = mk3(__ldg(&lt->radiance[0]), __ldg(&lt->radiance[1]), __ldg(&lt->radiance[2]));
+              if (lt_kind == B2RT_LIGHT_AREA) {
                 // AreaLight::sample_L, src/static_scene/light.cpp:81-92
                 const uint4 r4 = philox4x32_10(pix, sample, b, 1 + j, wp.k0, wp.k1);
                 const float ux = u01(r4.x) - 0.5f, uy = u01(r4.y) - 0.5f;
-                const f3 dv = lp + mk3(lt.dim_x[0], lt.dim_x[1], lt.dim_x[2]) * ux + mk3(lt.dim_y[0], lt.dim_y[1], lt.dim_y[2]) * uy - P;
+                const f3 dv = lp + mk3(__ldg(&lt->dim_x[0]), __ldg(&lt->dim_x[1]), __ldg(&lt->dim_x[2])) * ux + mk3(__ldg(&lt->dim_y[0]), __ldg(&lt->dim_y[1]), __ldg(&lt->dim_y[2])) * uy - P;
                 const float sq = dot3(dv, dv);
                 dist = __fsqrt_rn(sq);
                 const float invd = __fdiv_rn(1.0f, dist);
@@ -251,7 +254,7 @@ k_shade(WaveParams wp, SceneDev sc, PathBufs pb, uint32_t b) {
                 const float cosT = dot3(wi, ld);
                 pdf = __fdiv_rn(sq, sc.light_area[li] * fabsf(cosT));
                 Lr = cosT < 0.0f ? radc : mk3(0, 0, 0);
-              } else if (lt.kind == B2RT_LIGHT_POINT) {
+              } else if (lt_kind == B2RT_LIGHT_POINT) {
                 const f3 dv = lp - P;
                 const float sq = dot3(dv, dv);
                 dist = __fsqrt_rn(sq);
@@ -265,7 +268,7 @@ k_shade(WaveParams wp, SceneDev sc, PathBufs pb, uint32_t b) {
               const uint32_t q = q0 + j;
               if (valid) {
                 const float wgt = __fdiv_rn(cos_in, (float)ns * pdf);
-                const f3 f = mk3(m.albedo[0], m.albedo[1], m.albedo[2]) * 0.318309886183790672f;
+                const f3 f = mk3(__ldg(&mp->albedo[0]), __ldg(&mp->albedo[1]), __ldg(&mp->albedo[2])) * 0.318309886183790672f;
                 const f3 c = thr * f * Lr * wgt;
                 const float tmx = dist - wp.eps;
                 pb.s_o[q] = make_float4(P.x, P.y, P.z, wp.eps);
@@ -288,40 +291,40 @@ k_shade(WaveParams wp, SceneDev sc, PathBufs pb, uint32_t b) {
           const float u2 = u01(r4.z), u3 = u01(r4.w);
           f3 wi_l, weight;
           bool delta = false;
-          if (m.kind == B2RT_MAT_DIFFUSE) {
+          if (m_kind == B2RT_MAT_DIFFUSE) {
             const float r = __fsqrt_rn(u2);
             float s, c;
             sincos2pi(u3, &s, &c);
             const float zz = 1.0f - u2;
             wi_l = mk3(r * c, r * s, __fsqrt_rn(zz < 0.0f ? 0.0f : zz));
-            weight = mk3(m.albedo[0], m.albedo[1], m.albedo[2]);
-          } else if (m.kind == B2RT_MAT_MIRROR) {
+            weight = mk3(__ldg(&mp->albedo[0]), __ldg(&mp->albedo[1]), __ldg(&mp->albedo[2]));
+          } else if (m_kind == B2RT_MAT_MIRROR) {
             wi_l = mk3(-wo.x, -wo.y, wo.z);
-            weight = mk3(m.albedo[0], m.albedo[1], m.albedo[2]);
+            weight = mk3(__ldg(&mp->albedo[0]), __ldg(&mp->albedo[1]), __ldg(&mp->albedo[2]));
             delta = true;
           } else {
             delta = true;
-            const float eta = backface ? m.ior : __fdiv_rn(1.0f, m.ior);
+            const float eta = backface ? __ldg(&mp->ior) : __fdiv_rn(1.0f, __ldg(&mp->ior));
             const float cos_i = wo.z;
             const float sin2_t = eta * eta * (1.0f - cos_i * cos_i);
             const bool tir = !(sin2_t < 1.0f);
             const float cos_t = tir ? 0.0f : __fsqrt_rn(1.0f - sin2_t);
             float Fr = 1.0f;
             if (!tir) {
-              const float ni = backface ? m.ior : 1.0f, nt = backface ? 1.0f : m.ior;
+              const float ni = backface ? __ldg(&mp->ior) : 1.0f, nt = backface ? 1.0f : __ldg(&mp->ior);
               const float rs = __fdiv_rn(ni * cos_i - nt * cos_t, ni * cos_i + nt * cos_t);
               const float rp = __fdiv_rn(nt * cos_i - ni * cos_t, nt * cos_i + ni * cos_t);
               Fr = 0.5f * (rs * rs + rp * rp);
             }
             bool reflect;
-            if (m.kind == B2RT_MAT_GLASS) reflect = tir || (u2 < Fr);
+            if (m_kind == B2RT_MAT_GLASS) reflect = tir || (u2 < Fr);
             else reflect = tir;
             if (reflect) {
               wi_l = mk3(-wo.x, -wo.y, wo.z);
-              weight = m.kind == B2RT_MAT_GLASS ? mk3(m.albedo[0], m.albedo[1], m.albedo[2]) : mk3(1, 1, 1);
+              weight = m_kind == B2RT_MAT_GLASS ? mk3(__ldg(&mp->albedo[0]), __ldg(&mp->albedo[1]), __ldg(&mp->albedo[2])) : mk3(1, 1, 1);
             } else {
               wi_l = mk3(-wo.x * eta, -wo.y * eta, -cos_t);
-              weight = mk3(m.transmittance[0], m.transmittance[1], m.transmittance[2]);
+              weight = mk3(__ldg(&mp->transmittance[0]), __ldg(&mp->transmittance[1]), __ldg(&mp->transmittance[2]));
             }
           }
           if (weight.x > 0.0f || weight.y > 0.0f || weight.z > 0.0f) {
