@@ -252,7 +252,7 @@ def main():
         pt.start_raytracing(); pt.wait()
         if world > 1:
             dist.reduce(accum, dst=0)
-        img = pt.rgba32f()
+        img = pt.image()       # CudaRenderer::getImage: device -> renderer-owned pinned host buffer
         st = pt.stats()
         rays_e += st["rays_camera"] + st["rays_bounce"] + st["rays_shadow"]
     torch.cuda.synchronize()
@@ -266,7 +266,7 @@ def main():
         rays_e = int(r.item())
     e2e = {"value": rays_e / e2e_s / 1e6, "unit": "Mrays/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
            "s_per_frame": e2e_s / args.steps,
-           "what": "b2rt_set_scene (host BVH build + upload) + set_camera + start/wait + read_rgba32f to host, per step"}
+           "what": "b2rt_set_scene (host BVH build + upload) + set_camera + start/wait + b2rt_get_image (frame to host), per step"}
 
     if rank != 0:
         if world > 1:

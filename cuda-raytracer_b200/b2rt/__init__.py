@@ -26,7 +26,7 @@ EXPORTS = [
     "b2rt_bvh_occluded", "b2rt_bvh_bench_rays", "b2rt_bvh_get_stats", "b2rt_bvh_get_bbox", "b2rt_bvh_destroy",
     "b2rt_create", "b2rt_set_config", "b2rt_set_scene", "b2rt_set_camera", "b2rt_set_frame_size", "b2rt_start",
     "b2rt_is_done", "b2rt_wait", "b2rt_stop", "b2rt_clear", "b2rt_render", "b2rt_read_hdr", "b2rt_read_ldr",
-    "b2rt_read_rgba32f", "b2rt_get_stats", "b2rt_accum_device_ptr", "b2rt_stream_handle", "b2rt_set_stream",
+    "b2rt_read_rgba32f", "b2rt_get_image", "b2rt_get_stats", "b2rt_accum_device_ptr", "b2rt_stream_handle", "b2rt_set_stream",
     "b2rt_set_profiling", "b2rt_destroy", "b2rt_bvh_validate_host",
     "b2rt_scene_load", "b2rt_scene_save", "b2rt_load_dae", "b2rt_scene_free", "b2rt_camera_place",
 ]
@@ -68,6 +68,7 @@ def lib():
         L.b2rt_read_hdr.argtypes = [vp, vp, C.c_size_t]
         L.b2rt_read_ldr.argtypes = [vp, vp, C.c_size_t]
         L.b2rt_read_rgba32f.argtypes = [vp, vp, C.c_size_t]
+        L.b2rt_get_image.argtypes = [vp, C.POINTER(C.POINTER(C.c_float)), C.POINTER(C.c_size_t)]
         L.b2rt_get_stats.argtypes = [vp, C.POINTER(Stats)]
         L.b2rt_accum_device_ptr.argtypes = [vp, C.POINTER(vp), C.POINTER(C.c_size_t)]
         L.b2rt_stream_handle.argtypes = [vp, C.POINTER(vp)]
@@ -308,6 +309,13 @@ class PathTracer:
         _check(lib().b2rt_read_rgba32f(self._h, out.ctypes.data, out.size))
         return out
 
+    def image(self):
+        """CudaRenderer::getImage: float4 RGBA view (height, width, 4) of the renderer-owned page-locked host buffer;
+        valid until the next call on this object (copy it to keep it)."""
+        p = C.POINTER(C.c_float)(); n = C.c_size_t(0)
+        _check(lib().b2rt_get_image(self._h, C.byref(p), C.byref(n)))
+        return np.ctypeslib.as_array(p, shape=(self.height, self.width, 4))
+
     def save_image(self, filename):
         """PNG, vertically flipped like PathTracer::save_image (src/pathtracer.cpp:577-591)."""
         from PIL import Image
@@ -379,4 +387,4 @@ class CudaRenderer:
         self.frames += 1
 
     def getImage(self):
-        return self.pt.rgba32f()
+        return self.pt.image()   # renderer-owned, valid until the next call (src/cudaRenderer.h:196)

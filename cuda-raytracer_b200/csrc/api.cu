@@ -373,6 +373,24 @@ int b2rt_read_rgba32f(b2rt_renderer* h, float* rgba, size_t n_floats) {
   B2RT_CUDA_OK(cudaStreamSynchronize(h->r.stream));
   return B2RT_OK;
 }
+int b2rt_get_image(b2rt_renderer* h, const float** rgba, size_t* n_floats) {
+  int rc = read_common(h, false);
+  if (rc) return rc;
+  if (!rgba) { set_error("null argument"); return B2RT_ERR_INVALID; }
+  Renderer& R = h->r;
+  const size_t np = (size_t)R.width * R.height;
+  if (R.host_image_cap < np * 4) {   // grow-only page-locked buffer
+    if (R.host_image) cudaFreeHost(R.host_image);
+    R.host_image = nullptr; R.host_image_cap = 0;
+    B2RT_CUDA_OK(cudaMallocHost(&R.host_image, np * 16));
+    R.host_image_cap = np * 4;
+  }
+  B2RT_CUDA_OK(cudaMemcpyAsync(R.host_image, R.resolved, np * 16, cudaMemcpyDeviceToHost, R.stream));
+  B2RT_CUDA_OK(cudaStreamSynchronize(R.stream));
+  *rgba = R.host_image;
+  if (n_floats) *n_floats = np * 4;
+  return B2RT_OK;
+}
 int b2rt_read_hdr(b2rt_renderer* h, float* rgb, size_t n_floats) {
   if (!h) { set_error("null handle"); return B2RT_ERR_INVALID; }
   const size_t np = (size_t)h->r.width * h->r.height;

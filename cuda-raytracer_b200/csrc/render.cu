@@ -498,6 +498,7 @@ void Renderer::destroy() {
   tracer.release();
   release_scene();
   free_ptr(accum); free_ptr(img_a); free_ptr(img_b); free_ptr(ldr);
+  if (host_image) { cudaFreeHost(host_image); host_image = nullptr; host_image_cap = 0; }
   if (ev_start) cudaEventDestroy(ev_start);
   if (ev_done) cudaEventDestroy(ev_done);
   if (own_stream) cudaStreamDestroy(own_stream);

@@ -26,6 +26,7 @@ struct Renderer {
   uint32_t width = 0, height = 0;
   void* accum = nullptr; void* img_a = nullptr; void* img_b = nullptr; uint32_t* ldr = nullptr;
   void* resolved = nullptr;
+  float* host_image = nullptr; size_t host_image_cap = 0;   // page-locked buffer behind b2rt_get_image (floats)
   uint64_t samples_done = 0, samples_pending = 0;
   // wave buffers
   uint64_t wave_cap = 0; uint32_t wave_S = 0;

@@ -225,7 +225,7 @@ class CudaRenderer {
     check(b2rt_create(&cfg_, &h_));
   }
   ~CudaRenderer() { b2rt_destroy(h_); delete scene_; }
-  void allocOutputImage(int width, int height) { w_ = width; hgt_ = height; check(b2rt_set_frame_size(h_, width, height)); image_.assign((size_t)w_ * hgt_ * 4, 0.f); }
+  void allocOutputImage(int width, int height) { w_ = width; hgt_ = height; check(b2rt_set_frame_size(h_, width, height)); }
   void loadScene(const std::string& name) { delete scene_; scene_ = new SceneFile(name); check(b2rt_set_scene(h_, scene_->desc())); }
   void setup() { b2rt_camera c = scene_->camera(w_, hgt_); check(b2rt_set_camera(h_, &c)); frames_ = 0; }
   void setViewpoint(const b2rt_camera& cam) { check(b2rt_set_camera(h_, &cam)); frames_ = 0; }   // resets accumulation, :1866-1869
@@ -237,8 +237,9 @@ class CudaRenderer {
     ++frames_;
   }
   const float* getImage() {                         // float4 RGBA, row-major x + y*w (NOT the reference's x*H + y)
-    check(b2rt_read_rgba32f(h_, image_.data(), image_.size()));
-    return image_.data();
+    const float* img = nullptr;                     // renderer-owned, valid until the next call (like the reference)
+    check(b2rt_get_image(h_, &img, nullptr));
+    return img;
   }
   b2rt_renderer* handle() const { return h_; }
 
@@ -246,7 +247,6 @@ class CudaRenderer {
   b2rt_renderer* h_ = nullptr;
   b2rt_config cfg_;
   SceneFile* scene_ = nullptr;
-  std::vector<float> image_;
   int w_ = 0, hgt_ = 0;
   uint32_t frames_ = 0;
 };

@@ -216,6 +216,11 @@ int b2rt_render(b2rt_renderer* r);
 int b2rt_read_hdr(b2rt_renderer* r, float* rgb, size_t n_floats);
 int b2rt_read_ldr(b2rt_renderer* r, uint32_t* rgba8, size_t n_pixels);
 int b2rt_read_rgba32f(b2rt_renderer* r, float* rgba, size_t n_floats);
+/* CudaRenderer::getImage (src/cudaRenderer.cu:1539-1570, src/cudaRenderer.h:196): resolves the current mean
+ * (+ median filter below the threshold), copies it into a renderer-owned page-locked host buffer and returns that
+ * buffer: float4 RGBA, row-major x + y*w, valid until the next call on this handle or b2rt_destroy.  No copy into a
+ * caller buffer, like the reference (`const Image* getImage()`). */
+int b2rt_get_image(b2rt_renderer* r, const float** rgba, size_t* n_floats);
 int b2rt_get_stats(b2rt_renderer* r, b2rt_stats* out);
 /* Multi-GPU: the per-GPU accumulation buffer (float4 per pixel: rgb SUM + sample count) that
  * one NCCL reduce combines (no reference equivalent; the reference is single-GPU).  The

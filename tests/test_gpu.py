@@ -336,3 +336,20 @@ def test_cpp_host_example(tmp_path):
     got = np.asarray(Image.open(out).convert("RGBA"))
     assert got.shape == ref.shape
     assert np.abs(got.astype(np.int32) - ref.astype(np.int32)).max() <= 1     # double vs float camera placement: <= 1 LSB
+
+
+def test_get_image_matches_read_rgba32f():
+    """b2rt_get_image (CudaRenderer::getImage: renderer-owned page-locked buffer) returns the same frame as the copying
+    b2rt_read_rgba32f, survives a resize, and stays valid until the next call."""
+    sc = Scene.load(scene_path("CBspheres_lambertian"))
+    pt = b2rt.PathTracer(ns_aa=4, max_ray_depth=3, ns_area_light=1, seed=5)
+    pt.set_scene(sc)
+    for (w, h) in ((96, 72), (160, 120), (64, 48)):
+        pt.set_camera(place_camera(sc, w, h)); pt.set_frame_size(w, h)
+        pt.render()
+        a = pt.rgba32f()
+        v = pt.image()
+        assert v.shape == (h, w, 4) and np.array_equal(v, a)
+        assert np.array_equal(pt.hdr(), a[..., :3])
+        assert np.array_equal(v, a)          # the view is not disturbed by other read-backs
+    pt.close()
