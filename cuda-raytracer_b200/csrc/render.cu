@@ -16,6 +16,9 @@
 
 #include <algorithm>
 #include <cmath>
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 
 #include "render.cuh"
@@ -514,11 +517,19 @@ int Renderer::set_stream(cudaStream_t s) {
 int Renderer::set_scene(const b2rt_scene_desc* d) {
   RCHECK(set_device());
   if (running) RCHECK(wait());
+  const bool verbose = getenv("B2RT_VERBOSE") != nullptr;
+  const auto t0 = std::chrono::steady_clock::now();
+  auto lap = [&](const char* what) {
+    if (verbose) fprintf(stderr, "b2rt: set_scene %-12s %8.3f ms\n", what, std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count());
+  };
   HostScene hs;
   RCHECK(make_host_scene(d, &hs));
+  lap("host scene");
   WideBVH wb;
   RCHECK(build_wide_bvh(hs, cfg.max_leaf_size, cfg.bvh_width, cfg.treelet_bytes, &wb));
+  lap("bvh build");
   RCHECK(upload_bvh(wb, &dbvh));   // grow-only device buffers: no cudaMalloc/cudaFree when the scene fits
+  lap("bvh upload");
   bvh_stale = true;                // wave buffers are kept; the tracer re-binds its (small) per-subtree arrays
   n_wide_nodes = wb.n_wide_nodes;
   build_ms = wb.build_ms;
@@ -575,6 +586,7 @@ int Renderer::set_scene(const b2rt_scene_desc* d) {
   lights_host = hs.lights;
   have_scene = true;
   B2RT_CUDA_OK(cudaDeviceSynchronize());   // uploads above used the legacy stream; work runs on `stream`
+  lap("scene upload");
   return B2RT_OK;
 }
 
