@@ -15,6 +15,9 @@
 #include <algorithm>
 #include <atomic>
 #include <chrono>
+#include <condition_variable>
+#include <functional>
+#include <mutex>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -53,18 +56,105 @@ struct BinNode {
   uint32_t start = 0, count = 0;  // primitive range in the index array
 };
 
-// Binned-SAH binary builder.  The per-primitive passes (bounds, 3-axis binning) run on SSE registers: a box is two
-// __m128 (min xyz_, max xyz_), the centroid is recomputed instead of stored, and all three axes are binned in the
-// same pass over the primitives.
+// ---- worker pool of the host builder ---------------------------------------------------------------------------
+// One lazily created pool per process.  Workers sleep on a condition variable between builds and spin while a build
+// is running (a build is a few milliseconds of many short parallel regions; a condition-variable wake-up per region
+// would cost more than the region).  parallel_for hands out items one at a time under the pool mutex -- items are
+// coarse (thousands of primitives each).
+class BuildPool {
+ public:
+  static BuildPool& get() { static BuildPool p; return p; }
+  int workers() const { return (int)threads_.size(); }
+  // a build owns the pool from begin() to end(); a second concurrent build in the same process runs without it
+  bool begin() {
+    if (threads_.empty() || !owner_.try_lock()) return false;
+    { std::lock_guard<std::mutex> lk(m_); hot_ = true; hot_flag_.store(true); }
+    cv_.notify_all();
+    return true;
+  }
+  void end() {
+    { std::lock_guard<std::mutex> lk(m_); hot_ = false; hot_flag_.store(false); }
+    owner_.unlock();
+  }
+  void parallel_for(uint32_t n, const std::function<void(uint32_t)>& fn) {
+    if (n == 0) return;
+    {
+      std::lock_guard<std::mutex> lk(m_);
+      job_ = &fn; n_ = n; next_ = 0; remaining_.store(n); epoch_.fetch_add(1, std::memory_order_release);
+    }
+    for (;;) {   // the caller works too
+      uint32_t i;
+      { std::lock_guard<std::mutex> lk(m_); if (next_ >= n_) break; i = next_++; }
+      fn(i);
+      remaining_.fetch_sub(1);
+    }
+    while (remaining_.load() != 0) _mm_pause();
+  }
+
+ private:
+  BuildPool() {
+    unsigned hw = std::max(1u, std::thread::hardware_concurrency());
+    unsigned share = 1;   // ranks of one node share the host cores (torchrun exports LOCAL_WORLD_SIZE)
+    if (const char* e = getenv("LOCAL_WORLD_SIZE")) share = (unsigned)std::max(1, atoi(e));
+    unsigned want = std::min(16u, std::max(1u, hw / share));
+    if (const char* e = getenv("B2RT_BUILD_THREADS")) want = (unsigned)std::max(1, atoi(e));
+    for (unsigned t = 1; t < want; ++t) threads_.emplace_back([this] { worker(); });
+  }
+  ~BuildPool() {
+    { std::lock_guard<std::mutex> lk(m_); stop_ = true; }
+    cv_.notify_all();
+    for (auto& t : threads_) t.join();
+  }
+  void worker() {
+    uint64_t seen = 0;
+    std::unique_lock<std::mutex> lk(m_);
+    for (;;) {
+      while (epoch_.load() == seen && !stop_) {
+        if (hot_) {   // a build is running: spin on the epoch without touching the mutex
+          lk.unlock();
+          while (epoch_.load(std::memory_order_acquire) == seen && hot_flag_.load(std::memory_order_relaxed)) _mm_pause();
+          lk.lock();
+        } else cv_.wait(lk);
+      }
+      if (stop_) return;
+      seen = epoch_.load();
+      while (epoch_.load() == seen && next_ < n_) {
+        const uint32_t i = next_++;
+        const std::function<void(uint32_t)>* job = job_;
+        lk.unlock();
+        (*job)(i);
+        remaining_.fetch_sub(1);
+        lk.lock();
+      }
+    }
+  }
+  std::vector<std::thread> threads_;
+  std::mutex m_, owner_;
+  std::condition_variable cv_;
+  const std::function<void(uint32_t)>* job_ = nullptr;
+  uint32_t n_ = 0, next_ = 0;
+  std::atomic<uint64_t> epoch_{0};
+  std::atomic<uint32_t> remaining_{0};
+  std::atomic<bool> hot_flag_{false};
+  bool hot_ = false, stop_ = false;
+};
+
+// Binned-SAH binary builder.  The per-primitive passes (bounds, 3-axis binning, partition) run on SSE registers: a box
+// is two __m128 (min xyz_, max xyz_), the centroid is recomputed instead of stored, and all three axes are binned in
+// the same pass over the primitives.  Large nodes run their passes in parallel over chunks of the index range (the
+// merged bounds / bins / stable partition are exactly what the serial passes produce, so the tree does not depend on
+// the thread count); the subtrees below them are then built independently, one pool item each.
 struct BinaryBuilder {
+  static constexpr int NBMAX = 16;
+  struct Bounds { __m128 nmn, nmx, cmn, cmx; };
+  struct Bins { __m128 mn[3][NBMAX], mx[3][NBMAX]; uint32_t c[3][NBMAX]; };
+  struct Split { int axis = -1, bin = -1, nb = 0; float lo = 0.f, sc = 0.f; };
+
   std::vector<__m128> pmn, pmx;    // primitive boxes, lane 3 unused
   std::vector<uint32_t> idx, scratch_l, scratch_r;
   std::vector<BinNode> nodes;
   std::atomic<uint32_t> next_node{0};
-  std::atomic<int> live_threads{0};
   uint32_t max_leaf;
-  int max_threads;
-  uint32_t par_threshold = 8192;   // subtrees above this size are built by their own thread (up to max_threads)
 
   BinaryBuilder(const std::vector<Box>& pb, uint32_t ml) : max_leaf(ml) {
     size_t n = pb.size();
@@ -76,8 +166,6 @@ struct BinaryBuilder {
       pmx[i] = _mm_set_ps(0.f, pb[i].mx[2], pb[i].mx[1], pb[i].mx[0]);
     }
     nodes.resize(std::max<size_t>(1, 2 * n));
-    max_threads = (int)std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
-    if (const char* e = getenv("B2RT_BUILD_PAR")) par_threshold = (uint32_t)std::max(64, atoi(e));
   }
 
   static float area_of(__m128 mn, __m128 mx) {
@@ -86,110 +174,194 @@ struct BinaryBuilder {
     if (e[0] < 0 || e[1] < 0 || e[2] < 0) return 0.f;
     return 2.f * (e[0] * e[1] + e[1] * e[2] + e[2] * e[0]);
   }
-
-  uint32_t build(uint32_t b, uint32_t e) {
-    uint32_t me = next_node.fetch_add(1);
-    BinNode& nd = nodes[me];
+  static Bounds empty_bounds() {
     const __m128 pinf = _mm_set1_ps(std::numeric_limits<float>::infinity()), ninf = _mm_set1_ps(-std::numeric_limits<float>::infinity());
+    return Bounds{pinf, ninf, pinf, ninf};
+  }
+  static void merge(Bounds& a, const Bounds& b) {
+    a.nmn = _mm_min_ps(a.nmn, b.nmn); a.nmx = _mm_max_ps(a.nmx, b.nmx); a.cmn = _mm_min_ps(a.cmn, b.cmn); a.cmx = _mm_max_ps(a.cmx, b.cmx);
+  }
+  Bounds bounds_range(uint32_t b, uint32_t e) const {
+    Bounds r = empty_bounds();
     const __m128 half = _mm_set1_ps(0.5f);
-    __m128 nmn = pinf, nmx = ninf, cmn = pinf, cmx = ninf;
     for (uint32_t i = b; i < e; ++i) {
       const uint32_t p = idx[i];
       const __m128 mn = pmn[p], mx = pmx[p], c = _mm_mul_ps(half, _mm_add_ps(mn, mx));
-      nmn = _mm_min_ps(nmn, mn); nmx = _mm_max_ps(nmx, mx);
-      cmn = _mm_min_ps(cmn, c); cmx = _mm_max_ps(cmx, c);
+      r.nmn = _mm_min_ps(r.nmn, mn); r.nmx = _mm_max_ps(r.nmx, mx);
+      r.cmn = _mm_min_ps(r.cmn, c); r.cmx = _mm_max_ps(r.cmx, c);
     }
-    alignas(16) float t4[4];
-    _mm_store_ps(t4, nmn); nd.box.mn[0] = t4[0]; nd.box.mn[1] = t4[1]; nd.box.mn[2] = t4[2];
-    _mm_store_ps(t4, nmx); nd.box.mx[0] = t4[0]; nd.box.mx[1] = t4[1]; nd.box.mx[2] = t4[2];
-    nd.start = b; nd.count = e - b; nd.left = nd.right = 0;
-    if (e - b <= max_leaf) return me;
-
-    // bins: 16 for big nodes, fewer for small ones (most nodes are small; resetting and sweeping 3 x 16 bins
-    // would dominate the build)
-    constexpr int NBMAX = 16;
-    const int NB = (e - b) >= 64 ? 16 : ((e - b) >= 16 ? 8 : 4);
-    alignas(16) float lo3[4], hi3[4], scale3[4];
-    _mm_store_ps(lo3, cmn); _mm_store_ps(hi3, cmx);
-    bool use[3];
+    return r;
+  }
+  // bin geometry of a node: 16 bins for big nodes, fewer for small ones (most nodes are small; resetting and sweeping
+  // 3 x 16 bins would dominate the build)
+  struct BinSetup { int nb; bool use[3]; alignas(16) float lo3[4]; alignas(16) float scale3[4]; };
+  static BinSetup bin_setup(const Bounds& bd, uint32_t count) {
+    BinSetup s;
+    s.nb = count >= 64 ? 16 : (count >= 16 ? 8 : 4);
+    alignas(16) float hi3[4];
+    _mm_store_ps(s.lo3, bd.cmn); _mm_store_ps(hi3, bd.cmx);
     for (int a = 0; a < 3; ++a) {
-      const float ext = hi3[a] - lo3[a];
-      use[a] = ext > 0.f;
-      scale3[a] = use[a] ? (float)NB / ext : 0.f;
+      const float ext = hi3[a] - s.lo3[a];
+      s.use[a] = ext > 0.f;
+      s.scale3[a] = s.use[a] ? (float)s.nb / ext : 0.f;
     }
-    scale3[3] = 0.f;
-    const __m128 scale = _mm_load_ps(scale3), kmax = _mm_set1_ps((float)(NB - 1)), zero = _mm_setzero_ps();
-    __m128 bmn[3][NBMAX], bmx[3][NBMAX]; uint32_t bc[3][NBMAX];
+    s.scale3[3] = 0.f;
+    return s;
+  }
+  static void reset(Bins& B, int nb) {
+    const __m128 pinf = _mm_set1_ps(std::numeric_limits<float>::infinity()), ninf = _mm_set1_ps(-std::numeric_limits<float>::infinity());
     for (int a = 0; a < 3; ++a)
-      for (int k = 0; k < NB; ++k) { bmn[a][k] = pinf; bmx[a][k] = ninf; bc[a][k] = 0; }
+      for (int k = 0; k < nb; ++k) { B.mn[a][k] = pinf; B.mx[a][k] = ninf; B.c[a][k] = 0; }
+  }
+  static void merge(Bins& A, const Bins& B, int nb) {
+    for (int a = 0; a < 3; ++a)
+      for (int k = 0; k < nb; ++k) { A.mn[a][k] = _mm_min_ps(A.mn[a][k], B.mn[a][k]); A.mx[a][k] = _mm_max_ps(A.mx[a][k], B.mx[a][k]); A.c[a][k] += B.c[a][k]; }
+  }
+  void bin_range(uint32_t b, uint32_t e, const Bounds& bd, const BinSetup& s, Bins& B) const {
+    const __m128 half = _mm_set1_ps(0.5f), scale = _mm_load_ps(s.scale3), kmax = _mm_set1_ps((float)(s.nb - 1)), zero = _mm_setzero_ps();
     for (uint32_t i = b; i < e; ++i) {
       const uint32_t p = idx[i];
       const __m128 mn = pmn[p], mx = pmx[p], c = _mm_mul_ps(half, _mm_add_ps(mn, mx));
-      const __m128 kf = _mm_min_ps(_mm_max_ps(_mm_mul_ps(_mm_sub_ps(c, cmn), scale), zero), kmax);
+      const __m128 kf = _mm_min_ps(_mm_max_ps(_mm_mul_ps(_mm_sub_ps(c, bd.cmn), scale), zero), kmax);
       alignas(16) int k4[4];
       _mm_store_si128(reinterpret_cast<__m128i*>(k4), _mm_cvttps_epi32(kf));
       for (int a = 0; a < 3; ++a) {
-        if (!use[a]) continue;
+        if (!s.use[a]) continue;
         const int k = k4[a];
-        bmn[a][k] = _mm_min_ps(bmn[a][k], mn); bmx[a][k] = _mm_max_ps(bmx[a][k], mx); bc[a][k]++;
+        B.mn[a][k] = _mm_min_ps(B.mn[a][k], mn); B.mx[a][k] = _mm_max_ps(B.mx[a][k], mx); B.c[a][k]++;
       }
     }
+  }
+  static Split pick_split(const Bins& B, const BinSetup& s) {
+    const __m128 pinf = _mm_set1_ps(std::numeric_limits<float>::infinity()), ninf = _mm_set1_ps(-std::numeric_limits<float>::infinity());
+    Split sp; sp.nb = s.nb;
     float best_cost = std::numeric_limits<float>::infinity();
-    int best_axis = -1, best_bin = -1;
+    const int NB = s.nb;
     for (int a = 0; a < 3; ++a) {
-      if (!use[a]) continue;
+      if (!s.use[a]) continue;
       float ra[NBMAX]; uint32_t rc[NBMAX];
       __m128 amn = pinf, amx = ninf; uint32_t c = 0;
-      for (int k = NB - 1; k > 0; --k) { amn = _mm_min_ps(amn, bmn[a][k]); amx = _mm_max_ps(amx, bmx[a][k]); c += bc[a][k]; ra[k] = area_of(amn, amx); rc[k] = c; }
+      for (int k = NB - 1; k > 0; --k) { amn = _mm_min_ps(amn, B.mn[a][k]); amx = _mm_max_ps(amx, B.mx[a][k]); c += B.c[a][k]; ra[k] = area_of(amn, amx); rc[k] = c; }
       amn = pinf; amx = ninf; c = 0;
       for (int k = 0; k < NB - 1; ++k) {
-        amn = _mm_min_ps(amn, bmn[a][k]); amx = _mm_max_ps(amx, bmx[a][k]); c += bc[a][k];
+        amn = _mm_min_ps(amn, B.mn[a][k]); amx = _mm_max_ps(amx, B.mx[a][k]); c += B.c[a][k];
         if (c == 0 || rc[k + 1] == 0) continue;
         float cost = area_of(amn, amx) * (float)c + ra[k + 1] * (float)rc[k + 1];
-        if (cost < best_cost) { best_cost = cost; best_axis = a; best_bin = k; }
+        if (cost < best_cost) { best_cost = cost; sp.axis = a; sp.bin = k; }
       }
     }
-    uint32_t mid;
-    if (best_axis >= 0) {
-      const float lo = lo3[best_axis], sc = scale3[best_axis];
-      const int ax = best_axis;
-      // branch-free stable partition through two scratch ranges (the side of a primitive is a coin flip for the
-      // branch predictor; std::partition spent a third of the build in mispredictions)
-      uint32_t nl = 0, nr = 0;
+    if (sp.axis >= 0) { sp.lo = s.lo3[sp.axis]; sp.sc = s.scale3[sp.axis]; }
+    return sp;
+  }
+  // branch-free stable partition of idx[b, e) into L / R scratch (the side of a primitive is a coin flip for the branch
+  // predictor; std::partition spent a third of the build in mispredictions); returns the number that went left
+  uint32_t split_range(uint32_t b, uint32_t e, const Split& sp, uint32_t* L, uint32_t* R) const {
+    uint32_t nl = 0, nr = 0;
+    const float kmaxf = (float)(sp.nb - 1);
+    const int ax = sp.axis;
+    for (uint32_t i = b; i < e; ++i) {
+      const uint32_t p = idx[i];
+      const float* mn = reinterpret_cast<const float*>(&pmn[p]); const float* mx = reinterpret_cast<const float*>(&pmx[p]);
+      float kf = (0.5f * (mn[ax] + mx[ax]) - sp.lo) * sp.sc;
+      kf = std::min(std::max(kf, 0.f), kmaxf);
+      const uint32_t left = (int)kf <= sp.bin ? 1u : 0u;
+      L[nl] = p; R[nr] = p;
+      nl += left; nr += 1u - left;
+    }
+    return nl;
+  }
+  void set_node(uint32_t me, uint32_t b, uint32_t e, const Bounds& bd) {
+    BinNode& nd = nodes[me];
+    alignas(16) float t4[4];
+    _mm_store_ps(t4, bd.nmn); nd.box.mn[0] = t4[0]; nd.box.mn[1] = t4[1]; nd.box.mn[2] = t4[2];
+    _mm_store_ps(t4, bd.nmx); nd.box.mx[0] = t4[0]; nd.box.mx[1] = t4[1]; nd.box.mx[2] = t4[2];
+    nd.start = b; nd.count = e - b; nd.left = nd.right = 0;
+  }
+
+  // serial recursive build of idx[b, e)
+  uint32_t build(uint32_t b, uint32_t e) {
+    const uint32_t me = next_node.fetch_add(1);
+    const Bounds bd = bounds_range(b, e);
+    set_node(me, b, e, bd);
+    if (e - b <= max_leaf) return me;
+    const BinSetup bs = bin_setup(bd, e - b);
+    Bins B; reset(B, bs.nb);
+    bin_range(b, e, bd, bs, B);
+    const Split sp = pick_split(B, bs);
+    uint32_t mid = b;
+    if (sp.axis >= 0) {
       uint32_t* L = scratch_l.data() + b; uint32_t* R = scratch_r.data() + b;
-      const float kmaxf = (float)(NB - 1);
-      for (uint32_t i = b; i < e; ++i) {
-        const uint32_t p = idx[i];
-        const float* mn = reinterpret_cast<const float*>(&pmn[p]); const float* mx = reinterpret_cast<const float*>(&pmx[p]);
-        float kf = (0.5f * (mn[ax] + mx[ax]) - lo) * sc;
-        kf = std::min(std::max(kf, 0.f), kmaxf);
-        const uint32_t left = (int)kf <= best_bin ? 1u : 0u;
-        L[nl] = p; R[nr] = p;
-        nl += left; nr += 1u - left;
-      }
+      const uint32_t nl = split_range(b, e, sp, L, R);
       memcpy(idx.data() + b, L, (size_t)nl * 4);
-      memcpy(idx.data() + b + nl, R, (size_t)nr * 4);
+      memcpy(idx.data() + b + nl, R, (size_t)(e - b - nl) * 4);
       mid = b + nl;
-    } else {
-      mid = b;
     }
-    if (mid == b || mid == e) {  // all centroids coincide (or binning degenerate): split by index
-      mid = b + (e - b) / 2;
-    }
-    uint32_t l, r;
-    if (e - b > par_threshold && live_threads.load() < max_threads) {
-      live_threads.fetch_add(1);
-      uint32_t lres = 0;
-      std::thread t([&]() { lres = build(b, mid); live_threads.fetch_sub(1); });
-      r = build(mid, e);
-      t.join();
-      l = lres;
-    } else {
-      l = build(b, mid);
-      r = build(mid, e);
-    }
+    if (mid == b || mid == e) mid = b + (e - b) / 2;   // all centroids coincide (or binning degenerate): split by index
+    const uint32_t l = build(b, mid);
+    const uint32_t r = build(mid, e);
     nodes[me].left = l; nodes[me].right = r;
     return me;
+  }
+
+  // one large node with its three passes spread over the pool; returns mid
+  uint32_t split_node_parallel(BuildPool& pool, uint32_t me, uint32_t b, uint32_t e) {
+    const uint32_t n = e - b;
+    const uint32_t nchunk = std::min<uint32_t>((uint32_t)pool.workers() + 1, std::max(1u, n / 1024u));
+    auto lo_of = [&](uint32_t c) { return b + (uint32_t)((uint64_t)n * c / nchunk); };
+    std::vector<Bounds> cb(nchunk);
+    pool.parallel_for(nchunk, [&](uint32_t c) { cb[c] = bounds_range(lo_of(c), lo_of(c + 1)); });
+    Bounds bd = empty_bounds();
+    for (auto& x : cb) merge(bd, x);
+    set_node(me, b, e, bd);
+    if (n <= max_leaf) return b;
+    const BinSetup bs = bin_setup(bd, n);
+    std::vector<Bins> bins(nchunk);
+    pool.parallel_for(nchunk, [&](uint32_t c) { reset(bins[c], bs.nb); bin_range(lo_of(c), lo_of(c + 1), bd, bs, bins[c]); });
+    for (uint32_t c = 1; c < nchunk; ++c) merge(bins[0], bins[c], bs.nb);
+    const Split sp = pick_split(bins[0], bs);
+    uint32_t mid = b;
+    if (sp.axis >= 0) {
+      // chunk c partitions into scratch[lo_of(c) ..); the left parts are then packed in chunk order, then the right parts
+      std::vector<uint32_t> nl(nchunk);
+      pool.parallel_for(nchunk, [&](uint32_t c) { nl[c] = split_range(lo_of(c), lo_of(c + 1), sp, scratch_l.data() + lo_of(c), scratch_r.data() + lo_of(c)); });
+      std::vector<uint32_t> offl(nchunk), offr(nchunk);
+      uint32_t tl = 0;
+      for (uint32_t c = 0; c < nchunk; ++c) { offl[c] = tl; tl += nl[c]; }
+      uint32_t tr = 0;
+      for (uint32_t c = 0; c < nchunk; ++c) { offr[c] = tl + tr; tr += (lo_of(c + 1) - lo_of(c)) - nl[c]; }
+      pool.parallel_for(nchunk, [&](uint32_t c) {
+        memcpy(idx.data() + b + offl[c], scratch_l.data() + lo_of(c), (size_t)nl[c] * 4);
+        memcpy(idx.data() + b + offr[c], scratch_r.data() + lo_of(c), (size_t)((lo_of(c + 1) - lo_of(c)) - nl[c]) * 4);
+      });
+      mid = b + tl;
+    }
+    if (mid == b || mid == e) mid = b + n / 2;
+    return mid;
+  }
+
+  void build_all(uint32_t n) {
+    BuildPool& pool = BuildPool::get();
+    uint32_t serial_below = 4096;   // subtrees this small are pool items, built by build()
+    if (const char* e = getenv("B2RT_BUILD_SERIAL_BELOW")) serial_below = (uint32_t)std::max(256, atoi(e));
+    if (n <= serial_below || !pool.begin()) { build(0, n); return; }
+    struct Item { uint32_t b, e, parent, side; };   // side 0 / 1 = left / right of `parent`; parent 0xFFFFFFFF = root
+    std::vector<Item> level{{0u, n, 0xFFFFFFFFu, 0u}}, small;
+    while (!level.empty()) {
+      std::vector<Item> next;
+      for (const Item& it : level) {
+        if (it.e - it.b <= serial_below) { small.push_back(it); continue; }
+        const uint32_t me = next_node.fetch_add(1);
+        if (it.parent != 0xFFFFFFFFu) (it.side ? nodes[it.parent].right : nodes[it.parent].left) = me;
+        const uint32_t mid = split_node_parallel(pool, me, it.b, it.e);
+        next.push_back({it.b, mid, me, 0u});
+        next.push_back({mid, it.e, me, 1u});
+      }
+      level.swap(next);
+    }
+    std::vector<uint32_t> res(small.size());
+    pool.parallel_for((uint32_t)small.size(), [&](uint32_t k) { res[k] = build(small[k].b, small[k].e); });
+    for (size_t k = 0; k < small.size(); ++k) (small[k].side ? nodes[small[k].parent].right : nodes[small[k].parent].left) = res[k];
+    pool.end();
   }
 };
 
@@ -307,7 +479,7 @@ int build_wide_bvh(const HostScene& sc, uint32_t max_leaf, uint32_t width, uint3
   lap("boxes");
   // ---- binary build ----
   BinaryBuilder bb(pbox, max_leaf);
-  if (n) bb.build(0, n);
+  if (n) bb.build_all(n);
   lap("binary");
 
   // ---- collapse to W-wide ----

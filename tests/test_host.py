@@ -259,3 +259,17 @@ REF_SCENES = {"CBbunny": "advanced/CBbunny.dae", "CBcoil": "advanced/CBcoil.dae"
 def test_load_dae_reference_media(name):
     """Every bundled scene under scenes/ is what the C++ loader makes of the reference's own .dae."""
     _same_scene(b2rt.load_dae(os.path.join(REF_MEDIA, REF_SCENES[name])), Scene.load(scene_path(name)))
+
+
+def test_parallel_build_matches_serial_build():
+    """The host builder's worker pool (parallel bounds / binning / partition of large nodes, subtrees as pool items)
+    must produce the tree the single-threaded build produces: same subtree / node / leaf / exit counts and blob size."""
+    code = ("import sys, json; sys.path.insert(0, %r); import b2rt; from b2rt.scene import Scene, random_soup; "
+            "sc = Scene.load(%r); out = [b2rt.validate_bvh_host(sc, 4, 4, 0), b2rt.validate_bvh_host(sc, 2, 8, 0), "
+            "b2rt.validate_bvh_host(random_soup(150000), 4, 4, 0)]; print(json.dumps(out))"
+            % (os.path.join(ROOT, "cuda-raytracer_b200"), scene_path("CBbunny")))
+    res = []
+    for threads in ("1", "3", "8"):
+        env = dict(os.environ, B2RT_BUILD_THREADS=threads)
+        res.append(subprocess.check_output([sys.executable, "-c", code], env=env, text=True).strip().splitlines()[-1])
+    assert res[0] == res[1] == res[2], res
