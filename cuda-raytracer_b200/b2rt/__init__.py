@@ -23,7 +23,7 @@ LIB_PATH = os.environ.get("B2RT_LIB") or os.path.join(os.path.dirname(_HERE), "l
 
 EXPORTS = [
     "b2rt_last_error", "b2rt_abi_version", "b2rt_device_count", "b2rt_bvh_build", "b2rt_bvh_intersect",
-    "b2rt_bvh_occluded", "b2rt_bvh_bench_rays", "b2rt_bvh_get_stats", "b2rt_bvh_get_bbox", "b2rt_bvh_destroy",
+    "b2rt_bvh_occluded", "b2rt_bvh_bench_rays", "b2rt_bvh_set_slicing", "b2rt_bvh_get_stats", "b2rt_bvh_get_bbox", "b2rt_bvh_destroy",
     "b2rt_create", "b2rt_set_config", "b2rt_set_scene", "b2rt_set_camera", "b2rt_set_frame_size", "b2rt_start",
     "b2rt_is_done", "b2rt_wait", "b2rt_stop", "b2rt_clear", "b2rt_render", "b2rt_read_hdr", "b2rt_read_ldr",
     "b2rt_read_rgba32f", "b2rt_get_image", "b2rt_get_stats", "b2rt_accum_device_ptr", "b2rt_stream_handle", "b2rt_set_stream",
@@ -55,6 +55,7 @@ def lib():
         L.b2rt_bvh_intersect.argtypes = [vp, vp, vp, vp, vp, u64, vp, vp]
         L.b2rt_bvh_occluded.argtypes = [vp, vp, vp, vp, vp, u64, vp]
         L.b2rt_bvh_bench_rays.argtypes = [vp, u64, C.c_int, u64, C.c_int, C.c_int, C.POINTER(C.c_double), C.POINTER(u64)]
+        L.b2rt_bvh_set_slicing.argtypes = [vp, C.c_float, C.c_float, i32]
         L.b2rt_bvh_get_stats.argtypes = [vp, C.POINTER(Stats)]
         L.b2rt_bvh_get_bbox.argtypes = [vp, vp]
         L.b2rt_bvh_destroy.argtypes = [vp]; L.b2rt_bvh_destroy.restype = None
@@ -189,6 +190,10 @@ class BVHAccel:
         ms = C.c_double(0); hits = C.c_uint64(0)
         _check(lib().b2rt_bvh_bench_rays(self._h, n, mode, seed, repeats, int(any_hit), C.byref(ms), C.byref(hits)))
         return ms.value, hits.value
+
+    def set_slicing(self, first_slice=-1.0, growth=4.0, passes=4):
+        """Distance slices of the batch traversal (b2rt_bvh_set_slicing): > 0 explicit first slice, 0 off, < 0 automatic."""
+        _check(lib().b2rt_bvh_set_slicing(self._h, first_slice, growth, passes))
 
     def stats(self):
         s = Stats()

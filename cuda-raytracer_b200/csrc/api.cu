@@ -111,6 +111,22 @@ int ensure_rays(b2rt_bvh* b, uint64_t n, uint32_t pair_factor = 6) {
   return B2RT_OK;
 }
 
+// distance slicing of the batch traversal (b2rt_bvh_set_slicing)
+void configure_slicing(b2rt_bvh* b, float first, float growth, int passes) {
+  Tracer& T = b->tracer;
+  const float* bb = b->host_meta.bbox;
+  for (int k = 0; k < 6; ++k) T.slice_bbox[k] = bb[k];
+  const float ex = bb[3] - bb[0], ey = bb[4] - bb[1], ez = bb[5] - bb[2];
+  const float diag = std::sqrt(ex * ex + ey * ey + ez * ez);
+  if (first < 0.f) {
+    const float want = 2.f * b->host_meta.mean_free_path;   // profiles/r01_sweep_slices.txt
+    first = (b->dbvh.n_levels >= 3 && want > 0.f && want < 0.125f * diag) ? want : 0.f;
+  }
+  T.slice_first = first;
+  T.slice_growth = growth > 1.f ? growth : 4.f;
+  T.slice_passes = passes >= 2 ? std::min(passes, 16) : 4;
+}
+
 int has_device() {
   int n = 0;
   if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
@@ -150,7 +166,7 @@ int intersect_host(b2rt_bvh* b, const float* org, const float* dir, const float*
       cudaMemcpyAsync(b->n_dev, &m32, 4, cudaMemcpyHostToDevice, s);
       cudaEventRecord(e0, s);
       k_pack_rays<<<(m32 + 255) / 256, 256, 0, s>>>(d_org, d_dir, d_tmin, d_tmax, m32, b->ray_o, b->ray_d, b->hits);
-      rc = b->tracer.trace(s, b->ray_o, b->ray_d, b->hits, b->n_dev, any_hit);
+      rc = b->tracer.trace_sliced(s, b->ray_o, b->ray_d, b->hits, b->n_dev, m, any_hit);
       if (rc) { cleanup(); return rc; }
       k_unpack_hits<<<(m32 + 255) / 256, 256, 0, s>>>(b->hits, m32, d_t, d_prim, d_occ);
       cudaEventRecord(e1, s);
@@ -213,7 +229,15 @@ int b2rt_bvh_build(const b2rt_scene_desc* scene, uint32_t max_leaf_size, uint32_
   B2RT_CUDA_OK(cudaMalloc(&b->n_dev, 4));
   b->tracer.bvh = b->dbvh;
   b->tracer.collect_stats = true;
+  configure_slicing(b, -1.f, 0.f, 0);
   *out = b;
+  return B2RT_OK;
+}
+
+int b2rt_bvh_set_slicing(b2rt_bvh* b, float first_slice, float growth, int32_t passes) {
+  if (!b) { set_error("null argument"); return B2RT_ERR_INVALID; }
+  if (!(first_slice == first_slice)) { set_error("first_slice is NaN"); return B2RT_ERR_INVALID; }
+  configure_slicing(b, first_slice, growth, passes);
   return B2RT_OK;
 }
 
@@ -246,7 +270,7 @@ int b2rt_bvh_bench_rays(b2rt_bvh* b, uint64_t n, int mode, uint64_t seed, int re
     for (uint32_t first = 0; first < n32; first += sub) {
       const uint32_t m = std::min(sub, n32 - first);
       B2RT_CUDA_OK(cudaMemcpyAsync(b->n_dev, &m, 4, cudaMemcpyHostToDevice, s));
-      int r2 = b->tracer.trace(s, b->ray_o + first, b->ray_d + first, b->hits + first, b->n_dev, any_hit != 0);
+      int r2 = b->tracer.trace_sliced(s, b->ray_o + first, b->ray_d + first, b->hits + first, b->n_dev, m, any_hit != 0);
       if (r2) return r2;
     }
     return B2RT_OK;

@@ -55,6 +55,7 @@ struct WideBVH {
   uint32_t n_wide_nodes = 0;
   uint32_t max_treelet_bytes = 0;
   float bbox[6] = {0, 0, 0, 0, 0, 0};
+  float mean_free_path = 0;             // scene-box volume / summed projected primitive area (slice length scale)
   double build_ms = 0;
 };
 

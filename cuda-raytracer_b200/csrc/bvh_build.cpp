@@ -449,14 +449,19 @@ int build_wide_bvh(const HostScene& sc, uint32_t max_leaf, uint32_t width, uint3
   // primitive boxes, padded so the fp32 slab test stays conservative w.r.t. the primitive tests
   std::vector<Box> pbox(n);
   Box scene_box; scene_box.reset();
+  double projected = 0;   // sum of the primitives' direction-averaged projected areas (triangle: area / 2)
   for (uint32_t i = 0; i < n; ++i) {
     const float* g = &sc.prim_geom[(size_t)i * 12];
     Box b; b.reset();
     if (i < sc.n_tris) {
       float p1[3] = {g[0], g[1], g[2]}, p2[3] = {g[0] + g[3], g[1] + g[4], g[2] + g[5]}, p3[3] = {g[0] + g[6], g[1] + g[7], g[2] + g[8]};
       b.grow(p1); b.grow(p2); b.grow(p3);
+      const double cx = (double)g[4] * g[8] - (double)g[5] * g[7], cy = (double)g[5] * g[6] - (double)g[3] * g[8],
+                   cz = (double)g[3] * g[7] - (double)g[4] * g[6];
+      projected += 0.25 * std::sqrt(cx * cx + cy * cy + cz * cz);
     } else {
       for (int a = 0; a < 3; ++a) { b.mn[a] = g[a] - g[3]; b.mx[a] = g[a] + g[3]; }
+      projected += 3.14159265358979 * (double)g[3] * g[3];
     }
     pbox[i] = b;
     scene_box.grow(b);
@@ -471,6 +476,13 @@ int build_wide_bvh(const HostScene& sc, uint32_t max_leaf, uint32_t width, uint3
   for (auto& b : pbox)
     for (int a = 0; a < 3; ++a) { b.mn[a] -= pad; b.mx[a] += pad; }
   for (int a = 0; a < 3; ++a) { out->bbox[a] = n ? scene_box.mn[a] : 0.f; out->bbox[3 + a] = n ? scene_box.mx[a] : 0.f; }
+  // mean free path of a random ray through the scene box if the primitives were spread evenly in it: volume / summed
+  // projected area.  Only a scale for the distance slices of Tracer::trace_sliced, never a correctness input.
+  out->mean_free_path = 0.f;
+  if (n && projected > 0) {
+    const double vol = (double)(scene_box.mx[0] - scene_box.mn[0]) * (scene_box.mx[1] - scene_box.mn[1]) * (scene_box.mx[2] - scene_box.mn[2]);
+    out->mean_free_path = (float)(vol / projected);
+  }
 
   const bool verbose = getenv("B2RT_VERBOSE") != nullptr;
   auto lap = [&](const char* what) {

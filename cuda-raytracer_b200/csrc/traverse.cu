@@ -743,6 +743,128 @@ k_traverse(const TravParams P) {
   }
 }
 
+// ---- distance-sliced tracing: list set-up and advance (Tracer::trace_sliced) ------------------------------------
+// CTA-aggregated append (256 threads): one global atomic per CTA; returns the list index of the flagged threads.
+// Called by every thread of the CTA.
+__device__ __forceinline__ uint32_t cta_append(bool flag, uint32_t* counter, uint32_t* s_warp) {
+  const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const uint32_t m = __ballot_sync(0xffffffffu, flag);
+  if (lane == 0) s_warp[warp] = __popc(m);
+  __syncthreads();
+  if (warp == 0) {
+    const uint32_t c = lane < 8 ? s_warp[lane] : 0u;
+    uint32_t incl = c;
+#pragma unroll
+    for (int dlt = 1; dlt < 8; dlt <<= 1) {
+      const uint32_t v = __shfl_up_sync(0xffffffffu, incl, dlt);
+      if (lane >= (uint32_t)dlt) incl += v;
+    }
+    const uint32_t total = __shfl_sync(0xffffffffu, incl, 7);
+    uint32_t base = 0;
+    if (lane == 0 && total) base = atomicAdd(counter, total);
+    base = __shfl_sync(0xffffffffu, base, 0);
+    if (lane < 8) s_warp[lane] = base + incl - c;
+  }
+  __syncthreads();
+  const uint32_t r = s_warp[warp] + __popc(m & ((1u << lane) - 1u));
+  __syncthreads();
+  return r;
+}
+
+// entry / exit distance of the ray against the scene box (conservativeness comes from the caller's margin)
+__device__ __forceinline__ void clip_scene_box(float4 o, float4 d, const float* bb, float* t_enter, float* t_exit) {
+  const float ix = fabsf(d.x) > 1e-18f ? __frcp_rn(d.x) : copysignf(1e18f, d.x);
+  const float iy = fabsf(d.y) > 1e-18f ? __frcp_rn(d.y) : copysignf(1e18f, d.y);
+  const float iz = fabsf(d.z) > 1e-18f ? __frcp_rn(d.z) : copysignf(1e18f, d.z);
+  const float ax = (bb[0] - o.x) * ix, bx = (bb[3] - o.x) * ix;
+  const float ay = (bb[1] - o.y) * iy, by = (bb[4] - o.y) * iy;
+  const float az = (bb[2] - o.z) * iz, bz = (bb[5] - o.z) * iz;
+  *t_enter = fmaxf(fmaxf(fminf(ax, bx), fminf(ay, by)), fminf(az, bz));
+  *t_exit = fminf(fminf(fmaxf(ax, bx), fmaxf(ay, by)), fmaxf(az, bz));
+}
+
+struct SliceList {
+  float4* o; float4* d; unsigned long long* h; uint32_t* map; float* exit; uint32_t* n;
+};
+struct SliceBox { float v[6]; float margin; };
+
+// First list: every ray that can hit the scene at all, with the interval [tmin, max(tmin, t_enter) + first].
+__global__ void __launch_bounds__(256)
+k_slice_init(const uint32_t* n_dev, const float4* __restrict__ ray_o, const float4* __restrict__ ray_d,
+             const unsigned long long* __restrict__ hits, SliceBox box, float first, bool any_hit, SliceList out) {
+  __shared__ uint32_t s_warp[8];
+  const uint32_t n = *n_dev;
+  const uint32_t per = (n + gridDim.x - 1) / gridDim.x;   // a contiguous range per CTA keeps neighbouring rays neighbours
+  const uint32_t lo = blockIdx.x * per, hi = min(n, lo + per);
+  for (uint32_t at = lo; at < hi; at += 256) {
+    const uint32_t i = at + threadIdx.x;
+    bool keep = false;
+    float4 o = make_float4(0, 0, 0, 0), d = make_float4(0, 0, 1, 0);
+    float t_end = 0.f, t_exit = 0.f;
+    if (i < hi) {
+      o = ray_o[i]; d = ray_d[i];
+      float t_enter;
+      clip_scene_box(o, d, box.v, &t_enter, &t_exit);
+      t_exit = t_exit + box.margin + 1e-4f * fabsf(t_exit);
+      t_enter = t_enter - box.margin - 1e-4f * fabsf(t_enter);
+      // dropped only when the comparison is TRUE (a NaN keeps the ray): the ray misses the padded box, the box is
+      // behind tmin, or beyond tmax
+      const bool miss = (t_enter > t_exit) || (t_exit < o.w) || (t_enter > d.w);
+      const bool done = any_hit && (uint32_t)hits[i] != 0xFFFFFFFFu;
+      keep = !miss && !done;
+      t_end = fminf(d.w, fmaxf(o.w, t_enter) + first);
+    }
+    const uint32_t k = cta_append(keep, out.n, s_warp);
+    if (keep) {
+      out.o[k] = o;
+      out.d[k] = make_float4(d.x, d.y, d.z, t_end);
+      out.h[k] = pack_hit(t_end, 0xFFFFFFFFu);
+      out.map[k] = i;
+      out.exit[k] = t_exit;
+    }
+  }
+}
+
+// After a pass: rays with a hit are final (their word goes to the caller's array); the others move on to the next
+// slice [end, end + len] unless they have left the scene or reached their own tmax.
+__global__ void __launch_bounds__(256)
+k_slice_advance(SliceList in, const float4* __restrict__ ray_d, unsigned long long* hits, float len, bool last, SliceList out) {
+  __shared__ uint32_t s_warp[8];
+  const uint32_t n = *in.n;
+  const uint32_t per = (n + gridDim.x - 1) / gridDim.x;
+  const uint32_t lo = blockIdx.x * per, hi = min(n, lo + per);
+  for (uint32_t at = lo; at < hi; at += 256) {
+    const uint32_t j = at + threadIdx.x;
+    bool keep = false;
+    float4 o = make_float4(0, 0, 0, 0), d = make_float4(0, 0, 1, 0);
+    float t_end = 0.f, t_exit = 0.f;
+    uint32_t i = 0;
+    if (j < hi) {
+      const unsigned long long h = in.h[j];
+      i = in.map[j];
+      if ((uint32_t)h != 0xFFFFFFFFu) {
+        hits[i] = h;
+      } else if (!last) {
+        d = in.d[j];
+        t_exit = in.exit[j];
+        const float t_user = ray_d[i].w;
+        const float t_lo = d.w;                    // the slice just traced ended here
+        keep = !(t_lo >= t_user) && !(t_lo > t_exit);
+        if (keep) { o = in.o[j]; o.w = t_lo; t_end = fminf(t_user, t_lo + len); }
+      }
+    }
+    if (last) continue;
+    const uint32_t k = cta_append(keep, out.n, s_warp);
+    if (keep) {
+      out.o[k] = o;
+      out.d[k] = make_float4(d.x, d.y, d.z, t_end);
+      out.h[k] = pack_hit(t_end, 0xFFFFFFFFu);
+      out.map[k] = i;
+      out.exit[k] = t_exit;
+    }
+  }
+}
+
 }  // namespace
 
 
@@ -878,6 +1000,11 @@ void Tracer::release() {
   cudaFree(ctrl); cudaFree(counters);
   cnt = seg_off = cursor = ids_sorted = ctrl = nullptr; pairs = nullptr; chunks = nullptr; counters = nullptr;
   pair_cap = 0; max_rays = 0; nt_cap = 0; chunk_alloc = 0;
+  for (int k = 0; k < 2; ++k) {
+    cudaFree(sl_o[k]); cudaFree(sl_d[k]); cudaFree(sl_h[k]); cudaFree(sl_map[k]); cudaFree(sl_exit[k]);
+    sl_o[k] = sl_d[k] = nullptr; sl_h[k] = nullptr; sl_map[k] = nullptr; sl_exit[k] = nullptr;
+  }
+  cudaFree(sl_n); sl_n = nullptr; slice_cap = 0;
 }
 
 template <int W>
@@ -936,6 +1063,57 @@ int Tracer::trace(cudaStream_t s, const float4* ray_o, const float4* ray_d, unsi
     else launch_traverse<4>(*this, s, P, any_hit, collect_stats);
     if (time_kernels) cudaEventRecord(e1, s);
     launches++; traverse_launches++;
+  }
+  B2RT_CUDA_OK(cudaGetLastError());
+  return B2RT_OK;
+}
+
+int Tracer::ensure_slices(uint64_t n) {
+  if (slice_cap >= n && sl_n) return B2RT_OK;
+  for (int k = 0; k < 2; ++k) {
+    cudaFree(sl_o[k]); cudaFree(sl_d[k]); cudaFree(sl_h[k]); cudaFree(sl_map[k]); cudaFree(sl_exit[k]);
+    sl_o[k] = sl_d[k] = nullptr; sl_h[k] = nullptr; sl_map[k] = nullptr; sl_exit[k] = nullptr;
+  }
+  slice_cap = 0;
+  for (int k = 0; k < 2; ++k) {
+    B2RT_CUDA_OK(cudaMalloc(&sl_o[k], (n + 16) * sizeof(float4)));
+    B2RT_CUDA_OK(cudaMalloc(&sl_d[k], (n + 16) * sizeof(float4)));
+    B2RT_CUDA_OK(cudaMalloc(&sl_h[k], (n + 16) * 8));
+    B2RT_CUDA_OK(cudaMalloc(&sl_map[k], (n + 16) * 4));
+    B2RT_CUDA_OK(cudaMalloc(&sl_exit[k], (n + 16) * 4));
+  }
+  if (!sl_n) B2RT_CUDA_OK(cudaMalloc(&sl_n, 2 * 4));
+  slice_cap = n;
+  return B2RT_OK;
+}
+
+int Tracer::trace_sliced(cudaStream_t s, const float4* ray_o, const float4* ray_d, unsigned long long* hits,
+                         const uint32_t* n_active_dev, uint64_t n_max, bool any_hit) {
+  if (!(slice_first > 0.f) || slice_passes < 2 || bvh.n_levels == 0) return trace(s, ray_o, ray_d, hits, n_active_dev, any_hit);
+  if (n_max > max_rays) { set_error("trace_sliced: batch larger than the tracer was initialised for"); return B2RT_ERR_INVALID; }
+  int rc = ensure_slices(n_max);
+  if (rc) return rc;
+  SliceBox box;
+  for (int k = 0; k < 6; ++k) box.v[k] = slice_bbox[k];
+  const float ex = slice_bbox[3] - slice_bbox[0], ey = slice_bbox[4] - slice_bbox[1], ez = slice_bbox[5] - slice_bbox[2];
+  box.margin = 1e-3f * std::sqrt(ex * ex + ey * ey + ez * ez);
+  SliceList L[2];
+  for (int k = 0; k < 2; ++k) L[k] = SliceList{sl_o[k], sl_d[k], sl_h[k], sl_map[k], sl_exit[k], sl_n + k};
+  const dim3 grid(num_sms * 8);
+  B2RT_CUDA_OK(cudaMemsetAsync(sl_n, 0, 8, s));
+  k_slice_init<<<grid, 256, 0, s>>>(n_active_dev, ray_o, ray_d, hits, box, slice_first, any_hit, L[0]);
+  launches++;
+  float len = slice_first;
+  for (int p = 0; p < slice_passes; ++p) {
+    const int cur = p & 1, nxt = cur ^ 1;
+    const bool last = p + 1 == slice_passes;
+    rc = trace(s, sl_o[cur], sl_d[cur], sl_h[cur], sl_n + cur, any_hit);
+    if (rc) return rc;
+    len *= slice_growth;
+    B2RT_CUDA_OK(cudaMemsetAsync(sl_n + nxt, 0, 4, s));
+    // the pass before the last hands the whole remainder to the last one
+    k_slice_advance<<<grid, 256, 0, s>>>(L[cur], ray_d, hits, p + 2 == slice_passes ? __builtin_huge_valf() : len, last, L[nxt]);
+    launches++;
   }
   B2RT_CUDA_OK(cudaGetLastError());
   return B2RT_OK;

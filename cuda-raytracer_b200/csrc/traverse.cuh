@@ -59,6 +59,28 @@ struct Tracer {
   int trace(cudaStream_t s, const float4* ray_o, const float4* ray_d, unsigned long long* hits,
             const uint32_t* n_active_dev, bool any_hit);
   int check_overflow(cudaStream_t s, bool* overflow);  // synchronises the stream
+
+  // ---- distance-sliced tracing (deep subtree graphs) ---------------------------------------------------------
+  // The breadth-first scheme has no front-to-back order ACROSS subtrees: a ray is queued at every subtree its whole
+  // interval overlaps before any hit is known.  trace_sliced() restores the order at batch granularity: pass p traces
+  // only the interval [lo_p, lo_p + first * growth^p] of every ray still without a hit (the last pass takes the rest),
+  // so the slab test culls everything behind the slice and rays that hit early never reach the far subtrees.  The
+  // result is the same (t, prim) argmin: a hit inside a slice beats everything in the later slices.
+  float slice_first = 0.f;         // length of the first slice (0 = slicing off)
+  float slice_growth = 4.f;
+  int slice_passes = 4;
+  float slice_bbox[6] = {0, 0, 0, 0, 0, 0};
+  uint64_t slice_cap = 0;
+  float4* sl_o[2] = {nullptr, nullptr};
+  float4* sl_d[2] = {nullptr, nullptr};
+  unsigned long long* sl_h[2] = {nullptr, nullptr};
+  uint32_t* sl_map[2] = {nullptr, nullptr};
+  float* sl_exit[2] = {nullptr, nullptr};
+  uint32_t* sl_n = nullptr;        // [2] device counts of the two lists
+  int ensure_slices(uint64_t n);
+  // same contract as trace(); n_max = host upper bound of *n_active_dev
+  int trace_sliced(cudaStream_t s, const float4* ray_o, const float4* ray_d, unsigned long long* hits,
+                   const uint32_t* n_active_dev, uint64_t n_max, bool any_hit);
 };
 
 enum { CTRL_PAIRS0 = 0, CTRL_PAIRS1 = 1, CTRL_NEXT0 = 2, CTRL_NEXT1 = 3, CTRL_OVERFLOW = 4, CTRL_NCHUNKS = 5 };

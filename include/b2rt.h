@@ -175,6 +175,14 @@ int b2rt_bvh_occluded(b2rt_bvh* bvh, const float* org, const float* dir, const f
  * times whole frames, src/cudaRenderer.cu:2558). */
 int b2rt_bvh_bench_rays(b2rt_bvh* bvh, uint64_t n, int mode, uint64_t seed, int repeats,
                         int any_hit, double* ms_per_repeat, uint64_t* hits);
+/* Distance slicing of the batch traversal (no reference equivalent; the reference's level-synchronous
+ * traversal, src/cudaRenderer.cu:2304-2331, has the same lack of front-to-back order across
+ * nodes).  Pass p traces only [lo, lo + first_slice * growth^p] of every ray still without a
+ * hit, the last of `passes` takes the remainder; results are identical to the unsliced trace.
+ * first_slice > 0: explicit length; 0: off; < 0: automatic (2 mean free paths of the scene, and
+ * only when the subtree graph has >= 3 levels and that length is below 1/8 of the scene
+ * diagonal -- the default after b2rt_bvh_build).  growth <= 1 or passes < 2 select 4 / 4. */
+int b2rt_bvh_set_slicing(b2rt_bvh* bvh, float first_slice, float growth, int32_t passes);
 int b2rt_bvh_get_stats(b2rt_bvh* bvh, b2rt_stats* out);
 /* get_bbox(): src/bvh.h:120-126.  out[6] = min xyz, max xyz */
 int b2rt_bvh_get_bbox(b2rt_bvh* bvh, float* out6);

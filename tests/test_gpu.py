@@ -151,6 +151,53 @@ def test_soup_parity_and_multilevel():
     assert (p != MISS).mean() > 0.5
 
 
+@pytest.mark.parametrize("first,growth,passes", [(0.05, 2.0, 3), (0.3, 4.0, 4), (1e-3, 8.0, 6), (10.0, 4.0, 2)])
+def test_distance_sliced_trace_is_identical(first, growth, passes):
+    """b2rt_bvh_set_slicing: tracing the rays slice by slice (front-to-back order across subtrees) must return the same
+    (t, prim) argmin and the same any-hit flags as the oracle, whatever the slice lengths -- including windows
+    [tmin, tmax], rays that start outside the scene box, rays that miss it, and slices far longer than the scene."""
+    sc = Scene.load(scene_path("CBbunny"))
+    o = orc.OracleScene(sc, 4)
+    bvh = b2rt.BVHAccel(sc, treelet_bytes=4096, max_leaf_size=2)
+    assert bvh.stats()["bvh_levels"] >= 3
+    bvh.set_slicing(first, growth, passes)
+    org, dirs = _mixed_rays(sc, 150001, 5)
+    far = _rays(sc, 5000, 6)
+    org = np.concatenate([org, far[0] * 3 + 5]); dirs = np.concatenate([dirs, -far[1]])     # from outside, mostly missing
+    t, p = bvh.intersect(org, dirs)
+    tr, pr = o.intersect(org, dirs, mode="bvh")
+    assert np.array_equal(p, pr), f"{np.sum(p != pr)} primitive ids differ of {len(org)}"
+    assert np.array_equal(t, tr)
+    rng = np.random.default_rng(2)
+    tmin = (rng.random(len(org)) * 0.5).astype(np.float32)
+    tmax = (tmin + rng.random(len(org)) * 3).astype(np.float32)
+    t, p = bvh.intersect(org, dirs, tmin, tmax)
+    tr, pr = o.intersect(org, dirs, tmin, tmax)
+    assert np.array_equal(p, pr) and np.array_equal(t, tr)
+    occ = bvh.occluded(org, dirs, tmin, tmax)
+    assert np.array_equal(occ, pr != MISS)
+    bvh.close()
+
+
+def test_soup_automatic_slicing_parity_and_fewer_visits():
+    """On a deep subtree graph the automatic slices (2 mean free paths) are on by default: same hits as the oracle and
+    as the unsliced trace, with fewer subtree visits per ray."""
+    sc = random_soup(300000, size=0.02)
+    o = orc.OracleScene(sc, 4)
+    bvh = b2rt.BVHAccel(sc, treelet_bytes=16384)
+    org, dirs = _rays(sc, 200000, 22)
+    t, p = bvh.intersect(org, dirs)
+    v_sliced = bvh.stats()["subtree_visits"]
+    bvh.set_slicing(0.0)
+    t0, p0 = bvh.intersect(org, dirs)
+    v_plain = bvh.stats()["subtree_visits"]
+    assert np.array_equal(p, p0) and np.array_equal(t, t0)
+    tr, pr = o.intersect(org[:50000], dirs[:50000])
+    assert np.array_equal(p[:50000], pr) and np.array_equal(t[:50000], tr)
+    assert v_sliced < v_plain, (v_sliced, v_plain)
+    bvh.close()
+
+
 RENDER_CASES = [
     # scene, w, h, spp, depth, ns_area_light
     ("CBspheres_lambertian", 480, 360, 16, 4, 1),   # BASELINE configs[0] at full size
