@@ -22,7 +22,8 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("B2RT_LIB") or os.path.join(os.path.dirname(_HERE), "libb2rt.so")
 
 EXPORTS = [
-    "b2rt_last_error", "b2rt_abi_version", "b2rt_device_count", "b2rt_bvh_build", "b2rt_bvh_intersect",
+    "b2rt_last_error", "b2rt_abi_version", "b2rt_device_count", "b2rt_bvh_build", "b2rt_bvh_build_device", "b2rt_bvh_validate",
+    "b2rt_bvh_intersect",
     "b2rt_bvh_occluded", "b2rt_bvh_bench_rays", "b2rt_bvh_set_slicing", "b2rt_bvh_get_stats", "b2rt_bvh_get_bbox", "b2rt_bvh_destroy",
     "b2rt_create", "b2rt_set_config", "b2rt_set_scene", "b2rt_set_camera", "b2rt_set_frame_size", "b2rt_start",
     "b2rt_is_done", "b2rt_wait", "b2rt_stop", "b2rt_clear", "b2rt_render", "b2rt_read_hdr", "b2rt_read_ldr",
@@ -52,6 +53,8 @@ def lib():
         L.b2rt_last_error.restype = C.c_char_p
         vp, u32, u64, i32 = C.c_void_p, C.c_uint32, C.c_uint64, C.c_int32
         L.b2rt_bvh_build.argtypes = [C.POINTER(SceneDesc), u32, u32, u32, i32, C.POINTER(vp)]
+        L.b2rt_bvh_build_device.argtypes = [C.POINTER(SceneDesc), u32, u32, u32, i32, C.POINTER(vp)]
+        L.b2rt_bvh_validate.argtypes = [vp, C.POINTER(SceneDesc), vp]
         L.b2rt_bvh_intersect.argtypes = [vp, vp, vp, vp, vp, u64, vp, vp]
         L.b2rt_bvh_occluded.argtypes = [vp, vp, vp, vp, vp, u64, vp]
         L.b2rt_bvh_bench_rays.argtypes = [vp, u64, C.c_int, u64, C.c_int, C.c_int, C.POINTER(C.c_double), C.POINTER(u64)]
@@ -146,12 +149,23 @@ def validate_bvh_host(scene, max_leaf_size=4, width=4, treelet_bytes=0):
 class BVHAccel:
     """BVHAccel(primitives, max_leaf_size) -- src/bvh.h:110-112; closest / any-hit queries are batched."""
 
-    def __init__(self, scene, max_leaf_size=4, width=4, treelet_bytes=0, device=-1):
+    def __init__(self, scene, max_leaf_size=4, width=4, treelet_bytes=0, device=-1, builder="host"):
+        """builder: "host" = binned-SAH build on the host cores (b2rt_bvh_build), "gpu" = LBVH build on the device
+        (b2rt_bvh_build_device)."""
         d, keep = scene.desc()
         h = C.c_void_p()
-        _check(lib().b2rt_bvh_build(C.byref(d), max_leaf_size, width, treelet_bytes, device, C.byref(h)))
+        fn = {"host": lib().b2rt_bvh_build, "gpu": lib().b2rt_bvh_build_device}[builder]
+        _check(fn(C.byref(d), max_leaf_size, width, treelet_bytes, device, C.byref(h)))
         self._h = h
         self.scene = scene
+
+    def validate(self):
+        """Structural check of the device-resident BVH (b2rt_bvh_validate); returns the counts."""
+        d, keep = self.scene.desc()
+        out = np.zeros(8, np.uint64)
+        _check(lib().b2rt_bvh_validate(self._h, C.byref(d), out.ctypes.data))
+        keys = ("subtrees", "levels", "wide_nodes", "leaves", "blob_bytes", "max_subtree_bytes", "stack_bound", "exits")
+        return dict(zip(keys, (int(v) for v in out)))
 
     def close(self):
         if getattr(self, "_h", None):

@@ -30,6 +30,7 @@ struct b2rt_bvh {
   float4 *ray_o = nullptr, *ray_d = nullptr;
   unsigned long long* hits = nullptr;
   uint32_t* n_dev = nullptr;
+  uint32_t max_leaf = 4, treelet_budget = 0;   // as given to the builder (b2rt_bvh_validate)
   b2rt_stats last{};
 };
 struct b2rt_renderer { Renderer r; };
@@ -225,6 +226,7 @@ int b2rt_bvh_build(const b2rt_scene_desc* scene, uint32_t max_leaf_size, uint32_
   rc = upload_bvh(b->host_meta, &b->dbvh);
   if (rc) { delete b; return rc; }
   b->host_meta.blob.clear(); b->host_meta.blob.shrink_to_fit();
+  b->max_leaf = max_leaf_size ? max_leaf_size : 4; b->treelet_budget = treelet_bytes;
   B2RT_CUDA_OK(cudaStreamCreateWithFlags(&b->stream, cudaStreamNonBlocking));
   B2RT_CUDA_OK(cudaMalloc(&b->n_dev, 4));
   b->tracer.bvh = b->dbvh;
@@ -232,6 +234,48 @@ int b2rt_bvh_build(const b2rt_scene_desc* scene, uint32_t max_leaf_size, uint32_
   configure_slicing(b, -1.f, 0.f, 0);
   *out = b;
   return B2RT_OK;
+}
+
+int b2rt_bvh_build_device(const b2rt_scene_desc* scene, uint32_t max_leaf_size, uint32_t width, uint32_t treelet_bytes,
+                          int32_t device, b2rt_bvh** out) {
+  if (!out) { set_error("out is null"); return B2RT_ERR_INVALID; }
+  *out = nullptr;
+  if (!has_device()) { set_error("no CUDA device available (b2rt has no CPU fallback)"); return B2RT_ERR_NO_DEVICE; }
+  HostScene hs;
+  int rc = make_host_scene(scene, &hs);
+  if (rc) return rc;
+  b2rt_bvh* b = new (std::nothrow) b2rt_bvh();
+  if (!b) return B2RT_ERR_OOM;
+  if (device < 0) cudaGetDevice(&device);
+  b->device = device;
+  B2RT_CUDA_OK(cudaSetDevice(device));
+  B2RT_CUDA_OK(cudaStreamCreateWithFlags(&b->stream, cudaStreamNonBlocking));
+  rc = build_wide_bvh_device(hs, max_leaf_size, width, treelet_bytes, b->stream, &b->dbvh, &b->host_meta);
+  if (rc) { b2rt_bvh_destroy(b); return rc; }
+  b->max_leaf = max_leaf_size ? max_leaf_size : 4; b->treelet_budget = treelet_bytes;
+  B2RT_CUDA_OK(cudaMalloc(&b->n_dev, 4));
+  b->tracer.bvh = b->dbvh;
+  b->tracer.collect_stats = true;
+  configure_slicing(b, -1.f, 0.f, 0);
+  *out = b;
+  return B2RT_OK;
+}
+
+int b2rt_bvh_validate(b2rt_bvh* b, const b2rt_scene_desc* scene, uint64_t out8[8]) {
+  if (!b || !scene) { set_error("null argument"); return B2RT_ERR_INVALID; }
+  HostScene hs;
+  int rc = make_host_scene(scene, &hs);
+  if (rc) return rc;
+  B2RT_CUDA_OK(cudaSetDevice(b->device));
+  WideBVH wb;
+  wb.width = b->dbvh.width; wb.n_levels = b->dbvh.n_levels; wb.max_treelet_bytes = b->dbvh.max_treelet_bytes;
+  wb.levels.assign(b->dbvh.levels, b->dbvh.levels + b->dbvh.n_levels);
+  wb.treelets.resize(b->dbvh.n_treelets);
+  wb.blob.resize(b->dbvh.blob_bytes);
+  B2RT_CUDA_OK(cudaStreamSynchronize(b->stream));
+  B2RT_CUDA_OK(cudaMemcpy(wb.treelets.data(), b->dbvh.treelets, wb.treelets.size() * sizeof(TreeletDesc), cudaMemcpyDeviceToHost));
+  B2RT_CUDA_OK(cudaMemcpy(wb.blob.data(), b->dbvh.blob, wb.blob.size(), cudaMemcpyDeviceToHost));
+  return validate_wide_bvh(hs, wb, b->max_leaf, b->treelet_budget, out8);
 }
 
 int b2rt_bvh_set_slicing(b2rt_bvh* b, float first_slice, float growth, int32_t passes) {

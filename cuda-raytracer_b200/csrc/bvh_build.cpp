@@ -705,6 +705,10 @@ extern "C" int b2rt_bvh_validate_host(const b2rt_scene_desc* scene, uint32_t max
   WideBVH wb;
   rc = build_wide_bvh(hs, max_leaf, width, treelet_bytes, &wb);
   if (rc) return rc;
+  return validate_wide_bvh(hs, wb, max_leaf, treelet_bytes, out);
+}
+
+int b2rt::validate_wide_bvh(const HostScene& hs, const WideBVH& wb, uint32_t max_leaf, uint32_t treelet_bytes, uint64_t out[8]) {
   const uint32_t W = wb.width, NB = node_bytes(W);
   const uint32_t n = hs.n_prims();
   std::vector<uint32_t> seen(n, 0);

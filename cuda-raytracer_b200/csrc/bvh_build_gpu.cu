@@ -1,0 +1,606 @@
+// Device BVH construction (replaces BVHAccel::BVHAccel + compactTree + compress,
+// src/bvh.cpp:339-365, 275-337, 234-273, for scenes where the host build dominates set-up: the 10 M triangle soup
+// takes seconds on the host and tens of milliseconds here).
+//
+// Pipeline, everything on the device, one host read-back per tree level (a 4-byte count):
+//   1. k_bounds          primitive boxes -> scene box + summed projected area (block reduction + ordered-int atomics)
+//   2. k_morton          63-bit Morton code of the box centre            3. cub::DeviceRadixSort (key, primitive)
+//   4. k_karras          binary radix tree over the sorted codes (Karras 2012; ties broken by position)
+//   5. k_refit           bottom-up boxes, second arrival at a node proceeds (one atomic counter per node)
+//   6. k_collapse        top-down, one launch per wide level: a wide node adopts its binary node's two children and
+//                        keeps replacing the largest-area internal child by that child's children until it has W
+//                        (same rule as the host builder); binary subtrees of <= max_leaf primitives become leaves
+//   7. k_sizes           bottom-up per wide level: bytes / node count / height of every wide subtree
+//   8. k_partition       one thread per subtree root, one launch per subtree level: breadth-first packing under the
+//                        byte / depth / node budgets with the host builder's rule "a node whose whole subtree fits a
+//                        blob of its own is never split", writing finished wide nodes straight into the subtree's slab
+//   9. k_compact + k_copy_prims   slabs -> dense blob, primitive records gathered behind each subtree's nodes
+// The result is the same DeviceBVH the host builder's upload produces (same node / reference / primitive formats), so
+// the traversal kernels and the structural validator do not know which builder ran.  Tree quality is LBVH (spatial
+// median), not SAH: good for evenly spread primitives (the soup), measurably worse on meshes inside large boxes.
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
+
+#include <algorithm>
+#include <chrono>
+#include <cmath>
+#include <cub/device/device_radix_sort.cuh>
+
+#include "traverse.cuh"
+
+namespace b2rt {
+namespace {
+
+__host__ __device__ __forceinline__ uint32_t f2o(float f) {   // order-preserving float -> uint
+  uint32_t u;
+#ifdef __CUDA_ARCH__
+  u = __float_as_uint(f);
+#else
+  memcpy(&u, &f, 4);
+#endif
+  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__host__ __forceinline__ float o2f(uint32_t o) {
+  uint32_t u = (o & 0x80000000u) ? (o & 0x7FFFFFFFu) : ~o;
+  float f; memcpy(&f, &u, 4);
+  return f;
+}
+
+struct SceneBounds { uint32_t lo[3], hi[3]; double projected; };
+
+__device__ __forceinline__ void prim_box(const float4* geom, uint32_t i, uint32_t n_tris, float lo[3], float hi[3]) {
+  const float4 a = geom[3 * (size_t)i], b = geom[3 * (size_t)i + 1], c = geom[3 * (size_t)i + 2];
+  if (i < n_tris) {
+    const float p1[3] = {a.x, a.y, a.z};
+    const float p2[3] = {a.x + a.w, a.y + b.x, a.z + b.y};
+    const float p3[3] = {a.x + b.z, a.y + b.w, a.z + c.x};
+#pragma unroll
+    for (int k = 0; k < 3; ++k) { lo[k] = fminf(p1[k], fminf(p2[k], p3[k])); hi[k] = fmaxf(p1[k], fmaxf(p2[k], p3[k])); }
+  } else {
+    const float p[3] = {a.x, a.y, a.z};
+#pragma unroll
+    for (int k = 0; k < 3; ++k) { lo[k] = p[k] - a.w; hi[k] = p[k] + a.w; }
+  }
+}
+
+__global__ void __launch_bounds__(256) k_bounds(const float4* __restrict__ geom, uint32_t n, uint32_t n_tris, SceneBounds* out) {
+  float lo[3] = {INFINITY, INFINITY, INFINITY}, hi[3] = {-INFINITY, -INFINITY, -INFINITY};
+  double proj = 0;
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    float l[3], h[3];
+    prim_box(geom, i, n_tris, l, h);
+#pragma unroll
+    for (int k = 0; k < 3; ++k) { lo[k] = fminf(lo[k], l[k]); hi[k] = fmaxf(hi[k], h[k]); }
+    const float4 a = geom[3 * (size_t)i], b = geom[3 * (size_t)i + 1], c = geom[3 * (size_t)i + 2];
+    if (i < n_tris) {
+      const double e1x = a.w, e1y = b.x, e1z = b.y, e2x = b.z, e2y = b.w, e2z = c.x;
+      const double cx = e1y * e2z - e1z * e2y, cy = e1z * e2x - e1x * e2z, cz = e1x * e2y - e1y * e2x;
+      proj += 0.25 * sqrt(cx * cx + cy * cy + cz * cz);
+    } else {
+      proj += 3.14159265358979 * (double)a.w * a.w;
+    }
+  }
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) {
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      lo[k] = fminf(lo[k], __shfl_xor_sync(0xffffffffu, lo[k], d));
+      hi[k] = fmaxf(hi[k], __shfl_xor_sync(0xffffffffu, hi[k], d));
+    }
+    proj += __shfl_xor_sync(0xffffffffu, proj, d);
+  }
+  if ((threadIdx.x & 31) == 0) {
+#pragma unroll
+    for (int k = 0; k < 3; ++k) { atomicMin(&out->lo[k], f2o(lo[k])); atomicMax(&out->hi[k], f2o(hi[k])); }
+    atomicAdd(&out->projected, proj);
+  }
+}
+
+__device__ __forceinline__ uint64_t spread21(uint32_t v) {   // 21 bits -> every third bit of 63
+  uint64_t x = v & 0x1FFFFFull;
+  x = (x | x << 32) & 0x1F00000000FFFFull;
+  x = (x | x << 16) & 0x1F0000FF0000FFull;
+  x = (x | x << 8) & 0x100F00F00F00F00Full;
+  x = (x | x << 4) & 0x10C30C30C30C30C3ull;
+  x = (x | x << 2) & 0x1249249249249249ull;
+  return x;
+}
+
+struct BuildBox { float lo[3], inv[3]; };   // scene box origin and 2^21 / extent per axis
+
+__global__ void __launch_bounds__(256) k_morton(const float4* __restrict__ geom, uint32_t n, uint32_t n_tris, BuildBox bx,
+                                                uint64_t* keys, uint32_t* vals) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float l[3], h[3];
+  prim_box(geom, i, n_tris, l, h);
+  uint32_t q[3];
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    const float c = (0.5f * (l[k] + h[k]) - bx.lo[k]) * bx.inv[k];
+    q[k] = (uint32_t)fminf(fmaxf(c, 0.f), 2097151.f);
+  }
+  keys[i] = spread21(q[0]) | (spread21(q[1]) << 1) | (spread21(q[2]) << 2);
+  vals[i] = i;
+}
+
+// ---- binary radix tree.  Unified node ids: internal i in [0, n-1), leaf (sorted position j) = n - 1 + j ----
+struct BinTree {
+  uint32_t n;
+  const uint64_t* keys;
+  uint32_t* left; uint32_t* right;        // [n-1] unified ids
+  uint32_t* first; uint32_t* last;        // [n-1] sorted range covered
+  uint32_t* parent;                       // [2n-1]
+  uint32_t* flag;                         // [n-1] refit arrival counters
+  float4* box_lo; float4* box_hi;         // [2n-1]
+};
+
+__device__ __forceinline__ int delta(const uint64_t* keys, uint32_t n, int i, int j) {
+  if (j < 0 || j >= (int)n) return -1;
+  const uint64_t a = keys[i], b = keys[j];
+  if (a == b) return 64 + __clz((uint32_t)i ^ (uint32_t)j);
+  return __clzll((long long)(a ^ b));
+}
+
+__global__ void __launch_bounds__(256) k_karras(BinTree T) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int n = (int)T.n;
+  if (i >= n - 1) return;
+  const int d = (delta(T.keys, n, i, i + 1) - delta(T.keys, n, i, i - 1)) >= 0 ? 1 : -1;
+  const int dmin = delta(T.keys, n, i, i - d);
+  int lmax = 2;
+  while (delta(T.keys, n, i, i + lmax * d) > dmin) lmax <<= 1;
+  int l = 0;
+  for (int t = lmax >> 1; t >= 1; t >>= 1)
+    if (delta(T.keys, n, i, i + (l + t) * d) > dmin) l += t;
+  const int j = i + l * d;
+  const int dnode = delta(T.keys, n, i, j);
+  int s = 0;
+  for (int t = (l + 1) >> 1;; t = (t + 1) >> 1) {
+    if (delta(T.keys, n, i, i + (s + t) * d) > dnode) s += t;
+    if (t <= 1) break;
+  }
+  const int gamma = i + s * d + min(d, 0);
+  const int lo = min(i, j), hi = max(i, j);
+  const uint32_t L = (lo == gamma) ? (uint32_t)(n - 1 + gamma) : (uint32_t)gamma;
+  const uint32_t R = (hi == gamma + 1) ? (uint32_t)(n - 1 + gamma + 1) : (uint32_t)(gamma + 1);
+  T.left[i] = L; T.right[i] = R; T.first[i] = (uint32_t)lo; T.last[i] = (uint32_t)hi;
+  T.parent[L] = (uint32_t)i; T.parent[R] = (uint32_t)i;
+  if (i == 0) T.parent[0] = 0xFFFFFFFFu;
+}
+
+__global__ void __launch_bounds__(256) k_refit(BinTree T, const float4* __restrict__ geom, const uint32_t* __restrict__ sorted,
+                                               uint32_t n_tris, float pad) {
+  const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= T.n) return;
+  float l[3], h[3];
+  prim_box(geom, sorted[j], n_tris, l, h);
+  float4 lo = make_float4(l[0] - pad, l[1] - pad, l[2] - pad, 0.f), hi = make_float4(h[0] + pad, h[1] + pad, h[2] + pad, 0.f);
+  uint32_t id = T.n - 1 + j;
+  T.box_lo[id] = lo; T.box_hi[id] = hi;
+  if (T.n == 1) return;
+  uint32_t p = T.parent[id];
+  while (p != 0xFFFFFFFFu) {
+    __threadfence();
+    if (atomicAdd(&T.flag[p], 1u) == 0u) return;     // first arrival: the sibling's thread finishes the node
+    __threadfence();
+    const uint32_t a = T.left[p], b = T.right[p];
+    const float4 al = __ldcg(&T.box_lo[a]), ah = __ldcg(&T.box_hi[a]), bl = __ldcg(&T.box_lo[b]), bh = __ldcg(&T.box_hi[b]);
+    lo = make_float4(fminf(al.x, bl.x), fminf(al.y, bl.y), fminf(al.z, bl.z), 0.f);
+    hi = make_float4(fmaxf(ah.x, bh.x), fmaxf(ah.y, bh.y), fmaxf(ah.z, bh.z), 0.f);
+    T.box_lo[p] = lo; T.box_hi[p] = hi;
+    p = T.parent[p];
+  }
+}
+
+// ---- wide collapse ----
+struct WideTmp {
+  uint8_t* nodes;          // [cap] temporary wide nodes in the final node layout; INTERNAL payload = global wide index,
+                           // LEAF payload = unified binary id of the leaf subtree
+  uint32_t* own_prims;     // [cap] primitives in this node's leaf children
+  uint32_t* sub_bytes;     // [cap] bytes of the whole wide subtree (saturating)
+  uint32_t* sub_nodes;     // [cap]
+  uint32_t* height;        // [cap]
+  uint32_t* count;         // wide nodes allocated so far
+};
+
+__device__ __forceinline__ bool bin_is_leaf(const BinTree& T, uint32_t id, uint32_t max_leaf) {
+  return id >= T.n - 1 || (T.last[id] - T.first[id] + 1u) <= max_leaf;
+}
+__device__ __forceinline__ float box_area(float4 lo, float4 hi) {
+  const float dx = hi.x - lo.x, dy = hi.y - lo.y, dz = hi.z - lo.z;
+  return 2.f * (dx * dy + dy * dz + dz * dx);
+}
+
+template <int W>
+__global__ void __launch_bounds__(128) k_collapse(BinTree T, WideTmp Wt, const uint32_t* __restrict__ cur_q, uint32_t level_first,
+                                                  uint32_t level_count, uint32_t next_first, uint32_t* next_q, uint32_t cap,
+                                                  uint32_t max_leaf, uint32_t* overflow) {
+  const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= level_count) return;
+  constexpr uint32_t NB = 32 * W;
+  const uint32_t bin = cur_q[k];
+  uint32_t kids[W]; float area[W]; int nk = 0;
+  if (bin_is_leaf(T, bin, max_leaf)) { kids[nk++] = bin; }
+  else { kids[nk++] = T.left[bin]; kids[nk++] = T.right[bin]; }
+  for (int q = 0; q < nk; ++q)
+    area[q] = bin_is_leaf(T, kids[q], max_leaf) ? -1.f : box_area(T.box_lo[kids[q]], T.box_hi[kids[q]]);
+  while (nk < W) {
+    int best = -1; float ba = -1.f;
+    for (int q = 0; q < nk; ++q) if (area[q] > ba) { ba = area[q]; best = q; }
+    if (best < 0) break;
+    const uint32_t c = kids[best];
+    const uint32_t l = T.left[c], r = T.right[c];
+    kids[best] = l; kids[nk] = r;
+    area[best] = bin_is_leaf(T, l, max_leaf) ? -1.f : box_area(T.box_lo[l], T.box_hi[l]);
+    area[nk] = bin_is_leaf(T, r, max_leaf) ? -1.f : box_area(T.box_lo[r], T.box_hi[r]);
+    ++nk;
+  }
+  float* f = reinterpret_cast<float*>(Wt.nodes + (size_t)(level_first + k) * NB);
+  uint32_t* refs = reinterpret_cast<uint32_t*>(f + 6 * W);
+  uint32_t own = 0;
+  for (int q = 0; q < W; ++q) {
+    if (q < nk) {
+      const uint32_t c = kids[q];
+      const float4 lo = T.box_lo[c], hi = T.box_hi[c];
+      f[0 * W + q] = lo.x; f[1 * W + q] = lo.y; f[2 * W + q] = lo.z;
+      f[3 * W + q] = hi.x; f[4 * W + q] = hi.y; f[5 * W + q] = hi.z;
+      if (area[q] < 0.f) {
+        refs[q] = (REF_LEAF << 30) | c;
+        own += c >= T.n - 1 ? 1u : (T.last[c] - T.first[c] + 1u);
+      } else {
+        const uint32_t idx = atomicAdd(Wt.count, 1u);
+        if (idx >= cap) { *overflow = 1; refs[q] = REF_EMPTY_WORD; continue; }
+        next_q[idx - next_first] = c;
+        refs[q] = (REF_INTERNAL << 30) | idx;
+      }
+    } else {
+      f[0 * W + q] = INFINITY; f[1 * W + q] = INFINITY; f[2 * W + q] = INFINITY;
+      f[3 * W + q] = -INFINITY; f[4 * W + q] = -INFINITY; f[5 * W + q] = -INFINITY;
+      refs[q] = REF_EMPTY_WORD;
+    }
+  }
+  Wt.own_prims[level_first + k] = own;
+}
+
+template <int W>
+__global__ void __launch_bounds__(256) k_sizes(WideTmp Wt, uint32_t level_first, uint32_t level_count) {
+  const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= level_count) return;
+  constexpr uint32_t NB = 32 * W;
+  const uint32_t idx = level_first + k;
+  const uint32_t* refs = reinterpret_cast<const uint32_t*>(Wt.nodes + (size_t)idx * NB + 24 * W);
+  uint64_t bytes = NB + (uint64_t)Wt.own_prims[idx] * PRIM_BYTES;
+  uint64_t nodes = 1; uint32_t h = 1;
+  for (int q = 0; q < W; ++q) {
+    const uint32_t r = refs[q];
+    if (r != REF_EMPTY_WORD && (r >> 30) == REF_INTERNAL) {
+      const uint32_t c = r & 0x3FFFFFFFu;
+      bytes += Wt.sub_bytes[c]; nodes += Wt.sub_nodes[c]; h = max(h, Wt.height[c] + 1u);
+    }
+  }
+  Wt.sub_bytes[idx] = (uint32_t)min(bytes, (uint64_t)0xFFFFFFFFu);
+  Wt.sub_nodes[idx] = (uint32_t)min(nodes, (uint64_t)0xFFFFFFFFu);
+  Wt.height[idx] = h;
+}
+
+// ---- partition into subtrees + serialisation ----
+struct PartParams {
+  uint8_t* slabs; uint32_t stride;           // one slab of `stride` bytes per subtree id
+  TreeletDesc* descs;
+  const uint32_t* roots; uint32_t n_roots; uint32_t first_id;   // this level: wide index of each subtree root
+  uint32_t* next_roots; uint32_t* next_count; uint32_t next_first_id; uint32_t cap_subtrees;
+  uint2* prim_dest;                          // [n] sorted position -> (subtree id, local primitive index)
+  uint32_t budget, depth_limit, node_limit;
+  uint32_t* overflow;
+};
+
+template <int W>
+__global__ void __launch_bounds__(64) k_partition(BinTree T, WideTmp Wt, PartParams P) {
+  const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= P.n_roots) return;
+  constexpr uint32_t NB = 32 * W;
+  constexpr uint32_t PAD = 28 * W;            // byte offset of a node's unused tail (queue bookkeeping while building)
+  const uint32_t tid = P.first_id + k;
+  uint8_t* slab = P.slabs + (size_t)tid * P.stride;
+  // the slab's node array doubles as the breadth-first queue: node q's tail holds (wide index, depth | whole << 8)
+  uint32_t n_nodes = 1, committed = 1, n_prims = 0;
+  uint64_t used = NB + (uint64_t)Wt.own_prims[P.roots[k]] * PRIM_BYTES;
+  { uint32_t* tail = reinterpret_cast<uint32_t*>(slab + PAD); tail[0] = P.roots[k]; tail[1] = 1u; }
+  for (uint32_t q = 0; q < n_nodes; ++q) {
+    uint8_t* node = slab + (size_t)q * NB;
+    uint32_t* tail = reinterpret_cast<uint32_t*>(node + PAD);
+    const uint32_t widx = tail[0], depth = tail[1] & 0xFFu; const bool whole = (tail[1] >> 8) != 0;
+    const uint4* src = reinterpret_cast<const uint4*>(Wt.nodes + (size_t)widx * NB);
+    uint4* dst = reinterpret_cast<uint4*>(node);
+#pragma unroll
+    for (int v = 0; v < (int)(24 * W / 16); ++v) dst[v] = src[v];
+    const uint32_t* srefs = reinterpret_cast<const uint32_t*>(Wt.nodes + (size_t)widx * NB + 24 * W);
+    uint32_t* drefs = reinterpret_cast<uint32_t*>(node + 24 * W);
+    tail[0] = 0; tail[1] = 0;
+    for (int c = 0; c < W; ++c) {
+      const uint32_t r = srefs[c];
+      if (r == REF_EMPTY_WORD) { drefs[c] = r; continue; }
+      const uint32_t pay = r & 0x3FFFFFFFu;
+      if ((r >> 30) == REF_LEAF) {
+        const uint32_t first = pay >= T.n - 1 ? pay - (T.n - 1) : T.first[pay];
+        const uint32_t cnt = pay >= T.n - 1 ? 1u : T.last[pay] - first + 1u;
+        drefs[c] = (REF_LEAF << 30) | ((cnt - 1u) << 24) | n_prims;
+        for (uint32_t p = 0; p < cnt; ++p) P.prim_dest[first + p] = make_uint2(tid, n_prims + p);
+        n_prims += cnt;
+        continue;
+      }
+      // internal child: whole subtree / partial / exit (host builder's rules, breadth-first instead of by area)
+      const uint32_t sb = Wt.sub_bytes[pay], sn = Wt.sub_nodes[pay], sh = Wt.height[pay];
+      bool take = whole, take_whole = whole;
+      if (!take) {
+        if (used + sb <= P.budget && depth + sh <= P.depth_limit && (uint64_t)committed + sn <= P.node_limit) {
+          take = take_whole = true; used += sb; committed += sn;
+        } else {
+          const bool fits_alone = sb <= P.budget && sh <= P.depth_limit && sn <= P.node_limit;
+          const uint64_t own = NB + (uint64_t)Wt.own_prims[pay] * PRIM_BYTES;
+          if (!fits_alone && used + own <= P.budget && depth + 1 <= P.depth_limit && committed < P.node_limit) {
+            take = true; used += own; committed += 1;
+          }
+        }
+      }
+      if (take) {
+        uint32_t* ct = reinterpret_cast<uint32_t*>(slab + (size_t)n_nodes * NB + PAD);
+        ct[0] = pay; ct[1] = (depth + 1u) | (take_whole ? 0x100u : 0u);
+        drefs[c] = (REF_INTERNAL << 30) | n_nodes;
+        ++n_nodes;
+      } else {
+        const uint32_t e = atomicAdd(P.next_count, 1u);
+        if (P.next_first_id + e >= P.cap_subtrees) { *P.overflow = 2; drefs[c] = REF_EMPTY_WORD; continue; }
+        P.next_roots[e] = pay;
+        drefs[c] = (REF_EXIT << 30) | (P.next_first_id + e);
+      }
+    }
+  }
+  TreeletDesc d;
+  d.offset16 = 0;   // assigned by the compaction
+  d.bytes = (uint32_t)(((uint64_t)n_nodes * NB + (uint64_t)n_prims * PRIM_BYTES + 15u) & ~15ull);
+  d.n_nodes = n_nodes; d.n_prims = n_prims;
+  P.descs[tid] = d;
+}
+
+// slabs -> dense blob (one CTA per subtree, node part only; primitives are gathered by k_copy_prims)
+__global__ void __launch_bounds__(128) k_compact(const uint8_t* __restrict__ slabs, uint32_t stride, const TreeletDesc* __restrict__ descs,
+                                                 uint32_t node_bytes_, uint8_t* blob) {
+  const uint32_t t = blockIdx.x;
+  const TreeletDesc d = descs[t];
+  const uint4* src = reinterpret_cast<const uint4*>(slabs + (size_t)t * stride);
+  uint4* dst = reinterpret_cast<uint4*>(blob + (size_t)d.offset16 * 16);
+  const uint32_t n16 = d.n_nodes * (node_bytes_ / 16);
+  for (uint32_t i = threadIdx.x; i < n16; i += blockDim.x) dst[i] = src[i];
+}
+
+__global__ void __launch_bounds__(256) k_copy_prims(const float4* __restrict__ geom, const uint32_t* __restrict__ sorted,
+                                                    const uint2* __restrict__ prim_dest, const TreeletDesc* __restrict__ descs,
+                                                    uint32_t n, uint32_t node_bytes_, uint8_t* blob) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const uint2 pd = prim_dest[i];
+  const TreeletDesc d = descs[pd.x];
+  float4* dst = reinterpret_cast<float4*>(blob + (size_t)d.offset16 * 16 + (size_t)d.n_nodes * node_bytes_ + (size_t)pd.y * PRIM_BYTES);
+  const float4* src = geom + 3 * (size_t)sorted[i];
+  dst[0] = src[0]; dst[1] = src[1]; dst[2] = src[2];
+}
+
+// Scratch buffers come from the device's stream-ordered pool (cudaMallocAsync) with the release threshold lifted, so a
+// rebuild reuses the previous build's memory instead of paying cudaMalloc / cudaFree (tens of milliseconds for GBs).
+struct DevBuf {
+  cudaStream_t s;
+  std::vector<void*> ptrs;
+  explicit DevBuf(cudaStream_t s_) : s(s_) {
+    int dev = 0; cudaGetDevice(&dev);
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+      uint64_t keep = ~0ull;
+      cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+    }
+  }
+  ~DevBuf() { for (void* p : ptrs) cudaFreeAsync(p, s); }
+  template <typename T>
+  cudaError_t alloc(T** p, size_t count) {
+    cudaError_t e = cudaMallocAsync(p, std::max<size_t>(count, 1) * sizeof(T), s);
+    if (e == cudaSuccess) ptrs.push_back(*p);
+    return e;
+  }
+};
+
+}  // namespace
+
+template <int W>
+static int build_device_w(const HostScene& sc, uint32_t max_leaf, uint32_t treelet_bytes, cudaStream_t s, DeviceBVH* dev, WideBVH* meta) {
+  auto t0 = std::chrono::steady_clock::now();
+  const bool verbose = getenv("B2RT_VERBOSE") != nullptr;
+  auto lap = [&](const char* what) {
+    if (!verbose) return;
+    cudaStreamSynchronize(s);
+    fprintf(stderr, "b2rt: gpu build %-10s %8.3f ms\n", what, std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count());
+  };
+  constexpr uint32_t NB = 32 * W;
+  const uint32_t n = sc.n_prims();
+  const uint32_t depth_limit = stack_entries(W) / (W - 1);
+  const uint32_t node_limit = max_treelet_nodes(W);
+  DevBuf buf(s);
+  float4* geom = nullptr;
+  B2RT_CUDA_OK(buf.alloc(&geom, (size_t)n * 3));
+  B2RT_CUDA_OK(cudaMemcpyAsync(geom, sc.prim_geom.data(), (size_t)n * PRIM_BYTES, cudaMemcpyHostToDevice, s));
+  // 1. scene bounds
+  SceneBounds* d_sb = nullptr;
+  B2RT_CUDA_OK(buf.alloc(&d_sb, 1));
+  SceneBounds sb;
+  for (int k = 0; k < 3; ++k) { sb.lo[k] = 0xFFFFFFFFu; sb.hi[k] = 0u; }
+  sb.projected = 0;
+  B2RT_CUDA_OK(cudaMemcpyAsync(d_sb, &sb, sizeof sb, cudaMemcpyHostToDevice, s));
+  k_bounds<<<148 * 8, 256, 0, s>>>(geom, n, sc.n_tris, d_sb);
+  B2RT_CUDA_OK(cudaMemcpyAsync(&sb, d_sb, sizeof sb, cudaMemcpyDeviceToHost, s));
+  B2RT_CUDA_OK(cudaStreamSynchronize(s));
+  float lo[3], hi[3];
+  for (int k = 0; k < 3; ++k) { lo[k] = o2f(sb.lo[k]); hi[k] = o2f(sb.hi[k]); }
+  float diag = 0.f, maxabs = 0.f;
+  { const float ex = hi[0] - lo[0], ey = hi[1] - lo[1], ez = hi[2] - lo[2];
+    diag = std::sqrt(ex * ex + ey * ey + ez * ez);
+    for (int k = 0; k < 3; ++k) maxabs = std::max(maxabs, std::max(std::fabs(lo[k]), std::fabs(hi[k]))); }
+  const float pad = std::max(1e-30f, 1e-5f * std::max(diag, maxabs));   // same padding rule as the host builder
+  for (int k = 0; k < 3; ++k) { meta->bbox[k] = lo[k]; meta->bbox[3 + k] = hi[k]; }
+  meta->mean_free_path = 0.f;
+  if (sb.projected > 0) meta->mean_free_path = (float)((double)(hi[0] - lo[0]) * (hi[1] - lo[1]) * (hi[2] - lo[2]) / sb.projected);
+  lap("bounds");
+  // 2./3. Morton codes, sort
+  uint64_t *keys_a = nullptr, *keys_b = nullptr; uint32_t *vals_a = nullptr, *vals_b = nullptr;
+  B2RT_CUDA_OK(buf.alloc(&keys_a, n)); B2RT_CUDA_OK(buf.alloc(&keys_b, n));
+  B2RT_CUDA_OK(buf.alloc(&vals_a, n)); B2RT_CUDA_OK(buf.alloc(&vals_b, n));
+  BuildBox bx;
+  for (int k = 0; k < 3; ++k) { bx.lo[k] = lo[k]; const float e = hi[k] - lo[k]; bx.inv[k] = e > 0.f ? 2097152.f / e : 0.f; }
+  k_morton<<<(n + 255) / 256, 256, 0, s>>>(geom, n, sc.n_tris, bx, keys_a, vals_a);
+  size_t temp_bytes = 0;
+  B2RT_CUDA_OK(cub::DeviceRadixSort::SortPairs(nullptr, temp_bytes, keys_a, keys_b, vals_a, vals_b, (int)n, 0, 63, s));
+  uint8_t* temp = nullptr;
+  B2RT_CUDA_OK(buf.alloc(&temp, temp_bytes));
+  B2RT_CUDA_OK(cub::DeviceRadixSort::SortPairs(temp, temp_bytes, keys_a, keys_b, vals_a, vals_b, (int)n, 0, 63, s));
+  const uint64_t* keys = keys_b; const uint32_t* sorted = vals_b;
+  lap("sort");
+  // 4./5. radix tree + boxes
+  BinTree T;
+  T.n = n; T.keys = keys;
+  B2RT_CUDA_OK(buf.alloc(&T.left, n)); B2RT_CUDA_OK(buf.alloc(&T.right, n));
+  B2RT_CUDA_OK(buf.alloc(&T.first, n)); B2RT_CUDA_OK(buf.alloc(&T.last, n));
+  B2RT_CUDA_OK(buf.alloc(&T.parent, (size_t)2 * n)); B2RT_CUDA_OK(buf.alloc(&T.flag, n));
+  B2RT_CUDA_OK(buf.alloc(&T.box_lo, (size_t)2 * n)); B2RT_CUDA_OK(buf.alloc(&T.box_hi, (size_t)2 * n));
+  B2RT_CUDA_OK(cudaMemsetAsync(T.flag, 0, (size_t)n * 4, s));
+  if (n > 1) k_karras<<<(n + 255) / 256, 256, 0, s>>>(T);
+  k_refit<<<(n + 255) / 256, 256, 0, s>>>(T, geom, sorted, sc.n_tris, pad);
+  lap("radix tree");
+  // 6. wide collapse, one launch per wide level
+  const uint32_t cap = n + 1;
+  WideTmp Wt;
+  B2RT_CUDA_OK(buf.alloc(&Wt.nodes, (size_t)cap * NB));
+  B2RT_CUDA_OK(buf.alloc(&Wt.own_prims, cap)); B2RT_CUDA_OK(buf.alloc(&Wt.sub_bytes, cap));
+  B2RT_CUDA_OK(buf.alloc(&Wt.sub_nodes, cap)); B2RT_CUDA_OK(buf.alloc(&Wt.height, cap));
+  uint32_t* ctr = nullptr;    // [0] wide count, [1] overflow, [2] next subtree count
+  B2RT_CUDA_OK(buf.alloc(&ctr, 4));
+  Wt.count = ctr;
+  uint32_t *q_a = nullptr, *q_b = nullptr;
+  B2RT_CUDA_OK(buf.alloc(&q_a, cap)); B2RT_CUDA_OK(buf.alloc(&q_b, cap));
+  const uint32_t root_bin = n == 1 ? 0u /* unified id of the only leaf */ : 0u;
+  { uint32_t init[4] = {1u, 0u, 0u, 0u};
+    B2RT_CUDA_OK(cudaMemcpyAsync(ctr, init, 16, cudaMemcpyHostToDevice, s));
+    B2RT_CUDA_OK(cudaMemcpyAsync(q_a, &root_bin, 4, cudaMemcpyHostToDevice, s)); }
+  std::vector<std::pair<uint32_t, uint32_t>> wide_levels;   // (first, count)
+  uint32_t level_first = 0, level_count = 1;
+  while (level_count) {
+    wide_levels.push_back({level_first, level_count});
+    const uint32_t next_first = level_first + level_count;
+    k_collapse<W><<<(level_count + 127) / 128, 128, 0, s>>>(T, Wt, q_a, level_first, level_count, next_first, q_b, cap, max_leaf, ctr + 1);
+    uint32_t h[2];
+    B2RT_CUDA_OK(cudaMemcpyAsync(h, ctr, 8, cudaMemcpyDeviceToHost, s));
+    B2RT_CUDA_OK(cudaStreamSynchronize(s));
+    if (h[1]) { set_error("gpu bvh build: wide node capacity exceeded"); return B2RT_ERR_INVALID; }
+    level_first = next_first; level_count = h[0] - next_first;
+    std::swap(q_a, q_b);
+    if (wide_levels.size() > 4096) { set_error("gpu bvh build: tree too deep"); return B2RT_ERR_INVALID; }
+  }
+  const uint32_t n_wide = level_first;
+  meta->n_wide_nodes = n_wide;
+  lap("collapse");
+  // 7. subtree sizes, bottom-up
+  for (size_t L = wide_levels.size(); L-- > 0;)
+    k_sizes<W><<<(wide_levels[L].second + 255) / 256, 256, 0, s>>>(Wt, wide_levels[L].first, wide_levels[L].second);
+  uint32_t total_bytes_sat = 0;
+  B2RT_CUDA_OK(cudaMemcpyAsync(&total_bytes_sat, Wt.sub_bytes, 4, cudaMemcpyDeviceToHost, s));
+  B2RT_CUDA_OK(cudaStreamSynchronize(s));
+  const uint64_t total_est = total_bytes_sat == 0xFFFFFFFFu ? (uint64_t)n_wide * NB + (uint64_t)n * PRIM_BYTES : total_bytes_sat;
+  lap("sizes");
+  // 8. partition, one launch per subtree level
+  const uint32_t stride = (treelet_bytes + 127u) & ~127u;
+  uint32_t cap_subtrees = (uint32_t)std::min<uint64_t>(8 * (total_est / treelet_bytes) + 1024, 0x3FFFFFFFull);
+  uint8_t* slabs = nullptr;
+  B2RT_CUDA_OK(buf.alloc(&slabs, (size_t)cap_subtrees * stride));
+  TreeletDesc* descs_tmp = nullptr;
+  B2RT_CUDA_OK(buf.alloc(&descs_tmp, cap_subtrees));
+  uint2* prim_dest = nullptr;
+  B2RT_CUDA_OK(buf.alloc(&prim_dest, n));
+  uint32_t *r_a = nullptr, *r_b = nullptr;
+  B2RT_CUDA_OK(buf.alloc(&r_a, cap_subtrees)); B2RT_CUDA_OK(buf.alloc(&r_b, cap_subtrees));
+  { const uint32_t zero = 0; B2RT_CUDA_OK(cudaMemcpyAsync(r_a, &zero, 4, cudaMemcpyHostToDevice, s)); }
+  meta->levels.clear();
+  uint32_t first_id = 0, n_roots = 1;
+  while (n_roots) {
+    if (meta->levels.size() >= MAX_LEVELS) { set_error("too many subtree levels; increase treelet_bytes"); return B2RT_ERR_INVALID; }
+    meta->levels.push_back(LevelRange{first_id, n_roots});
+    B2RT_CUDA_OK(cudaMemsetAsync(ctr + 2, 0, 4, s));
+    PartParams P;
+    P.slabs = slabs; P.stride = stride; P.descs = descs_tmp; P.roots = r_a; P.n_roots = n_roots; P.first_id = first_id;
+    P.next_roots = r_b; P.next_count = ctr + 2; P.next_first_id = first_id + n_roots; P.cap_subtrees = cap_subtrees;
+    P.prim_dest = prim_dest; P.budget = treelet_bytes; P.depth_limit = depth_limit; P.node_limit = node_limit; P.overflow = ctr + 1;
+    k_partition<W><<<(n_roots + 63) / 64, 64, 0, s>>>(T, Wt, P);
+    uint32_t h[2];
+    B2RT_CUDA_OK(cudaMemcpyAsync(h, ctr + 1, 8, cudaMemcpyDeviceToHost, s));
+    B2RT_CUDA_OK(cudaStreamSynchronize(s));
+    if (h[0]) { set_error("gpu bvh build: subtree capacity exceeded"); return B2RT_ERR_INVALID; }
+    first_id += n_roots; n_roots = h[1];
+    std::swap(r_a, r_b);
+  }
+  const uint32_t n_subtrees = first_id;
+  lap("partition");
+  // 9. dense blob
+  std::vector<TreeletDesc> descs(n_subtrees);
+  B2RT_CUDA_OK(cudaMemcpyAsync(descs.data(), descs_tmp, (size_t)n_subtrees * sizeof(TreeletDesc), cudaMemcpyDeviceToHost, s));
+  B2RT_CUDA_OK(cudaStreamSynchronize(s));
+  uint64_t total = 0; uint32_t max_bytes = 0;
+  for (auto& d : descs) {
+    total = (total + 127) & ~127ull;
+    if (total / 16 > 0xFFFFFFFFull) { set_error("BVH blob too large"); return B2RT_ERR_INVALID; }
+    d.offset16 = (uint32_t)(total / 16);
+    total += d.bytes;
+    max_bytes = std::max(max_bytes, d.bytes);
+  }
+  const uint64_t blob_bytes = ((total + 127) & ~127ull) + 128;
+  if (dev->blob_cap < blob_bytes) {
+    cudaFree(dev->blob); dev->blob = nullptr; dev->blob_cap = 0;
+    B2RT_CUDA_OK(cudaMallocAsync(&dev->blob, blob_bytes, s));   // pool memory; free_bvh's cudaFree accepts it
+    dev->blob_cap = blob_bytes;
+  }
+  if (dev->treelet_cap < n_subtrees) {
+    cudaFree(dev->treelets); dev->treelets = nullptr; dev->treelet_cap = 0;
+    B2RT_CUDA_OK(cudaMallocAsync(&dev->treelets, (size_t)n_subtrees * sizeof(TreeletDesc), s));
+    dev->treelet_cap = n_subtrees;
+  }
+  B2RT_CUDA_OK(cudaMemcpyAsync(dev->treelets, descs.data(), (size_t)n_subtrees * sizeof(TreeletDesc), cudaMemcpyHostToDevice, s));
+  k_compact<<<n_subtrees, 128, 0, s>>>(slabs, stride, dev->treelets, NB, dev->blob);
+  k_copy_prims<<<(n + 255) / 256, 256, 0, s>>>(geom, sorted, prim_dest, dev->treelets, n, NB, dev->blob);
+  B2RT_CUDA_OK(cudaStreamSynchronize(s));
+  B2RT_CUDA_OK(cudaGetLastError());
+  lap("blob");
+  dev->n_treelets = n_subtrees; dev->n_levels = (uint32_t)meta->levels.size(); dev->width = W;
+  dev->max_treelet_bytes = max_bytes; dev->blob_bytes = blob_bytes;
+  for (uint32_t i = 0; i < dev->n_levels; ++i) dev->levels[i] = meta->levels[i];
+  meta->width = W; meta->n_levels = dev->n_levels; meta->max_treelet_bytes = max_bytes;
+  meta->treelets = std::move(descs);
+  meta->blob.clear();
+  meta->build_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+  return B2RT_OK;
+}
+
+int build_wide_bvh_device(const HostScene& sc, uint32_t max_leaf, uint32_t width, uint32_t treelet_bytes, cudaStream_t s,
+                          DeviceBVH* dev, WideBVH* meta) {
+  if (width == 0) width = 4;
+  if (width != 4 && width != 8) { set_error("bvh width must be 4 or 8"); return B2RT_ERR_INVALID; }
+  if (max_leaf == 0) max_leaf = 4;
+  if (max_leaf > 64) { set_error("max_leaf_size must be <= 64"); return B2RT_ERR_INVALID; }
+  if (sc.n_prims() == 0) { set_error("gpu bvh build: empty scene"); return B2RT_ERR_INVALID; }
+  if (sc.n_prims() >= (1u << 29)) { set_error("gpu bvh build: too many primitives"); return B2RT_ERR_INVALID; }
+  const uint32_t min_budget = node_bytes(width) + width * max_leaf * PRIM_BYTES;
+  if (treelet_bytes == 0) treelet_bytes = (sc.n_prims() >= 65536 ? 24 : 16) * 1024;
+  treelet_bytes = std::max(treelet_bytes, min_budget) & ~15u;
+  if (treelet_bytes > 160 * 1024) { set_error("treelet_bytes exceeds the shared-memory budget (160 KiB)"); return B2RT_ERR_INVALID; }
+  return width == 8 ? build_device_w<8>(sc, max_leaf, treelet_bytes, s, dev, meta)
+                    : build_device_w<4>(sc, max_leaf, treelet_bytes, s, dev, meta);
+}
+
+}  // namespace b2rt

@@ -86,6 +86,9 @@ struct Tracer {
 enum { CTRL_PAIRS0 = 0, CTRL_PAIRS1 = 1, CTRL_NEXT0 = 2, CTRL_NEXT1 = 3, CTRL_OVERFLOW = 4, CTRL_NCHUNKS = 5 };
 
 int upload_bvh(const WideBVH& h, DeviceBVH* d);
+// device builder (bvh_build_gpu.cu): fills *d directly; *meta gets everything of WideBVH but the blob
+int build_wide_bvh_device(const HostScene& sc, uint32_t max_leaf, uint32_t width, uint32_t treelet_bytes, cudaStream_t s,
+                          DeviceBVH* d, WideBVH* meta);
 void free_bvh(DeviceBVH* d);
 
 #define B2RT_CUDA_OK(call)                                                                          \

@@ -165,6 +165,17 @@ typedef struct b2rt_bvh b2rt_bvh;
 
 int b2rt_bvh_build(const b2rt_scene_desc* scene, uint32_t max_leaf_size, uint32_t width,
                    uint32_t treelet_bytes, int32_t device, b2rt_bvh** out);
+/* Same result type, built on the device (Morton codes, radix sort, binary radix
+ * tree, bottom-up boxes, wide collapse, subtree packing and serialisation all as CUDA kernels).
+ * Replaces the same reference functions as b2rt_bvh_build; meant for scenes whose host build
+ * dominates set-up (millions of primitives).  Tree quality is LBVH, not SAH. */
+int b2rt_bvh_build_device(const b2rt_scene_desc* scene, uint32_t max_leaf_size, uint32_t width,
+                          uint32_t treelet_bytes, int32_t device, b2rt_bvh** out);
+/* Structural check of the BVH a handle holds (either builder): the subtree blobs are read back
+ * and walked the way the traversal kernel decodes them (every primitive stored once, child boxes
+ * contain their contents, exits point to the next level, byte / stack budgets).  out8 as in
+ * b2rt_bvh_validate_host.  Mirrors the invariants of SURVEY 8c(iii). */
+int b2rt_bvh_validate(b2rt_bvh* bvh, const b2rt_scene_desc* scene, uint64_t out8[8]);
 int b2rt_bvh_intersect(b2rt_bvh* bvh, const float* org, const float* dir, const float* tmin,
                        const float* tmax, uint64_t n, float* hit_t, uint32_t* hit_prim);
 int b2rt_bvh_occluded(b2rt_bvh* bvh, const float* org, const float* dir, const float* tmin,
