@@ -241,16 +241,13 @@ int b2rt_bvh_build_device(const b2rt_scene_desc* scene, uint32_t max_leaf_size, 
   if (!out) { set_error("out is null"); return B2RT_ERR_INVALID; }
   *out = nullptr;
   if (!has_device()) { set_error("no CUDA device available (b2rt has no CPU fallback)"); return B2RT_ERR_NO_DEVICE; }
-  HostScene hs;
-  int rc = make_host_scene(scene, &hs);
-  if (rc) return rc;
   b2rt_bvh* b = new (std::nothrow) b2rt_bvh();
   if (!b) return B2RT_ERR_OOM;
   if (device < 0) cudaGetDevice(&device);
   b->device = device;
   B2RT_CUDA_OK(cudaSetDevice(device));
   B2RT_CUDA_OK(cudaStreamCreateWithFlags(&b->stream, cudaStreamNonBlocking));
-  rc = build_wide_bvh_device(hs, max_leaf_size, width, treelet_bytes, b->stream, &b->dbvh, &b->host_meta);
+  int rc = build_wide_bvh_device(scene, max_leaf_size, width, treelet_bytes, b->stream, &b->dbvh, &b->host_meta);
   if (rc) { b2rt_bvh_destroy(b); return rc; }
   b->max_leaf = max_leaf_size ? max_leaf_size : 4; b->treelet_budget = treelet_bytes;
   B2RT_CUDA_OK(cudaMalloc(&b->n_dev, 4));

@@ -65,6 +65,26 @@ __device__ __forceinline__ void prim_box(const float4* geom, uint32_t i, uint32_
   }
 }
 
+// scene arrays as the caller holds them (9 floats per triangle, 4 per sphere) -> 48-byte primitive records; the same
+// fp32 subtractions as the host path's make_host_scene (e1 = p2 - p1, e2 = p3 - p1, src/static_scene/triangle.cpp:172)
+__global__ void __launch_bounds__(256) k_make_prims(const float* __restrict__ tri_verts, const float* __restrict__ spheres,
+                                                    uint32_t n_tris, uint32_t n, float4* geom) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  if (i < n_tris) {
+    const float* v = tri_verts + (size_t)i * 9;
+    const float v0 = v[0], v1 = v[1], v2 = v[2];
+    geom[3 * (size_t)i] = make_float4(v0, v1, v2, v[3] - v0);
+    geom[3 * (size_t)i + 1] = make_float4(v[4] - v1, v[5] - v2, v[6] - v0, v[7] - v1);
+    geom[3 * (size_t)i + 2] = make_float4(v[8] - v2, __uint_as_float(i), __uint_as_float(0u), 0.f);
+  } else {
+    const float* sp = spheres + (size_t)(i - n_tris) * 4;
+    geom[3 * (size_t)i] = make_float4(sp[0], sp[1], sp[2], sp[3]);
+    geom[3 * (size_t)i + 1] = make_float4(0.f, 0.f, 0.f, 0.f);
+    geom[3 * (size_t)i + 2] = make_float4(0.f, __uint_as_float(i), __uint_as_float(1u), 0.f);
+  }
+}
+
 __global__ void __launch_bounds__(256) k_bounds(const float4* __restrict__ geom, uint32_t n, uint32_t n_tris, SceneBounds* out) {
   float lo[3] = {INFINITY, INFINITY, INFINITY}, hi[3] = {-INFINITY, -INFINITY, -INFINITY};
   double proj = 0;
@@ -414,7 +434,7 @@ struct DevBuf {
 }  // namespace
 
 template <int W>
-static int build_device_w(const HostScene& sc, uint32_t max_leaf, uint32_t treelet_bytes, cudaStream_t s, DeviceBVH* dev, WideBVH* meta) {
+static int build_device_w(const b2rt_scene_desc& sc, uint32_t max_leaf, uint32_t treelet_bytes, cudaStream_t s, DeviceBVH* dev, WideBVH* meta) {
   auto t0 = std::chrono::steady_clock::now();
   const bool verbose = getenv("B2RT_VERBOSE") != nullptr;
   auto lap = [&](const char* what) {
@@ -423,13 +443,18 @@ static int build_device_w(const HostScene& sc, uint32_t max_leaf, uint32_t treel
     fprintf(stderr, "b2rt: gpu build %-10s %8.3f ms\n", what, std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count());
   };
   constexpr uint32_t NB = 32 * W;
-  const uint32_t n = sc.n_prims();
+  const uint32_t n = sc.n_tris + sc.n_spheres;
   const uint32_t depth_limit = stack_entries(W) / (W - 1);
   const uint32_t node_limit = max_treelet_nodes(W);
   DevBuf buf(s);
   float4* geom = nullptr;
-  B2RT_CUDA_OK(buf.alloc(&geom, (size_t)n * 3));
-  B2RT_CUDA_OK(cudaMemcpyAsync(geom, sc.prim_geom.data(), (size_t)n * PRIM_BYTES, cudaMemcpyHostToDevice, s));
+  { float *d_tv = nullptr, *d_sp = nullptr;
+    B2RT_CUDA_OK(buf.alloc(&geom, (size_t)n * 3));
+    B2RT_CUDA_OK(buf.alloc(&d_tv, (size_t)sc.n_tris * 9));
+    B2RT_CUDA_OK(buf.alloc(&d_sp, (size_t)sc.n_spheres * 4));
+    if (sc.n_tris) B2RT_CUDA_OK(cudaMemcpyAsync(d_tv, sc.tri_verts, (size_t)sc.n_tris * 36, cudaMemcpyHostToDevice, s));
+    if (sc.n_spheres) B2RT_CUDA_OK(cudaMemcpyAsync(d_sp, sc.spheres, (size_t)sc.n_spheres * 16, cudaMemcpyHostToDevice, s));
+    k_make_prims<<<(n + 255) / 256, 256, 0, s>>>(d_tv, d_sp, sc.n_tris, n, geom); }
   // 1. scene bounds
   SceneBounds* d_sb = nullptr;
   B2RT_CUDA_OK(buf.alloc(&d_sb, 1));
@@ -587,20 +612,24 @@ static int build_device_w(const HostScene& sc, uint32_t max_leaf, uint32_t treel
   return B2RT_OK;
 }
 
-int build_wide_bvh_device(const HostScene& sc, uint32_t max_leaf, uint32_t width, uint32_t treelet_bytes, cudaStream_t s,
+int build_wide_bvh_device(const b2rt_scene_desc* sc, uint32_t max_leaf, uint32_t width, uint32_t treelet_bytes, cudaStream_t s,
                           DeviceBVH* dev, WideBVH* meta) {
+  if (!sc) { set_error("scene desc is null"); return B2RT_ERR_INVALID; }
+  if (sc->n_tris && !sc->tri_verts) { set_error("tri_verts is null"); return B2RT_ERR_INVALID; }
+  if (sc->n_spheres && !sc->spheres) { set_error("spheres is null"); return B2RT_ERR_INVALID; }
+  const uint64_t n = (uint64_t)sc->n_tris + sc->n_spheres;
   if (width == 0) width = 4;
   if (width != 4 && width != 8) { set_error("bvh width must be 4 or 8"); return B2RT_ERR_INVALID; }
   if (max_leaf == 0) max_leaf = 4;
   if (max_leaf > 64) { set_error("max_leaf_size must be <= 64"); return B2RT_ERR_INVALID; }
-  if (sc.n_prims() == 0) { set_error("gpu bvh build: empty scene"); return B2RT_ERR_INVALID; }
-  if (sc.n_prims() >= (1u << 29)) { set_error("gpu bvh build: too many primitives"); return B2RT_ERR_INVALID; }
+  if (n == 0) { set_error("gpu bvh build: empty scene"); return B2RT_ERR_INVALID; }
+  if (n >= (1u << 29)) { set_error("gpu bvh build: too many primitives"); return B2RT_ERR_INVALID; }
   const uint32_t min_budget = node_bytes(width) + width * max_leaf * PRIM_BYTES;
-  if (treelet_bytes == 0) treelet_bytes = (sc.n_prims() >= 65536 ? 24 : 16) * 1024;
+  if (treelet_bytes == 0) treelet_bytes = (n >= 65536 ? 24 : 16) * 1024;
   treelet_bytes = std::max(treelet_bytes, min_budget) & ~15u;
   if (treelet_bytes > 160 * 1024) { set_error("treelet_bytes exceeds the shared-memory budget (160 KiB)"); return B2RT_ERR_INVALID; }
-  return width == 8 ? build_device_w<8>(sc, max_leaf, treelet_bytes, s, dev, meta)
-                    : build_device_w<4>(sc, max_leaf, treelet_bytes, s, dev, meta);
+  return width == 8 ? build_device_w<8>(*sc, max_leaf, treelet_bytes, s, dev, meta)
+                    : build_device_w<4>(*sc, max_leaf, treelet_bytes, s, dev, meta);
 }
 
 }  // namespace b2rt
