@@ -188,3 +188,23 @@ def camera_rays(cam, width, height, jitter=None):
     d = d / np.linalg.norm(d, axis=-1, keepdims=True)
     o = np.broadcast_to(np.array(cam.pos[:], np.float32), d.shape)
     return np.ascontiguousarray(o.reshape(-1, 3), np.float32), np.ascontiguousarray(d.reshape(-1, 3), np.float32)
+
+
+def cfg3_standin(cbbunny):
+    """BASELINE configs[2] stand-in (the dragon asset is missing from the reference checkout, .MISSING_LARGE_BLOBS):
+    CBbunny with the bunny mesh midpoint-subdivided once -> 114,316 triangles."""
+    return subdivide(cbbunny, 1, select=lambda tv, tm: tm == np.argmax(np.bincount(tm)))
+
+
+def cfg4_standin(cbbunny, levels=2):
+    """BASELINE configs[3] stand-in ("Lucy / largest bundled mesh, mirror + glass BSDFs"; no such asset is bundled): the
+    CBbunny Cornell box with the bunny subdivided twice (457,228 triangles) and made of the glass of CBspheres.dae
+    (ior 1.45), plus two analytic mirror spheres of CBspheres.dae's mirror material beside it."""
+    sc = subdivide(cbbunny, levels, select=lambda tv, tm: tm == np.argmax(np.bincount(tm))) if levels else cbbunny
+    mats = [dict(m) for m in sc.materials]
+    glass = int(np.argmax(np.bincount(sc.tri_material)))
+    mats[glass] = dict(kind=MAT_GLASS, albedo=(1.0, 1.0, 1.0), transmittance=(1.0, 1.0, 1.0), ior=1.45)
+    mats.append(dict(kind=MAT_MIRROR, albedo=(1.0, 1.0, 1.0)))
+    spheres = np.array([[0.68, 0.25, 0.45, 0.25], [-0.66, 0.3, -0.45, 0.3]], np.float32)
+    return Scene(sc.tri_verts, sc.tri_normals, sc.tri_material, spheres, np.full(2, len(mats) - 1, np.uint32), mats, sc.lights,
+                 sc.cam_dir, sc.hfov, sc.vfov, sc.bbox)

@@ -533,6 +533,12 @@ int Renderer::set_scene(const b2rt_scene_desc* d) {
   bvh_stale = true;                // wave buffers are kept; the tracer re-binds its (small) per-subtree arrays
   n_wide_nodes = wb.n_wide_nodes;
   build_ms = wb.build_ms;
+  for (int k = 0; k < 6; ++k) tracer.slice_bbox[k] = wb.bbox[k];
+  tracer.slice_first = 0.f;
+  if (const char* e = getenv("B2RT_RENDER_SLICE")) {   // experiment: distance-sliced traversal inside the renderer
+    float f = 0.f, g = 4.f; int p = 2;
+    if (sscanf(e, "%f,%f,%d", &f, &g, &p) >= 1) { tracer.slice_first = f; tracer.slice_growth = g > 1.f ? g : 4.f; tracer.slice_passes = p >= 2 ? p : 2; }
+  }
   n_tris = hs.n_tris;
   n_lights = (uint32_t)hs.lights.size();
   const size_t np = std::max<size_t>(1, hs.n_prims());
@@ -725,10 +731,10 @@ int Renderer::start() {
       cam_rays_enqueued += n;
       for (uint32_t b = 0; b < max_depth; ++b) {
         bind_lists(b & 1u);
-        RCHECK(tracer.trace(stream, pb.lo, pb.ld, pb.lh, counts + ACT0 + b, false));
+        RCHECK(tracer.trace_sliced(stream, pb.lo, pb.ld, pb.lh, counts + ACT0 + b, n, false));
         k_shade<<<(n + SHADE_THREADS - 1) / SHADE_THREADS, SHADE_THREADS, 0, stream>>>(wp, sd, pb, b); launches++;
         if (S > 0) {
-          RCHECK(tracer.trace(stream, pb.s_o, pb.s_d, pb.s_hits, counts + SH0 + b, true));
+          RCHECK(tracer.trace_sliced(stream, pb.s_o, pb.s_d, pb.s_hits, counts + SH0 + b, (uint64_t)n * S, true));
           k_resolve_shadow<<<g, 256, 0, stream>>>(wp, pb, b); launches++;
         }
       }

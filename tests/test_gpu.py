@@ -338,6 +338,25 @@ def test_dragon_class_standin_parity():
     assert float(np.sqrt(np.mean((pt.hdr() - ref) ** 2))) <= 1e-6
 
 
+def test_cfg4_standin_material_mix_parity():
+    """BASELINE configs[3] stand-in (glass mesh + mirror spheres in the Cornell box) at test size, mesh not subdivided:
+    HDR frame identical to the oracle."""
+    from b2rt.scene import cfg4_standin
+    sc = cfg4_standin(Scene.load(scene_path("CBbunny")), levels=0)
+    w, h = 128, 96
+    cam = place_camera(sc, w, h)
+    cfg = dict(ns_aa=4, max_ray_depth=8, ns_area_light=1, seed=9)
+    pt = b2rt.PathTracer(**cfg)
+    pt.set_scene(sc); pt.set_camera(cam); pt.set_frame_size(w, h)
+    pt.render()
+    img = pt.hdr()
+    ref = orc.OracleScene(sc, 4).render(cam, Config(**cfg), w, h)
+    assert np.isfinite(img).all()
+    rmse = float(np.sqrt(np.mean((img - ref) ** 2)))
+    assert rmse <= 1e-6 and float(np.abs(img - ref).max()) <= 1e-5, rmse
+    pt.close()
+
+
 def test_median_filter_and_progressive_renderer():
     sc = Scene.load(scene_path("CBspheres_lambertian"))
     w, h = 100, 75
