@@ -34,7 +34,15 @@ constexpr uint32_t MAX_LEVELS = 32;
 constexpr uint32_t stack_entries(uint32_t width) { return width == 8 ? (uint32_t)B2RT_STACK8 : (uint32_t)B2RT_STACK4; }
 constexpr uint32_t max_treelet_nodes(uint32_t width) { return width == 8 ? 512u : 1024u; }
 
-inline uint32_t node_bytes(uint32_t width) { return width == 8 ? 256u : 128u; }
+// Byte stride of a wide node inside a subtree blob: 32 * W bytes of rows (6 box rows + child references + 16 B spare)
+// plus B2RT_NODE_PAD.  With a stride of 128 B the same row of every node falls into the same four shared-memory banks,
+// so lanes of a warp that sit at DIFFERENT nodes (incoherent rays) serialise 8-fold on every 128-bit row load; a stride
+// of 144 B rotates the bank group by one per node.
+// Measured (tools/ab_pad.sh): 10 M soup 584 -> 605 Mrays/s incoherent, cfg2 traversal 8.99 -> 8.87 ms, cfg3 stand-in 17.28 -> 17.05 ms.
+#ifndef B2RT_NODE_PAD
+#define B2RT_NODE_PAD 16
+#endif
+constexpr uint32_t node_bytes(uint32_t width) { return (width == 8 ? 256u : 128u) + (uint32_t)B2RT_NODE_PAD; }
 
 struct TreeletDesc {      // one per subtree ("treelet"), 16 B
   uint32_t offset16;      // blob offset / 16

@@ -240,7 +240,7 @@ __global__ void __launch_bounds__(128) k_collapse(BinTree T, WideTmp Wt, const u
                                                   uint32_t max_leaf, uint32_t* overflow) {
   const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
   if (k >= level_count) return;
-  constexpr uint32_t NB = 32 * W;
+  constexpr uint32_t NB = 32u * W + (uint32_t)B2RT_NODE_PAD;   // = node_bytes(W)
   const uint32_t bin = cur_q[k];
   uint32_t kids[W]; float area[W]; int nk = 0;
   if (bin_is_leaf(T, bin, max_leaf)) { kids[nk++] = bin; }
@@ -289,7 +289,7 @@ template <int W>
 __global__ void __launch_bounds__(256) k_sizes(WideTmp Wt, uint32_t level_first, uint32_t level_count) {
   const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
   if (k >= level_count) return;
-  constexpr uint32_t NB = 32 * W;
+  constexpr uint32_t NB = 32u * W + (uint32_t)B2RT_NODE_PAD;   // = node_bytes(W)
   const uint32_t idx = level_first + k;
   const uint32_t* refs = reinterpret_cast<const uint32_t*>(Wt.nodes + (size_t)idx * NB + 24 * W);
   uint64_t bytes = NB + (uint64_t)Wt.own_prims[idx] * PRIM_BYTES;
@@ -321,7 +321,7 @@ template <int W>
 __global__ void __launch_bounds__(64) k_partition(BinTree T, WideTmp Wt, PartParams P) {
   const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
   if (k >= P.n_roots) return;
-  constexpr uint32_t NB = 32 * W;
+  constexpr uint32_t NB = 32u * W + (uint32_t)B2RT_NODE_PAD;   // = node_bytes(W)
   constexpr uint32_t PAD = 28 * W;            // byte offset of a node's unused tail (queue bookkeeping while building)
   const uint32_t tid = P.first_id + k;
   uint8_t* slab = P.slabs + (size_t)tid * P.stride;
@@ -442,7 +442,7 @@ static int build_device_w(const b2rt_scene_desc& sc, uint32_t max_leaf, uint32_t
     cudaStreamSynchronize(s);
     fprintf(stderr, "b2rt: gpu build %-10s %8.3f ms\n", what, std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count());
   };
-  constexpr uint32_t NB = 32 * W;
+  constexpr uint32_t NB = 32u * W + (uint32_t)B2RT_NODE_PAD;   // = node_bytes(W)
   const uint32_t n = sc.n_tris + sc.n_spheres;
   const uint32_t depth_limit = stack_entries(W) / (W - 1);
   const uint32_t node_limit = max_treelet_nodes(W);

@@ -306,12 +306,12 @@ template <int W>
 struct NodeView;
 template <>
 struct NodeView<4> {
-  static constexpr int BYTES = 128;
+  static constexpr int BYTES = (int)node_bytes(4);
   static constexpr int SLOT_BITS = 2;
 };
 template <>
 struct NodeView<8> {
-  static constexpr int BYTES = 256;
+  static constexpr int BYTES = (int)node_bytes(8);
   static constexpr int SLOT_BITS = 3;
 };
 constexpr uint32_t STACK_TN_MASK = 0xFFFFF000u;   // stack entry: [31:12] entry distance bits, [11:0] node << SLOT_BITS | slot

@@ -18,9 +18,10 @@ ap.add_argument("--bvh-width", type=int, default=4)
 ap.add_argument("--max-leaf", type=int, default=4)
 ap.add_argument("--treelet-bytes", type=int, default=0)
 ap.add_argument("--repeats", type=int, default=1)
+ap.add_argument("--builder", default="host", choices=["host", "gpu"])
 a = ap.parse_args()
 soup = random_soup(a.tris)
-bvh = b2rt.BVHAccel(soup, max_leaf_size=a.max_leaf, width=a.bvh_width, treelet_bytes=a.treelet_bytes)
+bvh = b2rt.BVHAccel(soup, max_leaf_size=a.max_leaf, width=a.bvh_width, treelet_bytes=a.treelet_bytes, builder=a.builder)
 ms, hits = bvh.bench_rays(a.rays, mode=a.mode, repeats=a.repeats)
 st = bvh.stats()
 print(f"soup {a.tris} tris, {a.rays} rays mode {a.mode}: {ms:.2f} ms, {a.rays / ms / 1e3:.1f} Mrays/s, {st['bvh_subtrees']} subtrees in "
