@@ -21,7 +21,7 @@ for r in rows[1:]:
         n += 1
 out = {"kernel": "k_traverse", "dram_bytes_per_launch": tot / max(1, n), "launches": n,
        "source": f"{src} (ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none, "
-                 "tools/profile_frame.py --spp 32: one 25 Mi-path wave of cfg2, all traversal launches)",
+                 "one frame of the command named in the file header / profiles/r01_launch_summary.txt, all traversal launches)",
        "note": "dram__bytes_read.sum + dram__bytes_write.sum averaged over the traversal launches of the frame"}
 root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 json.dump(out, open(os.path.join(root, "profiles", "traverse_traffic.json"), "w"), indent=1)
