@@ -128,7 +128,7 @@ __device__ __forceinline__ uint64_t spread21(uint32_t v) {   // 21 bits -> every
   return x;
 }
 
-struct BuildBox { float lo[3], inv[3]; };   // scene box origin and 2^21 / extent per axis
+struct BuildBox { float lo[3], inv[3]; float large2; };   // scene box origin, 2^21 / extent per axis, (large-primitive diagonal)^2
 
 __global__ void __launch_bounds__(256) k_morton(const float4* __restrict__ geom, uint32_t n, uint32_t n_tris, BuildBox bx,
                                                 uint64_t* keys, uint32_t* vals) {
@@ -142,7 +142,12 @@ __global__ void __launch_bounds__(256) k_morton(const float4* __restrict__ geom,
     const float c = (0.5f * (l[k] + h[k]) - bx.lo[k]) * bx.inv[k];
     q[k] = (uint32_t)fminf(fmaxf(c, 0.f), 2097151.f);
   }
-  keys[i] = spread21(q[0]) | (spread21(q[1]) << 1) | (spread21(q[2]) << 2);
+  // Primitives much larger than their neighbours (the walls of a box around a fine mesh) poison a spatial-median tree:
+  // sorted by centre they end up deep among the small ones and inflate every ancestor box.  They get the top key bit, so
+  // the radix tree's first split separates them into a small subtree of their own next to the root.
+  const float dx = h[0] - l[0], dy = h[1] - l[1], dz = h[2] - l[2];
+  const uint64_t big = (dx * dx + dy * dy + dz * dz > bx.large2) ? (1ull << 63) : 0ull;
+  keys[i] = big | spread21(q[0]) | (spread21(q[1]) << 1) | (spread21(q[2]) << 2);
   vals[i] = i;
 }
 
@@ -482,12 +487,14 @@ static int build_device_w(const b2rt_scene_desc& sc, uint32_t max_leaf, uint32_t
   B2RT_CUDA_OK(buf.alloc(&vals_a, n)); B2RT_CUDA_OK(buf.alloc(&vals_b, n));
   BuildBox bx;
   for (int k = 0; k < 3; ++k) { bx.lo[k] = lo[k]; const float e = hi[k] - lo[k]; bx.inv[k] = e > 0.f ? 2097152.f / e : 0.f; }
+  { float f = 0.125f; if (const char* e = getenv("B2RT_LARGE_PRIM")) f = (float)atof(e);   // fraction of the scene diagonal; 0 = off
+    bx.large2 = f > 0.f ? (f * diag) * (f * diag) : INFINITY; }
   k_morton<<<(n + 255) / 256, 256, 0, s>>>(geom, n, sc.n_tris, bx, keys_a, vals_a);
   size_t temp_bytes = 0;
-  B2RT_CUDA_OK(cub::DeviceRadixSort::SortPairs(nullptr, temp_bytes, keys_a, keys_b, vals_a, vals_b, (int)n, 0, 63, s));
+  B2RT_CUDA_OK(cub::DeviceRadixSort::SortPairs(nullptr, temp_bytes, keys_a, keys_b, vals_a, vals_b, (int)n, 0, 64, s));
   uint8_t* temp = nullptr;
   B2RT_CUDA_OK(buf.alloc(&temp, temp_bytes));
-  B2RT_CUDA_OK(cub::DeviceRadixSort::SortPairs(temp, temp_bytes, keys_a, keys_b, vals_a, vals_b, (int)n, 0, 63, s));
+  B2RT_CUDA_OK(cub::DeviceRadixSort::SortPairs(temp, temp_bytes, keys_a, keys_b, vals_a, vals_b, (int)n, 0, 64, s));
   const uint64_t* keys = keys_b; const uint32_t* sorted = vals_b;
   lap("sort");
   // 4./5. radix tree + boxes

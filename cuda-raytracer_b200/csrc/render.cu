@@ -526,10 +526,15 @@ int Renderer::set_scene(const b2rt_scene_desc* d) {
   RCHECK(make_host_scene(d, &hs));
   lap("host scene");
   WideBVH wb;
-  RCHECK(build_wide_bvh(hs, cfg.max_leaf_size, cfg.bvh_width, cfg.treelet_bytes, &wb));
-  lap("bvh build");
-  RCHECK(upload_bvh(wb, &dbvh));   // grow-only device buffers: no cudaMalloc/cudaFree when the scene fits
-  lap("bvh upload");
+  if (getenv("B2RT_BUILDER") && !strcmp(getenv("B2RT_BUILDER"), "gpu")) {   // experiment: device builder inside the renderer
+    RCHECK(build_wide_bvh_device(d, cfg.max_leaf_size, cfg.bvh_width, cfg.treelet_bytes, stream, &dbvh, &wb));
+    lap("bvh build (device)");
+  } else {
+    RCHECK(build_wide_bvh(hs, cfg.max_leaf_size, cfg.bvh_width, cfg.treelet_bytes, &wb));
+    lap("bvh build");
+    RCHECK(upload_bvh(wb, &dbvh));   // grow-only device buffers: no cudaMalloc/cudaFree when the scene fits
+    lap("bvh upload");
+  }
   bvh_stale = true;                // wave buffers are kept; the tracer re-binds its (small) per-subtree arrays
   n_wide_nodes = wb.n_wide_nodes;
   build_ms = wb.build_ms;
