@@ -176,9 +176,12 @@ k_shade(WaveParams wp, SceneDev sc, PathBufs pb, uint32_t b) {
   // and the 64-byte light record in registers across the kernel was the main source of spills at 64 registers
   const b2rt_material* mp = sc.materials;
   int32_t m_kind = -1;
+  float4 ro = make_float4(0.f, 0.f, 0.f, 0.f), rd = make_float4(0.f, 0.f, 1.f, 0.f), thr4 = make_float4(0.f, 0.f, 0.f, 0.f);
   if (i < n) {
     slot = pb.lslot[i];
     h = pb.lh[i];
+    // independent of the hit word: issued together with it instead of behind the material lookup (shorter dependent chain)
+    ro = pb.lo[i]; rd = pb.ld[i]; thr4 = pb.thr[slot];
     prim = (uint32_t)h;
     if (prim != 0xFFFFFFFFu) { mp = sc.materials + sc.prim_material[prim]; m_kind = __ldg(&mp->kind); }
   }
@@ -193,7 +196,6 @@ k_shade(WaveParams wp, SceneDev sc, PathBufs pb, uint32_t b) {
     pb.s_q0[slot] = q0;
     if (prim != 0xFFFFFFFFu) {
       const float t = __uint_as_float((uint32_t)(h >> 32));
-      const float4 thr4 = pb.thr[slot];
       f3 thr = mk3(thr4.x, thr4.y, thr4.z);
       const bool count_emission = thr4.w != 0.f;
       if (m_kind == B2RT_MAT_EMISSION) {
@@ -204,7 +206,6 @@ k_shade(WaveParams wp, SceneDev sc, PathBufs pb, uint32_t b) {
           pb.rad[slot] = L;
         }
       } else {
-        const float4 ro = pb.lo[i], rd = pb.ld[i];
         const f3 o = mk3(ro.x, ro.y, ro.z), d = mk3(rd.x, rd.y, rd.z);
         const f3 P = o + d * t;
         PrimRec pr;
