@@ -38,6 +38,16 @@ def test_fails_loudly_without_device():
     with pytest.raises(b2rt.B2rtError) as e:
         b2rt.PathTracer()
     assert e.value.code == -2
+    with pytest.raises(b2rt.B2rtError) as e:
+        b2rt.BVHAccel(sc, builder="gpu")      # b2rt_bvh_build_device: the device builder has no host fallback either
+    assert e.value.code == -2 and "no CPU fallback" in str(e.value)
+
+
+def test_new_bvh_entry_points_reject_null_handles():
+    lib = b2rt.lib()
+    assert lib.b2rt_bvh_set_slicing(None, C.c_float(1.0), C.c_float(4.0), 4) == -1
+    assert lib.b2rt_bvh_validate(None, None, None) == -1
+    assert lib.b2rt_bvh_build_device(None, 4, 4, 0, -1, None) == -1
 
 
 def test_product_does_not_link_oracle():
@@ -112,9 +122,14 @@ def test_scene_file_roundtrip_and_camera(tmp_path):
 
 
 def test_subdivide_standin():
+    from b2rt.scene import cfg3_standin, cfg4_standin
     sc = Scene.load(scene_path("CBbunny"))
-    big = subdivide(sc, 1, select=lambda tv, tm: tm == tm[np.argmax(np.bincount(tm))])
+    big = cfg3_standin(sc)
     assert big.n_tris == 12 + 28576 * 4     # "CBdragon_standin" = 114,316 triangles
+    c4 = cfg4_standin(sc)                    # BASELINE configs[3] stand-in: glass mesh subdivided twice + mirror spheres
+    assert c4.n_tris == 12 + 28576 * 16 and len(c4.spheres) == 2
+    kinds = [m["kind"] for m in c4.materials]
+    assert 2 in kinds and 1 in kinds         # MAT_GLASS, MAT_MIRROR
     st = b2rt.validate_bvh_host(big, 4, 4, 0)
     assert st["leaves"] > 20000
 
