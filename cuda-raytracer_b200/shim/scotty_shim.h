@@ -59,9 +59,13 @@ struct Intersection {  // src/intersection.h:21-32 (t, primitive); n / bsdf are 
 class BVHAccel {
  public:
   // BVHAccel(const std::vector<Primitive*>&, size_t max_leaf_size = 4)   src/bvh.h:110-112
-  explicit BVHAccel(const b2rt_scene_desc* prims, size_t max_leaf_size = 4, uint32_t width = 4) {
-    check(b2rt_bvh_build(prims, (uint32_t)max_leaf_size, width, 0, -1, &h_));
+  // build_on_device: construct the tree with the CUDA builder (b2rt_bvh_build_device) instead of on the host cores
+  explicit BVHAccel(const b2rt_scene_desc* prims, size_t max_leaf_size = 4, uint32_t width = 4, bool build_on_device = false) {
+    check(build_on_device ? b2rt_bvh_build_device(prims, (uint32_t)max_leaf_size, width, 0, -1, &h_)
+                          : b2rt_bvh_build(prims, (uint32_t)max_leaf_size, width, 0, -1, &h_));
   }
+  // distance slices of the batch traversal (b2rt_bvh_set_slicing): > 0 first slice length, 0 off, < 0 automatic
+  void set_slicing(float first_slice, float growth = 4.f, int passes = 4) { check(b2rt_bvh_set_slicing(h_, first_slice, growth, passes)); }
   ~BVHAccel() { b2rt_bvh_destroy(h_); }
   BVHAccel(const BVHAccel&) = delete;
   BVHAccel& operator=(const BVHAccel&) = delete;
