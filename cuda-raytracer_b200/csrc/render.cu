@@ -527,7 +527,10 @@ int Renderer::set_scene(const b2rt_scene_desc* d) {
   RCHECK(make_host_scene(d, &hs));
   lap("host scene");
   WideBVH wb;
-  if (getenv("B2RT_BUILDER") && !strcmp(getenv("B2RT_BUILDER"), "gpu")) {   // experiment: device builder inside the renderer
+  // cfg.bvh_builder: 0 automatic (device build from 2^20 primitives on), 1 host, 2 device; B2RT_BUILDER=gpu|host overrides
+  bool on_device = cfg.bvh_builder == 2 || (cfg.bvh_builder == 0 && hs.n_prims() >= (1u << 20));
+  if (const char* e = getenv("B2RT_BUILDER")) on_device = !strcmp(e, "gpu");
+  if (on_device && hs.n_prims() > 0) {
     RCHECK(build_wide_bvh_device(d, cfg.max_leaf_size, cfg.bvh_width, cfg.treelet_bytes, stream, &dbvh, &wb));
     lap("bvh build (device)");
   } else {

@@ -122,6 +122,9 @@ typedef struct b2rt_config {
      s = sample_first + k*sample_stride, k = 0..ns_aa_local-1 (ns_aa is the LOCAL count). */
   uint32_t sample_first;
   uint32_t sample_stride;    /* 0 -> 1 */
+  uint32_t bvh_builder;      /* 0 -> automatic: host binned-SAH build (better trees for meshes inside large boxes) below
+                                2^20 primitives, device LBVH build (b2rt_bvh_build_device) from there on, where the
+                                host build would take seconds; 1 -> host; 2 -> device */
 } b2rt_config;
 
 typedef struct b2rt_stats {

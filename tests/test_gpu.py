@@ -182,9 +182,10 @@ def test_distance_sliced_trace_is_identical(first, growth, passes):
 def test_soup_automatic_slicing_parity_and_fewer_visits():
     """On a deep subtree graph the automatic slices (2 mean free paths) are on by default: same hits as the oracle and
     as the unsliced trace, with fewer subtree visits per ray."""
-    sc = random_soup(300000, size=0.02)
+    sc = random_soup(300000, size=0.05)     # mean free path ~0.02: the automatic first slice (2 mfp) is far below diagonal / 8
     o = orc.OracleScene(sc, 4)
     bvh = b2rt.BVHAccel(sc, treelet_bytes=16384)
+    assert bvh.stats()["bvh_levels"] >= 3
     org, dirs = _rays(sc, 200000, 22)
     t, p = bvh.intersect(org, dirs)
     v_sliced = bvh.stats()["subtree_visits"]
@@ -194,7 +195,7 @@ def test_soup_automatic_slicing_parity_and_fewer_visits():
     assert np.array_equal(p, p0) and np.array_equal(t, t0)
     tr, pr = o.intersect(org[:50000], dirs[:50000])
     assert np.array_equal(p[:50000], pr) and np.array_equal(t[:50000], tr)
-    assert v_sliced < v_plain, (v_sliced, v_plain)
+    assert v_sliced < 0.8 * v_plain, (v_sliced, v_plain)
     bvh.close()
 
 
@@ -336,6 +337,27 @@ def test_dragon_class_standin_parity():
     pt.set_scene(sc); pt.set_camera(cam); pt.set_frame_size(w, h); pt.render()
     ref = o.render(cam, Config(ns_aa=2, max_ray_depth=8, ns_area_light=1, seed=4), w, h)
     assert float(np.sqrt(np.mean((pt.hdr() - ref) ** 2))) <= 1e-6
+
+
+@pytest.mark.parametrize("name", ["CBbunny", "CBspheres", "CBcoil"])
+def test_renderer_on_device_built_bvh(name):
+    """b2rt_config.bvh_builder = 2: b2rt_set_scene builds the BVH on the device; the frame stays identical to the oracle
+    (and therefore to the host-built path)."""
+    sc = Scene.load(scene_path(name))
+    w, h = 128, 96
+    cam = place_camera(sc, w, h)
+    cfg = dict(ns_aa=4, max_ray_depth=6, ns_area_light=1, seed=5)
+    pt = b2rt.PathTracer(bvh_builder=2, **cfg)
+    pt.set_scene(sc); pt.set_camera(cam); pt.set_frame_size(w, h)
+    pt.render()
+    img = pt.hdr()
+    ref = orc.OracleScene(sc, 4).render(cam, Config(**cfg), w, h)
+    rmse = float(np.sqrt(np.mean((img - ref) ** 2)))
+    assert rmse <= 1e-6 and float(np.abs(img - ref).max()) <= 1e-5, rmse
+    pt.set_scene(sc)                 # rebuild into the same device buffers
+    pt.clear(); pt.render()
+    assert np.array_equal(pt.hdr(), img)
+    pt.close()
 
 
 def test_cfg4_standin_material_mix_parity():
