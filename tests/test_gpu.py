@@ -179,6 +179,32 @@ def test_distance_sliced_trace_is_identical(first, growth, passes):
     bvh.close()
 
 
+def test_degenerate_rays_sliced_and_plain():
+    """Empty windows (tmin > tmax), zero and NaN directions, origins far outside the scene, infinite tmax: the sliced
+    and the plain trace agree with the oracle (a NaN never hits: every accept test is written positively)."""
+    sc = Scene.load(scene_path("CBbunny"))
+    o = orc.OracleScene(sc, 4)
+    bvh = b2rt.BVHAccel(sc, treelet_bytes=4096, max_leaf_size=2)
+    org, dirs = _mixed_rays(sc, 4000, 9, 64, 48)
+    n = len(org)
+    tmin = np.zeros(n, np.float32); tmax = np.full(n, np.inf, np.float32)
+    tmin[0::7] = 2.0; tmax[0::7] = 1.0                      # empty windows
+    dirs[1::11] = 0.0                                        # zero directions
+    dirs[2::13, 1] = np.nan                                  # NaN component
+    org[3::17] = org[3::17] * 1e4 + 3e4                      # far away
+    org[4::19, 0] = np.inf                                   # infinite origin component
+    tmax[5::23] = 0.0                                        # zero-length window at the origin
+    tr, pr = o.intersect(org, dirs, tmin, tmax)
+    for first in (0.0, 0.2, 5.0):
+        bvh.set_slicing(first, 3.0, 3)
+        t, p = bvh.intersect(org, dirs, tmin, tmax)
+        assert np.array_equal(p, pr), (first, int(np.sum(p != pr)))
+        assert np.array_equal(t, tr)
+        occ = bvh.occluded(org, dirs, tmin, tmax)
+        assert np.array_equal(occ, pr != MISS)
+    bvh.close()
+
+
 def test_soup_automatic_slicing_parity_and_fewer_visits():
     """On a deep subtree graph the automatic slices (2 mean free paths) are on by default: same hits as the oracle and
     as the unsliced trace, with fewer subtree visits per ray."""
