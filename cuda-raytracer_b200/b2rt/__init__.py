@@ -225,12 +225,14 @@ class PathTracer:
 
     def __init__(self, ns_aa=1, max_ray_depth=4, ns_area_light=1, ns_diff=1, ns_glsy=1, ns_refr=1, num_threads=1,
                  envmap=None, seed=0, device=-1, bvh_width=0, max_leaf_size=0, treelet_bytes=0, max_wave_paths=0,
-                 median_threshold=0, sample_first=0, sample_stride=1, ray_eps=0.0, bvh_builder=0):
+                 median_threshold=0, sample_first=0, sample_stride=1, ray_eps=0.0, bvh_builder=0, filter_kind=0,
+                 filter_sigma_r=0.0):
         self.cfg = Config(ns_aa=ns_aa, max_ray_depth=max_ray_depth, ns_area_light=ns_area_light, seed=seed,
                           ray_eps=ray_eps, bvh_width=bvh_width, max_leaf_size=max_leaf_size,
                           treelet_bytes=treelet_bytes, max_wave_paths=max_wave_paths,
                           median_threshold=median_threshold, device=device, sample_first=sample_first,
-                          sample_stride=sample_stride, bvh_builder=bvh_builder)
+                          sample_stride=sample_stride, bvh_builder=bvh_builder, filter_kind=filter_kind,
+                          filter_sigma_r=filter_sigma_r)
         h = C.c_void_p()
         _check(lib().b2rt_create(C.byref(self.cfg), C.byref(h)))
         self._h = h

@@ -36,7 +36,8 @@ class Config(C.Structure):
                 ("seed", C.c_uint64), ("ray_eps", C.c_float), ("bvh_width", C.c_uint32),
                 ("max_leaf_size", C.c_uint32), ("treelet_bytes", C.c_uint32), ("max_wave_paths", C.c_uint32),
                 ("median_threshold", C.c_uint32), ("device", C.c_int32), ("sample_first", C.c_uint32),
-                ("sample_stride", C.c_uint32), ("bvh_builder", C.c_uint32)]
+                ("sample_stride", C.c_uint32), ("bvh_builder", C.c_uint32), ("filter_kind", C.c_uint32),
+                ("filter_sigma_r", C.c_float)]
 
 
 class Stats(C.Structure):

@@ -432,6 +432,49 @@ k_median3x3(const float4* __restrict__ in, float4* __restrict__ out, uint32_t w,
   out[(size_t)y * w + x] = r;
 }
 
+// Gaussian / joint bilateral reconstruction filters (b2rt_config.filter_kind 1 / 2): R = 1 with binomial weights
+// (1,2,1) or R = 2 with (1,4,6,4,1); taps outside the image are dropped and the weights renormalised; the bilateral
+// range weight is 1 / (1 + |c_q - c_p|^2 * inv_s2).  Taps are accumulated in row-major order with separate multiply and
+// add (no contraction), the same order as the oracle's restatement, so the result is bit-identical to it.
+template <int R, bool BILATERAL>
+__global__ void __launch_bounds__(256)
+k_filter(const float4* __restrict__ in, float4* __restrict__ out, uint32_t w, uint32_t h, float inv_s2) {
+  constexpr int TW = 32 + 2 * R, TH = 8 + 2 * R;
+  __shared__ float4 tile[TH][TW];
+  const int bx = blockIdx.x * 32, by = blockIdx.y * 8;
+  for (int k = threadIdx.y * 32 + threadIdx.x; k < TH * TW; k += 256) {
+    const int ty = k / TW, tx = k % TW;
+    const int x = bx + tx - R, y = by + ty - R;
+    const bool inside = x >= 0 && y >= 0 && x < (int)w && y < (int)h;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);            // .w = 1 marks a tap inside the image
+    if (inside) { v = in[(size_t)y * w + x]; v.w = 1.f; }
+    tile[ty][tx] = v;
+  }
+  __syncthreads();
+  const int x = bx + threadIdx.x, y = by + threadIdx.y;
+  if (x >= (int)w || y >= (int)h) return;
+  const int tx = threadIdx.x + R, ty = threadIdx.y + R;
+  const float4 c = tile[ty][tx];
+  float ar = 0.f, ag = 0.f, ab = 0.f, ws = 0.f;
+#pragma unroll
+  for (int dy = -R; dy <= R; ++dy)
+#pragma unroll
+    for (int dx = -R; dx <= R; ++dx) {
+      const float4 q = tile[ty + dy][tx + dx];
+      if (q.w == 0.f) continue;
+      const float bw = R == 1 ? (float)((2 - (dx < 0 ? -dx : dx)) * (2 - (dy < 0 ? -dy : dy)))
+                              : (float)((dx == 0 ? 6 : (dx == 1 || dx == -1 ? 4 : 1)) * (dy == 0 ? 6 : (dy == 1 || dy == -1 ? 4 : 1)));
+      float wgt = bw;
+      if (BILATERAL) {
+        const float dr = q.x - c.x, dg = q.y - c.y, db = q.z - c.z;
+        const float d2 = (dr * dr + dg * dg) + db * db;
+        wgt = bw * __fdiv_rn(1.0f, 1.0f + d2 * inv_s2);
+      }
+      ar = ar + wgt * q.x; ag = ag + wgt * q.y; ab = ab + wgt * q.z; ws = ws + wgt;
+    }
+  out[(size_t)y * w + x] = make_float4(__fdiv_rn(ar, ws), __fdiv_rn(ag, ws), __fdiv_rn(ab, ws), 1.0f);
+}
+
 // toColor + update_pixel, src/image.h:49-58,173-188
 __global__ void __launch_bounds__(256)
 k_tonemap(const float4* __restrict__ img, uint32_t* __restrict__ out, uint32_t n_pix) {
@@ -819,7 +862,14 @@ int Renderer::resolve(bool want_ldr) {
   resolved = img_a;
   if (cfg.median_threshold && samples_done < cfg.median_threshold) {
     dim3 grid((width + 31) / 32, (height + 7) / 8), block(32, 8);
-    k_median3x3<<<grid, block, 0, stream>>>((const float4*)img_a, (float4*)img_b, width, height);
+    if (cfg.filter_kind == 1) {
+      k_filter<1, false><<<grid, block, 0, stream>>>((const float4*)img_a, (float4*)img_b, width, height, 0.f);
+    } else if (cfg.filter_kind == 2) {
+      const float sr = cfg.filter_sigma_r > 0.f ? cfg.filter_sigma_r : 0.25f;
+      k_filter<2, true><<<grid, block, 0, stream>>>((const float4*)img_a, (float4*)img_b, width, height, 1.0f / (sr * sr));
+    } else {
+      k_median3x3<<<grid, block, 0, stream>>>((const float4*)img_a, (float4*)img_b, width, height);
+    }
     resolved = img_b;
   }
   if (want_ldr) k_tonemap<<<(np + 255) / 256, 256, 0, stream>>>((const float4*)resolved, ldr, np);

@@ -125,6 +125,13 @@ typedef struct b2rt_config {
   uint32_t bvh_builder;      /* 0 -> automatic: host binned-SAH build (better trees for meshes inside large boxes) below
                                 2^20 primitives, device LBVH build (b2rt_bvh_build_device) from there on, where the
                                 host build would take seconds; 1 -> host; 2 -> device */
+  /* Reconstruction filter applied while total spp < median_threshold.  0 = the reference's 3x3
+     per-channel median (kernelMedianFilter, src/cudaRenderer.cu:773-842); 1 = 3x3 binomial Gaussian (the reference
+     has one commented out, :755-771; weights (1,2,1)x(1,2,1), taps outside the image dropped and the rest
+     renormalised); 2 = 5x5 joint bilateral: binomial (1,4,6,4,1)^2 spatial weights times the range weight
+     1 / (1 + |c_q - c_p|^2 / sigma_r^2) on the RGB difference to the centre pixel. */
+  uint32_t filter_kind;
+  float filter_sigma_r;      /* bilateral range scale; 0 -> 0.25 */
 } b2rt_config;
 
 typedef struct b2rt_stats {

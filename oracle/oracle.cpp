@@ -763,6 +763,38 @@ void orc_median3x3(const float* rgb, uint32_t w, uint32_t h, float* out) {
       }
 }
 
+// Gaussian (kind 1: 3x3 binomial) / joint bilateral (kind 2: 5x5 binomial x 1/(1 + |dc|^2/sigma_r^2)) reconstruction
+// filters, b2rt_config.filter_kind.  No reference implementation exists (the reference's Gaussian is commented out,
+// src/cudaRenderer.cu:755-771); this restatement fixes the definition: taps outside the image are dropped, weights
+// renormalised, taps accumulated in row-major order with separate multiply and add.
+void orc_filter(uint32_t kind, float sigma_r, const float* rgb, uint32_t w, uint32_t h, float* out) {
+  const int R = kind == 2 ? 2 : 1;
+  const float sr = sigma_r > 0.f ? sigma_r : 0.25f;
+  const float inv_s2 = 1.0f / (sr * sr);
+  static const int B1[3] = {1, 2, 1}, B2[5] = {1, 4, 6, 4, 1};
+  for (uint32_t y = 0; y < h; ++y)
+    for (uint32_t x = 0; x < w; ++x) {
+      const float* c = rgb + 3 * ((size_t)x + (size_t)y * w);
+      float a[3] = {0.f, 0.f, 0.f}, ws = 0.f;
+      for (int dy = -R; dy <= R; ++dy)
+        for (int dx = -R; dx <= R; ++dx) {
+          const int xx = (int)x + dx, yy = (int)y + dy;
+          if (xx < 0 || yy < 0 || xx >= (int)w || yy >= (int)h) continue;
+          const float* q = rgb + 3 * ((size_t)xx + (size_t)yy * w);
+          const float bw = R == 1 ? (float)(B1[dx + 1] * B1[dy + 1]) : (float)(B2[dx + 2] * B2[dy + 2]);
+          float wgt = bw;
+          if (kind == 2) {
+            const float dr = q[0] - c[0], dg = q[1] - c[1], db = q[2] - c[2];
+            const float d2 = (dr * dr + dg * dg) + db * db;
+            wgt = bw * (1.0f / (1.0f + d2 * inv_s2));
+          }
+          for (int k = 0; k < 3; ++k) a[k] = a[k] + wgt * q[k];
+          ws = ws + wgt;
+        }
+      for (int k = 0; k < 3; ++k) out[3 * ((size_t)x + (size_t)y * w) + k] = a[k] / ws;
+    }
+}
+
 // known-answer helpers for tests
 void orc_philox(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1, uint32_t* out4) {
   philox4x32_10(c0, c1, c2, c3, k0, k1, out4);

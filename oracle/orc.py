@@ -34,6 +34,7 @@ def lib():
                                     C.c_int, C.c_void_p, C.c_void_p, C.POINTER(C.c_double), C.c_uint32]
         _lib.orc_tonemap.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p]
         _lib.orc_median3x3.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p]
+        _lib.orc_filter.argtypes = [C.c_uint32, C.c_float, C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p]
         _lib.orc_philox.argtypes = [C.c_uint32] * 6 + [C.c_void_p]
         _lib.orc_sincos2pi.argtypes = [C.c_float, C.POINTER(C.c_float), C.POINTER(C.c_float)]
     return _lib
@@ -90,6 +91,14 @@ def tonemap(rgb):
     rgb = np.ascontiguousarray(rgb, np.float32)
     out = np.zeros(rgb.shape[:-1], np.uint32)
     lib().orc_tonemap(rgb.ctypes.data, out.size, out.ctypes.data)
+    return out
+
+
+def recon_filter(rgb, kind, sigma_r=0.0):
+    """b2rt_config.filter_kind 1 (3x3 Gaussian) / 2 (5x5 joint bilateral)."""
+    rgb = np.ascontiguousarray(rgb, np.float32)
+    out = np.zeros_like(rgb)
+    lib().orc_filter(kind, sigma_r, rgb.ctypes.data, rgb.shape[1], rgb.shape[0], out.ctypes.data)
     return out
 
 

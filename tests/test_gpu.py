@@ -425,6 +425,24 @@ def test_median_filter_and_progressive_renderer():
     np.testing.assert_array_equal(r.getImage()[..., :3], orc.median3x3(ref1))
 
 
+@pytest.mark.parametrize("kind,sigma_r", [(1, 0.0), (2, 0.0), (2, 0.05)])
+def test_gaussian_and_bilateral_reconstruction_filters(kind, sigma_r):
+    """b2rt_config.filter_kind 1 / 2: the filtered frame is bit-identical to the oracle's restatement
+    applied to the oracle's frame, on an image size that is not a multiple of the 32 x 8 tile."""
+    sc = Scene.load(scene_path("CBspheres_lambertian"))
+    w, h = 101, 75
+    r = b2rt.CudaRenderer(samples_per_frame=2, max_ray_depth=3, ns_area_light=2, median_threshold=32, seed=6,
+                          filter_kind=kind, filter_sigma_r=sigma_r)
+    r.allocOutputImage(w, h); r.loadScene(sc); r.setup()
+    r.render()
+    img = r.getImage()
+    cam = place_camera(sc, w, h)
+    ref = orc.OracleScene(sc, 4).render(cam, Config(ns_aa=2, max_ray_depth=3, ns_area_light=2, seed=6), w, h)
+    np.testing.assert_array_equal(img[..., :3], orc.recon_filter(ref, kind, sigma_r))
+    assert np.all(img[..., 3] == 1.0)
+    assert not np.array_equal(img[..., :3], ref)
+
+
 def test_state_machine_and_errors():
     sc = Scene.load(scene_path("CBempty"))
     pt = b2rt.PathTracer(ns_aa=1)

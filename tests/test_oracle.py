@@ -155,3 +155,24 @@ def test_soup_bvh_equals_exhaustive():
     tb, pb = o.intersect(org, dirs, mode="brute")
     tv, pv = o.intersect(org, dirs, mode="bvh")
     assert np.array_equal(pb, pv) and np.array_equal(tb, tv)
+
+
+def test_reconstruction_filters_properties():
+    """Oracle restatement of the Gaussian / joint bilateral filters (b2rt_config.filter_kind): normalised weights (a
+    constant image is a fixed point, also at the border), a very wide range scale turns the bilateral filter into the
+    5x5 binomial blur, a narrow one keeps a step edge that the Gaussian smears."""
+    rng = np.random.default_rng(4)
+    const = np.full((9, 13, 3), 0.37, np.float32)
+    for kind in (1, 2):
+        np.testing.assert_allclose(orc.recon_filter(const, kind), const, rtol=1e-6)
+    img = rng.random((20, 31, 3)).astype(np.float32)
+    b = np.array([1, 4, 6, 4, 1], np.float64)
+    k5 = np.outer(b, b)
+    wide = orc.recon_filter(img, 2, 1e6)
+    y, x = 10, 15                                   # interior pixel: plain 5x5 binomial average
+    want = (img[y - 2:y + 3, x - 2:x + 3].astype(np.float64) * k5[..., None]).sum((0, 1)) / k5.sum()
+    np.testing.assert_allclose(wide[y, x], want, rtol=1e-5)
+    step = np.zeros((16, 16, 3), np.float32); step[:, 8:] = 1.0
+    g = orc.recon_filter(step, 1); bl = orc.recon_filter(step, 2, 0.05)
+    assert 0.2 < g[8, 7, 0] < 0.3 and g[8, 8, 0] > 0.7          # Gaussian: (1,2,1)/4 across the edge
+    assert bl[8, 7, 0] < 0.01 and bl[8, 8, 0] > 0.99             # bilateral: the edge survives
