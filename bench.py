@@ -10,7 +10,10 @@ traversals per path, shading, accumulation.  `value` counts every ray actually t
 shadow) over all ranks / max-over-ranks device time of the K timed steps.  Multi-GPU: samples are
 sharded by index (rank r renders samples r, r+N, ...; per-GPU work fixed => weak scaling) with the scene
 replicated, and the per-GPU accumulation buffers are combined with ONE NCCL reduce per frame, inside the
-timed region.  Prints exactly one JSON line on rank 0.
+timed region.  `roofline` (per-launch timing of k_traverse) comes from a second pass of the same K frames with
+per-launch CUDA events, in which the renderer runs on one stream (in the timed region it overlaps the shadow-ray trace
+of bounce b with the closest-hit trace of bounce b + 1 on two streams, so launches have no duration of their own).
+Prints exactly one JSON line on rank 0.
 """
 import argparse
 import json
@@ -213,7 +216,7 @@ def main():
     pt.set_profiling(counters=True, time_kernels=False)
     frame()
     cst = pt.stats()
-    pt.set_profiling(counters=False, time_kernels=True)
+    pt.set_profiling(counters=False, time_kernels=False)
     for _ in range(args.warmup):
         frame()
     if world > 1:
@@ -224,23 +227,33 @@ def main():
         clocks.start()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     rays = 0
-    ms_trav = 0.0
     launches = 0
-    trav_launches = 0
     ev0.record(stream)
     for _ in range(args.steps):
         frame()
         st = pt.stats()
         rays += st["rays_camera"] + st["rays_bounce"] + st["rays_shadow"]
-        ms_trav += st["ms_traverse"]
         launches += st["kernel_launches"]
-        trav_launches += st["traverse_launches"]
     ev1.record(stream)
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
     clk = clocks.stop() if rank == 0 else None
     ms = ev0.elapsed_time(ev1)
+    # Per-launch timing of k_traverse (roofline): the SAME K frames again with CUDA events around every traversal launch.
+    # In the timed region above the renderer runs the shadow-ray trace of bounce b on a second stream next to the
+    # closest-hit trace of bounce b + 1, so launches overlap and have no duration of their own; with per-launch timing on
+    # the renderer uses one stream and every launch is timed alone (the same serialisation an ncu launch list shows).
+    ms_trav = 0.0
+    trav_launches = 0
+    ms_iso = 0.0
+    pt.set_profiling(counters=False, time_kernels=True)
+    for _ in range(args.steps):
+        frame()
+        st = pt.stats()
+        ms_trav += st["ms_traverse"]
+        trav_launches += st["traverse_launches"]
+        ms_iso += st["ms_total"]
     if world > 1:
         t = torch.tensor([ms], device="cuda", dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -320,7 +333,9 @@ def main():
                 "kernel": "k_traverse", "peak_source": peak_src, "launches_per_step": tl,
                 "avg_launch_ms": trav_ms_frame / tl, "alg_bytes_per_launch": alg_bytes / tl,
                 "alg_bytes_per_ray": alg_bytes / max(1, cst["rays_camera"] + cst["rays_bounce"] + cst["rays_shadow"]),
-                "kernel_share_of_step": trav_ms_frame / (ms / args.steps),
+                "kernel_share_of_step": ms_trav / ms_iso,
+                "timing": "per-launch CUDA events in a second pass of the same K frames on one stream (launches timed alone; "
+                          f"that pass: {ms_iso / args.steps:.3f} ms/frame); the timed region overlaps launches on two streams",
                 "fp32": {"achieved_tflops": fp32_ach, "peak_tflops": fp32_peak, "frac": fp32_ach / fp32_peak,
                          "peak_source": f"148 SMs x 128 lanes x 2 x {sm_mhz:.0f} MHz (clock observed under load)"},
                 "binding_term": "hbm" if achieved / hbm >= fp32_ach / fp32_peak else "fp32",

@@ -14,6 +14,11 @@ struct Renderer {
   // scene
   DeviceBVH dbvh;
   Tracer tracer;
+  // second scheduler + stream: the shadow-ray trace of bounce b runs next to the closest-hit trace of bounce b + 1
+  Tracer tracer2;
+  cudaStream_t stream2 = nullptr;
+  std::vector<cudaEvent_t> ev_sync;     // [2 * MAX_DEPTH] shade(b) done / resolve(b) done
+  bool overlap = false;
   void* d_prim_geom = nullptr; float* d_tri_normals = nullptr; float* d_tri_normals_buf = nullptr; uint32_t* d_prim_material = nullptr;
   b2rt_material* d_materials = nullptr; b2rt_light* d_lights = nullptr; float* d_light_area = nullptr;
   std::vector<b2rt_light> lights_host;

@@ -22,6 +22,7 @@ ap.add_argument("--treelet-bytes", type=int, default=0)
 ap.add_argument("--wave", type=int, default=0)
 ap.add_argument("--frames", type=int, default=1)
 ap.add_argument("--max-leaf", type=int, default=0)
+ap.add_argument("--overlap", action="store_true", help="no per-launch timing: the renderer overlaps the shadow and closest-hit traces on two streams")
 ap.add_argument("--subdivide", type=int, default=0, help="subdivide the scene's largest mesh n times (cfg3 stand-in: CBbunny, 1)")
 a = ap.parse_args()
 sc = Scene.load(os.path.join(ROOT, "scenes", a.scene + ".b2s"))
@@ -31,7 +32,7 @@ cam = place_camera(sc, a.width, a.height)
 pt = b2rt.PathTracer(ns_aa=a.spp, max_ray_depth=a.depth, ns_area_light=1, seed=1, bvh_width=a.bvh_width,
                      treelet_bytes=a.treelet_bytes, max_wave_paths=a.wave, max_leaf_size=a.max_leaf)
 pt.set_scene(sc); pt.set_camera(cam); pt.set_frame_size(a.width, a.height)
-pt.set_profiling(counters=False, time_kernels=True)
+pt.set_profiling(counters=False, time_kernels=not a.overlap)
 for _ in range(a.frames):
     pt.clear(); pt.render()
 st = pt.stats()
