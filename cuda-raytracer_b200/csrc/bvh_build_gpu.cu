@@ -467,7 +467,10 @@ static int build_device_w(const b2rt_scene_desc& sc, uint32_t max_leaf, uint32_t
   for (int k = 0; k < 3; ++k) { sb.lo[k] = 0xFFFFFFFFu; sb.hi[k] = 0u; }
   sb.projected = 0;
   B2RT_CUDA_OK(cudaMemcpyAsync(d_sb, &sb, sizeof sb, cudaMemcpyHostToDevice, s));
-  k_bounds<<<148 * 8, 256, 0, s>>>(geom, n, sc.n_tris, d_sb);
+  int dev_id = 0, n_sms = 148;
+  cudaGetDevice(&dev_id);
+  cudaDeviceGetAttribute(&n_sms, cudaDevAttrMultiProcessorCount, dev_id);
+  k_bounds<<<n_sms * 8, 256, 0, s>>>(geom, n, sc.n_tris, d_sb);
   B2RT_CUDA_OK(cudaMemcpyAsync(&sb, d_sb, sizeof sb, cudaMemcpyDeviceToHost, s));
   B2RT_CUDA_OK(cudaStreamSynchronize(s));
   float lo[3], hi[3];
