@@ -288,3 +288,18 @@ def test_parallel_build_matches_serial_build():
         env = dict(os.environ, B2RT_BUILD_THREADS=threads)
         res.append(subprocess.check_output([sys.executable, "-c", code], env=env, text=True).strip().splitlines()[-1])
     assert res[0] == res[1] == res[2], res
+
+
+def test_bench_workloads_and_strong_scaling_split():
+    """bench.py --workload: cfg2 keeps its spp per GPU (weak scaling, the driver's run); cfg3 / cfg4 divide the job's spp
+    over the ranks (BASELINE configs[2] / [3]: "spp sharded across 1/2/4/8 B200") and refuse a split that does not divide."""
+    sys.path.insert(0, ROOT)
+    import bench
+    sc, cam, wl = bench.load_workload("cfg2", 0, 8)
+    assert (wl["spp"], wl["scaling"], wl["width"], wl["height"], wl["depth"]) == (64, "weak", 1024, 768, 8)
+    for world, spp in ((1, 256), (2, 128), (4, 64), (8, 32)):
+        sc3, cam3, wl3 = bench.load_workload("cfg3", 0, world)
+        assert wl3["spp"] == spp and wl3["spp_job"] == 256 and wl3["scaling"] == "strong" and sc3.n_tris == 114316
+    with pytest.raises(SystemExit):
+        bench.load_workload("cfg3", 0, 3)
+    assert set(bench.BASELINE_INDEX) == set(bench.WORKLOADS)
