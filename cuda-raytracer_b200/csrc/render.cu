@@ -586,11 +586,18 @@ int Renderer::set_scene(const b2rt_scene_desc* d) {
     RCHECK(upload_bvh(wb, &dbvh));   // grow-only device buffers: no cudaMalloc/cudaFree when the scene fits
     lap("bvh upload");
   }
-  bvh_stale = true;                // wave buffers are kept; the tracer re-binds its (small) per-subtree arrays
+  bvh_stale = true;                // wave buffers are kept; the tracers re-bind their (small) per-subtree arrays
   n_wide_nodes = wb.n_wide_nodes;
   build_ms = wb.build_ms;
+  // distance slices (Tracer::trace_sliced): the same automatic rule as b2rt_bvh_build -- on for deep subtree graphs over
+  // dense geometry (first slice = 2 mean free paths when that is < 1/8 of the scene diagonal), off for the box scenes
   for (int k = 0; k < 6; ++k) tracer.slice_bbox[k] = wb.bbox[k];
-  tracer.slice_first = 0.f;
+  tracer.slice_first = 0.f; tracer.slice_growth = 4.f; tracer.slice_passes = 4;
+  {
+    const float ex = wb.bbox[3] - wb.bbox[0], ey = wb.bbox[4] - wb.bbox[1], ez = wb.bbox[5] - wb.bbox[2];
+    const float want = 2.f * wb.mean_free_path;
+    if (wb.n_levels >= 3 && want > 0.f && want < 0.125f * std::sqrt(ex * ex + ey * ey + ez * ez)) tracer.slice_first = want;
+  }
   if (const char* e = getenv("B2RT_RENDER_SLICE")) {   // experiment: distance-sliced traversal inside the renderer
     float f = 0.f, g = 4.f; int p = 2;
     if (sscanf(e, "%f,%f,%d", &f, &g, &p) >= 1) { tracer.slice_first = f; tracer.slice_growth = g > 1.f ? g : 4.f; tracer.slice_passes = p >= 2 ? p : 2; }
@@ -773,6 +780,8 @@ int Renderer::start() {
   tracer.launches = 0; tracer.traverse_launches = 0; tracer.ev_used = 0;
   tracer2.launches = 0; tracer2.traverse_launches = 0; tracer2.ev_used = 0;
   tracer2.collect_stats = tracer.collect_stats; tracer2.time_kernels = tracer.time_kernels;
+  tracer2.slice_first = tracer.slice_first; tracer2.slice_growth = tracer.slice_growth; tracer2.slice_passes = tracer.slice_passes;
+  for (int k = 0; k < 6; ++k) tracer2.slice_bbox[k] = tracer.slice_bbox[k];
   if (overlap) B2RT_CUDA_OK(cudaMemsetAsync(tracer2.counters, 0, sizeof(TraceCounters), stream));
   launches = 0;
   B2RT_CUDA_OK(cudaMemsetAsync(totals, 0, 8 * 8, stream));

@@ -386,6 +386,30 @@ def test_renderer_on_device_built_bvh(name):
     pt.close()
 
 
+def test_renderer_slices_dense_deep_scenes_automatically():
+    """A lit triangle soup through the path tracer: the subtree graph is deep and the geometry dense, so b2rt_set_scene
+    turns the distance slices on by the same rule as b2rt_bvh_build (4 passes per trace); the frame stays identical to
+    the oracle's."""
+    soup = random_soup(120000, size=0.05)
+    sc = Scene(soup.tri_verts, materials=[dict(kind=0, albedo=(0.7, 0.6, 0.5))],
+               lights=[dict(kind=1, radiance=(3.0, 3.0, 3.0), position=(0.5, 0.6, 2.0))], cam_dir=(0, 0, 1))
+    w, h = 64, 48
+    cam = place_camera(sc, w, h)
+    cfg = dict(ns_aa=2, max_ray_depth=3, ns_area_light=1, seed=4)
+    pt = b2rt.PathTracer(treelet_bytes=8192, **cfg)
+    pt.set_scene(sc); pt.set_camera(cam); pt.set_frame_size(w, h)
+    pt.render()
+    img = pt.hdr()
+    st = pt.stats()
+    assert st["bvh_levels"] >= 3
+    assert st["traverse_launches"] == 4 * st["bvh_levels"] * 2 * 3      # 4 slice passes x levels x (closest + shadow) x depth
+    ref = orc.OracleScene(sc, 4).render(cam, Config(**cfg), w, h)
+    assert img.max() > 0
+    rmse = float(np.sqrt(np.mean((img - ref) ** 2)))
+    assert rmse <= 1e-6 and float(np.abs(img - ref).max()) <= 1e-5, rmse
+    pt.close()
+
+
 def test_cfg4_standin_material_mix_parity():
     """BASELINE configs[3] stand-in (glass mesh + mirror spheres in the Cornell box) at test size, mesh not subdivided:
     HDR frame identical to the oracle."""
