@@ -171,7 +171,7 @@ def main():
                           f"max_ray_depth {wl['depth']}, ns_area_light {wl['ns_area_light']} "
                           f"(BASELINE configs[{BASELINE_INDEX[args.workload]}])",
               "scene_tris": int(sc.n_tris), "parallelism": f"spp-sharded x{world}, scene replicated",
-              "l2": "per-wave ray/path state (<= 32Mi paths x ~200 B = GBs) exceeds the 126 MB L2; no explicit flush"}
+              "l2": "per-wave ray/path state (<= 64Mi paths x ~200 B = GBs) exceeds the 126 MB L2; no explicit flush"}
 
     if args.impl == "reference":
         if rank != 0:

@@ -696,7 +696,7 @@ int Renderer::ensure_wave() {
   for (auto& l : lights_host) S += l.kind == B2RT_LIGHT_AREA ? std::max(1u, cfg.ns_area_light) : 1u;
   shadow_per_hit = S;
   const uint64_t n_pix = (uint64_t)width * height;
-  uint64_t cap = cfg.max_wave_paths ? cfg.max_wave_paths : (32u << 20);   // ~200 B of state per path: 6.4 GB of the 180 GB
+  uint64_t cap = cfg.max_wave_paths ? cfg.max_wave_paths : (64u << 20);   // ~180 B of state per path + two schedulers: ~19 GB of the 180 GB
   cap = std::max<uint64_t>(cap, 1024);
   const uint64_t want = std::min<uint64_t>(cap, n_pix * std::max(1u, cfg.ns_aa));
   const uint32_t Salloc = std::max(1u, S);
