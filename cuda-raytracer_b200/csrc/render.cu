@@ -154,6 +154,29 @@ __device__ __forceinline__ uint32_t block_append(uint32_t* counter, bool pred, u
   return pos;
 }
 
+// Two CTA-aggregated appends (one element per flagged thread each) behind ONE barrier sequence; `extra` as above.
+__device__ __forceinline__ uint2 block_append2(uint32_t* counter_a, bool pred_a, uint32_t* counter_b, bool pred_b, uint32_t* sh /* 10 words */,
+                                               uint32_t extra, uint32_t* extra_counter) {
+  const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const uint32_t ma = __ballot_sync(0xffffffffu, pred_a), mb = __ballot_sync(0xffffffffu, pred_b);
+  const uint32_t ex = __reduce_add_sync(0xffffffffu, extra);
+  if (lane == 0) sh[warp] = (uint32_t)__popc(ma) | ((uint32_t)__popc(mb) << 8) | (ex << 16);   // each <= 32 per warp
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    uint32_t ta = 0, tb = 0, tex = 0;
+    const uint32_t nw = blockDim.x >> 5;
+    for (uint32_t w = 0; w < nw; ++w) { const uint32_t v = sh[w]; sh[w] = ta | (tb << 16); ta += v & 0xFFu; tb += (v >> 8) & 0xFFu; tex += v >> 16; }
+    sh[8] = ta ? atomicAdd(counter_a, ta) : 0u;
+    sh[9] = tb ? atomicAdd(counter_b, tb) : 0u;
+    if (tex) atomicAdd(extra_counter, tex);
+  }
+  __syncthreads();
+  const uint32_t lt = (1u << lane) - 1u;
+  const uint2 pos = make_uint2(sh[8] + (sh[warp] & 0xFFFFu) + (uint32_t)__popc(ma & lt), sh[9] + (sh[warp] >> 16) + (uint32_t)__popc(mb & lt));
+  __syncthreads();
+  return pos;
+}
+
 // One surface interaction for every active path (bounce index b).
 #ifndef B2RT_SHADE_OCC
 #define B2RT_SHADE_OCC 4
@@ -187,13 +210,25 @@ k_shade(WaveParams wp, SceneDev sc, PathBufs pb, uint32_t b) {
   }
   // every diffuse hit reserves S consecutive entries of the bounce's shadow-ray list: one atomic per warp, blocks in
   // lane order, so the list stays coalesced against the path list
+  // S > 1: every diffuse hit reserves S consecutive entries up front (samples that cannot contribute become null rays, so
+  // the block keeps its sample order for the deterministic resolve).  S == 1 (one light sample per interaction, every
+  // BASELINE config): the one sample is kept in registers and appended at the end ONLY if it can contribute -- on the
+  // box scenes 45 % of the light samples lie behind the surface, and null rays cost the any-hit traversal a list
+  // entry each (stream + retire).
   const bool wants_shadow = prim != 0xFFFFFFFFu && m_kind == B2RT_MAT_DIFFUSE && S > 0;
+  const bool single = S == 1;
   __shared__ uint32_t s_app[10];
-  uint32_t q0 = block_append(&pb.counts[SH0 + b], wants_shadow, S, s_app);
-  if (!wants_shadow) q0 = 0xFFFFFFFFu;
+  uint32_t q0 = 0xFFFFFFFFu;
+  if (!single) {
+    q0 = block_append(&pb.counts[SH0 + b], wants_shadow, S, s_app);
+    if (!wants_shadow) q0 = 0xFFFFFFFFu;
+  }
   uint32_t n_valid = 0;
+  bool sh_valid = false;
+  float4 sh_d = make_float4(0.f, 0.f, 1.f, -1.f);
+  f3 sh_c = mk3(0.f, 0.f, 0.f);
   if (i < n) {
-    pb.s_q0[slot] = q0;
+    if (!single) pb.s_q0[slot] = q0;
     if (prim != 0xFFFFFFFFu) {
       const float t = __uint_as_float((uint32_t)(h >> 32));
       f3 thr = mk3(thr4.x, thr4.y, thr4.z);
@@ -208,6 +243,7 @@ k_shade(WaveParams wp, SceneDev sc, PathBufs pb, uint32_t b) {
       } else {
         const f3 o = mk3(ro.x, ro.y, ro.z), d = mk3(rd.x, rd.y, rd.z);
         const f3 P = o + d * t;
+        next_o = make_float4(P.x, P.y, P.z, wp.eps);   // origin of the shadow ray and of the continuing ray
         PrimRec pr;
         pr.a = sc.prim_geom[(size_t)prim * 3]; pr.b = sc.prim_geom[(size_t)prim * 3 + 1]; pr.c = sc.prim_geom[(size_t)prim * 3 + 2];
         const bool is_sphere = prim >= sc.n_tris;
@@ -270,7 +306,16 @@ k_shade(WaveParams wp, SceneDev sc, PathBufs pb, uint32_t b) {
               const float cos_in = dot3(wi, Z);
               const bool valid = cos_in >= 0.0f && (Lr.x > 0.0f || Lr.y > 0.0f || Lr.z > 0.0f) && pdf > 0.0f;
               const uint32_t q = q0 + j;
-              if (valid) {
+              if (single) {
+                if (valid) {
+                  const float wgt = __fdiv_rn(cos_in, (float)ns * pdf);
+                  const f3 f = mk3(__ldg(&mp->albedo[0]), __ldg(&mp->albedo[1]), __ldg(&mp->albedo[2])) * 0.318309886183790672f;
+                  sh_c = thr * f * Lr * wgt;
+                  sh_d = make_float4(wi.x, wi.y, wi.z, dist - wp.eps);
+                  sh_valid = true;
+                  n_valid++;
+                }
+              } else if (valid) {
                 const float wgt = __fdiv_rn(cos_in, (float)ns * pdf);
                 const f3 f = mk3(__ldg(&mp->albedo[0]), __ldg(&mp->albedo[1]), __ldg(&mp->albedo[2])) * 0.318309886183790672f;
                 const f3 c = thr * f * Lr * wgt;
@@ -334,7 +379,6 @@ k_shade(WaveParams wp, SceneDev sc, PathBufs pb, uint32_t b) {
           if (weight.x > 0.0f || weight.y > 0.0f || weight.z > 0.0f) {
             thr = thr * weight;
             const f3 nd = normalize3(X * wi_l.x + Y * wi_l.y + Z * wi_l.z);
-            next_o = make_float4(P.x, P.y, P.z, wp.eps);
             next_d = make_float4(nd.x, nd.y, nd.z, INF_F);
             pb.thr[slot] = make_float4(thr.x, thr.y, thr.z, delta ? 1.f : 0.f);
             cont = true;
@@ -344,7 +388,18 @@ k_shade(WaveParams wp, SceneDev sc, PathBufs pb, uint32_t b) {
     }
   }
   // the continuing paths form the next bounce's dense ray list
-  const uint32_t p = block_append(&pb.counts[ACT0 + b + 1], cont, 1, s_app, n_valid, &pb.counts[SHV0 + b]);
+  uint32_t p;
+  if (single) {
+    const uint2 pq = block_append2(&pb.counts[ACT0 + b + 1], cont, &pb.counts[SH0 + b], sh_valid, s_app, n_valid, &pb.counts[SHV0 + b]);
+    p = pq.x;
+    if (i < n) pb.s_q0[slot] = sh_valid ? pq.y : 0xFFFFFFFFu;
+    if (sh_valid) {
+      pb.s_o[pq.y] = next_o; pb.s_d[pq.y] = sh_d; pb.s_hits[pq.y] = pack_hit(sh_d.w, 0xFFFFFFFFu);
+      pb.s_contrib[pq.y] = make_float4(sh_c.x, sh_c.y, sh_c.z, 1.f);
+    }
+  } else {
+    p = block_append(&pb.counts[ACT0 + b + 1], cont, 1, s_app, n_valid, &pb.counts[SHV0 + b]);
+  }
   if (cont) {
     pb.no[p] = next_o; pb.nd[p] = next_d; pb.nh[p] = pack_hit(INF_F, 0xFFFFFFFFu); pb.nslot[p] = slot;
   }
