@@ -1,3 +1,6 @@
+#!/bin/sh
+# A/B recipe of a recorded (rejected) experiment: shadow block of list entry i at i * S.  The variant code is not in the tree any more
+# (see profiles/r01_shade_ncu.md); kept for the command lines.  Run on the GPU box.
 python -m pytest tests -m gpu -x -q -k "radiance or waves or full_size or sharding or median or renderer_on or cfg4 or dragon or slices_dense" 2>&1 | tail -2
 for lib in build/sapp/libb2rt.so cuda-raytracer_b200/libb2rt.so; do
   for rep in 1 2; do printf "%-34s cfg2/64spp overlap : " $lib; B2RT_LIB=$lib python tools/profile_frame.py --frames 3 --spp 64 --overlap 2>&1 | tail -1; done
