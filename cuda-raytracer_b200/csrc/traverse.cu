@@ -342,9 +342,9 @@ __device__ __forceinline__ void flush_pairs(uint2* stage, uint32_t& n_staged, co
 // Closest-hit merge.  At level 0 a ray is visited exactly once and nothing else touches its hit word, so the improved
 // word is simply stored; deeper levels can hold the same ray in several subtrees at once and merge with the packed
 // (t, prim) 64-bit atomicMin.
-__device__ __forceinline__ void retire_hit(const TravParams& P, uint32_t rid, float t, uint32_t prim) {
-  if (P.level == 0) P.hits[rid] = pack_hit(t, prim);
-  else atomicMin(&P.hits[rid], pack_hit(t, prim));
+__device__ __forceinline__ void retire_hit(const TravParams& P, uint32_t rid, unsigned long long word) {
+  if (P.level == 0) P.hits[rid] = word;
+  else atomicMin(&P.hits[rid], word);
 }
 
 #ifdef B2RT_CHECKS
@@ -375,6 +375,22 @@ __device__ __forceinline__ float fmin3(float a, float b, float c) {
   return r;
 }
 
+// Leaf work is DECOUPLED from the per-lane tree walk (round 2).  A lane that reaches a leaf does not test its
+// primitives itself: it appends (lane, primitive) items to a per-warp queue in shared memory and goes on walking.
+// Whenever 32 items are queued the whole warp drains them, one ray-primitive test per lane (the ray is fetched from
+// the owning lane with shuffles, the result is merged into the owner's packed (t, prim) word in shared memory with a
+// 64-bit atomicMin).  The node phase and the primitive phase therefore each run with (nearly) full warps; before, a
+// warp executed the node code and the leaf loop back to back for a handful of lanes each (19.7 of 32 lanes active per
+// instruction, profiles/r01_traverse_ncu.md).  The closest hit is the argmin of (t, prim) over every primitive tested,
+// so the result does not depend on the order of the tests; between a leaf visit and its drain a lane culls with a
+// stale (larger) best_t, which only adds visits.
+#ifndef B2RT_LEAF_TAKE
+#define B2RT_LEAF_TAKE 4
+#endif
+constexpr uint32_t LEAF_TAKE = B2RT_LEAF_TAKE;          // primitives a lane queues per iteration (1..4)
+constexpr uint32_t QCAP = 32 + 32 * LEAF_TAKE;          // < 32 left over + one round of appends
+constexpr uint32_t ITEM_PRIM_MASK = 0x07FFFFFFu;        // item: [31:27] owning lane, [26:0] primitive index in the blob
+
 template <int W, bool ANYHIT, bool STATS>
 __global__ void __launch_bounds__(TRAV_THREADS, (W == 4 ? B2RT_OCC4 : 2))
 k_traverse(const TravParams P) {
@@ -387,6 +403,8 @@ k_traverse(const TravParams P) {
   __shared__ uint4 s_chunk;
   __shared__ uint32_t s_next_ray;
   __shared__ __align__(8) uint2 s_stage[TRAV_WARPS][STAGE_PAIRS];
+  __shared__ __align__(16) uint32_t s_items[TRAV_WARPS][QCAP];            // per-warp primitive-test queue
+  __shared__ __align__(8) unsigned long long s_best[TRAV_WARPS][32];      // per-lane packed (t, prim) of the lane's ray
 
   const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const uint32_t lane_lt = (1u << lane) - 1u;
@@ -396,9 +414,12 @@ k_traverse(const TravParams P) {
   const uint32_t stack = smem_u32(smem) + P.stack_off + threadIdx.x * 4u;   // shared-space byte address
   const uint32_t ring = smem_u32(smem) + P.ring_off;
   uint8_t* const ring_generic = smem + P.ring_off;
+  const uint32_t q_addr = smem_u32(&s_items[warp][0]);
+  const uint32_t best_addr = smem_u32(&s_best[warp][0]);
   uint32_t cur_treelet = 0xFFFFFFFFu;
   uint32_t phase = 0;
   uint32_t n_staged = 0;   // warp-uniform
+  uint32_t qn = 0;         // warp-uniform: items in the warp's primitive-test queue
   uint2* stage = s_stage[warp];
   unsigned long long st_nodes = 0, st_prims = 0, st_visits = 0, st_push = 0, st_upd = 0;
 
@@ -468,34 +489,91 @@ k_traverse(const TravParams P) {
       if (STATS && threadIdx.x == 0) atomicAdd(&P.counters->staged_bytes, (unsigned long long)td.bytes);
     }
     const uint8_t* nodes = smem;
-    const uint8_t* prims = smem + (size_t)td.n_nodes * NB;
+    const uint32_t prims_addr = smem_u32(smem) + td.n_nodes * (uint32_t)NB;   // shared-space address of the primitive records
 
     // ---- per-lane ray state; lanes are refilled from the chunk as their rays finish -------------------
     uint32_t rid = 0;
-    float best_t = 0.f; uint32_t best_id = 0xFFFFFFFFu;
+    float best_t = 0.f;
+    uint32_t h0_t = 0, h0_id = 0xFFFFFFFFu;   // the ray's hit word when the lane took it (retire writes only if it improved)
     f3 o = mk3(0, 0, 0), d = mk3(0, 0, 1), inv = mk3(0, 0, 0), noi = mk3(0, 0, 0);
-    float tmin = 0.f, tmax_user = 0.f;
+    float tmin = 0.f;
     uint32_t nx = 0, ny = 0, nz = 0;   // byte offsets of the near plane rows (far rows: 12W - nx, 20W - ny, 28W - nz)
     int sp = 0;
     uint32_t cur = REF_NONE;
-    bool have = false, improved = false;
+    bool have = false;
     bool exhausted = false;   // warp-uniform: the chunk has no more rays to hand out
     uint32_t ring_ended = 0;  // warp-uniform: ring buffers on which this warp has seen the end-of-stream marker
 
-    // One convergence point per iteration: the ballot at the top.  The loop is left only there (all lanes idle
-    // and the chunk handed out); there is no other warp-level primitive on a conditional path except the
-    // warp-uniform refill / push blocks, each closed by __syncwarp().
+    // one batch of the warp's queue: items [head, head + n), one ray-primitive test per lane
+    auto drain = [&](uint32_t head, uint32_t n) {
+      const bool act = lane < n;
+      const uint32_t item = act ? lds_u32(q_addr + (head + lane) * 4u) : (lane << 27);
+      const uint32_t src = item >> 27;
+      const f3 io = mk3(__shfl_sync(0xffffffffu, o.x, src), __shfl_sync(0xffffffffu, o.y, src), __shfl_sync(0xffffffffu, o.z, src));
+      const f3 id = mk3(__shfl_sync(0xffffffffu, d.x, src), __shfl_sync(0xffffffffu, d.y, src), __shfl_sync(0xffffffffu, d.z, src));
+      const float itmin = __shfl_sync(0xffffffffu, tmin, src);
+      if (act) {
+        const uint32_t pa = prims_addr + (item & ITEM_PRIM_MASK) * (uint32_t)PRIM_BYTES;
+        B2_CHECK((item & ITEM_PRIM_MASK) < td.n_prims, 4, item);
+        PrimRec p;
+        p.a = lds_f4(pa); p.b = lds_f4(pa + 16u); p.c = lds_f4(pa + 32u);
+        if (STATS) st_prims++;
+        float t, u, v;
+        const uint32_t pid = __float_as_uint(p.c.y);
+        // the upper end of the ray's interval is the owner's packed word: it starts at (tmax, none) and only decreases
+        const bool h = (__float_as_uint(p.c.z) != 0u) ? hit_sphere(p, io, id, itmin, __builtin_huge_valf(), &t)
+                                                      : hit_triangle(p, io, id, itmin, __builtin_huge_valf(), &t, &u, &v);
+        if (h) {
+          const unsigned long long cand = pack_hit(t, pid);
+          const uint32_t ba = best_addr + src * 8u;
+          if (cand < lds_u64(ba)) {
+            unsigned long long* bp = &s_best[warp][src];
+            atomicMin(bp, ANYHIT ? pack_hit(0.0f, pid) : cand);
+          }
+        }
+      }
+      __syncwarp();
+    };
+    // after a drain: every lane re-reads its ray's packed word
+    auto refresh_best = [&]() {
+      const unsigned long long nb = lds_u64(best_addr + lane * 8u);
+      best_t = __uint_as_float((uint32_t)(nb >> 32));
+      if (ANYHIT && (uint32_t)nb != 0xFFFFFFFFu) { sp = 0; cur = REF_NONE; }   // occluded: the ray is done
+    };
+    auto drain_all = [&]() {
+      uint32_t head = 0;
+      while (qn) {
+        const uint32_t n = min(qn, 32u);
+        drain(head, n);
+        head += n; qn -= n;
+      }
+    };
+
     for (;;) {
+      // ---- pop: lanes without a current reference take the nearest entry of their stack that can still matter
+      if (cur == REF_NONE) {
+        while (sp > 0) {
+          const uint32_t e = lds_u32(stack + (uint32_t)(--sp) * (TRAV_THREADS * 4u));
+          if (__uint_as_float(e & STACK_TN_MASK) <= best_t) {
+            cur = *reinterpret_cast<const uint32_t*>(nodes + (size_t)((e & 0xFFFu) >> SLOT_BITS) * NB + 24 * W + (e & (uint32_t)(W - 1)) * 4u);
+            break;
+          }
+        }
+      }
       __syncwarp();
       const uint32_t m_idle = __ballot_sync(0xffffffffu, cur == REF_NONE);
       if (m_idle == 0xffffffffu && exhausted) break;
       if (m_idle && !exhausted && (__popc(m_idle) >= REFILL_MIN_IDLE || m_idle == 0xffffffffu)) {
-        // retire finished rays, then hand new rays to the idle lanes
+        // finish the queued tests (the idle lanes' rays may still have items pending), retire the finished rays,
+        // then hand new rays to the idle lanes
+        drain_all();
         const bool idle = cur == REF_NONE;
         if (idle && have) {
-          if (improved) { retire_hit(P, rid, best_t, best_id); if (STATS) st_upd++; }
+          const unsigned long long nb = lds_u64(best_addr + lane * 8u);
+          if ((uint32_t)(nb >> 32) != h0_t || (uint32_t)nb != h0_id) { retire_hit(P, rid, nb); if (STATS) st_upd++; }
           have = false;
         }
+        if (!idle) refresh_best();
         const uint32_t n_idle = __popc(m_idle);
         uint32_t base = 0;
         if (lane == 0) base = atomicAdd(&s_next_ray, n_idle);
@@ -581,9 +659,10 @@ k_traverse(const TravParams P) {
         }
         if (take) {
           o = mk3(ro.x, ro.y, ro.z); d = mk3(rd.x, rd.y, rd.z);
-          tmin = ro.w; tmax_user = rd.w;
-          best_t = __uint_as_float((uint32_t)(h >> 32));
-          best_id = (uint32_t)h;
+          tmin = ro.w;
+          h0_t = (uint32_t)(h >> 32); h0_id = (uint32_t)h;
+          best_t = __uint_as_float(h0_t);
+          asm volatile("st.shared.u64 [%0], %1;" ::"r"(best_addr + lane * 8u), "l"(h) : "memory");
           // reciprocal direction for the slab test; |d_k| < 1e-18 (incl. +-0) is clamped so that o_k * inv_k
           // stays finite: the ray is then parallel to the slab and the test reduces to lo_k <= o_k <= hi_k
           // (MUFU.RCP, 1 ulp: the slab test only has to be conservative, and the box padding + the 4-ulp slack on
@@ -595,132 +674,130 @@ k_traverse(const TravParams P) {
           nx = inv.x >= 0.f ? 0u : 12u * W;
           ny = inv.y >= 0.f ? 4u * W : 16u * W;
           nz = inv.z >= 0.f ? 8u * W : 20u * W;
-          have = true; improved = false; sp = 0;
-          const bool skip = ANYHIT && best_id != 0xFFFFFFFFu;
+          have = true; sp = 0;
+          const bool skip = ANYHIT && h0_id != 0xFFFFFFFFu;
           cur = skip ? REF_NONE : 0u;   // INTERNAL node 0 = subtree root
           if (STATS) st_visits++;
         }
         __syncwarp();
       }
 
-      // ---- one phase per iteration --------------------------------------------------------------------
-      // Lanes are INTERNAL (wide node to test), LEAF (primitives to test), EXIT (push to a child subtree) or idle.
-      // Exits are cheap and handled every iteration.  Of the two expensive phases only the one the majority of
-      // lanes needs is executed; the minority keeps its state and waits, so each phase runs with fuller warps
-      // instead of the warp executing node code and primitive code back to back for a few lanes each.
-      const uint32_t tag = cur >> 30;
-      const uint32_t m_node = __ballot_sync(0xffffffffu, tag == REF_INTERNAL);
-      const uint32_t m_leaf = __ballot_sync(0xffffffffu, tag == REF_LEAF);
-      const bool node_phase = __popc(m_node) >= __popc(m_leaf);
-      bool do_push = false;
-      uint32_t push_treelet = 0;
-      bool need_pop = false;
-      if (cur != REF_NONE) {
-        if (tag == REF_INTERNAL) {
-         if (node_phase) {
-          if (STATS) st_nodes++;
-          B2_CHECK((cur & 0x3FFFFFFFu) < td.n_nodes, 2, cur);
-          const uint8_t* nbase = nodes + (size_t)(cur & 0x3FFFFFFFu) * NB;
-          const uint32_t* nrefs = reinterpret_cast<const uint32_t*>(nbase + 24 * W);
-          const uint32_t fx = 12u * W - nx, fy = 20u * W - ny, fz = 28u * W - nz;
-          uint32_t keys[W];
-          // sign-ordered slab test: per axis the near plane row is lo (inv >= 0) or hi (inv < 0), chosen once
-          // per ray (row offsets nx/ny/nz, fx/fy/fz), so a box costs 6 fma + 3 max + 3 min.  Empty slots hold
-          // inverted infinite boxes (lo = +inf, hi = -inf) => t_near = +inf, t_far = -inf => never hit.
+      // ---- node phase: every lane whose reference is a wide node tests its W child boxes ------------------
+      if ((cur >> 30) == REF_INTERNAL) {
+        if (STATS) st_nodes++;
+        B2_CHECK((cur & 0x3FFFFFFFu) < td.n_nodes, 2, cur);
+        const uint8_t* nbase = nodes + (size_t)(cur & 0x3FFFFFFFu) * NB;
+        const uint32_t* nrefs = reinterpret_cast<const uint32_t*>(nbase + 24 * W);
+        const uint32_t fx = 12u * W - nx, fy = 20u * W - ny, fz = 28u * W - nz;
+        uint32_t keys[W];
+        // sign-ordered slab test: per axis the near plane row is lo (inv >= 0) or hi (inv < 0), chosen once
+        // per ray (row offsets nx/ny/nz, fx/fy/fz), so a box costs 6 fma + 3 max + 3 min.  Empty slots hold
+        // inverted infinite boxes (lo = +inf, hi = -inf) => t_near = +inf, t_far = -inf => never hit.
 #pragma unroll
-          for (int q = 0; q < W / 4; ++q) {
-            const float4 ax = *reinterpret_cast<const float4*>(nbase + nx + 16 * q), bx = *reinterpret_cast<const float4*>(nbase + fx + 16 * q);
-            const float4 ay = *reinterpret_cast<const float4*>(nbase + ny + 16 * q), by = *reinterpret_cast<const float4*>(nbase + fy + 16 * q);
-            const float4 az = *reinterpret_cast<const float4*>(nbase + nz + 16 * q), bz = *reinterpret_cast<const float4*>(nbase + fz + 16 * q);
-            const float axa[4] = {ax.x, ax.y, ax.z, ax.w}, aya[4] = {ay.x, ay.y, ay.z, ay.w}, aza[4] = {az.x, az.y, az.z, az.w};
-            const float bxa[4] = {bx.x, bx.y, bx.z, bx.w}, bya[4] = {by.x, by.y, by.z, by.w}, bza[4] = {bz.x, bz.y, bz.z, bz.w};
+        for (int q = 0; q < W / 4; ++q) {
+          const float4 ax = *reinterpret_cast<const float4*>(nbase + nx + 16 * q), bx = *reinterpret_cast<const float4*>(nbase + fx + 16 * q);
+          const float4 ay = *reinterpret_cast<const float4*>(nbase + ny + 16 * q), by = *reinterpret_cast<const float4*>(nbase + fy + 16 * q);
+          const float4 az = *reinterpret_cast<const float4*>(nbase + nz + 16 * q), bz = *reinterpret_cast<const float4*>(nbase + fz + 16 * q);
+          const float axa[4] = {ax.x, ax.y, ax.z, ax.w}, aya[4] = {ay.x, ay.y, ay.z, ay.w}, aza[4] = {az.x, az.y, az.z, az.w};
+          const float bxa[4] = {bx.x, bx.y, bx.z, bx.w}, bya[4] = {by.x, by.y, by.z, by.w}, bza[4] = {bz.x, bz.y, bz.z, bz.w};
 #pragma unroll
-            for (int c = 0; c < 4; ++c) {
-              const float tn = fmaxf(fmax3(__fmaf_rn(axa[c], inv.x, noi.x), __fmaf_rn(aya[c], inv.y, noi.y),
-                                           __fmaf_rn(aza[c], inv.z, noi.z)), tmin);
-              const float tf = fminf(fmin3(__fmaf_rn(bxa[c], inv.x, noi.x), __fmaf_rn(bya[c], inv.y, noi.y),
-                                           __fmaf_rn(bza[c], inv.z, noi.z)), best_t);
-              const bool hit = tn <= tf * 1.0000004f;
-              // key: entry distance (rounded down, keeps order for t >= 0) | child slot
-              keys[q * 4 + c] = hit ? ((__float_as_uint(tn) & ~(uint32_t)(W - 1)) | (uint32_t)(q * 4 + c)) : 0xFFFFFFFFu;
-            }
+          for (int c = 0; c < 4; ++c) {
+            const float tn = fmaxf(fmax3(__fmaf_rn(axa[c], inv.x, noi.x), __fmaf_rn(aya[c], inv.y, noi.y),
+                                         __fmaf_rn(aza[c], inv.z, noi.z)), tmin);
+            const float tf = fminf(fmin3(__fmaf_rn(bxa[c], inv.x, noi.x), __fmaf_rn(bya[c], inv.y, noi.y),
+                                         __fmaf_rn(bza[c], inv.z, noi.z)), best_t);
+            const bool hit = tn <= tf * 1.0000004f;
+            // key: entry distance (rounded down, keeps order for t >= 0) | child slot
+            keys[q * 4 + c] = hit ? ((__float_as_uint(tn) & ~(uint32_t)(W - 1)) | (uint32_t)(q * 4 + c)) : 0xFFFFFFFFu;
           }
-#define B2_CE(a, b) { const uint32_t lo_ = min(keys[a], keys[b]), hi_ = max(keys[a], keys[b]); keys[a] = lo_; keys[b] = hi_; }
-          if (W == 4) {
-            B2_CE(0, 1) B2_CE(2, 3) B2_CE(0, 2) B2_CE(1, 3) B2_CE(1, 2)
-          } else {
-            B2_CE(0, 1) B2_CE(2, 3) B2_CE(4, 5) B2_CE(6, 7)
-            B2_CE(0, 2) B2_CE(1, 3) B2_CE(4, 6) B2_CE(5, 7)
-            B2_CE(1, 2) B2_CE(5, 6) B2_CE(0, 4) B2_CE(3, 7)
-            B2_CE(1, 5) B2_CE(2, 6)
-            B2_CE(1, 4) B2_CE(3, 6)
-            B2_CE(2, 4) B2_CE(3, 5)
-            B2_CE(3, 4)
-          }
-#undef B2_CE
-          // far-to-near onto the stack; the nearest child becomes the current node without a stack round trip.
-          // An entry names the child by (node, slot); its reference is read from the node when it is popped.
-          const uint32_t node_tag = (cur & 0x3FFFFFFFu) << SLOT_BITS;
-#pragma unroll
-          for (int q = W - 1; q >= 1; --q) {
-            if (keys[q] != 0xFFFFFFFFu) {
-              B2_CHECK(sp < (W == 8 ? B2RT_STACK8 : B2RT_STACK4), 3, sp);
-              sts_u32(stack + (uint32_t)sp * (TRAV_THREADS * 4u), (keys[q] & (STACK_TN_MASK | (uint32_t)(W - 1))) | node_tag);
-              ++sp;
-            }
-          }
-          if (keys[0] != 0xFFFFFFFFu) cur = nrefs[keys[0] & (uint32_t)(W - 1)];
-          else need_pop = true;
-         }
-        } else if (tag == REF_LEAF) {
-         if (!node_phase) {
-          need_pop = true;
-          const uint32_t first = cur & 0x00FFFFFFu, count = ((cur >> 24) & 63u) + 1u;
-          const PrimRec* pr = reinterpret_cast<const PrimRec*>(prims) + first;
-          B2_CHECK(first + count <= td.n_prims, 4, cur);
-          for (uint32_t q = 0; q < count; ++q) {
-            const PrimRec p = pr[q];
-            if (STATS) st_prims++;
-            float t, u, v;
-            const uint32_t pid = __float_as_uint(p.c.y);
-            const bool h = (__float_as_uint(p.c.z) != 0u) ? hit_sphere(p, o, d, tmin, tmax_user, &t)
-                                                          : hit_triangle(p, o, d, tmin, tmax_user, &t, &u, &v);
-            if (h && (t < best_t || (t == best_t && pid < best_id))) {
-              best_t = t; best_id = pid; improved = true;
-              if (ANYHIT) { best_t = 0.0f; sp = 0; break; }
-            }
-          }
-         }
-        } else {   // EXIT
-          B2_CHECK(tag == REF_EXIT && (cur & 0x3FFFFFFFu) < P.n_treelets, 5, cur);
-          do_push = true;
-          push_treelet = cur & 0x3FFFFFFFu;
-          need_pop = true;
         }
-        if (need_pop) {
-          cur = REF_NONE;
-          while (sp > 0) {
-            const uint32_t e = lds_u32(stack + (uint32_t)(--sp) * (TRAV_THREADS * 4u));
-            if (__uint_as_float(e & STACK_TN_MASK) <= best_t) {
-              cur = *reinterpret_cast<const uint32_t*>(nodes + (size_t)((e & 0xFFFu) >> SLOT_BITS) * NB + 24 * W + (e & (uint32_t)(W - 1)) * 4u);
-              break;
-            }
+#define B2_CE(a, b) { const uint32_t lo_ = min(keys[a], keys[b]), hi_ = max(keys[a], keys[b]); keys[a] = lo_; keys[b] = hi_; }
+        if (W == 4) {
+          B2_CE(0, 1) B2_CE(2, 3) B2_CE(0, 2) B2_CE(1, 3) B2_CE(1, 2)
+        } else {
+          B2_CE(0, 1) B2_CE(2, 3) B2_CE(4, 5) B2_CE(6, 7)
+          B2_CE(0, 2) B2_CE(1, 3) B2_CE(4, 6) B2_CE(5, 7)
+          B2_CE(1, 2) B2_CE(5, 6) B2_CE(0, 4) B2_CE(3, 7)
+          B2_CE(1, 5) B2_CE(2, 6)
+          B2_CE(1, 4) B2_CE(3, 6)
+          B2_CE(2, 4) B2_CE(3, 5)
+          B2_CE(3, 4)
+        }
+#undef B2_CE
+        // far-to-near onto the stack; the nearest child becomes the current reference without a stack round trip.
+        // An entry names the child by (node, slot); its reference is read from the node when it is popped.
+        const uint32_t node_tag = (cur & 0x3FFFFFFFu) << SLOT_BITS;
+#pragma unroll
+        for (int q = W - 1; q >= 1; --q) {
+          if (keys[q] != 0xFFFFFFFFu) {
+            B2_CHECK(sp < (W == 8 ? B2RT_STACK8 : B2RT_STACK4), 3, sp);
+            sts_u32(stack + (uint32_t)sp * (TRAV_THREADS * 4u), (keys[q] & (STACK_TN_MASK | (uint32_t)(W - 1))) | node_tag);
+            ++sp;
           }
+        }
+        cur = keys[0] != 0xFFFFFFFFu ? nrefs[keys[0] & (uint32_t)(W - 1)] : REF_NONE;
+      }
+      __syncwarp();
+
+      // ---- leaf references: queue (lane, primitive) items; ballot/popc prefix sums of the per-lane counts -------
+      {
+        const bool is_leaf = (cur >> 30) == REF_LEAF;
+        const uint32_t m_leaf = __ballot_sync(0xffffffffu, is_leaf);
+        if (m_leaf) {
+          const uint32_t first = cur & 0x00FFFFFFu, count = ((cur >> 24) & 63u) + 1u;
+          const uint32_t take = is_leaf ? min(count, LEAF_TAKE) : 0u;
+          const uint32_t b0 = __ballot_sync(0xffffffffu, take & 1u), b1 = __ballot_sync(0xffffffffu, take & 2u);
+          uint32_t pre = __popc(b0 & lane_lt) + 2u * __popc(b1 & lane_lt), tot = __popc(b0) + 2u * __popc(b1);
+          if (LEAF_TAKE >= 4) {
+            const uint32_t b2 = __ballot_sync(0xffffffffu, take & 4u);
+            pre += 4u * __popc(b2 & lane_lt); tot += 4u * __popc(b2);
+          }
+          B2_CHECK(qn + tot <= QCAP, 6, qn);
+          if (is_leaf) {
+            const uint32_t at = q_addr + (qn + pre) * 4u, item = (lane << 27) | first;
+#pragma unroll
+            for (uint32_t j = 0; j < LEAF_TAKE; ++j)
+              if (j < take) sts_u32(at + j * 4u, item + j);
+            cur = count > take ? ((REF_LEAF << 30) | ((count - take - 1u) << 24) | (first + take)) : REF_NONE;
+          }
+          qn += tot;
+          __syncwarp();
         }
       }
-      // scheduler push: ballot + popc = exclusive scan of the 0/1 flags inside the warp
-      const uint32_t m = __ballot_sync(0xffffffffu, do_push);
-      if (m) {
-        B2_CHECK(n_staged + 32 <= STAGE_PAIRS, 6, n_staged);
-        if (do_push) stage[n_staged + __popc(m & lane_lt)] = make_uint2(push_treelet, rid);
-        n_staged += __popc(m);
-        if (STATS && do_push) st_push++;
-        __syncwarp();
-        if (n_staged > STAGE_PAIRS - 32) flush_pairs(stage, n_staged, P, lane);
+      // ---- exits: scheduler push; ballot + popc = exclusive scan of the 0/1 flags inside the warp -------------
+      {
+        const bool do_push = (cur >> 30) == REF_EXIT;
+        const uint32_t m = __ballot_sync(0xffffffffu, do_push);
+        if (m) {
+          B2_CHECK(n_staged + 32 <= STAGE_PAIRS, 6, n_staged);
+          if (do_push) {
+            B2_CHECK((cur & 0x3FFFFFFFu) < P.n_treelets, 5, cur);
+            stage[n_staged + __popc(m & lane_lt)] = make_uint2(cur & 0x3FFFFFFFu, rid);
+            cur = REF_NONE;
+            if (STATS) st_push++;
+          }
+          n_staged += __popc(m);
+          __syncwarp();
+          if (n_staged > STAGE_PAIRS - 32) flush_pairs(stage, n_staged, P, lane);
+        }
+      }
+      // ---- primitive phase: drain full batches of the queue, one test per lane --------------------------------
+      if (qn >= 32u) {
+        uint32_t head = 0;
+        do { drain(head, 32u); head += 32u; qn -= 32u; } while (qn >= 32u);
+        if (qn) {   // move the remainder to the front (source and destination ranges never overlap: head >= 32 > qn)
+          if (lane < qn) sts_u32(q_addr + lane * 4u, lds_u32(q_addr + (head + lane) * 4u));
+          __syncwarp();
+        }
+        refresh_best();
       }
     }
-    // retire the rays still held by the lanes
-    if (have && improved) { retire_hit(P, rid, best_t, best_id); if (STATS) st_upd++; }
+    // the warp is done with the chunk: finish the queued tests and retire the rays still held by the lanes
+    drain_all();
+    if (have) {
+      const unsigned long long nb = lds_u64(best_addr + lane * 8u);
+      if ((uint32_t)(nb >> 32) != h0_t || (uint32_t)nb != h0_id) { retire_hit(P, rid, nb); if (STATS) st_upd++; }
+    }
     __syncthreads();   // every warp is done with this chunk (s_chunk / s_next_ray / subtree smem reusable)
   }
   if (n_staged) flush_pairs(stage, n_staged, P, lane);
