@@ -93,6 +93,12 @@ __device__ __forceinline__ unsigned long long lds_u64(uint32_t a) {
   asm volatile("ld.shared.u64 %0, [%1];" : "=l"(v) : "r"(a) : "memory");
   return v;
 }
+__device__ __forceinline__ void sts_u64(uint32_t a, unsigned long long v) { asm volatile("st.shared.u64 [%0], %1;" ::"r"(a), "l"(v) : "memory"); }
+__device__ __forceinline__ uint32_t atoms_add(uint32_t a, uint32_t v) {
+  uint32_t old;
+  asm volatile("atom.shared.add.u32 %0, [%1], %2;" : "=r"(old) : "r"(a), "r"(v) : "memory");
+  return old;
+}
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
 // ---- k_schedule_level: exclusive scan of per-subtree ray counts -> segment offsets + chunk list ----
@@ -322,15 +328,15 @@ constexpr uint32_t RING_O = 0, RING_D = RING_TILE * 16, RING_H = RING_TILE * 32;
 constexpr uint32_t RING_BUF_BYTES = RING_TILE * 40;
 
 // flush one warp's staged pairs: one global reservation, coalesced 8-byte stores, per-subtree counts
-__device__ __forceinline__ void flush_pairs(uint2* stage, uint32_t& n_staged, const TravParams& P, uint32_t lane) {
+__device__ __forceinline__ void flush_pairs(uint32_t stage_addr, uint32_t& n_staged, const TravParams& P, uint32_t lane) {
   uint32_t n = n_staged;
   uint32_t base = 0;
   if (lane == 0) base = atomicAdd(&P.ctrl[P.level & 1], n);
   base = __shfl_sync(0xffffffffu, base, 0);
   for (uint32_t k = lane; k < n; k += 32) {
-    uint2 p = stage[k];
+    const unsigned long long p = lds_u64(stage_addr + k * 8u);
     if (base + k < P.pair_cap) {
-      P.pairs[base + k] = p;   // (per-subtree counts are taken by k_count_* afterwards, not with an atomic per push)
+      P.pairs[base + k] = make_uint2((uint32_t)p, (uint32_t)(p >> 32));   // (per-subtree counts are taken by k_count_* afterwards)
     } else {
       P.ctrl[CTRL_OVERFLOW] = 1;
     }
@@ -387,9 +393,24 @@ __device__ __forceinline__ float fmin3(float a, float b, float c) {
 #ifndef B2RT_LEAF_TAKE
 #define B2RT_LEAF_TAKE 4
 #endif
+#ifndef B2RT_ENQ_ATOMS
+#define B2RT_ENQ_ATOMS 0
+#endif
 constexpr uint32_t LEAF_TAKE = B2RT_LEAF_TAKE;          // primitives a lane queues per iteration (1..4)
 constexpr uint32_t QCAP = 32 + 32 * LEAF_TAKE;          // < 32 left over + one round of appends
 constexpr uint32_t ITEM_PRIM_MASK = 0x07FFFFFFu;        // item: [31:27] owning lane, [26:0] primitive index in the blob
+// Per-warp scratch in shared memory.  Everything a warp touches in the traversal loop hangs off ONE shared-space base
+// address (wb) plus immediates: through C++ pointers / arrays every access re-derived its address (S2UR SR_CgaCtaId +
+// ULEA ... per access, 6 % of the issue slots of the first version of this kernel).
+struct WarpLocal {
+  unsigned long long stage[STAGE_PAIRS];   // (child subtree | ray id << 32) pairs waiting for a flush
+  uint32_t items[QCAP];                    // primitive-test queue
+  unsigned long long best[32];             // packed (t, prim) of the ray each lane holds
+  uint32_t qn;                             // items queued (the appends reserve with a shared-memory atomic)
+  uint32_t pad[3];
+};
+constexpr uint32_t WL_STAGE = 0, WL_ITEMS = STAGE_PAIRS * 8, WL_BEST = WL_ITEMS + QCAP * 4, WL_QN = WL_BEST + 32 * 8;
+static_assert(sizeof(WarpLocal) == WL_QN + 16 && sizeof(WarpLocal) % 16 == 0, "WarpLocal layout");
 
 template <int W, bool ANYHIT, bool STATS>
 __global__ void __launch_bounds__(TRAV_THREADS, (W == 4 ? B2RT_OCC4 : 2))
@@ -402,31 +423,28 @@ k_traverse(const TravParams P) {
   __shared__ uint32_t s_ring_tile[RING_BUFS];     // global index of the tile the buffer holds, 0xFFFFFFFF = stream ended
   __shared__ uint4 s_chunk;
   __shared__ uint32_t s_next_ray;
-  __shared__ __align__(8) uint2 s_stage[TRAV_WARPS][STAGE_PAIRS];
-  __shared__ __align__(16) uint32_t s_items[TRAV_WARPS][QCAP];            // per-warp primitive-test queue
-  __shared__ __align__(8) unsigned long long s_best[TRAV_WARPS][32];      // per-lane packed (t, prim) of the lane's ray
+  __shared__ __align__(16) WarpLocal s_w[TRAV_WARPS];
 
   const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const uint32_t lane_lt = (1u << lane) - 1u;
-  constexpr int NB = NodeView<W>::BYTES;
+  constexpr uint32_t NB = NodeView<W>::BYTES;
   constexpr int SLOT_BITS = NodeView<W>::SLOT_BITS;
+  const uint32_t sbase = smem_u32(smem);           // shared-space address of the staged subtree (nodes, then primitives)
   // per-thread stack in shared memory, entry k of thread t at word k * TRAV_THREADS + t (conflict-free)
-  const uint32_t stack = smem_u32(smem) + P.stack_off + threadIdx.x * 4u;   // shared-space byte address
-  const uint32_t ring = smem_u32(smem) + P.ring_off;
+  const uint32_t stack = sbase + P.stack_off + threadIdx.x * 4u;
   uint8_t* const ring_generic = smem + P.ring_off;
-  const uint32_t q_addr = smem_u32(&s_items[warp][0]);
-  const uint32_t best_addr = smem_u32(&s_best[warp][0]);
+  const uint32_t wb = smem_u32(&s_w[warp]);        // this warp's scratch
   uint32_t cur_treelet = 0xFFFFFFFFu;
   uint32_t phase = 0;
   uint32_t n_staged = 0;   // warp-uniform
-  uint32_t qn = 0;         // warp-uniform: items in the warp's primitive-test queue
-  uint2* stage = s_stage[warp];
+  uint32_t qn = 0;         // warp-uniform copy of s_w[warp].qn
   unsigned long long st_nodes = 0, st_prims = 0, st_visits = 0, st_push = 0, st_upd = 0;
 
   if (threadIdx.x == 0) {
     mbar_init(&s_bar, 1);
     for (uint32_t b = 0; b < RING_BUFS; ++b) { mbar_init(&s_ring_bar[b], 1); s_ring_issued[b] = 0; s_ring_cons[b] = 0; s_ring_tile[b] = 0xFFFFFFFFu; }
   }
+  if (lane == 0) sts_u32(wb + WL_QN, 0u);
   asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   __syncthreads();
   // ---- level 0: every active ray visits the root subtree.  No chunks: the ray list is cut into 128-ray tiles and a
@@ -488,8 +506,7 @@ k_traverse(const TravParams P) {
       cur_treelet = chunk.x;
       if (STATS && threadIdx.x == 0) atomicAdd(&P.counters->staged_bytes, (unsigned long long)td.bytes);
     }
-    const uint8_t* nodes = smem;
-    const uint32_t prims_addr = smem_u32(smem) + td.n_nodes * (uint32_t)NB;   // shared-space address of the primitive records
+    const uint32_t prims_addr = sbase + td.n_nodes * NB;   // shared-space address of the primitive records
 
     // ---- per-lane ray state; lanes are refilled from the chunk as their rays finish -------------------
     uint32_t rid = 0;
@@ -507,7 +524,7 @@ k_traverse(const TravParams P) {
     // one batch of the warp's queue: items [head, head + n), one ray-primitive test per lane
     auto drain = [&](uint32_t head, uint32_t n) {
       const bool act = lane < n;
-      const uint32_t item = act ? lds_u32(q_addr + (head + lane) * 4u) : (lane << 27);
+      const uint32_t item = act ? lds_u32(wb + WL_ITEMS + (head + lane) * 4u) : (lane << 27);
       const uint32_t src = item >> 27;
       const f3 io = mk3(__shfl_sync(0xffffffffu, o.x, src), __shfl_sync(0xffffffffu, o.y, src), __shfl_sync(0xffffffffu, o.z, src));
       const f3 id = mk3(__shfl_sync(0xffffffffu, d.x, src), __shfl_sync(0xffffffffu, d.y, src), __shfl_sync(0xffffffffu, d.z, src));
@@ -525,28 +542,32 @@ k_traverse(const TravParams P) {
                                                       : hit_triangle(p, io, id, itmin, __builtin_huge_valf(), &t, &u, &v);
         if (h) {
           const unsigned long long cand = pack_hit(t, pid);
-          const uint32_t ba = best_addr + src * 8u;
-          if (cand < lds_u64(ba)) {
-            unsigned long long* bp = &s_best[warp][src];
-            atomicMin(bp, ANYHIT ? pack_hit(0.0f, pid) : cand);
-          }
+          if (cand < lds_u64(wb + WL_BEST + src * 8u)) atomicMin(&s_w[warp].best[src], ANYHIT ? pack_hit(0.0f, pid) : cand);
         }
       }
       __syncwarp();
     };
     // after a drain: every lane re-reads its ray's packed word
     auto refresh_best = [&]() {
-      const unsigned long long nb = lds_u64(best_addr + lane * 8u);
-      best_t = __uint_as_float((uint32_t)(nb >> 32));
-      if (ANYHIT && (uint32_t)nb != 0xFFFFFFFFu) { sp = 0; cur = REF_NONE; }   // occluded: the ray is done
+      if (ANYHIT) {
+        const unsigned long long nb = lds_u64(wb + WL_BEST + lane * 8u);
+        best_t = __uint_as_float((uint32_t)(nb >> 32));
+        if ((uint32_t)nb != 0xFFFFFFFFu) { sp = 0; cur = REF_NONE; }   // occluded: the ray is done
+      } else {
+        best_t = __uint_as_float(lds_u32(wb + WL_BEST + lane * 8u + 4u));
+      }
     };
     auto drain_all = [&]() {
-      uint32_t head = 0;
+      if (qn == 0) return;
       while (qn) {
         const uint32_t n = min(qn, 32u);
-        drain(head, n);
-        head += n; qn -= n;
+        qn -= n;
+        drain(qn, n);
       }
+#if B2RT_ENQ_ATOMS
+      if (lane == 0) sts_u32(wb + WL_QN, 0u);
+#endif
+      __syncwarp();
     };
 
     for (;;) {
@@ -555,21 +576,21 @@ k_traverse(const TravParams P) {
         while (sp > 0) {
           const uint32_t e = lds_u32(stack + (uint32_t)(--sp) * (TRAV_THREADS * 4u));
           if (__uint_as_float(e & STACK_TN_MASK) <= best_t) {
-            cur = *reinterpret_cast<const uint32_t*>(nodes + (size_t)((e & 0xFFFu) >> SLOT_BITS) * NB + 24 * W + (e & (uint32_t)(W - 1)) * 4u);
+            cur = lds_u32(sbase + ((e & 0xFFFu) >> SLOT_BITS) * NB + 24u * W + (e & (uint32_t)(W - 1)) * 4u);
             break;
           }
         }
       }
-      __syncwarp();
       const uint32_t m_idle = __ballot_sync(0xffffffffu, cur == REF_NONE);
-      if (m_idle == 0xffffffffu && exhausted) break;
-      if (m_idle && !exhausted && (__popc(m_idle) >= REFILL_MIN_IDLE || m_idle == 0xffffffffu)) {
+      if (m_idle) {
+        if (m_idle == 0xffffffffu && exhausted) break;
+        if (!exhausted && (__popc(m_idle) >= REFILL_MIN_IDLE || m_idle == 0xffffffffu)) {
         // finish the queued tests (the idle lanes' rays may still have items pending), retire the finished rays,
         // then hand new rays to the idle lanes
         drain_all();
         const bool idle = cur == REF_NONE;
         if (idle && have) {
-          const unsigned long long nb = lds_u64(best_addr + lane * 8u);
+          const unsigned long long nb = lds_u64(wb + WL_BEST + lane * 8u);
           if ((uint32_t)(nb >> 32) != h0_t || (uint32_t)nb != h0_id) { retire_hit(P, rid, nb); if (STATS) st_upd++; }
           have = false;
         }
@@ -596,6 +617,7 @@ k_traverse(const TravParams P) {
           }
         } else {
           // level 0: the warp takes slots base .. base + n_idle - 1 of the CTA's tile stream (at most two tiles)
+          const uint32_t ring = sbase + P.ring_off;
           const uint32_t tA = base / RING_TILE;
           const uint32_t nA = min(n_idle, (tA + 1) * RING_TILE - base), nB = n_idle - nA;
           uint32_t gA = 0xFFFFFFFFu, gB = 0xFFFFFFFFu;
@@ -662,7 +684,7 @@ k_traverse(const TravParams P) {
           tmin = ro.w;
           h0_t = (uint32_t)(h >> 32); h0_id = (uint32_t)h;
           best_t = __uint_as_float(h0_t);
-          asm volatile("st.shared.u64 [%0], %1;" ::"r"(best_addr + lane * 8u), "l"(h) : "memory");
+          sts_u64(wb + WL_BEST + lane * 8u, h);
           // reciprocal direction for the slab test; |d_k| < 1e-18 (incl. +-0) is clamped so that o_k * inv_k
           // stays finite: the ray is then parallel to the slab and the test reduces to lo_k <= o_k <= hi_k
           // (MUFU.RCP, 1 ulp: the slab test only has to be conservative, and the box padding + the 4-ulp slack on
@@ -680,14 +702,14 @@ k_traverse(const TravParams P) {
           if (STATS) st_visits++;
         }
         __syncwarp();
+        }
       }
 
       // ---- node phase: every lane whose reference is a wide node tests its W child boxes ------------------
       if ((cur >> 30) == REF_INTERNAL) {
         if (STATS) st_nodes++;
         B2_CHECK((cur & 0x3FFFFFFFu) < td.n_nodes, 2, cur);
-        const uint8_t* nbase = nodes + (size_t)(cur & 0x3FFFFFFFu) * NB;
-        const uint32_t* nrefs = reinterpret_cast<const uint32_t*>(nbase + 24 * W);
+        const uint32_t na = sbase + (cur & 0x3FFFFFFFu) * NB;
         const uint32_t fx = 12u * W - nx, fy = 20u * W - ny, fz = 28u * W - nz;
         uint32_t keys[W];
         // sign-ordered slab test: per axis the near plane row is lo (inv >= 0) or hi (inv < 0), chosen once
@@ -695,9 +717,9 @@ k_traverse(const TravParams P) {
         // inverted infinite boxes (lo = +inf, hi = -inf) => t_near = +inf, t_far = -inf => never hit.
 #pragma unroll
         for (int q = 0; q < W / 4; ++q) {
-          const float4 ax = *reinterpret_cast<const float4*>(nbase + nx + 16 * q), bx = *reinterpret_cast<const float4*>(nbase + fx + 16 * q);
-          const float4 ay = *reinterpret_cast<const float4*>(nbase + ny + 16 * q), by = *reinterpret_cast<const float4*>(nbase + fy + 16 * q);
-          const float4 az = *reinterpret_cast<const float4*>(nbase + nz + 16 * q), bz = *reinterpret_cast<const float4*>(nbase + fz + 16 * q);
+          const float4 ax = lds_f4(na + nx + 16 * q), bx = lds_f4(na + fx + 16 * q);
+          const float4 ay = lds_f4(na + ny + 16 * q), by = lds_f4(na + fy + 16 * q);
+          const float4 az = lds_f4(na + nz + 16 * q), bz = lds_f4(na + fz + 16 * q);
           const float axa[4] = {ax.x, ax.y, ax.z, ax.w}, aya[4] = {ay.x, ay.y, ay.z, ay.w}, aza[4] = {az.x, az.y, az.z, az.w};
           const float bxa[4] = {bx.x, bx.y, bx.z, bx.w}, bya[4] = {by.x, by.y, by.z, by.w}, bza[4] = {bz.x, bz.y, bz.z, bz.w};
 #pragma unroll
@@ -735,13 +757,31 @@ k_traverse(const TravParams P) {
             ++sp;
           }
         }
-        cur = keys[0] != 0xFFFFFFFFu ? nrefs[keys[0] & (uint32_t)(W - 1)] : REF_NONE;
+        cur = keys[0] != 0xFFFFFFFFu ? lds_u32(na + 24u * W + (keys[0] & (uint32_t)(W - 1)) * 4u) : REF_NONE;
       }
-      __syncwarp();
 
-      // ---- leaf references: queue (lane, primitive) items; ballot/popc prefix sums of the per-lane counts -------
+      // ---- leaf references: queue (lane, primitive) items ----------------------------------------------------------
       {
         const bool is_leaf = (cur >> 30) == REF_LEAF;
+#if B2RT_ENQ_ATOMS
+        // the lanes reserve queue space with a shared-memory atomic (few instructions, but the lanes of a warp serialise
+        // on the one counter)
+        if (__any_sync(0xffffffffu, is_leaf)) {
+          if (is_leaf) {
+            const uint32_t first = cur & 0x00FFFFFFu, count = ((cur >> 24) & 63u) + 1u;
+            const uint32_t take = min(count, LEAF_TAKE);
+            const uint32_t at = wb + WL_ITEMS + atoms_add(wb + WL_QN, take) * 4u, item = (lane << 27) | first;
+#pragma unroll
+            for (uint32_t j = 0; j < LEAF_TAKE; ++j)
+              if (j < take) sts_u32(at + j * 4u, item + j);
+            cur = count > take ? ((REF_LEAF << 30) | ((count - take - 1u) << 24) | (first + take)) : REF_NONE;
+          }
+          __syncwarp();
+          qn = lds_u32(wb + WL_QN);
+          B2_CHECK(qn <= QCAP, 6, qn);
+        }
+#else
+        // ballot / popc prefix sums of the per-lane counts (1..4: three ballots, one per bit)
         const uint32_t m_leaf = __ballot_sync(0xffffffffu, is_leaf);
         if (m_leaf) {
           const uint32_t first = cur & 0x00FFFFFFu, count = ((cur >> 24) & 63u) + 1u;
@@ -754,7 +794,7 @@ k_traverse(const TravParams P) {
           }
           B2_CHECK(qn + tot <= QCAP, 6, qn);
           if (is_leaf) {
-            const uint32_t at = q_addr + (qn + pre) * 4u, item = (lane << 27) | first;
+            const uint32_t at = wb + WL_ITEMS + (qn + pre) * 4u, item = (lane << 27) | first;
 #pragma unroll
             for (uint32_t j = 0; j < LEAF_TAKE; ++j)
               if (j < take) sts_u32(at + j * 4u, item + j);
@@ -763,6 +803,7 @@ k_traverse(const TravParams P) {
           qn += tot;
           __syncwarp();
         }
+#endif
       }
       // ---- exits: scheduler push; ballot + popc = exclusive scan of the 0/1 flags inside the warp -------------
       {
@@ -772,35 +813,34 @@ k_traverse(const TravParams P) {
           B2_CHECK(n_staged + 32 <= STAGE_PAIRS, 6, n_staged);
           if (do_push) {
             B2_CHECK((cur & 0x3FFFFFFFu) < P.n_treelets, 5, cur);
-            stage[n_staged + __popc(m & lane_lt)] = make_uint2(cur & 0x3FFFFFFFu, rid);
+            sts_u64(wb + WL_STAGE + (n_staged + __popc(m & lane_lt)) * 8u, (unsigned long long)(cur & 0x3FFFFFFFu) | ((unsigned long long)rid << 32));
             cur = REF_NONE;
             if (STATS) st_push++;
           }
           n_staged += __popc(m);
           __syncwarp();
-          if (n_staged > STAGE_PAIRS - 32) flush_pairs(stage, n_staged, P, lane);
+          if (n_staged > STAGE_PAIRS - 32) flush_pairs(wb + WL_STAGE, n_staged, P, lane);
         }
       }
-      // ---- primitive phase: drain full batches of the queue, one test per lane --------------------------------
+      // ---- primitive phase: drain full batches from the tail of the queue, one test per lane --------------------
       if (qn >= 32u) {
-        uint32_t head = 0;
-        do { drain(head, 32u); head += 32u; qn -= 32u; } while (qn >= 32u);
-        if (qn) {   // move the remainder to the front (source and destination ranges never overlap: head >= 32 > qn)
-          if (lane < qn) sts_u32(q_addr + lane * 4u, lds_u32(q_addr + (head + lane) * 4u));
-          __syncwarp();
-        }
+        do { qn -= 32u; drain(qn, 32u); } while (qn >= 32u);
+#if B2RT_ENQ_ATOMS
+        if (lane == 0) sts_u32(wb + WL_QN, qn);
+#endif
         refresh_best();
+        __syncwarp();
       }
     }
     // the warp is done with the chunk: finish the queued tests and retire the rays still held by the lanes
     drain_all();
     if (have) {
-      const unsigned long long nb = lds_u64(best_addr + lane * 8u);
+      const unsigned long long nb = lds_u64(wb + WL_BEST + lane * 8u);
       if ((uint32_t)(nb >> 32) != h0_t || (uint32_t)nb != h0_id) { retire_hit(P, rid, nb); if (STATS) st_upd++; }
     }
     __syncthreads();   // every warp is done with this chunk (s_chunk / s_next_ray / subtree smem reusable)
   }
-  if (n_staged) flush_pairs(stage, n_staged, P, lane);
+  if (n_staged) flush_pairs(wb + WL_STAGE, n_staged, P, lane);
   if (STATS) {
 #pragma unroll
     for (int dlt = 16; dlt > 0; dlt >>= 1) {
