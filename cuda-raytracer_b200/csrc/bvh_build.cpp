@@ -155,8 +155,10 @@ struct BinaryBuilder {
   std::vector<BinNode> nodes;
   std::atomic<uint32_t> next_node{0};
   uint32_t max_leaf;
+  float sah_ct = 1.5f;    // cost of one more child box in units of a primitive test (measured, profiles/r02_sweep_sah_ct.txt; 1e30 = never split a range that fits a leaf)
 
   BinaryBuilder(const std::vector<Box>& pb, uint32_t ml) : max_leaf(ml) {
+    if (const char* e = getenv("B2RT_SAH_CT")) sah_ct = (float)atof(e);
     size_t n = pb.size();
     pmn.resize(n); pmx.resize(n);
     idx.resize(n); scratch_l.resize(n + 1); scratch_r.resize(n + 1);
@@ -232,7 +234,7 @@ struct BinaryBuilder {
       }
     }
   }
-  static Split pick_split(const Bins& B, const BinSetup& s) {
+  static Split pick_split(const Bins& B, const BinSetup& s, float* cost_out = nullptr) {
     const __m128 pinf = _mm_set1_ps(std::numeric_limits<float>::infinity()), ninf = _mm_set1_ps(-std::numeric_limits<float>::infinity());
     Split sp; sp.nb = s.nb;
     float best_cost = std::numeric_limits<float>::infinity();
@@ -251,6 +253,7 @@ struct BinaryBuilder {
       }
     }
     if (sp.axis >= 0) { sp.lo = s.lo3[sp.axis]; sp.sc = s.scale3[sp.axis]; }
+    if (cost_out) *cost_out = best_cost;   // sum over the two sides of area x count
     return sp;
   }
   // branch-free stable partition of idx[b, e) into L / R scratch (the side of a primitive is a coin flip for the branch
@@ -283,11 +286,19 @@ struct BinaryBuilder {
     const uint32_t me = next_node.fetch_add(1);
     const Bounds bd = bounds_range(b, e);
     set_node(me, b, e, bd);
-    if (e - b <= max_leaf) return me;
+    if (e - b <= 1) return me;
     const BinSetup bs = bin_setup(bd, e - b);
     Bins B; reset(B, bs.nb);
     bin_range(b, e, bd, bs, B);
-    const Split sp = pick_split(B, bs);
+    float split_cost = 0.f;
+    const Split sp = pick_split(B, bs, &split_cost);
+    if (e - b <= max_leaf) {
+      // SAH leaf termination: a range that fits a leaf is still split when the expected primitive tests saved exceed
+      // the cost of the extra box (sah_ct, in units of one primitive test).  What this catches: a few LARGE primitives
+      // sharing a leaf (the walls of a box around a mesh) -- every ray that enters tests all of them.
+      const float node_area = area_of(bd.nmn, bd.nmx);
+      if (sp.axis < 0 || !(node_area > 0.f) || !(sah_ct + split_cost / node_area < (float)(e - b))) return me;
+    }
     uint32_t mid = b;
     if (sp.axis >= 0) {
       uint32_t* L = scratch_l.data() + b; uint32_t* R = scratch_r.data() + b;

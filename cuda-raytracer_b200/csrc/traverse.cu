@@ -391,14 +391,21 @@ __device__ __forceinline__ float fmin3(float a, float b, float c) {
 // so the result does not depend on the order of the tests; between a leaf visit and its drain a lane culls with a
 // stale (larger) best_t, which only adds visits.
 #ifndef B2RT_LEAF_TAKE
-#define B2RT_LEAF_TAKE 4
+#define B2RT_LEAF_TAKE 3
 #endif
-#ifndef B2RT_ENQ_ATOMS
-#define B2RT_ENQ_ATOMS 0
+// Items wait in the queue until DRAIN_MIN are there (measured: 32 = full batches only is best; the owners cull with a
+// stale best_t meanwhile, which costs about 1 % more primitive tests).
+#ifndef B2RT_DRAIN_MIN
+#define B2RT_DRAIN_MIN 32
 #endif
+constexpr uint32_t DRAIN_MIN = B2RT_DRAIN_MIN;
 constexpr uint32_t LEAF_TAKE = B2RT_LEAF_TAKE;          // primitives a lane queues per iteration (1..4)
 constexpr uint32_t QCAP = 32 + 32 * LEAF_TAKE;          // < 32 left over + one round of appends
 constexpr uint32_t ITEM_PRIM_MASK = 0x07FFFFFFu;        // item: [31:27] owning lane, [26:0] primitive index in the blob
+#ifndef B2RT_GRAB0
+#define B2RT_GRAB0 256
+#endif
+constexpr uint32_t GRAB0 = B2RT_GRAB0;                  // level 0: rays a warp claims from the global cursor at a time
 // Per-warp scratch in shared memory.  Everything a warp touches in the traversal loop hangs off ONE shared-space base
 // address (wb) plus immediates: through C++ pointers / arrays every access re-derived its address (S2UR SR_CgaCtaId +
 // ULEA ... per access, 6 % of the issue slots of the first version of this kernel).
@@ -406,21 +413,27 @@ struct WarpLocal {
   unsigned long long stage[STAGE_PAIRS];   // (child subtree | ray id << 32) pairs waiting for a flush
   uint32_t items[QCAP];                    // primitive-test queue
   unsigned long long best[32];             // packed (t, prim) of the ray each lane holds
-  uint32_t qn;                             // items queued (the appends reserve with a shared-memory atomic)
-  uint32_t pad[3];
+  float4 ray_o[32];                        // origin | t_min of the ray each lane holds (read by whichever lane tests
+  float4 ray_d[32];                        // one of its primitives; the owner itself walks with inv / -o*inv only)
 };
-constexpr uint32_t WL_STAGE = 0, WL_ITEMS = STAGE_PAIRS * 8, WL_BEST = WL_ITEMS + QCAP * 4, WL_QN = WL_BEST + 32 * 8;
-static_assert(sizeof(WarpLocal) == WL_QN + 16 && sizeof(WarpLocal) % 16 == 0, "WarpLocal layout");
+constexpr uint32_t WL_STAGE = 0, WL_ITEMS = STAGE_PAIRS * 8, WL_BEST = WL_ITEMS + QCAP * 4, WL_RO = WL_BEST + 32 * 8, WL_RD = WL_RO + 512;
+static_assert(sizeof(WarpLocal) == WL_RD + 512 && sizeof(WarpLocal) % 16 == 0 && WL_RO % 16 == 0, "WarpLocal layout");
+
+__device__ __forceinline__ void sts_f4(uint32_t a, float4 v) {
+  asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(a), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+// streaming loads of the level-0 ray list (read exactly once)
+__device__ __forceinline__ float4 ldg_stream_f4(const float4* p) {
+  float4 v;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+  return v;
+}
 
 template <int W, bool ANYHIT, bool STATS>
 __global__ void __launch_bounds__(TRAV_THREADS, (W == 4 ? B2RT_OCC4 : 2))
 k_traverse(const TravParams P) {
   extern __shared__ __align__(128) uint8_t smem[];
   __shared__ __align__(8) uint64_t s_bar;
-  __shared__ __align__(8) uint64_t s_ring_bar[RING_BUFS];
-  __shared__ uint32_t s_ring_cons[RING_BUFS];     // rays of the buffer's current tile already taken
-  __shared__ uint32_t s_ring_issued[RING_BUFS];   // tile loads issued on the buffer since the kernel started
-  __shared__ uint32_t s_ring_tile[RING_BUFS];     // global index of the tile the buffer holds, 0xFFFFFFFF = stream ended
   __shared__ uint4 s_chunk;
   __shared__ uint32_t s_next_ray;
   __shared__ __align__(16) WarpLocal s_w[TRAV_WARPS];
@@ -432,7 +445,6 @@ k_traverse(const TravParams P) {
   const uint32_t sbase = smem_u32(smem);           // shared-space address of the staged subtree (nodes, then primitives)
   // per-thread stack in shared memory, entry k of thread t at word k * TRAV_THREADS + t (conflict-free)
   const uint32_t stack = sbase + P.stack_off + threadIdx.x * 4u;
-  uint8_t* const ring_generic = smem + P.ring_off;
   const uint32_t wb = smem_u32(&s_w[warp]);        // this warp's scratch
   uint32_t cur_treelet = 0xFFFFFFFFu;
   uint32_t phase = 0;
@@ -440,49 +452,23 @@ k_traverse(const TravParams P) {
   uint32_t qn = 0;         // warp-uniform copy of s_w[warp].qn
   unsigned long long st_nodes = 0, st_prims = 0, st_visits = 0, st_push = 0, st_upd = 0;
 
-  if (threadIdx.x == 0) {
-    mbar_init(&s_bar, 1);
-    for (uint32_t b = 0; b < RING_BUFS; ++b) { mbar_init(&s_ring_bar[b], 1); s_ring_issued[b] = 0; s_ring_cons[b] = 0; s_ring_tile[b] = 0xFFFFFFFFu; }
-  }
-  if (lane == 0) sts_u32(wb + WL_QN, 0u);
+  if (threadIdx.x == 0) mbar_init(&s_bar, 1);
   asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   __syncthreads();
-  // ---- level 0: every active ray visits the root subtree.  No chunks: the ray list is cut into 128-ray tiles and a
-  // CTA claims the next tile from a global cursor whenever one of its ring buffers runs empty, so the CTAs stay
-  // balanced at tile granularity and the only barrier (and the only drain of half-empty warps) is at the kernel's end.
+  // ---- level 0: every active ray visits the root subtree; the dense ray list is the work list.  A warp claims GRAB0
+  // consecutive rays at a time from a global cursor and hands them to its lanes as they go idle (coalesced streaming
+  // loads), so the only barrier of the launch is the one at its end.  (Round 1 streamed the list through a CTA-wide
+  // shared-memory ring with TMA bulk copies; its bookkeeping -- slot accounting, mbarrier phases, re-arming -- cost
+  // more issue slots per refill than the load latency it hid, and its 10 KB now hold the lanes' ray records.)
   const uint32_t n_root = P.level == 0 ? *P.n_active : 0u;
-  // TMA load of the next unclaimed tile into ring buffer b.  Called by ONE thread, after every ray of the buffer's
-  // previous tile has been taken (or at the start).  Past the end of the list the buffer is marked "stream ended".
-  auto ring_issue = [&](uint32_t b) {
-    const uint32_t g = atomicAdd(&P.ctrl[CTRL_NEXT0], 1u);
-    const size_t at = (size_t)g * RING_TILE;
-    if (at < n_root) {
-      const uint32_t n = min(RING_TILE, n_root - (uint32_t)at), n4 = (n + 3u) & ~3u;
-      uint8_t* dst = ring_generic + b * RING_BUF_BYTES;
-      s_ring_tile[b] = g;
-      fence_proxy_async();
-      mbar_expect_tx(&s_ring_bar[b], n4 * 40u);
-      bulk_g2s(dst + RING_O, P.ray_o + at, n4 * 16u, &s_ring_bar[b]);
-      bulk_g2s(dst + RING_D, P.ray_d + at, n4 * 16u, &s_ring_bar[b]);
-      bulk_g2s(dst + RING_H, P.hits + at, n4 * 8u, &s_ring_bar[b]);
-    } else {
-      s_ring_tile[b] = 0xFFFFFFFFu;
-      __threadfence_block();
-      mbar_arrive(&s_ring_bar[b]);   // completes the phase without a copy, so waiters see the end marker
-    }
-    __threadfence_block();
-    atomicAdd(&s_ring_issued[b], 1u);
-  };
+  uint32_t w_next = 0, w_end = 0;   // warp-uniform: the warp's claimed range of the level-0 list
   const uint32_t n_chunks = P.level == 0 ? 1u : P.ctrl[CTRL_NCHUNKS];
   bool stream_started = false;
   for (;;) {
     if (threadIdx.x == 0) {
       uint4 ch = make_uint4(0xFFFFFFFFu, 0, 0, 0);
       if (P.level == 0) {
-        if (!stream_started) {   // the one pseudo-chunk of level 0: the whole ray list, as a tile stream
-          ch = make_uint4(0u, 0u, 0xFFFFFFFFu, 0u);
-          for (uint32_t b = 0; b < RING_BUFS; ++b) ring_issue(b);
-        }
+        if (!stream_started) ch = make_uint4(0u, 0u, 0xFFFFFFFFu, 0u);   // the one pseudo-chunk of level 0: the whole ray list
       } else {
         const uint32_t c = atomicAdd(&P.ctrl[CTRL_NEXT0 + (P.level & 1)], 1u);
         if (c < n_chunks) ch = P.chunks[c];
@@ -512,34 +498,31 @@ k_traverse(const TravParams P) {
     uint32_t rid = 0;
     float best_t = 0.f;
     uint32_t h0_t = 0, h0_id = 0xFFFFFFFFu;   // the ray's hit word when the lane took it (retire writes only if it improved)
-    f3 o = mk3(0, 0, 0), d = mk3(0, 0, 1), inv = mk3(0, 0, 0), noi = mk3(0, 0, 0);
+    f3 inv = mk3(0, 0, 0), noi = mk3(0, 0, 0);
     float tmin = 0.f;
     uint32_t nx = 0, ny = 0, nz = 0;   // byte offsets of the near plane rows (far rows: 12W - nx, 20W - ny, 28W - nz)
     int sp = 0;
     uint32_t cur = REF_NONE;
     bool have = false;
     bool exhausted = false;   // warp-uniform: the chunk has no more rays to hand out
-    uint32_t ring_ended = 0;  // warp-uniform: ring buffers on which this warp has seen the end-of-stream marker
 
     // one batch of the warp's queue: items [head, head + n), one ray-primitive test per lane
     auto drain = [&](uint32_t head, uint32_t n) {
-      const bool act = lane < n;
-      const uint32_t item = act ? lds_u32(wb + WL_ITEMS + (head + lane) * 4u) : (lane << 27);
-      const uint32_t src = item >> 27;
-      const f3 io = mk3(__shfl_sync(0xffffffffu, o.x, src), __shfl_sync(0xffffffffu, o.y, src), __shfl_sync(0xffffffffu, o.z, src));
-      const f3 id = mk3(__shfl_sync(0xffffffffu, d.x, src), __shfl_sync(0xffffffffu, d.y, src), __shfl_sync(0xffffffffu, d.z, src));
-      const float itmin = __shfl_sync(0xffffffffu, tmin, src);
-      if (act) {
+      if (lane < n) {
+        const uint32_t item = lds_u32(wb + WL_ITEMS + (head + lane) * 4u);
+        const uint32_t src = item >> 27;
         const uint32_t pa = prims_addr + (item & ITEM_PRIM_MASK) * (uint32_t)PRIM_BYTES;
         B2_CHECK((item & ITEM_PRIM_MASK) < td.n_prims, 4, item);
+        const float4 ro = lds_f4(wb + WL_RO + src * 16u), rd = lds_f4(wb + WL_RD + src * 16u);
         PrimRec p;
         p.a = lds_f4(pa); p.b = lds_f4(pa + 16u); p.c = lds_f4(pa + 32u);
         if (STATS) st_prims++;
         float t, u, v;
         const uint32_t pid = __float_as_uint(p.c.y);
+        const f3 io = mk3(ro.x, ro.y, ro.z), id = mk3(rd.x, rd.y, rd.z);
         // the upper end of the ray's interval is the owner's packed word: it starts at (tmax, none) and only decreases
-        const bool h = (__float_as_uint(p.c.z) != 0u) ? hit_sphere(p, io, id, itmin, __builtin_huge_valf(), &t)
-                                                      : hit_triangle(p, io, id, itmin, __builtin_huge_valf(), &t, &u, &v);
+        const bool h = (__float_as_uint(p.c.z) != 0u) ? hit_sphere(p, io, id, ro.w, __builtin_huge_valf(), &t)
+                                                      : hit_triangle(p, io, id, ro.w, __builtin_huge_valf(), &t, &u, &v);
         if (h) {
           const unsigned long long cand = pack_hit(t, pid);
           if (cand < lds_u64(wb + WL_BEST + src * 8u)) atomicMin(&s_w[warp].best[src], ANYHIT ? pack_hit(0.0f, pid) : cand);
@@ -564,9 +547,6 @@ k_traverse(const TravParams P) {
         qn -= n;
         drain(qn, n);
       }
-#if B2RT_ENQ_ATOMS
-      if (lane == 0) sts_u32(wb + WL_QN, 0u);
-#endif
       __syncwarp();
     };
 
@@ -582,9 +562,8 @@ k_traverse(const TravParams P) {
         }
       }
       const uint32_t m_idle = __ballot_sync(0xffffffffu, cur == REF_NONE);
-      if (m_idle) {
-        if (m_idle == 0xffffffffu && exhausted) break;
-        if (!exhausted && (__popc(m_idle) >= REFILL_MIN_IDLE || m_idle == 0xffffffffu)) {
+      if ((uint32_t)__popc(m_idle) >= (exhausted ? 32u : (uint32_t)REFILL_MIN_IDLE)) {
+        if (exhausted) break;
         // finish the queued tests (the idle lanes' rays may still have items pending), retire the finished rays,
         // then hand new rays to the idle lanes
         drain_all();
@@ -595,92 +574,43 @@ k_traverse(const TravParams P) {
           have = false;
         }
         if (!idle) refresh_best();
-        const uint32_t n_idle = __popc(m_idle);
-        uint32_t base = 0;
-        if (lane == 0) base = atomicAdd(&s_next_ray, n_idle);
-        base = __shfl_sync(0xffffffffu, base, 0);
-        // (chunk range and ring bookkeeping are re-read from shared memory here rather than held in registers
-        //  across the traversal loop: the kernel runs at 64 registers for 4 CTAs per SM)
-        const uint32_t chunk_first = s_chunk.y, chunk_count = s_chunk.z;
-        if (P.ids && base + n_idle >= chunk_count) exhausted = true;
-        const uint32_t k = base + __popc(m_idle & lane_lt);
-        bool take = idle && k < chunk_count;
+        const uint32_t n_idle = __popc(m_idle), rank = __popc(m_idle & lane_lt);
+        bool take;
         float4 ro = make_float4(0.f, 0.f, 0.f, 0.f), rd = make_float4(0.f, 0.f, 1.f, 0.f);
         unsigned long long h = 0;
         if (P.ids) {
-          // levels >= 1: ray ids grouped by subtree, gather the records
+          // levels >= 1: ray ids grouped by subtree; the CTA's warps share the chunk through a shared-memory cursor
+          uint32_t base = 0;
+          if (lane == 0) base = atomicAdd(&s_next_ray, n_idle);
+          base = __shfl_sync(0xffffffffu, base, 0);
+          const uint32_t chunk_first = s_chunk.y, chunk_count = s_chunk.z;
+          if (base + n_idle >= chunk_count) exhausted = true;
+          take = idle && base + rank < chunk_count;
           if (take) {
-            rid = P.ids[chunk_first + k];
+            rid = P.ids[chunk_first + base + rank];
             B2_CHECK(rid < P.n_rays_cap, 1, rid);
             if (rid >= P.n_rays_cap) rid = 0;
             ro = P.ray_o[rid]; rd = P.ray_d[rid]; h = P.hits[rid];
           }
         } else {
-          // level 0: the warp takes slots base .. base + n_idle - 1 of the CTA's tile stream (at most two tiles)
-          const uint32_t ring = sbase + P.ring_off;
-          const uint32_t tA = base / RING_TILE;
-          const uint32_t nA = min(n_idle, (tA + 1) * RING_TILE - base), nB = n_idle - nA;
-          uint32_t gA = 0xFFFFFFFFu, gB = 0xFFFFFFFFu;
-#pragma unroll
-          for (uint32_t j = 0; j < 2; ++j) {
-            if (j == 1 && nB == 0) break;
-            const uint32_t t = tA + j, b = t % RING_BUFS, load = t / RING_BUFS;
-            // the load must have been issued before its mbarrier phase can be waited for (a parity wait cannot tell
-            // "not started" from "completed" two phases apart)
-            uint32_t spins = 0;
-            bool stuck = false;
-            while ((int32_t)(*(volatile uint32_t*)&s_ring_issued[b] - load) <= 0) {
-              if (++spins == (1u << 24)) {   // watchdog: give up on the stream and report instead of hanging the device
-                if (lane == 0 && atomicCAS(&P.ctrl[8], 0u, 1u) == 0u) {
-                  P.ctrl[9] = blockIdx.x; P.ctrl[10] = warp | (j << 8) | (n_idle << 16); P.ctrl[11] = t; P.ctrl[12] = load;
-                  P.ctrl[13] = s_ring_issued[0] | (s_ring_issued[1] << 16); P.ctrl[14] = base;
-                  P.ctrl[15] = s_ring_cons[0] | (s_ring_cons[1] << 16);
-                  P.ctrl[CTRL_OVERFLOW] = 1;
-                }
-                stuck = true;
-                break;
-              }
-            }
-            if (!stuck) mbar_wait(&s_ring_bar[b], load & 1u);
-            const uint32_t g = stuck ? 0xFFFFFFFFu : *(volatile uint32_t*)&s_ring_tile[b];
-            if (j == 0) gA = g; else gB = g;
+          // level 0: the warp's claimed range of the dense list, re-claimed from the global cursor when it runs out
+          if (w_next >= w_end) {
+            uint32_t g = 0;
+            if (lane == 0) g = atomicAdd(&P.ctrl[CTRL_NEXT0], GRAB0);
+            g = __shfl_sync(0xffffffffu, g, 0);
+            if (g < n_root) { w_next = g; w_end = (n_root - g < GRAB0) ? n_root : g + GRAB0; }
+            else exhausted = true;
           }
-          // The ray list is handed out once BOTH buffers have shown the end marker: the buffers claim global tiles
-          // independently, so the last real tile can sit (in the CTA's slot order) behind the first end marker.
-          if (gA == 0xFFFFFFFFu) ring_ended |= 1u << (tA % RING_BUFS);
-          if (nB && gB == 0xFFFFFFFFu) ring_ended |= 1u << ((tA + 1) % RING_BUFS);
-          if (ring_ended == (1u << RING_BUFS) - 1u) exhausted = true;
-          const uint32_t t = k / RING_TILE, e = k % RING_TILE;
-          const uint32_t g = t == tA ? gA : gB;
-          take = idle && g != 0xFFFFFFFFu && g * RING_TILE + e < n_root;
+          const uint32_t avail = w_end - w_next;
+          take = idle && rank < avail;
           if (take) {
-            const uint32_t rb = ring + (t % RING_BUFS) * RING_BUF_BYTES;
-            ro = lds_f4(rb + RING_O + e * 16u); rd = lds_f4(rb + RING_D + e * 16u);
-            h = lds_u64(rb + RING_H + e * 8u);
-            rid = g * RING_TILE + e;
+            rid = w_next + rank;
+            ro = ldg_stream_f4(P.ray_o + rid); rd = ldg_stream_f4(P.ray_d + rid); h = __ldcs(P.hits + rid);
           }
-          __syncwarp();   // every lane's ring reads are done
-          if (lane == 0) {
-            // hand the slots back; whoever takes the last slot of a tile re-arms its buffer with the next unclaimed tile
-            __threadfence_block();
-#pragma unroll
-            for (uint32_t j = 0; j < 2; ++j) {
-              const uint32_t n = j ? nB : nA;
-              if (n == 0) continue;
-              const uint32_t b = (tA + j) % RING_BUFS;
-              const uint32_t old = atomicAdd(&s_ring_cons[b], n);
-              if (old + n == RING_TILE) {
-                s_ring_cons[b] = 0;
-                __threadfence_block();
-                // always, even after an end marker: the two buffers claim global tiles independently, so a buffer
-                // can hold the end marker while the other still gets a real tile and warps move on past both
-                ring_issue(b);
-              }
-            }
-          }
+          w_next += min(n_idle, avail);
         }
         if (take) {
-          o = mk3(ro.x, ro.y, ro.z); d = mk3(rd.x, rd.y, rd.z);
+          sts_f4(wb + WL_RO + lane * 16u, ro); sts_f4(wb + WL_RD + lane * 16u, rd);
           tmin = ro.w;
           h0_t = (uint32_t)(h >> 32); h0_id = (uint32_t)h;
           best_t = __uint_as_float(h0_t);
@@ -689,10 +619,10 @@ k_traverse(const TravParams P) {
           // stays finite: the ray is then parallel to the slab and the test reduces to lo_k <= o_k <= hi_k
           // (MUFU.RCP, 1 ulp: the slab test only has to be conservative, and the box padding + the 4-ulp slack on
           //  t_far cover it; the IEEE-rounded reciprocal cost 3 x 8 instructions per ray)
-          inv = mk3(fabsf(d.x) > 1e-18f ? fast_rcp(d.x) : copysignf(1e18f, d.x),
-                    fabsf(d.y) > 1e-18f ? fast_rcp(d.y) : copysignf(1e18f, d.y),
-                    fabsf(d.z) > 1e-18f ? fast_rcp(d.z) : copysignf(1e18f, d.z));
-          noi = mk3(-(o.x * inv.x), -(o.y * inv.y), -(o.z * inv.z));
+          inv = mk3(fabsf(rd.x) > 1e-18f ? fast_rcp(rd.x) : copysignf(1e18f, rd.x),
+                    fabsf(rd.y) > 1e-18f ? fast_rcp(rd.y) : copysignf(1e18f, rd.y),
+                    fabsf(rd.z) > 1e-18f ? fast_rcp(rd.z) : copysignf(1e18f, rd.z));
+          noi = mk3(-(ro.x * inv.x), -(ro.y * inv.y), -(ro.z * inv.z));
           nx = inv.x >= 0.f ? 0u : 12u * W;
           ny = inv.y >= 0.f ? 4u * W : 16u * W;
           nz = inv.z >= 0.f ? 8u * W : 20u * W;
@@ -702,7 +632,6 @@ k_traverse(const TravParams P) {
           if (STATS) st_visits++;
         }
         __syncwarp();
-        }
       }
 
       // ---- node phase: every lane whose reference is a wide node tests its W child boxes ------------------
@@ -763,24 +692,6 @@ k_traverse(const TravParams P) {
       // ---- leaf references: queue (lane, primitive) items ----------------------------------------------------------
       {
         const bool is_leaf = (cur >> 30) == REF_LEAF;
-#if B2RT_ENQ_ATOMS
-        // the lanes reserve queue space with a shared-memory atomic (few instructions, but the lanes of a warp serialise
-        // on the one counter)
-        if (__any_sync(0xffffffffu, is_leaf)) {
-          if (is_leaf) {
-            const uint32_t first = cur & 0x00FFFFFFu, count = ((cur >> 24) & 63u) + 1u;
-            const uint32_t take = min(count, LEAF_TAKE);
-            const uint32_t at = wb + WL_ITEMS + atoms_add(wb + WL_QN, take) * 4u, item = (lane << 27) | first;
-#pragma unroll
-            for (uint32_t j = 0; j < LEAF_TAKE; ++j)
-              if (j < take) sts_u32(at + j * 4u, item + j);
-            cur = count > take ? ((REF_LEAF << 30) | ((count - take - 1u) << 24) | (first + take)) : REF_NONE;
-          }
-          __syncwarp();
-          qn = lds_u32(wb + WL_QN);
-          B2_CHECK(qn <= QCAP, 6, qn);
-        }
-#else
         // ballot / popc prefix sums of the per-lane counts (1..4: three ballots, one per bit)
         const uint32_t m_leaf = __ballot_sync(0xffffffffu, is_leaf);
         if (m_leaf) {
@@ -803,7 +714,6 @@ k_traverse(const TravParams P) {
           qn += tot;
           __syncwarp();
         }
-#endif
       }
       // ---- exits: scheduler push; ballot + popc = exclusive scan of the 0/1 flags inside the warp -------------
       {
@@ -823,11 +733,12 @@ k_traverse(const TravParams P) {
         }
       }
       // ---- primitive phase: drain full batches from the tail of the queue, one test per lane --------------------
-      if (qn >= 32u) {
-        do { qn -= 32u; drain(qn, 32u); } while (qn >= 32u);
-#if B2RT_ENQ_ATOMS
-        if (lane == 0) sts_u32(wb + WL_QN, qn);
-#endif
+      if (qn >= DRAIN_MIN) {
+        if (DRAIN_MIN >= 32u) {
+          do { qn -= 32u; drain(qn, 32u); } while (qn >= 32u);
+        } else {
+          do { const uint32_t n = min(qn, 32u); qn -= n; drain(qn, n); } while (qn >= DRAIN_MIN);
+        }
         refresh_best();
         __syncwarp();
       }
@@ -1060,8 +971,8 @@ int Tracer::init(const DeviceBVH& b, uint64_t max_rays_, uint32_t pair_factor) {
   chunk_cap = pair_cap / chunk_rays + (uint64_t)bvh.n_treelets + 1024;
   // dynamic shared memory: the staged subtree blob, then the per-thread traversal stacks
   stack_off = (std::max<size_t>(bvh.max_treelet_bytes, 1024) + 127) & ~(size_t)127;
-  ring_off = stack_off + stack_bytes(bvh.width);
-  smem_bytes = ring_off + RING_BUFS * RING_BUF_BYTES;
+  ring_off = 0;
+  smem_bytes = stack_off + stack_bytes(bvh.width);
   if (const char* e = getenv("B2RT_CHUNK_RAYS")) { int v = atoi(e); if (v >= 32 && v <= (1 << 20)) chunk_rays = (uint32_t)v; }
   if (const char* e = getenv("B2RT_CHUNK0_MAX")) { int v = atoi(e); if (v >= 32 && v <= (1 << 24)) chunk0_max = (uint32_t)v; }
   int occ = 1, o2 = 1, o3 = 1, o4 = 1;
@@ -1080,7 +991,7 @@ int Tracer::init(const DeviceBVH& b, uint64_t max_rays_, uint32_t pair_factor) {
   ctas_per_sm = std::max(1, std::min(std::min(occ, o2), std::min(o3, o4)));
   if (getenv("B2RT_VERBOSE"))
     fprintf(stderr, "b2rt: k_traverse W=%u: %d threads, %zu B dynamic smem (subtree %u + stacks %zu + ring %u), %d CTAs/SM x %d SMs\n",
-            bvh.width, TRAV_THREADS, smem_bytes, bvh.max_treelet_bytes, stack_bytes(bvh.width), RING_BUFS * RING_BUF_BYTES,
+            bvh.width, TRAV_THREADS, smem_bytes, bvh.max_treelet_bytes, stack_bytes(bvh.width), 0u,
             ctas_per_sm, num_sms);
   B2RT_CUDA_OK(cudaFuncSetAttribute(k_scatter_tiled, cudaFuncAttributeMaxDynamicSharedMemorySize, 12288 * 8));
   B2RT_CUDA_OK(cudaFuncSetAttribute(k_count_tiled, cudaFuncAttributeMaxDynamicSharedMemorySize, 12288 * 4));
