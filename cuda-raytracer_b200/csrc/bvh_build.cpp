@@ -442,9 +442,9 @@ int build_wide_bvh(const HostScene& sc, uint32_t max_leaf, uint32_t width, uint3
   if (max_leaf > 64) { set_error("max_leaf_size must be <= 64"); return B2RT_ERR_INVALID; }
   const uint32_t NB = node_bytes(width);
   const uint32_t min_budget = NB + width * max_leaf * PRIM_BYTES;
-  // default subtree budget, by measurement (profiles/r01_sweep_subtree_budget.txt): 16 KiB for small scenes (cfg2,
-  // 28 K triangles), 24 KiB from 64 K primitives on (cfg3 stand-in, 114 K); 4 CTAs per SM fit either way
-  if (treelet_bytes == 0) treelet_bytes = (sc.n_prims() >= 65536 ? 24 : 16) * 1024;
+  // default subtree budget, by measurement (round 2 kernel, profiles/r02_sweep_subtree_chunk.txt): 20 KiB for small
+  // scenes (cfg2, 28 K triangles; 4 CTAs per SM), 24 KiB from 64 K primitives on (cfg3 stand-in, 114 K; 3 CTAs per SM)
+  if (treelet_bytes == 0) treelet_bytes = (sc.n_prims() >= 65536 ? 24 : 20) * 1024;
   treelet_bytes = std::max(treelet_bytes, min_budget) & ~15u;
   // 227 KiB per CTA = subtree blob + per-thread stacks (<= 35 KiB) + the push staging rings
   if (treelet_bytes > 160 * 1024) { set_error("treelet_bytes exceeds the shared-memory budget (160 KiB)"); return B2RT_ERR_INVALID; }

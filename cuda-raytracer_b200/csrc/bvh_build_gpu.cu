@@ -635,7 +635,7 @@ int build_wide_bvh_device(const b2rt_scene_desc* sc, uint32_t max_leaf, uint32_t
   if (n == 0) { set_error("gpu bvh build: empty scene"); return B2RT_ERR_INVALID; }
   if (n >= (1u << 29)) { set_error("gpu bvh build: too many primitives"); return B2RT_ERR_INVALID; }
   const uint32_t min_budget = node_bytes(width) + width * max_leaf * PRIM_BYTES;
-  if (treelet_bytes == 0) treelet_bytes = (n >= 65536 ? 24 : 16) * 1024;
+  if (treelet_bytes == 0) treelet_bytes = (n >= 65536 ? 24 : 20) * 1024;
   treelet_bytes = std::max(treelet_bytes, min_budget) & ~15u;
   if (treelet_bytes > 160 * 1024) { set_error("treelet_bytes exceeds the shared-memory budget (160 KiB)"); return B2RT_ERR_INVALID; }
   return width == 8 ? build_device_w<8>(*sc, max_leaf, treelet_bytes, s, dev, meta)

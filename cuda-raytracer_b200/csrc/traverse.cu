@@ -442,10 +442,14 @@ k_traverse(const TravParams P) {
   const uint32_t lane_lt = (1u << lane) - 1u;
   constexpr uint32_t NB = NodeView<W>::BYTES;
   constexpr int SLOT_BITS = NodeView<W>::SLOT_BITS;
-  const uint32_t sbase = smem_u32(smem);           // shared-space address of the staged subtree (nodes, then primitives)
+  // The three base addresses below go through an opaque asm move: left to itself ptxas re-derives each of them at
+  // every use (S2R SR_CgaCtaId + MOV + LEA + ..., 8 instructions for the stack address of every pop) instead of
+  // keeping them in a register.
+  uint32_t sbase, stack, wb;
+  asm volatile("mov.u32 %0, %1;" : "=r"(sbase) : "r"(smem_u32(smem)));   // the staged subtree (nodes, then primitives)
   // per-thread stack in shared memory, entry k of thread t at word k * TRAV_THREADS + t (conflict-free)
-  const uint32_t stack = sbase + P.stack_off + threadIdx.x * 4u;
-  const uint32_t wb = smem_u32(&s_w[warp]);        // this warp's scratch
+  asm volatile("mov.u32 %0, %1;" : "=r"(stack) : "r"(sbase + P.stack_off + threadIdx.x * 4u));
+  asm volatile("mov.u32 %0, %1;" : "=r"(wb) : "r"(smem_u32(&s_w[warp])));   // this warp's scratch
   uint32_t cur_treelet = 0xFFFFFFFFu;
   uint32_t phase = 0;
   uint32_t n_staged = 0;   // warp-uniform
@@ -505,6 +509,7 @@ k_traverse(const TravParams P) {
     uint32_t cur = REF_NONE;
     bool have = false;
     bool exhausted = false;   // warp-uniform: the chunk has no more rays to hand out
+    uint32_t idle_min = (uint32_t)REFILL_MIN_IDLE;   // idle lanes that trigger a refill; 32 (= leave the loop) once exhausted
 
     // one batch of the warp's queue: items [head, head + n), one ray-primitive test per lane
     auto drain = [&](uint32_t head, uint32_t n) {
@@ -562,7 +567,7 @@ k_traverse(const TravParams P) {
         }
       }
       const uint32_t m_idle = __ballot_sync(0xffffffffu, cur == REF_NONE);
-      if ((uint32_t)__popc(m_idle) >= (exhausted ? 32u : (uint32_t)REFILL_MIN_IDLE)) {
+      if ((uint32_t)__popc(m_idle) >= idle_min) {   // idle_min = 32 once the chunk is handed out
         if (exhausted) break;
         // finish the queued tests (the idle lanes' rays may still have items pending), retire the finished rays,
         // then hand new rays to the idle lanes
@@ -584,7 +589,7 @@ k_traverse(const TravParams P) {
           if (lane == 0) base = atomicAdd(&s_next_ray, n_idle);
           base = __shfl_sync(0xffffffffu, base, 0);
           const uint32_t chunk_first = s_chunk.y, chunk_count = s_chunk.z;
-          if (base + n_idle >= chunk_count) exhausted = true;
+          if (base + n_idle >= chunk_count) { exhausted = true; idle_min = 32u; }
           take = idle && base + rank < chunk_count;
           if (take) {
             rid = P.ids[chunk_first + base + rank];
@@ -599,7 +604,7 @@ k_traverse(const TravParams P) {
             if (lane == 0) g = atomicAdd(&P.ctrl[CTRL_NEXT0], GRAB0);
             g = __shfl_sync(0xffffffffu, g, 0);
             if (g < n_root) { w_next = g; w_end = (n_root - g < GRAB0) ? n_root : g + GRAB0; }
-            else exhausted = true;
+            else { exhausted = true; idle_min = 32u; }
           }
           const uint32_t avail = w_end - w_next;
           take = idle && rank < avail;
@@ -658,8 +663,8 @@ k_traverse(const TravParams P) {
             const float tf = fminf(fmin3(__fmaf_rn(bxa[c], inv.x, noi.x), __fmaf_rn(bya[c], inv.y, noi.y),
                                          __fmaf_rn(bza[c], inv.z, noi.z)), best_t);
             const bool hit = tn <= tf * 1.0000004f;
-            // key: entry distance (rounded down, keeps order for t >= 0) | child slot
-            keys[q * 4 + c] = hit ? ((__float_as_uint(tn) & ~(uint32_t)(W - 1)) | (uint32_t)(q * 4 + c)) : 0xFFFFFFFFu;
+            // key: entry distance (low byte dropped = rounded down, keeps order for t >= 0) | child slot in the low byte (one PRMT)
+            keys[q * 4 + c] = hit ? __byte_perm(__float_as_uint(tn), (uint32_t)(q * 4 + c), 0x3214) : 0xFFFFFFFFu;
           }
         }
 #define B2_CE(a, b) { const uint32_t lo_ = min(keys[a], keys[b]), hi_ = max(keys[a], keys[b]); keys[a] = lo_; keys[b] = hi_; }
