@@ -4,13 +4,16 @@
   python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path (one rank per GPU under torchrun)
   python bench.py --impl reference --steps K --warmup W    # CPU arm: the oracle port on the box's host cores
 
-A "step" is one full frame of the workload (BASELINE.json configs[1]: CBbunny.dae, 1024x768, 64 spp,
-max depth 8, area light, 1 B200): ray generation, <= 8 closest-hit traversals and <= 8 shadow-ray
-traversals per path, shading, accumulation.  `value` counts every ray actually traced (camera + bounce +
-shadow) over all ranks / max-over-ranks device time of the K timed steps.  Multi-GPU: samples are
-sharded by index (rank r renders samples r, r+N, ...; per-GPU work fixed => weak scaling) with the scene
-replicated, and the per-GPU accumulation buffers are combined with ONE NCCL reduce per frame, inside the
-timed region.  `roofline` (per-launch timing of k_traverse) comes from a second pass of the same K frames with
+A "step" is one full frame of the workload.  Default = the configuration north_star states its target on, BASELINE.json
+configs[2]: the dragon-class scene (stand-in: the CBbunny box with the bunny subdivided once, 114,316 triangles -- the
+named CBdragon.dae is absent from the reference checkout), 1920x1080, 256 spp, max depth 8, area light, the job's 256 spp
+sharded over the N ranks (STRONG scaling).  `--workload cfg2` is BASELINE configs[1] (CBbunny.dae 1024x768, 64 spp per
+GPU, weak scaling; the round-1 default).  A frame = ray generation, <= 8 closest-hit traversals and <= 8 shadow-ray
+traversals per path, shading, accumulation.  `value` counts every ray actually traced (camera + bounce + shadow) over
+all ranks / max-over-ranks device time of the K timed steps.  Multi-GPU: samples are sharded by index (rank r renders
+samples r, r+N, ...) with the scene replicated, and the per-GPU accumulation buffers are combined with ONE NCCL reduce
+per frame, issued by libb2rt.so on the render stream (b2rt_reduce_accum; torch.distributed only ships the 128-byte
+NCCL id and the timing scalars), inside the timed region.  `roofline` (per-launch timing of k_traverse) comes from a second pass of the same K frames with
 per-launch CUDA events, in which the renderer runs on one stream (in the timed region it overlaps the shadow-ray trace
 of bounce b with the closest-hit trace of bounce b + 1 on two streams, so launches have no duration of their own).
 Prints exactly one JSON line on rank 0.
@@ -32,7 +35,7 @@ WORKLOADS = {
     # name: (scene, width, height, spp, depth, ns_area_light, scaling).  "weak": spp per GPU; "strong": spp of the whole
     # job, divided over the ranks (BASELINE configs[2] / [3]: "spp sharded across 1/2/4/8 B200").  cfg3 / cfg4 use the
     # stand-in scenes of b2rt.scene (the named assets are missing from the reference checkout).  The default and the
-    # driver's run is cfg2; the others are for the extra measurements under profiles/.
+    # driver's run is cfg3 (the scene north_star states its target on); the others are extra measurements under profiles/.
     "cfg1": ("CBspheres_lambertian", 480, 360, 16, 4, 1, "weak"),
     "cfg2": ("CBbunny", 1024, 768, 64, 8, 1, "weak"),
     "cfg3": ("cfg3_standin", 1920, 1080, 256, 8, 1, "strong"),
@@ -47,9 +50,9 @@ def parse():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
+    ap.add_argument("--workload", default="cfg3", choices=sorted(WORKLOADS))
     ap.add_argument("--spp", type=int, default=0, help="override samples per pixel (debug only; invalidates the number)")
-    ap.add_argument("--cpu-spp", type=int, default=0, help="spp of the bounded CPU sample (default 4 of 64)")
+    ap.add_argument("--cpu-spp", type=int, default=0, help="spp of the bounded CPU sample (default 4 of the workload's spp)")
     ap.add_argument("--bvh-width", type=int, default=0)
     ap.add_argument("--treelet-bytes", type=int, default=0)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
@@ -171,6 +174,8 @@ def main():
                           f"max_ray_depth {wl['depth']}, ns_area_light {wl['ns_area_light']} "
                           f"(BASELINE configs[{BASELINE_INDEX[args.workload]}])",
               "scene_tris": int(sc.n_tris), "parallelism": f"spp-sharded x{world}, scene replicated",
+              "scene_source": ("generated stand-in: the bundled CBbunny.dae with its mesh midpoint-subdivided (the named asset is absent "
+                               "from the reference checkout)" if wl["scene"].endswith("_standin") else "bundled .dae scene of the reference"),
               "l2": "per-wave ray/path state (<= 64Mi paths x ~200 B = GBs) exceeds the 126 MB L2; no explicit flush"}
 
     if args.impl == "reference":
@@ -203,14 +208,18 @@ def main():
                          treelet_bytes=args.treelet_bytes)
     pt.set_stream(stream.cuda_stream)
     pt.set_scene(sc); pt.set_camera(cam); pt.set_frame_size(wl["width"], wl["height"])
-    accum = pt.accum_tensor() if world > 1 else None
+    comm = None
+    if world > 1:
+        # the NCCL communicator lives behind the C ABI; torch.distributed only carries its 128-byte id to the ranks
+        uid = [b2rt.Comm.unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(uid, src=0)
+        comm = b2rt.Comm(world, rank, uid[0], device=local_rank)
 
     def frame():
-        pt.clear()
-        pt.start_raytracing()
+        pt.start_raytracing()     # clears the accumulation buffer, then enqueues the frame
         pt.wait()
-        if world > 1:
-            dist.reduce(accum, dst=0)     # ONE collective per frame: sum of the per-GPU accumulation buffers
+        if comm is not None:
+            pt.reduce_accum(comm, root=0)   # ONE collective per frame (ncclReduce inside libb2rt.so, on the render stream)
 
     # counters pass (untimed): algorithmic work of one frame
     pt.set_profiling(counters=True, time_kernels=False)
@@ -245,14 +254,18 @@ def main():
     # closest-hit trace of bounce b + 1, so launches overlap and have no duration of their own; with per-launch timing on
     # the renderer uses one stream and every launch is timed alone (the same serialisation an ncu launch list shows).
     ms_trav = 0.0
+    ms_trav_l0 = 0.0
     trav_launches = 0
+    trav_launches_l0 = 0
     ms_iso = 0.0
     pt.set_profiling(counters=False, time_kernels=True)
     for _ in range(args.steps):
         frame()
         st = pt.stats()
         ms_trav += st["ms_traverse"]
+        ms_trav_l0 += st["ms_traverse_l0"]
         trav_launches += st["traverse_launches"]
+        trav_launches_l0 += st["traverse_launches_l0"]
         ms_iso += st["ms_total"]
     if world > 1:
         t = torch.tensor([ms], device="cuda", dtype=torch.float64)
@@ -269,7 +282,7 @@ def main():
     #      render + read-back of the HDR frame, every step ----
     h2d = int(cst["bvh_bytes"] + sc.n_prims * (48 + 4) + (sc.n_tris * 36 if sc.tri_normals is not None else 0)
               + len(sc.materials) * 48 + len(sc.lights) * 64)
-    d2h = wl["width"] * wl["height"] * 16
+    d2h = wl["width"] * wl["height"] * 16      # the combined frame, read back on rank 0 only
     pt.set_profiling(counters=False, time_kernels=False)
     torch.cuda.synchronize()
     if world > 1:
@@ -277,9 +290,12 @@ def main():
     def e2e_step():
         pt.set_scene(sc); pt.set_camera(cam)
         pt.start_raytracing(); pt.wait()
-        if world > 1:
-            dist.reduce(accum, dst=0)
-        pt.image()             # CudaRenderer::getImage: device -> renderer-owned pinned host buffer
+        if comm is not None:
+            pt.reduce_accum(comm, root=0)
+        if rank == 0:
+            pt.image()         # CudaRenderer::getImage on the root: device -> renderer-owned pinned host buffer
+        else:
+            torch.cuda.current_stream().synchronize()
         st = pt.stats()
         return st["rays_camera"] + st["rays_bounce"] + st["rays_shadow"]
 
@@ -303,9 +319,12 @@ def main():
         rays_e = int(r.item())
     e2e = {"value": rays_e / e2e_s / 1e6, "unit": "Mrays/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
            "s_per_frame": e2e_s / args.steps,
-           "what": "b2rt_set_scene (host BVH build + upload) + set_camera + start/wait + b2rt_get_image (frame to host), per step"}
+           "what": "per step and per rank: b2rt_set_scene (BVH build + upload of the scene's host arrays) + set_camera + start/wait "
+                   "+ b2rt_reduce_accum; b2rt_get_image (frame to host) on rank 0"}
 
     if rank != 0:
+        if comm is not None:
+            comm.close()
         if world > 1:
             dist.destroy_process_group()
         return 0
@@ -323,22 +342,46 @@ def main():
     tl = max(1, trav_launches // args.steps)
     achieved = alg_bytes / (trav_ms_frame * 1e-3) / 1e9
     sm_mhz = (clk or {}).get("sm_mhz") or 1965.0
-    fp32_peak = 148 * 128 * 2 * sm_mhz * 1e6 / 1e12
+    fp32_paper = 148 * 128 * 2 * sm_mhz * 1e6 / 1e12
+    try:
+        fp32_peak = b2rt.bench_fp32(local_rank); fp32_src = "measured on this GPU: b2rt_bench_fp32 (FFMA-saturating kernel, 16 chains per thread)"
+    except b2rt.B2rtError:
+        fp32_peak = fp32_paper; fp32_src = "computed (148 SMs x 128 lanes x 2 x clock under load)"
     fp32_ach = alg_flops / (trav_ms_frame * 1e-3) / 1e12
     traffic = None
     tpath = os.path.join(ROOT, "profiles", "traverse_traffic.json")
     if os.path.exists(tpath):
-        traffic = json.load(open(tpath)).get("dram_bytes_per_launch")
+        traffic = (json.load(open(tpath)).get(args.workload) or {}).get("dram_bytes_per_launch")   # ncu, keyed by workload
+    # per level class: level 0 streams the dense ray list (every ray once), the deeper levels gather rays by id
+    rays_frame = cst["rays_camera"] + cst["rays_bounce"] + cst["rays_shadow"]
+    l0 = {"visits": rays_frame, "pushes": cst["queue_pushes_l0"], "upd": cst["hit_updates_l0"], "staged": cst["staged_bytes_l0"],
+          "nodes": cst["node_visits_l0"], "prims": cst["leaf_prim_tests_l0"], "ms": ms_trav_l0 / args.steps,
+          "launches": max(1, trav_launches_l0 // args.steps)}
+    dp = {"visits": cst["subtree_visits"] - rays_frame, "pushes": cst["queue_pushes"] - cst["queue_pushes_l0"],
+          "upd": cst["hit_updates"] - cst["hit_updates_l0"], "staged": cst["staged_bytes"] - cst["staged_bytes_l0"],
+          "nodes": cst["node_visits"] - cst["node_visits_l0"], "prims": cst["leaf_prim_tests"] - cst["leaf_prim_tests_l0"],
+          "ms": (ms_trav - ms_trav_l0) / args.steps, "launches": max(1, (trav_launches - trav_launches_l0) // args.steps)}
+
+    def klass(c):
+        b = 40 * c["visits"] + 24 * c["pushes"] + 8 * c["upd"] + c["staged"]
+        f = 24 * W * c["nodes"] + 55 * c["prims"]
+        t = max(c["ms"], 1e-9) * 1e-3
+        return {"ms_per_frame": c["ms"], "launches_per_step": c["launches"], "alg_bytes": b, "alg_flops": f,
+                "hbm_gbs": b / t / 1e9, "hbm_frac": b / t / 1e9 / hbm, "fp32_tflops": f / t / 1e12, "fp32_frac": f / t / 1e12 / fp32_peak,
+                "visits": c["visits"], "node_visits": c["nodes"], "prim_tests": c["prims"], "pushes": c["pushes"]}
     roofline = {"bound": "hbm", "achieved": achieved, "peak": hbm, "unit": "GB/s", "frac": achieved / hbm, "traffic": traffic,
                 "kernel": "k_traverse", "peak_source": peak_src, "launches_per_step": tl,
                 "avg_launch_ms": trav_ms_frame / tl, "alg_bytes_per_launch": alg_bytes / tl,
-                "alg_bytes_per_ray": alg_bytes / max(1, cst["rays_camera"] + cst["rays_bounce"] + cst["rays_shadow"]),
+                "alg_bytes_per_ray": alg_bytes / max(1, rays_frame),
                 "kernel_share_of_step": ms_trav / ms_iso,
                 "timing": "per-launch CUDA events in a second pass of the same K frames on one stream (launches timed alone; "
                           f"that pass: {ms_iso / args.steps:.3f} ms/frame); the timed region overlaps launches on two streams",
-                "fp32": {"achieved_tflops": fp32_ach, "peak_tflops": fp32_peak, "frac": fp32_ach / fp32_peak,
-                         "peak_source": f"148 SMs x 128 lanes x 2 x {sm_mhz:.0f} MHz (clock observed under load)"},
+                "fp32": {"achieved_tflops": fp32_ach, "peak_tflops": fp32_peak, "frac": fp32_ach / fp32_peak, "peak_source": fp32_src,
+                         "paper_peak_tflops": fp32_paper},
                 "binding_term": "hbm" if achieved / hbm >= fp32_ach / fp32_peak else "fp32",
+                "by_level": {"level0": klass(l0), "deeper": klass(dp),
+                             "model": "bytes = 40 x (ray, subtree) visits + 24 x pushes + 8 x hit updates + staged subtree bytes; "
+                                      "flops = 24 x W x node visits + 55 x primitive tests (DESIGN.md)"},
                 "counters_per_frame": {k: cst[k] for k in ("subtree_visits", "queue_pushes", "hit_updates", "staged_bytes",
                                                            "node_visits", "leaf_prim_tests")}}
 
@@ -350,10 +393,14 @@ def main():
     line = {"metric": metric, "value": value, "unit": "Mrays/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms / args.steps, "s_per_frame": ms / args.steps / 1e3, "higher_is_better": True, "scaling": wl["scaling"],
             "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config, "clocks": clk, "e2e": e2e,
+            "collective": ("b2rt_reduce_accum: one ncclReduce (fp32 sum) of the accumulation buffers per frame, issued by libb2rt.so "
+                           f"(NCCL {b2rt.Comm.version()})" if world > 1 else None),
             "gpu_launches": launches_total, "roofline": roofline, "cpu_baseline": cpu_baseline,
             "rays_per_step": rays_total // args.steps, "bvh": {k: cst[k] for k in ("bvh_nodes", "bvh_subtrees", "bvh_levels",
                                                                                    "bvh_width", "bvh_bytes", "ms_build")}}
     emit(line)
+    if comm is not None:
+        comm.close()
     if world > 1:
         dist.destroy_process_group()
     return 0

@@ -30,6 +30,9 @@ EXPORTS = [
     "b2rt_read_rgba32f", "b2rt_get_image", "b2rt_get_stats", "b2rt_accum_device_ptr", "b2rt_stream_handle", "b2rt_set_stream",
     "b2rt_set_profiling", "b2rt_destroy", "b2rt_bvh_validate_host",
     "b2rt_scene_load", "b2rt_scene_save", "b2rt_load_dae", "b2rt_scene_free", "b2rt_camera_place",
+    "b2rt_comm_version", "b2rt_comm_unique_id", "b2rt_comm_create", "b2rt_comm_create_all", "b2rt_reduce_accum",
+    "b2rt_reduce_accum_all", "b2rt_comm_destroy", "b2rt_bench_fp32", "b2rt_camera_look_at", "b2rt_save_png", "b2rt_save_exr",
+    "b2rt_write_png", "b2rt_write_exr",
 ]
 
 
@@ -85,6 +88,18 @@ def lib():
             getattr(L, f).argtypes = [C.c_char_p, C.POINTER(vp)]
         L.b2rt_scene_save.argtypes = [C.c_char_p, vp]
         L.b2rt_scene_free.argtypes = [vp]; L.b2rt_scene_free.restype = None
+        L.b2rt_bench_fp32.argtypes = [i32, C.POINTER(C.c_double)]
+        L.b2rt_camera_look_at.argtypes = [vp, vp, C.c_float, C.POINTER(Camera)]
+        L.b2rt_save_png.argtypes = [C.c_char_p, vp, u32, u32]
+        L.b2rt_save_exr.argtypes = [C.c_char_p, vp, u32, u32]
+        L.b2rt_write_png.argtypes = [vp, C.c_char_p]
+        L.b2rt_write_exr.argtypes = [vp, C.c_char_p]
+        L.b2rt_comm_unique_id.argtypes = [vp]
+        L.b2rt_comm_create.argtypes = [i32, i32, vp, i32, C.POINTER(vp)]
+        L.b2rt_comm_create_all.argtypes = [i32, vp, vp]
+        L.b2rt_reduce_accum.argtypes = [vp, vp, i32]
+        L.b2rt_reduce_accum_all.argtypes = [vp, vp, i32, i32]
+        L.b2rt_comm_destroy.argtypes = [vp]; L.b2rt_comm_destroy.restype = None
         _lib = L
     return _lib
 
@@ -97,6 +112,33 @@ def _check(rc):
 
 def device_count():
     return lib().b2rt_device_count()
+
+
+def camera_look_at(origin, look_at, fov_deg=0.0):
+    """Camera of CudaRenderer::setViewpoint(origin, lookAt) (src/cudaRenderer.cu:1845-1870), b2rt_camera_look_at."""
+    o = np.ascontiguousarray(origin, np.float32); d = np.ascontiguousarray(look_at, np.float32)
+    cam = Camera()
+    _check(lib().b2rt_camera_look_at(o.ctypes.data, d.ctypes.data, fov_deg, C.byref(cam)))
+    return cam
+
+
+def save_png(path, rgba8):
+    """rgba8: uint32 [h, w] as PathTracer.ldr() returns it (row 0 = bottom); the file stores the top row first."""
+    a = np.ascontiguousarray(rgba8, np.uint32)
+    _check(lib().b2rt_save_png(os.fsencode(path), a.ctypes.data, a.shape[1], a.shape[0]))
+
+
+def save_exr(path, rgb):
+    """rgb: float32 [h, w, 3] as PathTracer.hdr() returns it; uncompressed fp32 OpenEXR scanline file."""
+    a = np.ascontiguousarray(rgb, np.float32)
+    _check(lib().b2rt_save_exr(os.fsencode(path), a.ctypes.data, a.shape[1], a.shape[0]))
+
+
+def bench_fp32(device=-1):
+    """Measured FP32 peak of the device in TFLOP/s (b2rt_bench_fp32)."""
+    v = C.c_double(0)
+    _check(lib().b2rt_bench_fp32(device, C.byref(v)))
+    return v.value
 
 
 def _scene_from_file(entry, path):
@@ -278,8 +320,11 @@ class PathTracer:
         self._maybe_ready()
 
     def start_raytracing(self):
-        if self.state not in (self.READY, self.DONE):   # pathtracer.cpp:184 (only from READY); DONE re-renders
+        """PathTracer::start_raytracing (src/pathtracer.cpp:183-213): only from READY (DONE re-renders); like the
+        reference it clears the sample / frame buffers first.  render() is the accumulating call."""
+        if self.state not in (self.READY, self.DONE):
             return False
+        _check(lib().b2rt_clear(self._h))
         _check(lib().b2rt_start(self._h))
         self.state = self.RENDERING
         return True
@@ -338,11 +383,11 @@ class PathTracer:
         return np.ctypeslib.as_array(p, shape=(self.height, self.width, 4))
 
     def save_image(self, filename):
-        """PNG, vertically flipped like PathTracer::save_image (src/pathtracer.cpp:577-591)."""
-        from PIL import Image
-        ldr = self.ldr()[::-1]
-        rgba = np.stack([(ldr >> s) & 255 for s in (0, 8, 16, 24)], -1).astype(np.uint8)
-        Image.fromarray(rgba, "RGBA").save(filename)
+        """PNG, vertically flipped like PathTracer::save_image (src/pathtracer.cpp:577-591); written by the library."""
+        _check(lib().b2rt_write_png(self._h, os.fsencode(filename)))
+
+    def save_exr(self, filename):
+        _check(lib().b2rt_write_exr(self._h, os.fsencode(filename)))
 
     def stats(self):
         s = Stats()
@@ -354,6 +399,11 @@ class PathTracer:
 
     def set_profiling(self, counters=False, time_kernels=False):
         _check(lib().b2rt_set_profiling(self._h, int(counters), int(time_kernels)))
+
+    def reduce_accum(self, comm, root=0):
+        """ONE NCCL reduce (fp32 sum) of the per-GPU accumulation buffers onto `root`, enqueued by libb2rt.so on the
+        renderer's stream (b2rt_reduce_accum); root < 0 = all-reduce.  `comm` is a b2rt.Comm."""
+        _check(lib().b2rt_reduce_accum(self._h, comm._h, root))
 
     def accum_device_ptr(self):
         p = C.c_void_p(); n = C.c_size_t(0)
@@ -372,6 +422,38 @@ class PathTracer:
         w.__cuda_array_interface__ = {"shape": (n,), "typestr": "<f4", "data": (ptr, False), "version": 2}
         dev = self.cfg.device if self.cfg.device >= 0 else torch.cuda.current_device()
         return torch.as_tensor(w, device=f"cuda:{dev}")
+
+
+class Comm:
+    """NCCL communicator behind the C ABI (b2rt_comm_*): one rank per GPU.
+
+    Comm.unique_id() on rank 0 -> 128 bytes, shipped to the other ranks by any means (bench.py broadcasts them with
+    torch.distributed), then Comm(n_ranks, rank, id, device) on every rank."""
+
+    def __init__(self, n_ranks, rank, uid, device=-1):
+        if len(uid) != 128:
+            raise ValueError("unique id must be 128 bytes")
+        buf = (C.c_uint8 * 128).from_buffer_copy(bytes(uid))
+        h = C.c_void_p()
+        _check(lib().b2rt_comm_create(n_ranks, rank, buf, device, C.byref(h)))
+        self._h = h
+        self.n_ranks, self.rank = n_ranks, rank
+
+    @staticmethod
+    def unique_id():
+        buf = (C.c_uint8 * 128)()
+        _check(lib().b2rt_comm_unique_id(buf))
+        return bytes(buf)
+
+    @staticmethod
+    def version():
+        return lib().b2rt_comm_version()
+
+    def close(self):
+        if getattr(self, "_h", None):
+            lib().b2rt_comm_destroy(self._h); self._h = None
+
+    __del__ = close
 
 
 class CudaRenderer:
@@ -394,8 +476,10 @@ class CudaRenderer:
         if self.pt._camera is None:
             self.pt.set_camera(place_camera(self.scene, self.pt.width, self.pt.height))
 
-    def setViewpoint(self, camera):
-        self.pt.set_camera(camera)       # resets accumulation, cudaRenderer.cu:1866-1869
+    def setViewpoint(self, camera_or_origin, look_at=None):
+        """setViewpoint(camera) or, like the reference (src/cudaRenderer.cu:1845-1870), setViewpoint(origin, lookAt)."""
+        cam = camera_or_origin if look_at is None else camera_look_at(camera_or_origin, look_at)
+        self.pt.set_camera(cam)          # resets accumulation, cudaRenderer.cu:1866-1869
         self.frames = 0
 
     def clearImage(self):

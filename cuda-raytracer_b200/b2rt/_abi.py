@@ -47,7 +47,9 @@ class Stats(C.Structure):
                 ("kernel_launches", C.c_uint64), ("traverse_launches", C.c_uint64), ("ms_total", C.c_double),
                 ("ms_traverse", C.c_double), ("ms_build", C.c_double), ("bvh_nodes", C.c_uint32),
                 ("bvh_subtrees", C.c_uint32), ("bvh_levels", C.c_uint32), ("bvh_width", C.c_uint32),
-                ("bvh_bytes", C.c_uint64)]
+                ("bvh_bytes", C.c_uint64), ("node_visits_l0", C.c_uint64), ("leaf_prim_tests_l0", C.c_uint64),
+                ("queue_pushes_l0", C.c_uint64), ("staged_bytes_l0", C.c_uint64), ("hit_updates_l0", C.c_uint64),
+                ("traverse_launches_l0", C.c_uint64), ("ms_traverse_l0", C.c_double)]
 
     def as_dict(self):
         return {n: getattr(self, n) for n, _ in self._fields_}

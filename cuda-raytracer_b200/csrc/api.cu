@@ -33,7 +33,6 @@ struct b2rt_bvh {
   uint32_t max_leaf = 4, treelet_budget = 0;   // as given to the builder (b2rt_bvh_validate)
   b2rt_stats last{};
 };
-struct b2rt_renderer { Renderer r; };
 
 namespace {
 
@@ -41,9 +40,13 @@ __global__ void k_pack_rays(const float* __restrict__ org, const float* __restri
                             const float* __restrict__ tmax, uint32_t n, float4* ro, float4* rd, unsigned long long* hits) {
   uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
-  ro[i] = make_float4(org[3 * i], org[3 * i + 1], org[3 * i + 2], tmin[i]);
-  rd[i] = make_float4(dir[3 * i], dir[3 * i + 1], dir[3 * i + 2], tmax[i]);
-  hits[i] = pack_hit(tmax[i], 0xFFFFFFFFu);
+  // The traversal orders distances as unsigned integers (packed (t, prim) words, stack / sort keys), which is the
+  // float order only for t >= 0: t_min is clamped to >= 0 and a negative or NaN t_max becomes 0 (b2rt.h documents the
+  // t >= 0 contract).
+  const float t0 = tmin[i] > 0.f ? tmin[i] : 0.f, t1 = tmax[i] >= 0.f ? tmax[i] : 0.f;
+  ro[i] = make_float4(org[3 * i], org[3 * i + 1], org[3 * i + 2], t0);
+  rd[i] = make_float4(dir[3 * i], dir[3 * i + 1], dir[3 * i + 2], t1);
+  hits[i] = pack_hit(t1, 0xFFFFFFFFu);
 }
 __global__ void k_unpack_hits(const unsigned long long* __restrict__ hits, uint32_t n, float* t, uint32_t* prim, uint8_t* occ) {
   uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -143,7 +146,12 @@ int intersect_host(b2rt_bvh* b, const float* org, const float* dir, const float*
   if (batch == 0) return B2RT_OK;
   float *d_org = nullptr, *d_dir = nullptr, *d_tmin = nullptr, *d_tmax = nullptr, *d_t = nullptr;
   uint32_t* d_prim = nullptr; uint8_t* d_occ = nullptr;
-  auto cleanup = [&]() { cudaFree(d_org); cudaFree(d_dir); cudaFree(d_tmin); cudaFree(d_tmax); cudaFree(d_t); cudaFree(d_prim); cudaFree(d_occ); };
+  cudaEvent_t e0 = nullptr, e1 = nullptr;
+  auto cleanup = [&]() {
+    cudaFree(d_org); cudaFree(d_dir); cudaFree(d_tmin); cudaFree(d_tmax); cudaFree(d_t); cudaFree(d_prim); cudaFree(d_occ);
+    if (e0) cudaEventDestroy(e0);
+    if (e1) cudaEventDestroy(e1);
+  };
   int rc = ensure_rays(b, batch);
   if (rc) return rc;
   if (cudaMalloc(&d_org, batch * 12) || cudaMalloc(&d_dir, batch * 12) || cudaMalloc(&d_tmin, batch * 4) ||
@@ -152,8 +160,9 @@ int intersect_host(b2rt_bvh* b, const float* org, const float* dir, const float*
   }
   cudaStream_t s = b->stream;
   b->tracer.launches = 0;
-  cudaEvent_t e0, e1;
-  cudaEventCreate(&e0); cudaEventCreate(&e1);
+  if (cudaEventCreate(&e0) != cudaSuccess || cudaEventCreate(&e1) != cudaSuccess) {
+    cleanup(); set_error("cudaEventCreate failed"); cudaGetLastError(); return B2RT_ERR_CUDA;
+  }
   double ms_sum = 0;
   uint64_t done = 0;
   while (done < n) {
@@ -186,14 +195,13 @@ int intersect_host(b2rt_bvh* b, const float* org, const float* dir, const float*
     if (e != cudaSuccess) { cleanup(); set_error(std::string("intersect: ") + cudaGetErrorString(e)); return B2RT_ERR_CUDA; }
     done += m;
   }
-  cudaEventDestroy(e0); cudaEventDestroy(e1);
   cleanup();
   TraceCounters tc;
-  cudaMemcpy(&tc, b->tracer.counters, sizeof tc, cudaMemcpyDeviceToHost);
+  b->tracer.read_counters(&tc, nullptr);
   b->last.node_visits = tc.node_visits; b->last.leaf_prim_tests = tc.prim_tests; b->last.subtree_visits = tc.subtree_visits;
   b->last.queue_pushes = tc.pushes; b->last.staged_bytes = tc.staged_bytes; b->last.hit_updates = tc.hit_updates;
   b->last.kernel_launches = b->tracer.launches; b->last.ms_total = ms_sum; b->last.ms_traverse = ms_sum;
-  cudaMemsetAsync(b->tracer.counters, 0, sizeof tc, b->stream);
+  b->tracer.reset_counters(b->stream);
   cudaStreamSynchronize(b->stream);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) { set_error(std::string("intersect: ") + cudaGetErrorString(e)); return B2RT_ERR_CUDA; }
@@ -208,6 +216,17 @@ const char* b2rt_last_error(void) { return g_error.c_str(); }
 int b2rt_abi_version(void) { return B2RT_ABI_VERSION; }
 int b2rt_device_count(void) { return has_device(); }
 
+// every failure after the handle exists goes through b2rt_bvh_destroy (stream, device buffers, the handle itself)
+#define B2RT_BVH_OK(call)                                                                            \
+  do {                                                                                               \
+    cudaError_t e__ = (call);                                                                        \
+    if (e__ != cudaSuccess) {                                                                        \
+      set_error(std::string(#call) + ": " + cudaGetErrorString(e__));                                \
+      b2rt_bvh_destroy(b);                                                                           \
+      return e__ == cudaErrorMemoryAllocation ? B2RT_ERR_OOM : B2RT_ERR_CUDA;                        \
+    }                                                                                                \
+  } while (0)
+
 int b2rt_bvh_build(const b2rt_scene_desc* scene, uint32_t max_leaf_size, uint32_t width, uint32_t treelet_bytes,
                    int32_t device, b2rt_bvh** out) {
   if (!out) { set_error("out is null"); return B2RT_ERR_INVALID; }
@@ -220,15 +239,15 @@ int b2rt_bvh_build(const b2rt_scene_desc* scene, uint32_t max_leaf_size, uint32_
   if (!b) return B2RT_ERR_OOM;
   if (device < 0) cudaGetDevice(&device);
   b->device = device;
-  B2RT_CUDA_OK(cudaSetDevice(device));
+  B2RT_BVH_OK(cudaSetDevice(device));
   rc = build_wide_bvh(hs, max_leaf_size, width, treelet_bytes, &b->host_meta);
-  if (rc) { delete b; return rc; }
+  if (rc) { b2rt_bvh_destroy(b); return rc; }
   rc = upload_bvh(b->host_meta, &b->dbvh);
-  if (rc) { delete b; return rc; }
+  if (rc) { b2rt_bvh_destroy(b); return rc; }
   b->host_meta.blob.clear(); b->host_meta.blob.shrink_to_fit();
   b->max_leaf = max_leaf_size ? max_leaf_size : 4; b->treelet_budget = treelet_bytes;
-  B2RT_CUDA_OK(cudaStreamCreateWithFlags(&b->stream, cudaStreamNonBlocking));
-  B2RT_CUDA_OK(cudaMalloc(&b->n_dev, 4));
+  B2RT_BVH_OK(cudaStreamCreateWithFlags(&b->stream, cudaStreamNonBlocking));
+  B2RT_BVH_OK(cudaMalloc(&b->n_dev, 4));
   b->tracer.bvh = b->dbvh;
   b->tracer.collect_stats = true;
   configure_slicing(b, -1.f, 0.f, 0);
@@ -245,18 +264,19 @@ int b2rt_bvh_build_device(const b2rt_scene_desc* scene, uint32_t max_leaf_size, 
   if (!b) return B2RT_ERR_OOM;
   if (device < 0) cudaGetDevice(&device);
   b->device = device;
-  B2RT_CUDA_OK(cudaSetDevice(device));
-  B2RT_CUDA_OK(cudaStreamCreateWithFlags(&b->stream, cudaStreamNonBlocking));
+  B2RT_BVH_OK(cudaSetDevice(device));
+  B2RT_BVH_OK(cudaStreamCreateWithFlags(&b->stream, cudaStreamNonBlocking));
   int rc = build_wide_bvh_device(scene, max_leaf_size, width, treelet_bytes, b->stream, &b->dbvh, &b->host_meta);
   if (rc) { b2rt_bvh_destroy(b); return rc; }
   b->max_leaf = max_leaf_size ? max_leaf_size : 4; b->treelet_budget = treelet_bytes;
-  B2RT_CUDA_OK(cudaMalloc(&b->n_dev, 4));
+  B2RT_BVH_OK(cudaMalloc(&b->n_dev, 4));
   b->tracer.bvh = b->dbvh;
   b->tracer.collect_stats = true;
   configure_slicing(b, -1.f, 0.f, 0);
   *out = b;
   return B2RT_OK;
 }
+#undef B2RT_BVH_OK
 
 int b2rt_bvh_validate(b2rt_bvh* b, const b2rt_scene_desc* scene, uint64_t out8[8]) {
   if (!b || !scene) { set_error("null argument"); return B2RT_ERR_INVALID; }
@@ -320,7 +340,7 @@ int b2rt_bvh_bench_rays(b2rt_bvh* b, uint64_t n, int mode, uint64_t seed, int re
   TraceCounters tc;
   for (;;) {
     b->tracer.launches = 0;
-    B2RT_CUDA_OK(cudaMemsetAsync(b->tracer.counters, 0, sizeof(TraceCounters), s));
+    { int r3 = b->tracer.reset_counters(s); if (r3) return r3; }
     b->tracer.collect_stats = true;
     rc = trace_all();
     b->tracer.collect_stats = false;
@@ -330,33 +350,41 @@ int b2rt_bvh_bench_rays(b2rt_bvh* b, uint64_t n, int mode, uint64_t seed, int re
     if (rc) { b->tracer.collect_stats = keep_stats; return rc; }
     if (!ovf) break;
     if (sub <= 65536) { b->tracer.collect_stats = keep_stats; set_error("ray queue overflow on a 64 Ki-ray batch"); return B2RT_ERR_OVERFLOW; }
-    sub = ((sub / 2) + 3u) & ~3u;   // sub-batch starts stay 16-byte aligned for the TMA tiles
+    sub = ((sub / 2) + 3u) & ~3u;
     k_reset_hits<<<(n32 + 255) / 256, 256, 0, s>>>(n32, b->ray_d, b->hits);
   }
-  B2RT_CUDA_OK(cudaMemcpy(&tc, b->tracer.counters, sizeof tc, cudaMemcpyDeviceToHost));
-  cudaEvent_t e0, e1;
-  cudaEventCreate(&e0); cudaEventCreate(&e1);
+  { int r3 = b->tracer.read_counters(&tc, nullptr); if (r3) return r3; }
+  struct EventPair {
+    cudaEvent_t a = nullptr, b = nullptr;
+    ~EventPair() { if (a) cudaEventDestroy(a); if (b) cudaEventDestroy(b); }
+  } ev;
+  struct StatsRestore {   // the timed passes run without counters; the caller's setting comes back on every exit path
+    Tracer& t; bool keep;
+    ~StatsRestore() { t.collect_stats = keep; }
+  } restore{b->tracer, keep_stats};
+  B2RT_CUDA_OK(cudaEventCreate(&ev.a));
+  B2RT_CUDA_OK(cudaEventCreate(&ev.b));
   double total = 0;
   for (int r = 0; r < repeats; ++r) {
     k_reset_hits<<<(n32 + 255) / 256, 256, 0, s>>>(n32, b->ray_d, b->hits);
-    cudaEventRecord(e0, s);
+    cudaEventRecord(ev.a, s);
     rc = trace_all();
-    cudaEventRecord(e1, s);
+    cudaEventRecord(ev.b, s);
     if (rc) return rc;
-    B2RT_CUDA_OK(cudaEventSynchronize(e1));
-    float ms = 0; cudaEventElapsedTime(&ms, e0, e1); total += ms;
+    B2RT_CUDA_OK(cudaEventSynchronize(ev.b));
+    float ms = 0; cudaEventElapsedTime(&ms, ev.a, ev.b); total += ms;
   }
-  cudaEventDestroy(e0); cudaEventDestroy(e1);
-  b->tracer.collect_stats = keep_stats;
   if (ms_per_repeat) *ms_per_repeat = total / repeats;
-  unsigned long long* d_cnt = nullptr;
-  B2RT_CUDA_OK(cudaMalloc(&d_cnt, 8));
-  B2RT_CUDA_OK(cudaMemsetAsync(d_cnt, 0, 8, s));
-  k_count_hits<<<(n32 + 255) / 256, 256, 0, s>>>(n32, b->hits, d_cnt);
+  struct DevWord {
+    unsigned long long* p = nullptr;
+    ~DevWord() { cudaFree(p); }
+  } cnt;
+  B2RT_CUDA_OK(cudaMalloc(&cnt.p, 8));
+  B2RT_CUDA_OK(cudaMemsetAsync(cnt.p, 0, 8, s));
+  k_count_hits<<<(n32 + 255) / 256, 256, 0, s>>>(n32, b->hits, cnt.p);
   unsigned long long hc = 0;
-  B2RT_CUDA_OK(cudaMemcpyAsync(&hc, d_cnt, 8, cudaMemcpyDeviceToHost, s));
+  B2RT_CUDA_OK(cudaMemcpyAsync(&hc, cnt.p, 8, cudaMemcpyDeviceToHost, s));
   B2RT_CUDA_OK(cudaStreamSynchronize(s));
-  cudaFree(d_cnt);
   if (hits_out) *hits_out = hc;
   b->last.node_visits = tc.node_visits; b->last.leaf_prim_tests = tc.prim_tests; b->last.subtree_visits = tc.subtree_visits;
   b->last.queue_pushes = tc.pushes; b->last.staged_bytes = tc.staged_bytes; b->last.hit_updates = tc.hit_updates;
@@ -510,3 +538,66 @@ void b2rt_destroy(b2rt_renderer* h) {
 }
 
 }  // extern "C"
+
+// ---- measured FP32 peak ("measure with an FMA-saturating microbenchmark on the box") -----------------
+namespace {
+__global__ void __launch_bounds__(256) k_fma_peak(float* out, float a, float b, int iters) {
+  // 16 independent FFMA chains per thread: enough ILP for one warp to keep its scheduler's FMA pipe fed
+  float x[16];
+#pragma unroll
+  for (int k = 0; k < 16; ++k) x[k] = (float)(threadIdx.x + k);
+  for (int i = 0; i < iters; ++i) {
+#pragma unroll
+    for (int k = 0; k < 16; ++k) x[k] = __fmaf_rn(x[k], a, b);
+  }
+  float s = 0.f;
+#pragma unroll
+  for (int k = 0; k < 16; ++k) s += x[k];
+  if (s == 123.456f) out[blockIdx.x * blockDim.x + threadIdx.x] = s;   // never true; keeps the chains alive
+}
+}  // namespace
+
+extern "C" int b2rt_bench_fp32(int32_t device, double* tflops) {
+  if (!tflops) { set_error("null argument"); return B2RT_ERR_INVALID; }
+  if (!has_device()) { set_error("no CUDA device available (b2rt has no CPU fallback)"); return B2RT_ERR_NO_DEVICE; }
+  if (device < 0) B2RT_CUDA_OK(cudaGetDevice(&device));
+  B2RT_CUDA_OK(cudaSetDevice(device));
+  int sms = 0;
+  B2RT_CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
+  float* d = nullptr;
+  const int blocks = sms * 8, iters = 4096;
+  B2RT_CUDA_OK(cudaMalloc(&d, (size_t)blocks * 256 * 4));
+  cudaEvent_t e0 = nullptr, e1 = nullptr;
+  cudaEventCreate(&e0); cudaEventCreate(&e1);
+  double best = 0;
+  for (int rep = 0; rep < 6; ++rep) {   // the first repetitions are the warm-up
+    cudaEventRecord(e0);
+    k_fma_peak<<<blocks, 256>>>(d, 0.999f, 0.001f, iters);
+    cudaEventRecord(e1);
+    if (cudaEventSynchronize(e1) != cudaSuccess) break;
+    float ms = 0; cudaEventElapsedTime(&ms, e0, e1);
+    const double fl = 2.0 * 16.0 * iters * (double)blocks * 256.0;
+    if (ms > 0 && rep >= 2) best = std::max(best, fl / (ms * 1e-3) / 1e12);
+  }
+  cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(d);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess || best == 0) { set_error(std::string("b2rt_bench_fp32: ") + cudaGetErrorString(e)); return B2RT_ERR_CUDA; }
+  *tflops = best;
+  return B2RT_OK;
+}
+
+// PathTracer::save_image (src/pathtracer.cpp:577-591) and the HDR counterpart
+extern "C" int b2rt_write_png(b2rt_renderer* h, const char* path) {
+  if (!h || !path) { set_error("null argument"); return B2RT_ERR_INVALID; }
+  std::vector<uint32_t> px((size_t)h->r.width * h->r.height);
+  int rc = b2rt_read_ldr(h, px.data(), px.size());
+  if (rc) return rc;
+  return b2rt_save_png(path, px.data(), h->r.width, h->r.height);
+}
+extern "C" int b2rt_write_exr(b2rt_renderer* h, const char* path) {
+  if (!h || !path) { set_error("null argument"); return B2RT_ERR_INVALID; }
+  std::vector<float> px((size_t)h->r.width * h->r.height * 3);
+  int rc = b2rt_read_hdr(h, px.data(), px.size());
+  if (rc) return rc;
+  return b2rt_save_exr(path, px.data(), h->r.width, h->r.height);
+}

@@ -31,19 +31,6 @@ namespace {
 constexpr float INF_F = __builtin_huge_valf();
 constexpr uint32_t MAX_DEPTH = 96, ACT0 = 8, SH0 = ACT0 + MAX_DEPTH + 8, SHV0 = SH0 + MAX_DEPTH + 8, N_COUNTS = 512;
 
-struct WaveParams {
-  // wave geometry
-  uint32_t pix0, n_pix;       // pixel range of this wave
-  uint32_t spp;               // samples per pixel in this wave
-  uint32_t sample0;           // global index of the wave's first sample
-  uint32_t sample_stride;
-  uint32_t width, height;
-  uint32_t jitter;            // 0 -> pixel centre
-  uint32_t k0, k1;            // Philox key
-  float eps;
-  uint32_t max_depth, ns_area_light, S;  // S = shadow rays per interaction
-};
-
 struct CamDev { f3 pos, cx, cy, cz; float tan_h, tan_v; };
 
 struct SceneDev {
@@ -427,16 +414,27 @@ k_resolve_shadow(WaveParams wp, PathBufs pb, uint32_t b) {
   if (any) pb.rad[slot] = L;
 }
 
-__global__ void k_wave_end(PathBufs pb, uint32_t max_depth, unsigned long long* totals) {
-  // totals: [0] bounce rays, [1] shadow rays
+// Closes a wave: status 1 = complete, 2 = a ray queue overflowed while it was traced (its paths are incomplete: the
+// wave is NOT accumulated and the host re-renders it in halves), 3 = cancelled (b2rt_stop).  Clears the schedulers'
+// overflow flags for the next wave.  totals: [0] bounce rays, [1] shadow rays, [2] camera rays of complete waves.
+__global__ void k_wave_end(PathBufs pb, uint32_t max_depth, unsigned long long* totals, uint32_t* ctrl_a, uint32_t* ctrl_b,
+                           uint32_t n_paths, uint32_t* status) {
+  uint32_t ovf = ctrl_a[CTRL_OVERFLOW];
+  ctrl_a[CTRL_OVERFLOW] = 0;
+  if (ctrl_b) { ovf |= ctrl_b[CTRL_OVERFLOW]; ctrl_b[CTRL_OVERFLOW] = 0; }
+  const uint32_t st = pb.counts[3] ? 3u : (ovf ? 2u : 1u);
+  *status = st;
+  if (st != 1u) return;
   unsigned long long nb = 0, ns = 0;
   for (uint32_t b = 0; b < max_depth; ++b) { if (b) nb += pb.counts[ACT0 + b]; ns += pb.counts[SHV0 + b]; }
-  totals[0] += nb; totals[1] += ns;
+  totals[0] += nb; totals[1] += ns; totals[2] += n_paths;
 }
 
-// per-pixel accumulation in sample order (deterministic): accum.rgb += L_s, accum.w += 1
+// per-pixel accumulation in sample order (deterministic): accum.rgb += L_s, accum.w += 1.  Only complete waves count
+// (a cancelled or overflowed wave must not touch the sums or the per-pixel sample count the image is divided by).
 __global__ void __launch_bounds__(256)
-k_accumulate(WaveParams wp, PathBufs pb, float4* __restrict__ accum) {
+k_accumulate(WaveParams wp, PathBufs pb, float4* __restrict__ accum, const uint32_t* __restrict__ status) {
+  if (*status != 1u) return;
   const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= wp.n_pix) return;
   float4 a = accum[wp.pix0 + p];
@@ -568,6 +566,7 @@ int Renderer::create(const b2rt_config* c) {
   if (device < 0) B2RT_CUDA_OK(cudaGetDevice(&device));
   RCHECK(set_device());
   B2RT_CUDA_OK(cudaStreamCreateWithFlags(&own_stream, cudaStreamNonBlocking));
+  B2RT_CUDA_OK(cudaStreamCreateWithFlags(&stream_cancel, cudaStreamNonBlocking));
   stream = own_stream;
   B2RT_CUDA_OK(cudaEventCreate(&ev_start));
   B2RT_CUDA_OK(cudaEventCreate(&ev_done));
@@ -608,6 +607,8 @@ void Renderer::destroy() {
   if (ev_start) cudaEventDestroy(ev_start);
   if (ev_done) cudaEventDestroy(ev_done);
   if (own_stream) cudaStreamDestroy(own_stream);
+  if (stream_cancel) cudaStreamDestroy(stream_cancel);
+  free_ptr(wave_status); wave_status = nullptr; wave_status_cap = 0;
 }
 
 int Renderer::set_stream(cudaStream_t s) {
@@ -798,6 +799,82 @@ int Renderer::ensure_wave() {
   return B2RT_OK;
 }
 
+// host copy of what a wave needs besides its WaveParams (same for every wave of a frame)
+struct Renderer::FrameCtx {
+  CamDev cd; SceneDev sd; PathBufs pb; uint32_t max_depth; uint32_t S;
+};
+
+int Renderer::make_frame_ctx(FrameCtx* fc) {
+  fc->max_depth = std::min(MAX_DEPTH, std::max(1u, cfg.max_ray_depth));
+  fc->S = shadow_per_hit;
+  CamDev& cd = fc->cd;
+  cd.pos = f3{cam.pos[0], cam.pos[1], cam.pos[2]};
+  cd.cx = f3{cam.c2w[0], cam.c2w[1], cam.c2w[2]};
+  cd.cy = f3{cam.c2w[3], cam.c2w[4], cam.c2w[5]};
+  cd.cz = f3{cam.c2w[6], cam.c2w[7], cam.c2w[8]};
+  cd.tan_h = tanf(cam.hfov_deg * 0.5f * 0.01745329251994329577f);
+  cd.tan_v = tanf(cam.vfov_deg * 0.5f * 0.01745329251994329577f);
+  SceneDev& sd = fc->sd;
+  sd.prim_geom = (const float4*)d_prim_geom; sd.tri_normals = d_tri_normals; sd.prim_material = d_prim_material;
+  sd.materials = d_materials; sd.lights = d_lights; sd.light_area = d_light_area; sd.n_tris = n_tris; sd.n_lights = n_lights;
+  PathBufs& pb = fc->pb;
+  pb.lo = (float4*)l_o[0]; pb.ld = (float4*)l_d[0]; pb.lh = l_h[0]; pb.lslot = l_slot[0];
+  pb.no = (float4*)l_o[1]; pb.nd = (float4*)l_d[1]; pb.nh = l_h[1]; pb.nslot = l_slot[1];
+  pb.thr = (float4*)thr; pb.rad = (float4*)rad;
+  pb.s_o = (float4*)s_o; pb.s_d = (float4*)s_d; pb.s_hits = s_hits; pb.s_contrib = (float4*)s_contrib;
+  pb.s_q0 = s_q0; pb.counts = counts;
+  return B2RT_OK;
+}
+
+// Enqueues one wave (ray generation, max_depth bounces, wave end, accumulation) on the renderer's streams; the wave's
+// outcome lands in wave_status[status_index] (k_wave_end).
+int Renderer::enqueue_wave(const FrameCtx& fc, const WaveParams& wp, uint32_t status_index) {
+  PathBufs pb = fc.pb;
+  auto bind_lists = [&](uint32_t cur) {   // list `cur` is read, the other one is appended to
+    const uint32_t nxt = cur ^ 1u;
+    pb.lo = (float4*)l_o[cur]; pb.ld = (float4*)l_d[cur]; pb.lh = l_h[cur]; pb.lslot = l_slot[cur];
+    pb.no = (float4*)l_o[nxt]; pb.nd = (float4*)l_d[nxt]; pb.nh = l_h[nxt]; pb.nslot = l_slot[nxt];
+  };
+  const uint32_t max_depth = fc.max_depth, S = fc.S;
+  const uint32_t n = wp.n_pix * wp.spp;
+  const uint32_t g = (n + 255) / 256;
+  bind_lists(0);   // k_raygen fills list 0; k_shade(b) appends the continuing paths to list (b+1)&1
+  k_raygen<<<g, 256, 0, stream>>>(wp, fc.cd, pb); launches++;
+  // The shadow rays of bounce b and the continuing rays of bounce b + 1 both come out of k_shade(b) and do not
+  // depend on each other: the any-hit trace + k_resolve_shadow(b) run on a second stream with a second scheduler
+  // next to the closest-hit trace of bounce b + 1, which fills the issue slots the level >= 1 launches and every
+  // launch's tail leave idle (cfg2 -4.9 %, cfg3 stand-in -5.2 % per frame, tools/ab_overlap.sh).  Not while
+  // per-launch timing is on (b2rt_set_profiling): launches are then timed alone, on one stream.
+  const bool ov = overlap && !tracer.time_kernels;
+  bool pending_resolve = false;
+  for (uint32_t b = 0; b < max_depth; ++b) {
+    bind_lists(b & 1u);
+    RCHECK(tracer.trace_sliced(stream, pb.lo, pb.ld, pb.lh, counts + ACT0 + b, n, false));
+    // shade(b) adds emission to the radiance that resolve(b - 1) updates and rewrites the shadow list it reads
+    if (pending_resolve) { B2RT_CUDA_OK(cudaStreamWaitEvent(stream, ev_sync[2 * (b - 1) + 1], 0)); pending_resolve = false; }
+    k_shade<<<(n + SHADE_THREADS - 1) / SHADE_THREADS, SHADE_THREADS, 0, stream>>>(wp, fc.sd, pb, b); launches++;
+    if (S > 0) {
+      if (ov) {
+        // shadow rays of bounce b on the second stream, next to the closest-hit trace of bounce b + 1
+        B2RT_CUDA_OK(cudaEventRecord(ev_sync[2 * b], stream));
+        B2RT_CUDA_OK(cudaStreamWaitEvent(stream2, ev_sync[2 * b], 0));
+        RCHECK(tracer2.trace_sliced(stream2, pb.s_o, pb.s_d, pb.s_hits, counts + SH0 + b, (uint64_t)n * S, true));
+        k_resolve_shadow<<<g, 256, 0, stream2>>>(wp, pb, b); launches++;
+        B2RT_CUDA_OK(cudaEventRecord(ev_sync[2 * b + 1], stream2));
+        pending_resolve = true;
+      } else {
+        RCHECK(tracer.trace_sliced(stream, pb.s_o, pb.s_d, pb.s_hits, counts + SH0 + b, (uint64_t)n * S, true));
+        k_resolve_shadow<<<g, 256, 0, stream>>>(wp, pb, b); launches++;
+      }
+    }
+  }
+  if (pending_resolve) B2RT_CUDA_OK(cudaStreamWaitEvent(stream, ev_sync[2 * (max_depth - 1) + 1], 0));
+  k_wave_end<<<1, 1, 0, stream>>>(pb, max_depth, totals, tracer.ctrl, (ov && tracer2.ctrl) ? tracer2.ctrl : nullptr, n,
+                                  wave_status + status_index); launches++;
+  k_accumulate<<<(wp.n_pix + 255) / 256, 256, 0, stream>>>(wp, pb, (float4*)accum, wave_status + status_index); launches++;
+  return B2RT_OK;
+}
+
 int Renderer::start() {
   if (!have_scene || !have_camera || !accum) { set_error("start: scene, camera and frame size must be set first"); return B2RT_ERR_INVALID; }
   if (cfg.ns_aa == 0) { set_error("ns_aa must be >= 1"); return B2RT_ERR_INVALID; }
@@ -805,42 +882,20 @@ int Renderer::start() {
   if (running) RCHECK(wait());
   RCHECK(ensure_wave());
   const uint32_t S = shadow_per_hit;
-  const uint32_t max_depth = std::min(MAX_DEPTH, std::max(1u, cfg.max_ray_depth));
   const uint32_t stride = cfg.sample_stride ? cfg.sample_stride : 1;
   const uint64_t n_pix = (uint64_t)width * height;
+  FrameCtx fc;
+  RCHECK(make_frame_ctx(&fc));
 
-  CamDev cd;
-  cd.pos = f3{cam.pos[0], cam.pos[1], cam.pos[2]};
-  cd.cx = f3{cam.c2w[0], cam.c2w[1], cam.c2w[2]};
-  cd.cy = f3{cam.c2w[3], cam.c2w[4], cam.c2w[5]};
-  cd.cz = f3{cam.c2w[6], cam.c2w[7], cam.c2w[8]};
-  cd.tan_h = tanf(cam.hfov_deg * 0.5f * 0.01745329251994329577f);
-  cd.tan_v = tanf(cam.vfov_deg * 0.5f * 0.01745329251994329577f);
-
-  SceneDev sd;
-  sd.prim_geom = (const float4*)d_prim_geom; sd.tri_normals = d_tri_normals; sd.prim_material = d_prim_material;
-  sd.materials = d_materials; sd.lights = d_lights; sd.light_area = d_light_area; sd.n_tris = n_tris; sd.n_lights = n_lights;
-
-  PathBufs pb;
-  auto bind_lists = [&](uint32_t cur) {   // list `cur` is read, the other one is appended to
-    const uint32_t nxt = cur ^ 1u;
-    pb.lo = (float4*)l_o[cur]; pb.ld = (float4*)l_d[cur]; pb.lh = l_h[cur]; pb.lslot = l_slot[cur];
-    pb.no = (float4*)l_o[nxt]; pb.nd = (float4*)l_d[nxt]; pb.nh = l_h[nxt]; pb.nslot = l_slot[nxt];
-  };
-  bind_lists(0);
-  pb.thr = (float4*)thr; pb.rad = (float4*)rad;
-  pb.s_o = (float4*)s_o; pb.s_d = (float4*)s_d; pb.s_hits = s_hits; pb.s_contrib = (float4*)s_contrib;
-  pb.s_q0 = s_q0; pb.counts = counts;
-
-  tracer.launches = 0; tracer.traverse_launches = 0; tracer.ev_used = 0;
-  tracer2.launches = 0; tracer2.traverse_launches = 0; tracer2.ev_used = 0;
+  tracer.launches = 0; tracer.traverse_launches = 0; tracer.traverse_launches_l0 = 0; tracer.ev_used = 0; tracer.ev_deeper.clear();
+  tracer2.launches = 0; tracer2.traverse_launches = 0; tracer2.traverse_launches_l0 = 0; tracer2.ev_used = 0; tracer2.ev_deeper.clear();
   tracer2.collect_stats = tracer.collect_stats; tracer2.time_kernels = tracer.time_kernels;
   tracer2.slice_first = tracer.slice_first; tracer2.slice_growth = tracer.slice_growth; tracer2.slice_passes = tracer.slice_passes;
   for (int k = 0; k < 6; ++k) tracer2.slice_bbox[k] = tracer.slice_bbox[k];
-  if (overlap) B2RT_CUDA_OK(cudaMemsetAsync(tracer2.counters, 0, sizeof(TraceCounters), stream));
+  if (overlap) RCHECK(tracer2.reset_counters(stream));
   launches = 0;
   B2RT_CUDA_OK(cudaMemsetAsync(totals, 0, 8 * 8, stream));
-  B2RT_CUDA_OK(cudaMemsetAsync(tracer.counters, 0, sizeof(TraceCounters), stream));
+  RCHECK(tracer.reset_counters(stream));
   B2RT_CUDA_OK(cudaMemsetAsync(counts + 3, 0, 4, stream));  // cancel flag
   B2RT_CUDA_OK(cudaEventRecord(ev_start, stream));
   ms_traverse_acc = 0;
@@ -849,7 +904,7 @@ int Renderer::start() {
   uint32_t spp_chunk, pix_chunk;
   if (n_pix >= wave_cap) { spp_chunk = 1; pix_chunk = (uint32_t)wave_cap; }
   else { spp_chunk = (uint32_t)std::min<uint64_t>(cfg.ns_aa, wave_cap / n_pix); pix_chunk = (uint32_t)n_pix; }
-  cam_rays_enqueued = 0;
+  waves.clear();
   for (uint32_t s0 = 0; s0 < cfg.ns_aa; s0 += spp_chunk) {
     const uint32_t spp = std::min(spp_chunk, cfg.ns_aa - s0);
     for (uint64_t p0 = 0; p0 < n_pix; p0 += pix_chunk) {
@@ -860,49 +915,21 @@ int Renderer::start() {
       wp.jitter = (cfg.ns_aa * stride) > 1 ? 1u : 0u;
       wp.k0 = (uint32_t)cfg.seed; wp.k1 = (uint32_t)(cfg.seed >> 32);
       wp.eps = cfg.ray_eps > 0.f ? cfg.ray_eps : 1e-4f;
-      wp.max_depth = max_depth; wp.ns_area_light = cfg.ns_area_light; wp.S = S;
-      const uint32_t n = wp.n_pix * wp.spp;
-      const uint32_t g = (n + 255) / 256;
-      bind_lists(0);   // k_raygen fills list 0; k_shade(b) appends the continuing paths to list (b+1)&1
-      k_raygen<<<g, 256, 0, stream>>>(wp, cd, pb); launches++;
-      cam_rays_enqueued += n;
-      // The shadow rays of bounce b and the continuing rays of bounce b + 1 both come out of k_shade(b) and do not
-      // depend on each other: the any-hit trace + k_resolve_shadow(b) run on a second stream with a second scheduler
-      // next to the closest-hit trace of bounce b + 1, which fills the issue slots the level >= 1 launches and every
-      // launch's tail leave idle (cfg2 -4.9 %, cfg3 stand-in -5.2 % per frame, tools/ab_overlap.sh).  Not while
-      // per-launch timing is on (b2rt_set_profiling): launches are then timed alone, on one stream.
-      const bool ov = overlap && !tracer.time_kernels;
-      bool pending_resolve = false;
-      for (uint32_t b = 0; b < max_depth; ++b) {
-        bind_lists(b & 1u);
-        RCHECK(tracer.trace_sliced(stream, pb.lo, pb.ld, pb.lh, counts + ACT0 + b, n, false));
-        // shade(b) adds emission to the radiance that resolve(b - 1) updates and rewrites the shadow list it reads
-        if (pending_resolve) { B2RT_CUDA_OK(cudaStreamWaitEvent(stream, ev_sync[2 * (b - 1) + 1], 0)); pending_resolve = false; }
-        k_shade<<<(n + SHADE_THREADS - 1) / SHADE_THREADS, SHADE_THREADS, 0, stream>>>(wp, sd, pb, b); launches++;
-        if (S > 0) {
-          if (ov) {
-            // shadow rays of bounce b on the second stream, next to the closest-hit trace of bounce b + 1
-            B2RT_CUDA_OK(cudaEventRecord(ev_sync[2 * b], stream));
-            B2RT_CUDA_OK(cudaStreamWaitEvent(stream2, ev_sync[2 * b], 0));
-            RCHECK(tracer2.trace_sliced(stream2, pb.s_o, pb.s_d, pb.s_hits, counts + SH0 + b, (uint64_t)n * S, true));
-            k_resolve_shadow<<<g, 256, 0, stream2>>>(wp, pb, b); launches++;
-            B2RT_CUDA_OK(cudaEventRecord(ev_sync[2 * b + 1], stream2));
-            pending_resolve = true;
-          } else {
-            RCHECK(tracer.trace_sliced(stream, pb.s_o, pb.s_d, pb.s_hits, counts + SH0 + b, (uint64_t)n * S, true));
-            k_resolve_shadow<<<g, 256, 0, stream>>>(wp, pb, b); launches++;
-          }
-        }
-      }
-      if (pending_resolve) B2RT_CUDA_OK(cudaStreamWaitEvent(stream, ev_sync[2 * (max_depth - 1) + 1], 0));
-      k_wave_end<<<1, 1, 0, stream>>>(pb, max_depth, totals); launches++;
-      k_accumulate<<<(wp.n_pix + 255) / 256, 256, 0, stream>>>(wp, pb, (float4*)accum); launches++;
+      wp.max_depth = fc.max_depth; wp.ns_area_light = cfg.ns_area_light; wp.S = S;
+      waves.push_back(wp);
     }
   }
+  // one status word per wave (+ one scratch word for re-rendered halves)
+  if (wave_status_cap < waves.size() + 1) {
+    free_ptr(wave_status); wave_status = nullptr;
+    wave_status_cap = waves.size() + 1 + 64;
+    B2RT_CUDA_OK(cudaMalloc(&wave_status, wave_status_cap * 4));
+  }
+  B2RT_CUDA_OK(cudaMemsetAsync(wave_status, 0, (waves.size() + 1) * 4, stream));
+  for (size_t w = 0; w < waves.size(); ++w) RCHECK(enqueue_wave(fc, waves[w], (uint32_t)w));
   B2RT_CUDA_OK(cudaGetLastError());
   B2RT_CUDA_OK(cudaEventRecord(ev_done, stream));
   running = true;
-  samples_pending = cfg.ns_aa;
   return B2RT_OK;
 }
 
@@ -915,53 +942,92 @@ int Renderer::is_done() {
   return B2RT_ERR_CUDA;
 }
 
+// A wave whose ray queues overflowed was not accumulated: render it again as two halves (samples, or pixels when it
+// has one sample), recursively, blocking.  The halves reuse the frame's buffers, whose queues were sized for the
+// whole wave.  Its samples are then added after those of the later waves, so the fp32 sums of such a frame can differ
+// in the last bits from a frame that never overflowed.
+int Renderer::retry_wave(const FrameCtx& fc, const WaveParams& wp, int depth) {
+  const uint64_t n = (uint64_t)wp.n_pix * wp.spp;
+  if (n < 2048 || depth > 24) { set_error("ray queue overflow on a minimal wave"); return B2RT_ERR_OVERFLOW; }
+  WaveParams half[2] = {wp, wp};
+  if (wp.spp > 1) {
+    half[0].spp = wp.spp / 2; half[1].spp = wp.spp - half[0].spp;
+    half[1].sample0 = wp.sample0 + half[0].spp * wp.sample_stride;
+  } else {
+    half[0].n_pix = wp.n_pix / 2; half[1].n_pix = wp.n_pix - half[0].n_pix;
+    half[1].pix0 = wp.pix0 + half[0].n_pix;
+  }
+  const uint32_t scratch = (uint32_t)waves.size();
+  for (int k = 0; k < 2; ++k) {
+    RCHECK(enqueue_wave(fc, half[k], scratch));
+    uint32_t st = 0;
+    B2RT_CUDA_OK(cudaMemcpyAsync(&st, wave_status + scratch, 4, cudaMemcpyDeviceToHost, stream));
+    B2RT_CUDA_OK(cudaStreamSynchronize(stream));
+    if (st == 2u) RCHECK(retry_wave(fc, half[k], depth + 1));
+    else if (st == 1u) waves_retried++;
+  }
+  return B2RT_OK;
+}
+
 int Renderer::wait() {
   if (!running) return B2RT_OK;
   RCHECK(set_device());
   B2RT_CUDA_OK(cudaEventSynchronize(ev_done));
   running = false;
-  samples_done += samples_pending;
-  samples_pending = 0;
   float ms = 0;
   B2RT_CUDA_OK(cudaEventElapsedTime(&ms, ev_start, ev_done));
   ms_total = ms;
+  // outcome of every wave; overflowed waves are rendered again in halves before anything is reported
+  std::vector<uint32_t> st(waves.size());
+  if (!st.empty()) B2RT_CUDA_OK(cudaMemcpy(st.data(), wave_status, st.size() * 4, cudaMemcpyDeviceToHost));
+  bool cancelled = false;
+  waves_retried = 0;
+  FrameCtx fc;
+  bool have_fc = false;
+  for (size_t w = 0; w < st.size(); ++w) {
+    if (st[w] == 3u) cancelled = true;
+    if (st[w] != 2u) continue;
+    if (!have_fc) { RCHECK(make_frame_ctx(&fc)); have_fc = true; }
+    RCHECK(retry_wave(fc, waves[w], 0));
+  }
   unsigned long long t[8];
   B2RT_CUDA_OK(cudaMemcpy(t, totals, sizeof t, cudaMemcpyDeviceToHost));
-  TraceCounters tc;
-  B2RT_CUDA_OK(cudaMemcpy(&tc, tracer.counters, sizeof tc, cudaMemcpyDeviceToHost));
-  uint32_t cancelled = 0;
-  B2RT_CUDA_OK(cudaMemcpy(&cancelled, counts + 3, 4, cudaMemcpyDeviceToHost));
+  // samples per pixel this call added: the frame's ns_aa, or (after b2rt_stop) the average over the pixels
+  const uint64_t n_pix = (uint64_t)width * height;
+  samples_done += cancelled ? (n_pix ? t[2] / n_pix : 0) : cfg.ns_aa;
+  TraceCounters tc, tc0;
+  RCHECK(tracer.read_counters(&tc, &tc0));
   last = b2rt_stats();
-  last.rays_camera = cancelled ? 0 : cam_rays_enqueued;
+  last.rays_camera = t[2];
   last.rays_bounce = t[0]; last.rays_shadow = t[1];
   last.node_visits = tc.node_visits; last.leaf_prim_tests = tc.prim_tests; last.subtree_visits = tc.subtree_visits;
   last.queue_pushes = tc.pushes; last.staged_bytes = tc.staged_bytes; last.hit_updates = tc.hit_updates;
+  last.node_visits_l0 = tc0.node_visits; last.leaf_prim_tests_l0 = tc0.prim_tests; last.queue_pushes_l0 = tc0.pushes;
+  last.staged_bytes_l0 = tc0.staged_bytes; last.hit_updates_l0 = tc0.hit_updates;
   if (overlap && tracer2.counters) {
-    TraceCounters t2;
-    B2RT_CUDA_OK(cudaMemcpy(&t2, tracer2.counters, sizeof t2, cudaMemcpyDeviceToHost));
+    TraceCounters t2, t20;
+    RCHECK(tracer2.read_counters(&t2, &t20));
     last.node_visits += t2.node_visits; last.leaf_prim_tests += t2.prim_tests; last.subtree_visits += t2.subtree_visits;
     last.queue_pushes += t2.pushes; last.staged_bytes += t2.staged_bytes; last.hit_updates += t2.hit_updates;
+    last.node_visits_l0 += t20.node_visits; last.leaf_prim_tests_l0 += t20.prim_tests; last.queue_pushes_l0 += t20.pushes;
+    last.staged_bytes_l0 += t20.staged_bytes; last.hit_updates_l0 += t20.hit_updates;
   }
   last.kernel_launches = launches + tracer.launches + tracer2.launches;
   last.traverse_launches = tracer.traverse_launches + tracer2.traverse_launches;
-  last.ms_traverse = tracer.harvest_traverse_ms() + tracer2.harvest_traverse_ms();
+  last.traverse_launches_l0 = tracer.traverse_launches_l0 + tracer2.traverse_launches_l0;
+  double l0a = 0, l0b = 0;
+  last.ms_traverse = tracer.harvest_traverse_ms(&l0a) + tracer2.harvest_traverse_ms(&l0b);
+  last.ms_traverse_l0 = l0a + l0b;
   last.ms_total = ms_total;
-  bool ovf = false;
-  RCHECK(tracer.check_overflow(stream, &ovf));
-  if (!ovf && overlap && tracer2.ctrl) RCHECK(tracer2.check_overflow(stream, &ovf));
-  if (ovf) { set_error("ray queue overflow: lower max_wave_paths"); return B2RT_ERR_OVERFLOW; }
   return B2RT_OK;
 }
 
 int Renderer::stop() {
   if (!running) return B2RT_OK;
   RCHECK(set_device());
-  // raise the cancel flag from a second stream; remaining waves generate no rays
-  cudaStream_t s2;
-  B2RT_CUDA_OK(cudaStreamCreateWithFlags(&s2, cudaStreamNonBlocking));
-  k_fill_u32<<<1, 1, 0, s2>>>(counts + 3, 1u);
-  B2RT_CUDA_OK(cudaStreamSynchronize(s2));
-  cudaStreamDestroy(s2);
+  // raise the cancel flag from the handle's cancel stream; the remaining waves generate no rays and are not accumulated
+  k_fill_u32<<<1, 1, 0, stream_cancel>>>(counts + 3, 1u);
+  B2RT_CUDA_OK(cudaStreamSynchronize(stream_cancel));
   return wait();
 }
 

@@ -6,10 +6,24 @@
 
 namespace b2rt {
 
+// one wave = a pixel range x a run of samples, traced to full depth before the next wave starts
+struct WaveParams {
+  uint32_t pix0, n_pix;       // pixel range of this wave
+  uint32_t spp;               // samples per pixel in this wave
+  uint32_t sample0;           // global index of the wave's first sample
+  uint32_t sample_stride;
+  uint32_t width, height;
+  uint32_t jitter;            // 0 -> pixel centre
+  uint32_t k0, k1;            // Philox key
+  float eps;
+  uint32_t max_depth, ns_area_light, S;  // S = shadow rays per interaction
+};
+
 struct Renderer {
   b2rt_config cfg{};
   int device = -1;
   cudaStream_t stream = nullptr, own_stream = nullptr;
+  cudaStream_t stream_cancel = nullptr;   // b2rt_stop raises the cancel flag from here while `stream` is busy
   cudaEvent_t ev_start = nullptr, ev_done = nullptr;
   // scene
   DeviceBVH dbvh;
@@ -32,7 +46,12 @@ struct Renderer {
   void* accum = nullptr; void* img_a = nullptr; void* img_b = nullptr; uint32_t* ldr = nullptr;
   void* resolved = nullptr;
   float* host_image = nullptr; size_t host_image_cap = 0;   // page-locked buffer behind b2rt_get_image (floats)
-  uint64_t samples_done = 0, samples_pending = 0;
+  uint64_t samples_done = 0;
+  // the waves of the frame in flight and their outcome (k_wave_end: 1 complete, 2 queue overflow, 3 cancelled)
+  struct FrameCtx;
+  std::vector<WaveParams> waves;
+  uint32_t* wave_status = nullptr; size_t wave_status_cap = 0;
+  uint64_t waves_retried = 0;
   // wave buffers
   uint64_t wave_cap = 0; uint32_t wave_S = 0;
   void *l_o[2] = {nullptr, nullptr}, *l_d[2] = {nullptr, nullptr};           // dense ray lists (double-buffered by bounce)
@@ -58,6 +77,9 @@ struct Renderer {
   int clear();
   int ensure_wave();
   int start();
+  int make_frame_ctx(FrameCtx* fc);
+  int enqueue_wave(const FrameCtx& fc, const WaveParams& wp, uint32_t status_index);
+  int retry_wave(const FrameCtx& fc, const WaveParams& wp, int depth);
   int is_done();
   int wait();
   int stop();
@@ -66,3 +88,6 @@ struct Renderer {
 };
 
 }  // namespace b2rt
+
+// the C handle is the Renderer (api.cu, comm.cu)
+struct b2rt_renderer { b2rt::Renderer r; };

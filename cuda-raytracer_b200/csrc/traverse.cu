@@ -9,9 +9,10 @@
 // per subtree LEVEL: rays are grouped by the subtree they must visit; a CTA owns one subtree at a
 // time, stages its blob (SoA wide nodes + 48-byte primitive records) with ONE TMA bulk copy
 // (cp.async.bulk + mbarrier).  Level 0 (the root subtree, visited by every ray) reads the caller's DENSE SoA ray list
-// (origin, direction, hit word): the CTA streams its chunk through a double-buffered shared-memory ring with TMA
-// bulk copies (128-ray tiles, one mbarrier per buffer) and the lanes of its warps pull rays from the ring as they go
-// idle.  Deeper levels read ray ids grouped by subtree and gather the three 8/16-byte records.  Rays that
+// (origin, direction, hit word): every warp claims runs of consecutive rays from a global cursor and hands them to its
+// lanes as they go idle (coalesced streaming loads).  Deeper levels read ray ids grouped by subtree and gather the
+// three 8/16-byte records.  A lane walks its ray through the subtree with a per-thread stack in shared memory; leaf
+// visits are decoupled: (lane, primitive) items go to a per-warp queue that the whole warp drains 32 at a time.  Rays that
 // leave through an EXIT child are pushed as (child subtree, ray id) pairs: warp ballot/popc exclusive
 // scan into a per-warp staging ring, one global atomicAdd per flush.  Between levels a single-CTA
 // scan turns per-subtree counts into segment offsets + a chunk work list and a scatter kernel
@@ -22,6 +23,7 @@
 #include <stdint.h>
 #include <stdio.h>
 #include <stdlib.h>
+#include <string.h>
 
 #include <algorithm>
 
@@ -322,10 +324,6 @@ struct NodeView<8> {
 };
 constexpr uint32_t STACK_TN_MASK = 0xFFFFF000u;   // stack entry: [31:12] entry distance bits, [11:0] node << SLOT_BITS | slot
 
-// ray ring: RING_BUFS buffers of RING_TILE rays, SoA inside a buffer
-constexpr uint32_t RING_TILE = 128, RING_BUFS = 2;
-constexpr uint32_t RING_O = 0, RING_D = RING_TILE * 16, RING_H = RING_TILE * 32;
-constexpr uint32_t RING_BUF_BYTES = RING_TILE * 40;
 
 // flush one warp's staged pairs: one global reservation, coalesced 8-byte stores, per-subtree counts
 __device__ __forceinline__ void flush_pairs(uint32_t stage_addr, uint32_t& n_staged, const TravParams& P, uint32_t lane) {
@@ -955,6 +953,8 @@ int Tracer::init(const DeviceBVH& b, uint64_t max_rays_, uint32_t pair_factor) {
   if (pair_factor == 0) pair_factor = 4;
   uint64_t want_pairs = max_rays_ * pair_factor + 65536;
   if (want_pairs > 0xFFFF0000ull) want_pairs = 0xFFFF0000ull;
+  // test hook: a small pair list forces the overflow / split-and-retry paths (tests/test_gpu.py)
+  if (const char* e = getenv("B2RT_DEBUG_PAIR_CAP")) { long long v = atoll(e); if (v >= 1024) want_pairs = (uint64_t)v; }
   int dev = 0;
   B2RT_CUDA_OK(cudaGetDevice(&dev));
   B2RT_CUDA_OK(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
@@ -967,9 +967,9 @@ int Tracer::init(const DeviceBVH& b, uint64_t max_rays_, uint32_t pair_factor) {
   max_rays = max_rays_;
   if (!ctrl) {
     B2RT_CUDA_OK(cudaMalloc(&ctrl, 16 * 4));
-    B2RT_CUDA_OK(cudaMalloc(&counters, sizeof(TraceCounters)));
+    B2RT_CUDA_OK(cudaMalloc(&counters, 2 * sizeof(TraceCounters)));
     B2RT_CUDA_OK(cudaMemset(ctrl, 0, 16 * 4));
-    B2RT_CUDA_OK(cudaMemset(counters, 0, sizeof(TraceCounters)));
+    B2RT_CUDA_OK(cudaMemset(counters, 0, 2 * sizeof(TraceCounters)));
   }
   // BVH dependent part (small, grow-only)
   bvh = b;
@@ -1018,14 +1018,37 @@ int Tracer::init(const DeviceBVH& b, uint64_t max_rays_, uint32_t pair_factor) {
   return B2RT_OK;
 }
 
-double Tracer::harvest_traverse_ms() {
-  double total = 0;
+double Tracer::harvest_traverse_ms(double* ms_l0) {
+  double total = 0, l0 = 0;
   for (size_t i = 0; i + 1 < ev_used; i += 2) {
     float ms = 0;
-    if (cudaEventElapsedTime(&ms, ev_pool[i], ev_pool[i + 1]) == cudaSuccess) total += ms;
+    if (cudaEventElapsedTime(&ms, ev_pool[i], ev_pool[i + 1]) == cudaSuccess) {
+      total += ms;
+      if (i / 2 < ev_deeper.size() && !ev_deeper[i / 2]) l0 += ms;
+    }
   }
   ev_used = 0;
+  ev_deeper.clear();
+  if (ms_l0) *ms_l0 = l0;
   return total;
+}
+
+int Tracer::read_counters(TraceCounters* total, TraceCounters* l0) {
+  TraceCounters c[2];
+  memset(c, 0, sizeof c);
+  if (counters) B2RT_CUDA_OK(cudaMemcpy(c, counters, sizeof c, cudaMemcpyDeviceToHost));
+  if (l0) *l0 = c[0];
+  if (total) {
+    total->node_visits = c[0].node_visits + c[1].node_visits; total->prim_tests = c[0].prim_tests + c[1].prim_tests;
+    total->subtree_visits = c[0].subtree_visits + c[1].subtree_visits; total->pushes = c[0].pushes + c[1].pushes;
+    total->staged_bytes = c[0].staged_bytes + c[1].staged_bytes; total->hit_updates = c[0].hit_updates + c[1].hit_updates;
+  }
+  return B2RT_OK;
+}
+
+int Tracer::reset_counters(cudaStream_t s) {
+  if (counters) B2RT_CUDA_OK(cudaMemsetAsync(counters, 0, 2 * sizeof(TraceCounters), s));
+  return B2RT_OK;
 }
 
 void Tracer::release() {
@@ -1083,19 +1106,20 @@ int Tracer::trace(cudaStream_t s, const float4* ray_o, const float4* ray_d, unsi
     P.blob = bvh.blob; P.treelets = bvh.treelets; P.ray_o = ray_o; P.ray_d = ray_d; P.hits = hits;
     P.ids = (L == 0) ? nullptr : ids_sorted;
     P.chunks = chunks; P.ctrl = ctrl; P.cnt = cnt; P.pairs = pairs; P.pair_cap = (uint32_t)pair_cap; P.level = L;
-    P.counters = counters; P.n_treelets = bvh.n_treelets; P.chunk_rays = chunk_rays; P.chunk0_max = std::max(chunk0_max, chunk_rays); P.stack_off = (uint32_t)stack_off; P.ring_off = (uint32_t)ring_off; P.n_active = n_active_dev; P.n_rays_cap = (uint32_t)std::min<uint64_t>(max_rays, 0xFFFFFFFFull);
+    P.counters = counters + (L ? 1 : 0); P.n_treelets = bvh.n_treelets; P.chunk_rays = chunk_rays; P.chunk0_max = std::max(chunk0_max, chunk_rays); P.stack_off = (uint32_t)stack_off; P.ring_off = (uint32_t)ring_off; P.n_active = n_active_dev; P.n_rays_cap = (uint32_t)std::min<uint64_t>(max_rays, 0xFFFFFFFFull);
     cudaEvent_t e0 = nullptr, e1 = nullptr;
     if (time_kernels) {
       if (ev_used + 2 > ev_pool.size()) {
         for (int k = 0; k < 64; ++k) { cudaEvent_t e; B2RT_CUDA_OK(cudaEventCreate(&e)); ev_pool.push_back(e); }
       }
       e0 = ev_pool[ev_used++]; e1 = ev_pool[ev_used++];
+      ev_deeper.push_back(L ? 1 : 0);
       cudaEventRecord(e0, s);
     }
     if (bvh.width == 8) launch_traverse<8>(*this, s, P, any_hit, collect_stats);
     else launch_traverse<4>(*this, s, P, any_hit, collect_stats);
     if (time_kernels) cudaEventRecord(e1, s);
-    launches++; traverse_launches++;
+    launches++; traverse_launches++; if (L == 0) traverse_launches_l0++;
   }
   B2RT_CUDA_OK(cudaGetLastError());
   return B2RT_OK;
@@ -1167,13 +1191,6 @@ int Tracer::check_overflow(cudaStream_t s, bool* overflow) {
     return B2RT_ERR_CUDA;
   }
 #endif
-  uint32_t wd[8] = {0};
-  cudaMemcpy(wd, ctrl + 8, 32, cudaMemcpyDeviceToHost);
-  if (wd[0]) {
-    fprintf(stderr, "b2rt: ray-ring watchdog: cta %u warp %u j %u n_idle %u tile %u load %u issued %u/%u base %u cons %u/%u\n", wd[1],
-            wd[2] & 255, (wd[2] >> 8) & 255, wd[2] >> 16, wd[3], wd[4], wd[5] & 0xFFFF, wd[5] >> 16, wd[6], wd[7] & 0xFFFF, wd[7] >> 16);
-    cudaMemset(ctrl + 8, 0, 32);
-  }
   if (v) B2RT_CUDA_OK(cudaMemsetAsync(ctrl + CTRL_OVERFLOW, 0, 4, s));
   return B2RT_OK;
 }

@@ -41,15 +41,20 @@ struct Tracer {
   uint32_t* ids_sorted = nullptr; // [pair_cap] ray ids grouped by subtree (levels >= 1)
   uint4* chunks = nullptr;        // [chunk_cap] (subtree, first, count, -)
   uint32_t* ctrl = nullptr;       // [16] pair_count[2], n_chunks, next_chunk, overflow, ...
-  TraceCounters* counters = nullptr;
+  TraceCounters* counters = nullptr;   // [2]: level 0 (the root subtree, every ray) and the deeper levels
   bool collect_stats = false;
   uint64_t launches = 0;
   // per-launch CUDA-event timing of k_traverse (the dominant kernel), on the launching stream
   bool time_kernels = false;
   std::vector<cudaEvent_t> ev_pool;
+  std::vector<uint8_t> ev_deeper;    // per event pair: 1 = a launch of a level >= 1
   size_t ev_used = 0;
-  uint64_t traverse_launches = 0;
-  double harvest_traverse_ms();      // call after the stream is synchronised; resets the pool cursor
+  uint64_t traverse_launches = 0, traverse_launches_l0 = 0;
+  // call after the stream is synchronised; resets the pool cursor.  Returns the total; *ms_l0 = the level-0 launches' share
+  double harvest_traverse_ms(double* ms_l0 = nullptr);
+  // sum of the two counter sets -> *total, the level-0 set -> *l0 (blocking copies)
+  int read_counters(TraceCounters* total, TraceCounters* l0);
+  int reset_counters(cudaStream_t s);
 
   int init(const DeviceBVH& b, uint64_t max_rays_, uint32_t pair_factor);
   void release();

@@ -117,6 +117,8 @@ class PathTracer {
     cfg_.device = -1; cfg_.sample_stride = 1;
     check(b2rt_create(&cfg_, &h_));
   }
+  // every knob of the C ABI at once (device ordinal, sample shard of a multi-GPU job, BVH parameters, ...)
+  explicit PathTracer(const b2rt_config& cfg) : cfg_(cfg) { check(b2rt_create(&cfg_, &h_)); }
   ~PathTracer() { b2rt_destroy(h_); }
   PathTracer(const PathTracer&) = delete;
   PathTracer& operator=(const PathTracer&) = delete;
@@ -133,6 +135,7 @@ class PathTracer {
   }
   void start_raytracing() {                                 // src/pathtracer.cpp:183-213: only from READY
     if (state_ != READY && state_ != DONE) return;
+    check(b2rt_clear(h_));                                  // the reference clears its sample / frame buffers here
     check(b2rt_start(h_)); state_ = RENDERING;
   }
   bool is_done() {                                          // src/pathtracer.cpp:572-575
@@ -155,60 +158,16 @@ class PathTracer {
   // ImageBuffer: RGBA8 via toColor (src/image.h:49-58,173-188)
   std::vector<uint32_t> frame() { std::vector<uint32_t> v((size_t)w_ * h_px_); check(b2rt_read_ldr(h_, v.data(), v.size())); return v; }
   b2rt_stats stats() { b2rt_stats s; check(b2rt_get_stats(h_, &s)); return s; }
-  // save_image: vertically flipped like src/pathtracer.cpp:577-591; PNG with stored (uncompressed) deflate blocks
-  void save_image(const std::string& filename) {
-    std::vector<uint32_t> fb = frame();
-    std::vector<uint8_t> raw;
-    raw.reserve(((size_t)w_ * 4 + 1) * h_px_);
-    for (uint32_t y = 0; y < h_px_; ++y) {
-      raw.push_back(0);
-      const uint8_t* row = reinterpret_cast<const uint8_t*>(&fb[(size_t)(h_px_ - 1 - y) * w_]);
-      raw.insert(raw.end(), row, row + (size_t)w_ * 4);
-    }
-    write_png(filename, raw);
-  }
+  // save_image: PNG, vertically flipped like src/pathtracer.cpp:577-591 (b2rt_write_png); save_exr: the HDR frame
+  void save_image(const std::string& filename) { check(b2rt_write_png(h_, filename.c_str())); }
+  void save_exr(const std::string& filename) { check(b2rt_write_exr(h_, filename.c_str())); }
+  void wait() { check(b2rt_wait(h_)); if (state_ == RENDERING) state_ = DONE; }
   b2rt_renderer* handle() const { return h_; }
 
  private:
   void to_ready() {
     if (state_ == INIT) { if (have_scene_ && have_camera_ && w_) state_ = READY; }
     else state_ = READY;
-  }
-  static uint32_t crc32(const uint8_t* p, size_t n, uint32_t c = 0) {
-    static uint32_t T[256]; static bool init = false;
-    if (!init) { for (uint32_t i = 0; i < 256; ++i) { uint32_t v = i; for (int k = 0; k < 8; ++k) v = (v & 1) ? 0xEDB88320u ^ (v >> 1) : v >> 1; T[i] = v; } init = true; }
-    c = ~c; for (size_t i = 0; i < n; ++i) c = T[(c ^ p[i]) & 255] ^ (c >> 8); return ~c;
-  }
-  void write_png(const std::string& fn, const std::vector<uint8_t>& raw) const {
-    FILE* f = fopen(fn.c_str(), "wb");
-    if (!f) throw std::runtime_error("cannot write " + fn);
-    auto be32 = [](uint32_t v, uint8_t* o) { o[0] = v >> 24; o[1] = v >> 16; o[2] = v >> 8; o[3] = v; };
-    auto chunk = [&](const char* tag, const std::vector<uint8_t>& data) {
-      uint8_t len[4]; be32((uint32_t)data.size(), len); fwrite(len, 1, 4, f);
-      std::vector<uint8_t> td(tag, tag + 4); td.insert(td.end(), data.begin(), data.end());
-      fwrite(td.data(), 1, td.size(), f);
-      uint8_t c[4]; be32(crc32(td.data(), td.size()), c); fwrite(c, 1, 4, f);
-    };
-    const uint8_t sig[8] = {137, 80, 78, 71, 13, 10, 26, 10};
-    fwrite(sig, 1, 8, f);
-    std::vector<uint8_t> ihdr(13); be32(w_, &ihdr[0]); be32(h_px_, &ihdr[4]); ihdr[8] = 8; ihdr[9] = 6; ihdr[10] = ihdr[11] = ihdr[12] = 0;
-    chunk("IHDR", ihdr);
-    std::vector<uint8_t> z; z.push_back(0x78); z.push_back(0x01);
-    uint32_t a = 1, b = 0;
-    for (uint8_t v : raw) { a = (a + v) % 65521; b = (b + a) % 65521; }
-    size_t pos = 0;
-    while (pos < raw.size() || raw.empty()) {
-      size_t n = std::min<size_t>(65535, raw.size() - pos);
-      z.push_back(pos + n >= raw.size() ? 1 : 0);
-      z.push_back(n & 255); z.push_back(n >> 8); z.push_back(~n & 255); z.push_back((~n >> 8) & 255);
-      z.insert(z.end(), raw.begin() + pos, raw.begin() + pos + n);
-      pos += n;
-      if (raw.empty()) break;
-    }
-    uint8_t ad[4]; be32((b << 16) | a, ad); z.insert(z.end(), ad, ad + 4);
-    chunk("IDAT", z);
-    chunk("IEND", {});
-    fclose(f);
   }
   b2rt_renderer* h_ = nullptr;
   b2rt_config cfg_;
@@ -233,6 +192,15 @@ class CudaRenderer {
   void loadScene(const std::string& name) { delete scene_; scene_ = new SceneFile(name); check(b2rt_set_scene(h_, scene_->desc())); }
   void setup() { b2rt_camera c = scene_->camera(w_, hgt_); check(b2rt_set_camera(h_, &c)); frames_ = 0; }
   void setViewpoint(const b2rt_camera& cam) { check(b2rt_set_camera(h_, &cam)); frames_ = 0; }   // resets accumulation, :1866-1869
+  // setViewpoint(Vector3D origin, Vector3D lookAt), src/cudaRenderer.cu:1845-1870, with the reference's camera basis
+  // (left = (0,1,0) x -lookAt, up = left x -lookAt, :1592-1599) and its fixed frustum k = (u - .5, -(v - .5), 1) (:347)
+  void setViewpoint(const float origin[3], const float lookAt[3]) {
+    memcpy(c_origin, origin, 12); memcpy(c_lookAt, lookAt, 12);
+    b2rt_camera c;
+    check(b2rt_camera_look_at(origin, lookAt, 0.f, &c));
+    setViewpoint(c);
+  }
+  float c_origin[3] = {0, 0, 0}, c_lookAt[3] = {0, 0, -1};   // public like the reference's (src/cudaRenderer.h:250-254)
   void clearImage() { check(b2rt_clear(h_)); frames_ = 0; }
   void render() {                                   // renderAccumulate, src/cudaRenderer.cu:2419-2457
     cfg_.sample_first = frames_ * cfg_.ns_aa;

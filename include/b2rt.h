@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define B2RT_ABI_VERSION 1
+#define B2RT_ABI_VERSION 2   /* 2: b2rt_stats grew the level-0 fields, b2rt_comm_*, b2rt_write_*, b2rt_bench_fp32 */
 
 typedef enum b2rt_status {
   B2RT_OK = 0,
@@ -154,6 +154,15 @@ typedef struct b2rt_stats {
   uint32_t bvh_levels;       /* subtree levels = traversal passes per ray batch */
   uint32_t bvh_width;
   uint64_t bvh_bytes;
+  /* the same traversal counters for LEVEL 0 alone (the root subtree: every ray, streamed from the dense ray list);
+     the deeper levels (rays gathered by id, 64-bit atomicMin merges) are the difference to the totals above */
+  uint64_t node_visits_l0;
+  uint64_t leaf_prim_tests_l0;
+  uint64_t queue_pushes_l0;
+  uint64_t staged_bytes_l0;
+  uint64_t hit_updates_l0;
+  uint64_t traverse_launches_l0;
+  double ms_traverse_l0;
 } b2rt_stats;
 
 const char* b2rt_last_error(void);
@@ -205,6 +214,9 @@ int b2rt_bvh_bench_rays(b2rt_bvh* bvh, uint64_t n, int mode, uint64_t seed, int 
  * diagonal -- the default after b2rt_bvh_build).  growth <= 1 or passes < 2 select 4 / 4. */
 int b2rt_bvh_set_slicing(b2rt_bvh* bvh, float first_slice, float growth, int32_t passes);
 int b2rt_bvh_get_stats(b2rt_bvh* bvh, b2rt_stats* out);
+/* Measured FP32 peak of the device (an FFMA-saturating kernel: 16 independent chains per thread, every SM full),
+ * the denominator of the roofline's arithmetic term.  No reference equivalent. */
+int b2rt_bench_fp32(int32_t device, double* tflops);
 /* get_bbox(): src/bvh.h:120-126.  out[6] = min xyz, max xyz */
 int b2rt_bvh_get_bbox(b2rt_bvh* bvh, float* out6);
 void b2rt_bvh_destroy(b2rt_bvh* bvh);
@@ -251,10 +263,29 @@ int b2rt_read_rgba32f(b2rt_renderer* r, float* rgba, size_t n_floats);
  * caller buffer, like the reference (`const Image* getImage()`). */
 int b2rt_get_image(b2rt_renderer* r, const float** rgba, size_t* n_floats);
 int b2rt_get_stats(b2rt_renderer* r, b2rt_stats* out);
-/* Multi-GPU: the per-GPU accumulation buffer (float4 per pixel: rgb SUM + sample count) that
- * one NCCL reduce combines (no reference equivalent; the reference is single-GPU).  The
- * pointer is device memory owned by the handle, valid until set_frame_size/destroy. */
+/* The per-GPU accumulation buffer (float4 per pixel: rgb SUM + sample count), for callers that combine
+ * the GPUs with their own collective (b2rt_reduce_accum below is the library's).  The pointer is device
+ * memory owned by the handle, valid until set_frame_size/destroy. */
 int b2rt_accum_device_ptr(b2rt_renderer* r, void** dev_ptr, size_t* n_floats);
+/* ---- multi-GPU combine (no reference equivalent: src/cudaRenderer.cu is single-GPU, it never calls
+ * cudaSetDevice; it replaces nothing and extends CudaRenderer::renderAccumulate, :2419-2457, across GPUs) ------
+ * Samples are sharded by index (b2rt_config.sample_first / sample_stride), the scene is replicated, and ONE
+ * ncclReduce (fp32 sum) of the float4 accumulation buffers combines the frame on `root`; root < 0 = all-reduce.
+ * The reduce is enqueued on the renderer's stream behind the frame (it first completes b2rt_wait's bookkeeping,
+ * incl. re-rendering overflowed waves); b2rt_read_* / b2rt_get_image on the root then resolve the combined frame.
+ * One process per GPU: rank 0 calls b2rt_comm_unique_id, ships the 128 bytes to the other ranks by any means
+ * (MPI, torch.distributed, a file) and every rank calls b2rt_comm_create.  One process, n GPUs:
+ * b2rt_comm_create_all (ncclCommInitAll) + b2rt_reduce_accum_all (one NCCL group).  NCCL is bound at run time
+ * (dlopen; the copy already loaded in the process wins); b2rt_comm_version() = 0 when none is available. */
+#define B2RT_COMM_ID_BYTES 128
+typedef struct b2rt_comm b2rt_comm;
+int b2rt_comm_version(void);
+int b2rt_comm_unique_id(uint8_t id[B2RT_COMM_ID_BYTES]);
+int b2rt_comm_create(int32_t n_ranks, int32_t rank, const uint8_t id[B2RT_COMM_ID_BYTES], int32_t device, b2rt_comm** out);
+int b2rt_comm_create_all(int32_t n, const int32_t* devices /* NULL = 0..n-1 */, b2rt_comm** out /* [n] */);
+int b2rt_reduce_accum(b2rt_renderer* r, b2rt_comm* comm, int32_t root);
+int b2rt_reduce_accum_all(b2rt_renderer** r, b2rt_comm** comm, int32_t n, int32_t root);
+void b2rt_comm_destroy(b2rt_comm* comm);
 int b2rt_stream_handle(b2rt_renderer* r, void** cuda_stream);
 /* Run on a caller-owned CUDA stream (e.g. the framework stream that also carries the NCCL reduce).
  * cuda_stream = NULL restores the handle's own stream. */
@@ -294,6 +325,21 @@ int b2rt_bvh_validate_host(const b2rt_scene_desc* scene, uint32_t max_leaf_size,
                            uint32_t treelet_bytes, uint64_t out[8]);
 int b2rt_camera_place(const float bbox[6], const float view_dir[3], float hfov_deg,
                       float vfov_deg, uint32_t width, uint32_t height, b2rt_camera* out);
+/* Camera of CudaRenderer::setViewpoint(origin, lookAt) (src/cudaRenderer.cu:1845-1870): eye at `origin`, viewing
+ * along `look_at` (a direction), the reference's basis left = (0,1,0) x -lookAt, up = left x -lookAt
+ * (src/cudaRenderer.cu:1592-1599; the screen's right axis is `left`, its up axis is -`up`) and, with fov_deg = 0, its
+ * fixed frustum k = (u - .5, -(v - .5), 1) (src/cudaRenderer.cu:347), i.e. 2 atan(.5) = 53.13 degrees on both axes.
+ * Fails for a look_at parallel to the y axis (the reference divides by zero there). */
+int b2rt_camera_look_at(const float origin[3], const float look_at[3], float fov_deg, b2rt_camera* out);
+/* Image files.  b2rt_save_png / b2rt_save_exr are plain host helpers (no device): RGBA8 words as b2rt_read_ldr
+ * returns them / RGB fp32 triples as b2rt_read_hdr returns them, row 0 = bottom row of the image; the files store the
+ * top row first.  b2rt_write_png = PathTracer::save_image (src/pathtracer.cpp:577-591: tone-mapped frame, flipped,
+ * PNG); b2rt_write_exr writes the HDR frame as an uncompressed fp32 OpenEXR scanline file (the reference reads EXR
+ * for its environment maps, src/main.cpp:38-70, and the C++ report tooling around it writes HDR frames). */
+int b2rt_save_png(const char* path, const uint32_t* rgba8, uint32_t width, uint32_t height);
+int b2rt_save_exr(const char* path, const float* rgb, uint32_t width, uint32_t height);
+int b2rt_write_png(b2rt_renderer* r, const char* path);
+int b2rt_write_exr(b2rt_renderer* r, const char* path);
 
 #ifdef __cplusplus
 }

@@ -5,6 +5,8 @@ Bars: closest-hit primitive ids and distances, any-hit flags: BIT-EXACT.  Radian
 arithmetic is restated identically in the oracle and in the kernels (explicit fma contract, -fmad=false), so the
 HDR frame is expected to be bit-identical; the asserted tolerance is per-pixel RMSE <= 1e-6 and max abs diff <= 1e-5
 (north_star: "within a stated per-pixel RMSE tolerance at equal spp").  8-bit tone-mapped output: +-1 LSB (powf)."""
+import os
+
 import numpy as np
 import pytest
 
@@ -547,3 +549,124 @@ def test_get_image_matches_read_rgba32f():
         assert np.array_equal(pt.hdr(), a[..., :3])
         assert np.array_equal(v, a)          # the view is not disturbed by other read-backs
     pt.close()
+
+
+def test_stop_leaves_an_unbiased_partial_frame():
+    """b2rt_stop (PathTracer::stop, src/pathtracer.cpp:116-139): cancelled waves must not touch the sums or the
+    per-pixel sample count; what was accumulated is exactly the complete waves, so the partial frame equals a frame of
+    that many samples."""
+    sc = Scene.load(scene_path("CBbunny"))
+    w, h, spp = 128, 96, 48
+    cam = place_camera(sc, w, h)
+    pt = b2rt.PathTracer(ns_aa=spp, max_ray_depth=4, ns_area_light=1, seed=9, max_wave_paths=w * h)   # one sample per wave
+    pt.set_scene(sc); pt.set_camera(cam); pt.set_frame_size(w, h)
+    assert pt.start_raytracing()
+    pt.stop()
+    acc = pt.accum_tensor().cpu().numpy().reshape(h, w, 4)
+    k = acc[..., 3]
+    assert np.all(k == k.flat[0]) and 0 <= k.flat[0] <= spp            # whole waves only, the same count for every pixel
+    done = int(k.flat[0])
+    st = pt.stats()
+    assert st["rays_camera"] == done * w * h
+    if done:
+        part = pt.hdr()
+        ref = b2rt.PathTracer(ns_aa=done, max_ray_depth=4, ns_area_light=1, seed=9, max_wave_paths=w * h)
+        ref.set_scene(sc); ref.set_camera(cam); ref.set_frame_size(w, h); ref.render()
+        np.testing.assert_array_equal(part, ref.hdr())
+        ref.close()
+    # a restart after stop() begins from cleared buffers (start_raytracing clears, like the reference)
+    pt.set_config(ns_aa=2)
+    assert pt.start_raytracing(); pt.wait()
+    acc = pt.accum_tensor().cpu().numpy().reshape(h, w, 4)
+    assert np.all(acc[..., 3] == 2.0)
+    pt.close()
+
+
+def test_renderer_splits_waves_on_queue_overflow(monkeypatch):
+    """A ray-queue overflow inside the renderer must not bias the frame: the wave is dropped on the device, rendered
+    again in halves by b2rt_wait, and the result matches the frame of a run that never overflowed (up to the order of
+    the fp32 sample sums)."""
+    sc = Scene.load(scene_path("CBbunny"))
+    w, h, spp = 160, 120, 8
+    cam = place_camera(sc, w, h)
+    good = b2rt.PathTracer(ns_aa=spp, max_ray_depth=4, ns_area_light=1, seed=4)
+    good.set_scene(sc); good.set_camera(cam); good.set_frame_size(w, h); good.render()
+    ref = good.hdr(); st_ref = good.stats(); good.close()
+    assert st_ref["queue_pushes"] > 40000
+    monkeypatch.setenv("B2RT_DEBUG_PAIR_CAP", "20000")                  # far fewer pairs than one wave pushes
+    pt = b2rt.PathTracer(ns_aa=spp, max_ray_depth=4, ns_area_light=1, seed=4)
+    pt.set_scene(sc); pt.set_camera(cam); pt.set_frame_size(w, h); pt.render()
+    img = pt.hdr(); st = pt.stats()
+    acc = pt.accum_tensor().cpu().numpy().reshape(h, w, 4)
+    assert np.all(acc[..., 3] == spp)                                   # every sample accumulated exactly once
+    assert st["rays_camera"] == spp * w * h
+    np.testing.assert_allclose(img, ref, rtol=2e-6, atol=1e-7)
+    pt.close()
+
+
+def test_image_writers_and_one_rank_reduce(tmp_path):
+    """b2rt_write_png / b2rt_write_exr store exactly what b2rt_read_ldr / b2rt_read_hdr return (top row first), and a
+    one-rank NCCL reduce through the C ABI (b2rt_comm_* + b2rt_reduce_accum) leaves the accumulation buffer as it was."""
+    from PIL import Image
+    import sys
+    sys.path.insert(0, os.path.dirname(__file__))
+    from test_host import _read_exr_scanlines
+    sc = Scene.load(scene_path("CBspheres_lambertian"))
+    pt = b2rt.PathTracer(ns_aa=4, max_ray_depth=3, ns_area_light=1, seed=8)
+    pt.set_scene(sc); pt.set_camera(place_camera(sc, 80, 60)); pt.set_frame_size(80, 60); pt.render()
+    hdr, ldr = pt.hdr(), pt.ldr()
+    pt.save_image(str(tmp_path / "a.png")); pt.save_exr(str(tmp_path / "a.exr"))
+    got = np.asarray(Image.open(tmp_path / "a.png").convert("RGBA"))
+    assert np.array_equal(got, np.stack([(ldr[::-1] >> s) & 255 for s in (0, 8, 16, 24)], -1).astype(np.uint8))
+    assert np.array_equal(_read_exr_scanlines(str(tmp_path / "a.exr")), hdr[::-1])
+    if b2rt.Comm.version() == 0:
+        pytest.skip("no NCCL library on this box")
+    before = pt.accum_tensor().clone()
+    comm = b2rt.Comm(1, 0, b2rt.Comm.unique_id(), device=0)
+    pt.reduce_accum(comm, root=0)
+    import torch
+    torch.cuda.synchronize()
+    assert torch.equal(pt.accum_tensor(), before)
+    assert np.array_equal(pt.hdr(), hdr)
+    comm.close(); pt.close()
+
+
+def test_cuda_renderer_set_viewpoint_origin_look_at():
+    """CudaRenderer::setViewpoint(origin, lookAt) (src/cudaRenderer.cu:1845-1870): the reference's camera basis and
+    frustum; the frame equals the oracle's for the same b2rt_camera and accumulation restarts."""
+    sc = Scene.load(scene_path("CBcoil"))
+    w = h = 64
+    r = b2rt.CudaRenderer(samples_per_frame=2, max_ray_depth=3, ns_area_light=2, median_threshold=0, seed=2)
+    r.allocOutputImage(w, h); r.loadScene(sc); r.setup()
+    r.render(); r.render()
+    o, L = np.array([0.0, 0.75, 3.0], np.float32), np.array([0.0, 0.0, -1.0], np.float32)   # the reference's CBcoil view
+    r.setViewpoint(o, L)
+    assert r.frames == 0
+    r.render()
+    img = r.getImage()[..., :3].copy()
+    cam = b2rt.camera_look_at(o, L)
+    ref = orc.OracleScene(sc, 4).render(cam, Config(ns_aa=2, max_ray_depth=3, ns_area_light=2, seed=2), w, h)
+    assert np.sqrt(np.mean((img - ref) ** 2)) <= 1e-6
+    assert img.max() > 0.05                          # the box is in view
+
+
+def test_cpp_example_multi_gpu_matches_single(tmp_path):
+    """examples/render_scene -g 2 (two handles in one process, samples dealt round-robin, b2rt_comm_create_all +
+    b2rt_reduce_accum_all) writes the same HDR frame as -g 1 up to the order of the fp32 sample sums."""
+    import subprocess
+    import sys
+    from conftest import ROOT
+    sys.path.insert(0, os.path.dirname(__file__))
+    from test_host import _read_exr_scanlines
+    if b2rt.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    exe = os.path.join(ROOT, "cuda-raytracer_b200", "examples", "render_scene")
+    imgs = []
+    for g in (1, 2):
+        exr = tmp_path / f"g{g}.exr"
+        r = subprocess.run([exe, "-s", "8", "-m", "4", "-l", "1", "-r", "128x96", "-g", str(g), "-w", str(tmp_path / f"g{g}.png"),
+                            "-x", str(exr), scene_path("CBbunny")], capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr
+        imgs.append(_read_exr_scanlines(str(exr)))
+    np.testing.assert_allclose(imgs[1], imgs[0], rtol=2e-6, atol=1e-7)
+    assert imgs[0].max() > 0.1

@@ -25,7 +25,7 @@ def test_header_symbols_exported():
     missing = [s for s in sorted(declared) if not hasattr(lib, s)]
     assert not missing, missing
     assert set(b2rt.EXPORTS) <= declared
-    assert lib.b2rt_abi_version() == 1
+    assert lib.b2rt_abi_version() == 2
 
 
 def test_fails_loudly_without_device():
@@ -303,3 +303,113 @@ def test_bench_workloads_and_strong_scaling_split():
     with pytest.raises(SystemExit):
         bench.load_workload("cfg3", 0, 3)
     assert set(bench.BASELINE_INDEX) == set(bench.WORKLOADS)
+
+
+# ---- host helpers added in round 2 ------------------------------------------------------------------------------
+def test_save_png_round_trip(tmp_path):
+    from PIL import Image
+    rng = np.random.default_rng(5)
+    h, w = 37, 53
+    px = rng.integers(0, 2 ** 32, size=(h, w), dtype=np.uint64).astype(np.uint32)
+    path = str(tmp_path / "t.png")
+    b2rt.save_png(path, px)
+    img = np.asarray(Image.open(path).convert("RGBA"))
+    want = np.stack([(px[::-1] >> s) & 255 for s in (0, 8, 16, 24)], -1).astype(np.uint8)   # top row first, R G B A bytes
+    assert np.array_equal(img, want)
+
+
+def _read_exr_scanlines(path):
+    """Minimal reader of the layout b2rt_save_exr writes (OpenEXR 2 scanline, NO_COMPRESSION, FLOAT B G R)."""
+    import struct
+    d = open(path, "rb").read()
+    assert struct.unpack_from("<II", d, 0) == (20000630, 2)
+    at = 8
+    attrs = {}
+    while d[at] != 0:
+        e = d.index(b"\0", at); name = d[at:e].decode(); at = e + 1
+        e = d.index(b"\0", at); typ = d[at:e].decode(); at = e + 1
+        (size,) = struct.unpack_from("<I", d, at); at += 4
+        attrs[name] = (typ, d[at:at + size]); at += size
+    at += 1
+    assert attrs["compression"] == ("compression", b"\0") and attrs["lineOrder"] == ("lineOrder", b"\0")
+    chans, c = [], attrs["channels"][1]
+    k = 0
+    while c[k] != 0:
+        e = c.index(b"\0", k); chans.append((c[k:e].decode(), struct.unpack_from("<I", c, e + 1)[0])); k = e + 1 + 16
+    assert chans == [("B", 2), ("G", 2), ("R", 2)]
+    x0, y0, x1, y1 = struct.unpack("<4i", attrs["dataWindow"][1])
+    w, h = x1 - x0 + 1, y1 - y0 + 1
+    offs = struct.unpack_from(f"<{h}Q", d, at)
+    out = np.zeros((h, w, 3), np.float32)
+    for y in range(h):
+        yy, nb = struct.unpack_from("<iI", d, offs[y])
+        assert yy == y and nb == w * 12
+        line = np.frombuffer(d, np.float32, 3 * w, offs[y] + 8).reshape(3, w)
+        out[y, :, 2], out[y, :, 1], out[y, :, 0] = line[0], line[1], line[2]
+    assert offs[-1] + 8 + w * 12 == len(d)
+    return out
+
+
+def test_save_exr_layout_and_values(tmp_path):
+    rng = np.random.default_rng(6)
+    rgb = rng.standard_normal((19, 31, 3)).astype(np.float32) * 100
+    path = str(tmp_path / "t.exr")
+    b2rt.save_exr(path, rgb)
+    got = _read_exr_scanlines(path)
+    assert np.array_equal(got, rgb[::-1])            # the file stores the top row first
+    os.environ["OPENCV_IO_ENABLE_OPENEXR"] = "1"
+    try:
+        import cv2
+        img = cv2.imread(path, cv2.IMREAD_UNCHANGED)
+    except Exception:
+        img = None
+    if img is not None:                              # an independent EXR reader, when this OpenCV build has one
+        assert np.array_equal(img[..., ::-1], rgb[::-1])
+
+
+def test_camera_look_at_reproduces_the_reference_basis():
+    """src/cudaRenderer.cu:1592-1599: c_dir = -lookAt, left = (0,1,0) x c_dir, up = left x c_dir; the ray through screen
+    coordinates (u, v) is k.x left + k.y up + k.z lookAt with k = (u - .5, -(v - .5), 1) (:347)."""
+    o = np.array([0.3, 0.75, 3.0], np.float32)
+    L = np.array([0.2, -0.1, -1.0], np.float64); L /= np.linalg.norm(L)
+    cam = b2rt.camera_look_at(o, L.astype(np.float32))
+    c2w = np.array(cam.c2w[:], np.float64).reshape(3, 3)
+    left = np.cross([0, 1, 0], -L); left /= np.linalg.norm(left)
+    up = np.cross(left, -L); up /= np.linalg.norm(up)
+    np.testing.assert_allclose(c2w[0], left, atol=1e-6)
+    np.testing.assert_allclose(c2w[1], -up, atol=1e-6)
+    np.testing.assert_allclose(c2w[2], -L, atol=1e-6)
+    assert list(cam.pos[:]) == [float(v) for v in o]
+    th = np.tan(np.radians(cam.hfov_deg) / 2)
+    assert abs(th - 0.5) < 1e-6 and cam.vfov_deg == cam.hfov_deg
+    for u, v in ((0.1, 0.8), (0.5, 0.5), (0.9, 0.2)):
+        k = np.array([u - .5, -(v - .5), 1.0])
+        ref = k[0] * left + k[1] * up + k[2] * L
+        ours = c2w[0] * (2 * u - 1) * th + c2w[1] * (2 * v - 1) * th - c2w[2]   # Camera::generate_ray, src/camera.h:71-81
+        np.testing.assert_allclose(ours / np.linalg.norm(ours), ref / np.linalg.norm(ref), atol=1e-6)
+    with pytest.raises(b2rt.B2rtError):
+        b2rt.camera_look_at(o, np.array([0, 1, 0], np.float32))
+
+
+def test_scene_load_rejects_corrupt_headers(tmp_path):
+    good = open(scene_path("CBempty"), "rb").read()
+    bad = bytearray(good); bad[8:12] = (0x7FFFFFFF).to_bytes(4, "little")       # n_tris far beyond the file size
+    p = tmp_path / "bad.b2s"; p.write_bytes(bytes(bad))
+    with pytest.raises(b2rt.B2rtError) as e:
+        b2rt.load_scene(str(p))
+    assert e.value.code == -5
+    bad = bytearray(good); bad[4:8] = (7).to_bytes(4, "little")                 # unknown version
+    p.write_bytes(bytes(bad))
+    with pytest.raises(b2rt.B2rtError):
+        b2rt.load_scene(str(p))
+    p.write_bytes(good[: len(good) // 2])                                       # truncated
+    with pytest.raises(b2rt.B2rtError):
+        b2rt.load_scene(str(p))
+
+
+def test_comm_api_fails_cleanly_without_a_device():
+    if b2rt.device_count() > 0:
+        pytest.skip("a CUDA device is visible")
+    assert b2rt.Comm.version() >= 0
+    with pytest.raises(b2rt.B2rtError):
+        b2rt.Comm(2, 0, b"\0" * 128, device=0)
