@@ -616,7 +616,7 @@ extern "C" {
 
 void* orc_scene_create(const b2rt_scene_desc* d, uint32_t max_leaf) {
   Scene* sc = make_scene(d);
-  build_bvh(*sc, max_leaf ? max_leaf : 4);
+  if (max_leaf != 0xFFFFFFFFu) build_bvh(*sc, max_leaf ? max_leaf : 4);   // 0xFFFFFFFF: exhaustive queries only (10 M soup)
   return sc;
 }
 void orc_scene_destroy(void* s) { delete (Scene*)s; }

@@ -42,8 +42,9 @@ def lib():
 
 class OracleScene:
     def __init__(self, scene, max_leaf=4):
+        """max_leaf=None: no BVH (the reference builder restated here is O(n log^2 n)); only mode="brute" queries."""
         d, keep = scene.desc()
-        self._h = lib().orc_scene_create(C.byref(d), max_leaf)
+        self._h = lib().orc_scene_create(C.byref(d), 0xFFFFFFFF if max_leaf is None else max_leaf)
         self.scene = scene
         self.n_prims = scene.n_prims
 
