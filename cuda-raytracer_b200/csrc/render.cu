@@ -165,11 +165,13 @@ __device__ __forceinline__ uint2 block_append2(uint32_t* counter_a, bool pred_a,
 }
 
 // One surface interaction for every active path (bounce index b).
+// 128-thread CTAs, 8 per SM: the two list appends end in CTA-wide barriers, where every warp waits for the slowest
+// one's dependent loads; four warps per barrier wait less than eight (cfg2 / cfg3 frame -1.8 % / -1.5 %, gpurun_out/r2_ab11)
 #ifndef B2RT_SHADE_OCC
-#define B2RT_SHADE_OCC 4
+#define B2RT_SHADE_OCC 8
 #endif
 #ifndef B2RT_SHADE_THREADS
-#define B2RT_SHADE_THREADS 256
+#define B2RT_SHADE_THREADS 128
 #endif
 constexpr int SHADE_THREADS = B2RT_SHADE_THREADS;   // <= 256 (block_append's scratch holds 8 warp counts)
 __global__ void __launch_bounds__(SHADE_THREADS, B2RT_SHADE_OCC)

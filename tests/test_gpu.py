@@ -697,51 +697,61 @@ def _reference_primary_dump(tmp_path, scene="CBbunny", size=512):
 
 def test_closest_hit_matches_the_reference_cuda_traversal(tmp_path):
     """The reference's OWN traversal (kernelRayIntersectSingle/Level + kernelMergeIntersections, src/cudaRenderer.cu:
-    846-1297, 515-540, compiled unmodified for sm_100a) and b2rt_bvh_intersect on the SAME camera rays: hit distances
-    agree.  The reference never records a primitive id (CuIntersection, src/cudaRenderer.h:155-171), its triangle test
-    is a different fp32 expression (plane + edge signs, :217-270) and its 16-slot candidate buffer can overflow, so the
-    bar is |dt| <= 2e-4 * max(1, t) on >= 99.9 % of the rays it reports a hit for; the histogram goes to gpurun_out/."""
+    846-1297, 515-540, compiled unmodified for sm_100a) and b2rt_bvh_intersect on the SAME camera rays (the reference's
+    view: eye (0, 0.75, -3), a quarter of the rays pass beside the box): the same rays hit, and the hit distances agree.
+    The reference never records a primitive id (CuIntersection, src/cudaRenderer.h:155-171) and its triangle test is a
+    different fp32 expression (plane + edge signs, :217-270), so the bar is on t: |dt| <= 1e-5 * max(1, t) on >= 99.99 % of
+    the rays both report a hit for (observed on B200: 100 % within 1e-6); the histogram goes to gpurun_out/ref_pin_r02.json."""
     import json
     from conftest import ROOT
     rays, _ = _reference_primary_dump(tmp_path)
     o, d, t_ref, valid = rays[:, 0:3].copy(), rays[:, 3:6].copy(), rays[:, 6], rays[:, 7] > 0
-    assert valid.mean() > 0.9 and np.all(np.isfinite(d))
+    assert valid.mean() > 0.5 and np.all(np.isfinite(d))
     sc = Scene.load(scene_path("CBbunny"))
     bvh = b2rt.BVHAccel(sc)
     t, prim = bvh.intersect(o, d)
     hit = prim != 0xFFFFFFFF
     both = valid & hit
     err = np.abs(t[both] - t_ref[both]) / np.maximum(1.0, t[both])
-    hist = {f"<= {b:g}": int((err <= b).sum()) for b in (1e-6, 1e-5, 1e-4, 2e-4, 1e-3, 1e-2)}
+    hist = {f"<= {b:g}": int((err <= b).sum()) for b in (0.0, 1e-7, 1e-6, 1e-5, 1e-4, 1e-3, 1e-2)}
     rec = dict(rays=int(len(rays)), reference_hits=int(valid.sum()), b2rt_hits=int(hit.sum()), both=int(both.sum()),
                only_reference=int((valid & ~hit).sum()), only_b2rt=int((~valid & hit).sum()), rel_err_hist=hist,
-               max_rel_err=float(err.max()), frac_within_2e4=float((err <= 2e-4).mean()))
+               max_rel_err=float(err.max()), frac_within_1e5=float((err <= 1e-5).mean()))
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
     json.dump(rec, open(os.path.join(ROOT, "gpurun_out", "ref_pin_r02.json"), "w"), indent=1)
-    assert rec["frac_within_2e4"] >= 0.999, rec
-    assert rec["only_reference"] <= 1e-3 * len(rays), rec            # a hit the reference finds and we do not would be a missed hit
+    assert rec["frac_within_1e5"] >= 0.9999, rec
+    assert rec["only_reference"] <= 1e-4 * len(rays), rec            # a hit the reference finds and we do not would be a missed hit
+    assert rec["only_b2rt"] <= 1e-3 * len(rays), rec                 # silhouette rays the reference's edge tests reject
     bvh.close()
 
 
 def test_loader_matches_the_reference_loader(tmp_path):
     """The triangles the reference's own loader hands its renderer (ColladaParser::load -> DynamicScene::Mesh ->
     StaticScene::Mesh -> CuTriangle, src/cudaRenderer.cu:1679-1792, host vector CudaRenderer::triangles) against the
-    scene b2rt loads for the same file: same triangle set -- positions, per-vertex shading normals, material class."""
+    scene b2rt loads for the same file: the same triangles (the reference stores each one rotated: a, b, c = p3, p1, p2),
+    positions to one float ulp, per-vertex shading normals, material class.  Stated divergence: for vertices on a mesh
+    BOUNDARY the reference's Vertex::normal() walks h->next()->twin() (src/halfEdgeMesh.h:625-632), which leaves the
+    vertex; on this scene that only negates the normals of the 12 planar wall / light triangles, which the integrator
+    cancels (shading normals are flipped towards the ray)."""
+    from scipy.spatial import cKDTree
     _, tris = _reference_primary_dump(tmp_path, size=64)
     sc = Scene.load(scene_path("CBbunny"))
-    assert len(tris) == sc.n_tris
-    ours = np.concatenate([sc.tri_verts.reshape(-1, 9), sc.tri_normals.reshape(-1, 9)], 1).astype(np.float64)
-    ref = tris[:, :18].astype(np.float64)
-    key = lambda a: np.lexsort(np.round(a[:, :9] * 1e4).astype(np.int64).T[::-1])   # order by the nine vertex coordinates
-    ours_s, ref_s = ours[key(ours)], ref[key(ref)]
-    np.testing.assert_allclose(ours_s[:, :9], ref_s[:, :9], atol=2e-6)               # double -> float conversions differ in the last bit
-    nrm = lambda v: v / np.maximum(np.linalg.norm(v, axis=-1, keepdims=True), 1e-30)
-    a, b = nrm(ours_s[:, 9:].reshape(-1, 3)), nrm(ref_s[:, 9:].reshape(-1, 3))
-    assert np.abs(a - b).max() <= 1e-4
+    nt = len(tris)
+    assert nt == sc.n_tris
+    ov, on = sc.tri_verts.reshape(-1, 3, 3).astype(np.float64), sc.tri_normals.reshape(-1, 3, 3).astype(np.float64)
+    rv, rn = tris[:, :9].reshape(-1, 3, 3).astype(np.float64), tris[:, 9:18].reshape(-1, 3, 3).astype(np.float64)
+    dist, idx = cKDTree(ov.mean(1)).query(rv.mean(1))
+    assert dist.max() <= 1e-6 and len(np.unique(idx)) == nt                      # a bijection between the two triangle sets
+    ours_v, ours_n = np.roll(ov[idx], -2, axis=1), np.roll(on[idx], -2, axis=1)  # the reference's vertex rotation
+    assert np.abs(ours_v - rv).max() <= 2e-7
+    unit = lambda v: v / np.maximum(np.linalg.norm(v, axis=-1, keepdims=True), 1e-30)
+    dn = np.abs(unit(ours_n) - unit(rn)).reshape(nt, -1).max(1)
+    flipped = np.abs(unit(ours_n) + unit(rn)).reshape(nt, -1).max(1) <= 1e-4
+    assert np.all((dn <= 1e-4) | flipped)
+    assert flipped.sum() <= 12 and (dn <= 1e-4).mean() >= 0.999
     # material class: the reference maps emitters and diffuse surfaces to fn 0 and every delta BSDF to fn 1 (:1694-1723)
     kinds = np.array([m["kind"] for m in sc.materials])[sc.tri_material]
-    ours_fn = np.isin(kinds, (1, 2, 4)).astype(np.int64)[key(ours)]
-    assert np.array_equal(ours_fn, tris[:, 18].astype(np.int64)[key(ref)])
+    assert np.array_equal(np.isin(kinds, (1, 2, 4)).astype(np.int64)[idx], tris[:, 18].astype(np.int64))
 
 
 def test_dae_to_frame_through_the_c_loader():
