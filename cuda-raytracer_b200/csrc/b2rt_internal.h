@@ -79,7 +79,8 @@ struct HostScene {
 };
 
 void set_error(const std::string& msg);
-int make_host_scene(const b2rt_scene_desc* d, HostScene* out);
+// with_geometry = false: only counts, materials and lights are copied (the caller uploads tri_verts / tri_normals itself)
+int make_host_scene(const b2rt_scene_desc* d, HostScene* out, bool with_geometry = true);
 int build_wide_bvh(const HostScene& sc, uint32_t max_leaf, uint32_t width, uint32_t treelet_bytes, WideBVH* out);
 // structural check of a serialised BVH (walks every subtree blob the way the kernel decodes it); out[8] = subtrees,
 // levels, wide nodes, leaves, blob bytes, max subtree bytes, stack bound, exits

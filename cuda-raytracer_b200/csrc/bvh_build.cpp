@@ -392,35 +392,38 @@ struct WNode {
 
 }  // namespace
 
-int make_host_scene(const b2rt_scene_desc* d, HostScene* out) {
+int make_host_scene(const b2rt_scene_desc* d, HostScene* out, bool with_geometry) {
   if (!d) { set_error("scene desc is null"); return B2RT_ERR_INVALID; }
   if (d->n_tris && !d->tri_verts) { set_error("tri_verts is null"); return B2RT_ERR_INVALID; }
   if (d->n_spheres && !d->spheres) { set_error("spheres is null"); return B2RT_ERR_INVALID; }
   if ((uint64_t)d->n_tris + d->n_spheres >= 0xFFFFFFF0ull) { set_error("too many primitives"); return B2RT_ERR_INVALID; }
   out->n_tris = d->n_tris; out->n_spheres = d->n_spheres;
   const uint32_t n = out->n_prims();
-  out->prim_geom.assign((size_t)n * 12, 0.f);
   out->prim_material.assign(n, 0u);
-  for (uint32_t i = 0; i < d->n_tris; ++i) {
-    const float* v = d->tri_verts + (size_t)i * 9;
-    float* g = &out->prim_geom[(size_t)i * 12];
-    g[0] = v[0]; g[1] = v[1]; g[2] = v[2];
-    g[3] = v[3] - v[0]; g[4] = v[4] - v[1]; g[5] = v[5] - v[2];   // e1 = p2 - p1 (triangle.cpp:172)
-    g[6] = v[6] - v[0]; g[7] = v[7] - v[1]; g[8] = v[8] - v[2];   // e2 = p3 - p1
-    uint32_t id = i, kind = 0;
-    memcpy(&g[9], &id, 4); memcpy(&g[10], &kind, 4);
-    if (d->tri_material) out->prim_material[i] = d->tri_material[i];
+  if (d->tri_material) memcpy(out->prim_material.data(), d->tri_material, (size_t)d->n_tris * 4);
+  if (d->sphere_material) memcpy(out->prim_material.data() + d->n_tris, d->sphere_material, (size_t)d->n_spheres * 4);
+  out->prim_geom.clear();
+  out->tri_normals.clear();
+  if (with_geometry) {   // (the device builder makes the same records from the caller's arrays on the GPU: k_make_prims)
+    out->prim_geom.assign((size_t)n * 12, 0.f);
+    for (uint32_t i = 0; i < d->n_tris; ++i) {
+      const float* v = d->tri_verts + (size_t)i * 9;
+      float* g = &out->prim_geom[(size_t)i * 12];
+      g[0] = v[0]; g[1] = v[1]; g[2] = v[2];
+      g[3] = v[3] - v[0]; g[4] = v[4] - v[1]; g[5] = v[5] - v[2];   // e1 = p2 - p1 (triangle.cpp:172)
+      g[6] = v[6] - v[0]; g[7] = v[7] - v[1]; g[8] = v[8] - v[2];   // e2 = p3 - p1
+      uint32_t id = i, kind = 0;
+      memcpy(&g[9], &id, 4); memcpy(&g[10], &kind, 4);
+    }
+    for (uint32_t i = 0; i < d->n_spheres; ++i) {
+      const float* s = d->spheres + (size_t)i * 4;
+      float* g = &out->prim_geom[((size_t)d->n_tris + i) * 12];
+      g[0] = s[0]; g[1] = s[1]; g[2] = s[2]; g[3] = s[3];
+      uint32_t id = d->n_tris + i, kind = 1;
+      memcpy(&g[9], &id, 4); memcpy(&g[10], &kind, 4);
+    }
+    if (d->tri_normals) out->tri_normals.assign(d->tri_normals, d->tri_normals + (size_t)d->n_tris * 9);
   }
-  for (uint32_t i = 0; i < d->n_spheres; ++i) {
-    const float* s = d->spheres + (size_t)i * 4;
-    float* g = &out->prim_geom[((size_t)d->n_tris + i) * 12];
-    g[0] = s[0]; g[1] = s[1]; g[2] = s[2]; g[3] = s[3];
-    uint32_t id = d->n_tris + i, kind = 1;
-    memcpy(&g[9], &id, 4); memcpy(&g[10], &kind, 4);
-    if (d->sphere_material) out->prim_material[d->n_tris + i] = d->sphere_material[i];
-  }
-  if (d->tri_normals) out->tri_normals.assign(d->tri_normals, d->tri_normals + (size_t)d->n_tris * 9);
-  else out->tri_normals.clear();
   if (d->n_materials && d->materials) out->materials.assign(d->materials, d->materials + d->n_materials);
   else {
     b2rt_material m; memset(&m, 0, sizeof m);

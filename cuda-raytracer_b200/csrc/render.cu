@@ -628,15 +628,28 @@ int Renderer::set_scene(const b2rt_scene_desc* d) {
   auto lap = [&](const char* what) {
     if (verbose) fprintf(stderr, "b2rt: set_scene %-12s %8.3f ms\n", what, std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count());
   };
-  HostScene hs;
-  RCHECK(make_host_scene(d, &hs));
-  lap("host scene");
-  WideBVH wb;
-  // cfg.bvh_builder: 0 automatic (device build from 2^20 primitives on), 1 host, 2 device; B2RT_BUILDER=gpu|host overrides
-  bool on_device = cfg.bvh_builder == 2 || (cfg.bvh_builder == 0 && hs.n_prims() >= (1u << 20));
+  if (!d) { set_error("scene desc is null"); return B2RT_ERR_INVALID; }
+  const uint64_t n_prims64 = (uint64_t)d->n_tris + d->n_spheres;
+  // cfg.bvh_builder: 0 automatic, 1 host, 2 device; B2RT_BUILDER=gpu|host overrides.  Automatic = the device builder
+  // (PLOC) from 2^14 primitives on: its trees trace 1.4 % (cfg3 stand-in) to 3.6 % (cfg2) slower than the host SAH
+  // builder's, but 114 K triangles build in 4 ms instead of 22 ms and the host cores are not shared between the ranks
+  // of a multi-GPU job (profiles/r02_device_builder_ploc.txt); below that the host build is a few milliseconds.
+  bool on_device = cfg.bvh_builder == 2 || (cfg.bvh_builder == 0 && n_prims64 >= (1u << 14));
   if (const char* e = getenv("B2RT_BUILDER")) on_device = !strcmp(e, "gpu");
-  if (on_device && hs.n_prims() > 0) {
-    RCHECK(build_wide_bvh_device(d, cfg.max_leaf_size, cfg.bvh_width, cfg.treelet_bytes, stream, &dbvh, &wb));
+  on_device = on_device && n_prims64 > 0;
+  HostScene hs;
+  RCHECK(make_host_scene(d, &hs, !on_device));   // device build: the primitive records are made on the GPU (k_make_prims)
+  lap("host scene");
+  const size_t np = std::max<size_t>(1, hs.n_prims());
+  if (cap_prims < np) {
+    free_ptr(d_prim_geom); free_ptr(d_prim_material); d_prim_geom = nullptr; d_prim_material = nullptr;
+    cap_prims = np + np / 4;
+    B2RT_CUDA_OK(cudaMalloc(&d_prim_geom, cap_prims * PRIM_BYTES));
+    B2RT_CUDA_OK(cudaMalloc(&d_prim_material, cap_prims * 4));
+  }
+  WideBVH wb;
+  if (on_device) {
+    RCHECK(build_wide_bvh_device(d, cfg.max_leaf_size, cfg.bvh_width, cfg.treelet_bytes, stream, &dbvh, &wb, d_prim_geom));
     lap("bvh build (device)");
   } else {
     RCHECK(build_wide_bvh(hs, cfg.max_leaf_size, cfg.bvh_width, cfg.treelet_bytes, &wb));
@@ -662,13 +675,6 @@ int Renderer::set_scene(const b2rt_scene_desc* d) {
   }
   n_tris = hs.n_tris;
   n_lights = (uint32_t)hs.lights.size();
-  const size_t np = std::max<size_t>(1, hs.n_prims());
-  if (cap_prims < np) {
-    free_ptr(d_prim_geom); free_ptr(d_prim_material); d_prim_geom = nullptr; d_prim_material = nullptr;
-    cap_prims = np + np / 4;
-    B2RT_CUDA_OK(cudaMalloc(&d_prim_geom, cap_prims * PRIM_BYTES));
-    B2RT_CUDA_OK(cudaMalloc(&d_prim_material, cap_prims * 4));
-  }
   if (cap_mats < hs.materials.size()) {
     free_ptr(d_materials); d_materials = nullptr;
     cap_mats = hs.materials.size() + 16;
@@ -681,18 +687,19 @@ int Renderer::set_scene(const b2rt_scene_desc* d) {
     B2RT_CUDA_OK(cudaMalloc(&d_light_area, cap_lights * 4));
   }
   if (hs.n_prims()) {
-    B2RT_CUDA_OK(cudaMemcpy(d_prim_geom, hs.prim_geom.data(), (size_t)hs.n_prims() * PRIM_BYTES, cudaMemcpyHostToDevice));
+    if (!on_device) B2RT_CUDA_OK(cudaMemcpy(d_prim_geom, hs.prim_geom.data(), (size_t)hs.n_prims() * PRIM_BYTES, cudaMemcpyHostToDevice));
     B2RT_CUDA_OK(cudaMemcpy(d_prim_material, hs.prim_material.data(), (size_t)hs.n_prims() * 4, cudaMemcpyHostToDevice));
   }
   B2RT_CUDA_OK(cudaMemcpy(d_materials, hs.materials.data(), hs.materials.size() * sizeof(b2rt_material), cudaMemcpyHostToDevice));
-  if (!hs.tri_normals.empty()) {
-    if (cap_normals < hs.tri_normals.size()) {
+  if (d->tri_normals && d->n_tris) {   // straight from the caller's array
+    const size_t nn = (size_t)d->n_tris * 9;
+    if (cap_normals < nn) {
       free_ptr(d_tri_normals_buf); d_tri_normals_buf = nullptr;
-      cap_normals = hs.tri_normals.size() + hs.tri_normals.size() / 4;
+      cap_normals = nn + nn / 4;
       B2RT_CUDA_OK(cudaMalloc(&d_tri_normals_buf, cap_normals * 4));
     }
     d_tri_normals = d_tri_normals_buf;
-    B2RT_CUDA_OK(cudaMemcpy(d_tri_normals, hs.tri_normals.data(), hs.tri_normals.size() * 4, cudaMemcpyHostToDevice));
+    B2RT_CUDA_OK(cudaMemcpy(d_tri_normals, d->tri_normals, nn * 4, cudaMemcpyHostToDevice));
   } else {
     d_tri_normals = nullptr;
   }

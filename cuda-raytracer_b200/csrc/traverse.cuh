@@ -92,8 +92,9 @@ enum { CTRL_PAIRS0 = 0, CTRL_PAIRS1 = 1, CTRL_NEXT0 = 2, CTRL_NEXT1 = 3, CTRL_OV
 
 int upload_bvh(const WideBVH& h, DeviceBVH* d);
 // device builder (bvh_build_gpu.cu): fills *d directly; *meta gets everything of WideBVH but the blob
+// geom_out (optional): device buffer of n_prims * 48 bytes that receives the primitive records in scene order
 int build_wide_bvh_device(const b2rt_scene_desc* sc, uint32_t max_leaf, uint32_t width, uint32_t treelet_bytes, cudaStream_t s,
-                          DeviceBVH* d, WideBVH* meta);
+                          DeviceBVH* d, WideBVH* meta, void* geom_out = nullptr);
 void free_bvh(DeviceBVH* d);
 
 #define B2RT_CUDA_OK(call)                                                                          \

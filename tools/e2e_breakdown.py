@@ -7,12 +7,17 @@ import time
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, os.path.join(ROOT, "cuda-raytracer_b200"))
 import b2rt  # noqa: E402
+from b2rt import scene as S  # noqa: E402
 from b2rt.scene import Scene, place_camera  # noqa: E402
 
+cfg3 = len(sys.argv) > 1 and sys.argv[1] == "cfg3"          # python tools/e2e_breakdown.py [cfg3 [spp]]
 sc = Scene.load(os.path.join(ROOT, "scenes", "CBbunny.b2s"))
-cam = place_camera(sc, 1024, 768)
-pt = b2rt.PathTracer(ns_aa=64, max_ray_depth=8, ns_area_light=1, seed=1)
-pt.set_scene(sc); pt.set_camera(cam); pt.set_frame_size(1024, 768)
+W, H, SPP = (1920, 1080, int(sys.argv[2]) if len(sys.argv) > 2 else 32) if cfg3 else (1024, 768, 64)
+if cfg3:
+    sc = S.cfg3_standin(sc)
+cam = place_camera(sc, W, H)
+pt = b2rt.PathTracer(ns_aa=SPP, max_ray_depth=8, ns_area_light=1, seed=1)
+pt.set_scene(sc); pt.set_camera(cam); pt.set_frame_size(W, H)
 for _ in range(2):
     pt.start_raytracing(); pt.wait(); pt.image()
 acc = {}
