@@ -32,7 +32,7 @@ EXPORTS = [
     "b2rt_scene_load", "b2rt_scene_save", "b2rt_load_dae", "b2rt_scene_free", "b2rt_camera_place",
     "b2rt_comm_version", "b2rt_comm_unique_id", "b2rt_comm_create", "b2rt_comm_create_all", "b2rt_reduce_accum",
     "b2rt_reduce_accum_all", "b2rt_comm_destroy", "b2rt_bench_fp32", "b2rt_camera_look_at", "b2rt_save_png", "b2rt_save_exr",
-    "b2rt_write_png", "b2rt_write_exr",
+    "b2rt_write_png", "b2rt_write_exr", "b2rt_set_envmap",
 ]
 
 
@@ -94,6 +94,7 @@ def lib():
         L.b2rt_save_exr.argtypes = [C.c_char_p, vp, u32, u32]
         L.b2rt_write_png.argtypes = [vp, C.c_char_p]
         L.b2rt_write_exr.argtypes = [vp, C.c_char_p]
+        L.b2rt_set_envmap.argtypes = [vp, vp, u32, u32]
         L.b2rt_comm_unique_id.argtypes = [vp]
         L.b2rt_comm_create.argtypes = [i32, i32, vp, i32, C.POINTER(vp)]
         L.b2rt_comm_create_all.argtypes = [i32, vp, vp]
@@ -281,6 +282,8 @@ class PathTracer:
         self._scene = self._camera = None
         self.width = self.height = 0
         self.state = self.INIT
+        if envmap is not None:
+            self.set_envmap(envmap)
 
     def close(self):
         if getattr(self, "_h", None):
@@ -311,6 +314,15 @@ class PathTracer:
         if self.state != self.INIT:
             self.state = self.READY
         self._maybe_ready()
+
+    def set_envmap(self, rgb):
+        """Environment light (the `envmap` argument of PathTracer::PathTracer, src/pathtracer.h:57-60): float32 [h, w, 3],
+        row 0 = the +y pole, x = azimuth atan2(d.z, d.x) / 2 pi; None removes it."""
+        if rgb is None:
+            _check(lib().b2rt_set_envmap(self._h, None, 0, 0))
+        else:
+            a = np.ascontiguousarray(rgb, np.float32)
+            _check(lib().b2rt_set_envmap(self._h, a.ctypes.data, a.shape[1], a.shape[0]))
 
     def set_frame_size(self, width, height):
         _check(lib().b2rt_set_frame_size(self._h, width, height))

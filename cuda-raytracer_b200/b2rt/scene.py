@@ -11,7 +11,7 @@ import numpy as np
 
 from ._abi import Camera, Light, Material, SceneDesc
 
-MAT_DIFFUSE, MAT_MIRROR, MAT_GLASS, MAT_EMISSION, MAT_REFRACTION = 0, 1, 2, 3, 4
+MAT_DIFFUSE, MAT_MIRROR, MAT_GLASS, MAT_EMISSION, MAT_REFRACTION, MAT_GLOSSY = 0, 1, 2, 3, 4, 5
 LIGHT_AREA, LIGHT_POINT, LIGHT_DIRECTIONAL = 0, 1, 2
 
 

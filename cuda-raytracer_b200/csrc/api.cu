@@ -439,6 +439,7 @@ int b2rt_set_config(b2rt_renderer* h, const b2rt_config* cfg) {
   return B2RT_OK;
 }
 int b2rt_set_scene(b2rt_renderer* h, const b2rt_scene_desc* s) { if (!h) { set_error("null handle"); return B2RT_ERR_INVALID; } return h->r.set_scene(s); }
+int b2rt_set_envmap(b2rt_renderer* h, const float* rgb, uint32_t w, uint32_t hh) { if (!h) { set_error("null handle"); return B2RT_ERR_INVALID; } return h->r.set_envmap(rgb, w, hh); }
 int b2rt_set_camera(b2rt_renderer* h, const b2rt_camera* c) { if (!h || !c) { set_error("null argument"); return B2RT_ERR_INVALID; } return h->r.set_camera(c); }
 int b2rt_set_frame_size(b2rt_renderer* h, uint32_t w, uint32_t hh) { if (!h) { set_error("null handle"); return B2RT_ERR_INVALID; } return h->r.set_frame_size(w, hh); }
 int b2rt_start(b2rt_renderer* h) { if (!h) { set_error("null handle"); return B2RT_ERR_INVALID; } return h->r.start(); }

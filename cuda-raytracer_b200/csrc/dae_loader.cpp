@@ -317,6 +317,9 @@ struct Loader {
           m.kind = B2RT_MAT_EMISSION; set3(m.emission, floats_of(b->child("radiance"), "radiance", 3)); zero3(m.albedo);
         } else if (b->tag == "mirror") {
           m.kind = B2RT_MAT_MIRROR; set3(m.albedo, floats_of(b->child("reflectance"), "reflectance", 3));
+        } else if (b->tag == "glossy") {   // commented out in the reference's parser (collada.cpp:898-907); accepted here
+          m.kind = B2RT_MAT_GLOSSY; set3(m.albedo, floats_of(b->child("reflectance"), "reflectance", 3));
+          m.roughness = (float)floats_of(b->child("roughness"), "roughness", 1)[0];
         } else if (b->tag == "refraction") {
           m.kind = B2RT_MAT_REFRACTION; set3(m.transmittance, floats_of(b->child("transmittance"), "transmittance", 3));
           m.roughness = (float)floats_of(b->child("roughness"), "roughness", 1)[0];

@@ -41,6 +41,8 @@ struct SceneDev {
   const b2rt_light* lights;
   const float* light_area;
   uint32_t n_tris, n_lights;
+  const float* env;             // environment map, RGB triples, index x + y*w (row 0 = the +y pole), or nullptr
+  uint32_t env_w, env_h;
 };
 
 // Rays live in DENSE lists (what the traversal streams with TMA): entry i of the bounce-b list is the ray of path
@@ -90,6 +92,35 @@ k_raygen(WaveParams wp, CamDev cam, PathBufs pb) {
   pb.lslot[slot] = slot;
   pb.thr[slot] = make_float4(1.f, 1.f, 1.f, 1.f);
   pb.rad[slot] = make_float4(0.f, 0.f, 0.f, 0.f);
+}
+
+// bilinear look-up of the environment map in direction d (unit): wraps in azimuth, clamps at the poles.  Not inlined:
+// only scenes with an environment map pay for its registers.
+__device__ __noinline__ f3 env_lookup(const float* __restrict__ env, uint32_t ew, uint32_t eh, f3 d) {
+  const float u = atan2_turns(d.z, d.x);
+  const float cy = d.y > 1.0f ? 1.0f : (d.y < -1.0f ? -1.0f : d.y);
+  const float sy = 1.0f - cy * cy;
+  const float v = 2.0f * atan2_turns(__fsqrt_rn(sy < 0.0f ? 0.0f : sy), cy);
+  const float fx = u * (float)ew - 0.5f, fy = v * (float)eh - 0.5f;
+  const float flx = floorf(fx), fly = floorf(fy);
+  const float tx = fx - flx, ty = fy - fly;
+  int x0 = (int)flx, y0 = (int)fly;
+  int x1 = x0 + 1, y1 = y0 + 1;
+  const int W = (int)ew, H = (int)eh;
+  x0 = ((x0 % W) + W) % W; x1 = ((x1 % W) + W) % W;
+  y0 = y0 < 0 ? 0 : (y0 > H - 1 ? H - 1 : y0); y1 = y1 < 0 ? 0 : (y1 > H - 1 ? H - 1 : y1);
+  auto px = [&](int x, int y) { const float* p = env + 3 * ((size_t)y * W + x); return mk3(__ldg(p), __ldg(p + 1), __ldg(p + 2)); };
+  const f3 a = px(x0, y0) * (1.0f - tx) + px(x1, y0) * tx;
+  const f3 b = px(x0, y1) * (1.0f - tx) + px(x1, y1) * tx;
+  return a * (1.0f - ty) + b * ty;
+}
+
+// f(wo, wi) of the glossy BSDF in the local frame: reflectance * (n + 2) / (2 pi) * cos^n(wi, mirror direction of wo)
+__device__ __noinline__ f3 glossy_f(const b2rt_material* mp, f3 wo, f3 wi) {
+  const uint32_t n = glossy_exponent(__ldg(&mp->roughness));
+  float c = dot3(mk3(-wo.x, -wo.y, wo.z), wi);
+  if (!(c > 0.0f)) c = 0.0f;
+  return mk3(__ldg(&mp->albedo[0]), __ldg(&mp->albedo[1]), __ldg(&mp->albedo[2])) * (((float)(n + 2u) * 0.159154943091895336f) * powi(c, n));
 }
 
 // make_coord_space, src/bsdf.cpp:14-33
@@ -174,6 +205,9 @@ __device__ __forceinline__ uint2 block_append2(uint32_t* counter_a, bool pred_a,
 #define B2RT_SHADE_THREADS 128
 #endif
 constexpr int SHADE_THREADS = B2RT_SHADE_THREADS;   // <= 256 (block_append's scratch holds 8 warp counts)
+// EXT = the scene has an environment map or a glossy material; the common instantiation carries neither (their
+// look-up / lobe calls cost registers the 64-register kernel does not have to spare)
+template <bool EXT>
 __global__ void __launch_bounds__(SHADE_THREADS, B2RT_SHADE_OCC)
 k_shade(WaveParams wp, SceneDev sc, PathBufs pb, uint32_t b) {
   const uint32_t n = pb.counts[ACT0 + b];
@@ -204,7 +238,7 @@ k_shade(WaveParams wp, SceneDev sc, PathBufs pb, uint32_t b) {
   // BASELINE config): the one sample is kept in registers and appended at the end ONLY if it can contribute -- on the
   // box scenes 45 % of the light samples lie behind the surface, and null rays cost the any-hit traversal a list
   // entry each (stream + retire).
-  const bool wants_shadow = prim != 0xFFFFFFFFu && m_kind == B2RT_MAT_DIFFUSE && S > 0;
+  const bool wants_shadow = prim != 0xFFFFFFFFu && (m_kind == B2RT_MAT_DIFFUSE || (EXT && m_kind == B2RT_MAT_GLOSSY)) && S > 0;
   const bool single = S == 1;
   __shared__ uint32_t s_app[10];
   uint32_t q0 = 0xFFFFFFFFu;
@@ -218,7 +252,16 @@ k_shade(WaveParams wp, SceneDev sc, PathBufs pb, uint32_t b) {
   f3 sh_c = mk3(0.f, 0.f, 0.f);
   if (i < n) {
     if (!single) pb.s_q0[slot] = q0;
-    if (prim != 0xFFFFFFFFu) {
+    if (prim == 0xFFFFFFFFu) {
+      // the ray left the scene: EnvironmentLight::sample_dir, counted like emitted radiance (camera rays, delta bounces)
+      if (EXT && sc.env && thr4.w != 0.f) {
+        const f3 e = env_lookup(sc.env, sc.env_w, sc.env_h, mk3(rd.x, rd.y, rd.z));
+        float4 L = pb.rad[slot];
+        const f3 add = mk3(thr4.x, thr4.y, thr4.z) * e;
+        L.x = L.x + add.x; L.y = L.y + add.y; L.z = L.z + add.z;
+        pb.rad[slot] = L;
+      }
+    } else {
       const float t = __uint_as_float((uint32_t)(h >> 32));
       f3 thr = mk3(thr4.x, thr4.y, thr4.z);
       const bool count_emission = thr4.w != 0.f;
@@ -259,19 +302,35 @@ k_shade(WaveParams wp, SceneDev sc, PathBufs pb, uint32_t b) {
         const uint32_t pix = wp.pix0 + slot / wp.spp;
         const uint32_t sample = wp.sample0 + (slot % wp.spp) * wp.sample_stride;
 
-        if (m_kind == B2RT_MAT_DIFFUSE) {
-          // direct lighting: src/pathtracer.cpp:439-478 + shadow ray (Task 4)
+        if (m_kind == B2RT_MAT_DIFFUSE || (EXT && m_kind == B2RT_MAT_GLOSSY)) {
+          // direct lighting: src/pathtracer.cpp:439-478 + shadow ray (Task 4); the environment map is one more light
           uint32_t j = 0;
-          for (uint32_t li = 0; li < sc.n_lights; ++li) {
-            const b2rt_light* lt = sc.lights + li;
-            const int32_t lt_kind = __ldg(&lt->kind);
+          const uint32_t n_lights_all = sc.n_lights + ((EXT && sc.env) ? 1u : 0u);
+          for (uint32_t li = 0; li < n_lights_all; ++li) {
+            const bool is_env = EXT && li == sc.n_lights;
+            const b2rt_light* lt = sc.lights + (is_env ? 0u : li);     // (never dereferenced for the environment light)
+            const int32_t lt_kind = is_env ? 3 : __ldg(&lt->kind);
             const uint32_t ns = lt_kind == B2RT_LIGHT_AREA ? max(1u, wp.ns_area_light) : 1u;
             for (uint32_t k = 0; k < ns; ++k, ++j) {
               f3 wi; float dist, pdf; f3 Lr;
-              const f3 lp = mk3(__ldg(&lt->position[0]), __ldg(&lt->position[1]), __ldg(&lt->position[2]));
-              const f3 ld = mk3(__ldg(&lt->direction[0]), __ldg(&lt->direction[1]), __ldg(&lt->direction[2]));
-              const f3 radc = mk3(__ldg(&lt->radiance[0]), __ldg(&lt->radiance[1]), __ldg(&lt->radiance[2]));
-              if (lt_kind == B2RT_LIGHT_AREA) {
+              f3 lp = mk3(0, 0, 0), ld = mk3(0, 0, 0), radc = mk3(0, 0, 0);
+              if (!is_env) {
+                lp = mk3(__ldg(&lt->position[0]), __ldg(&lt->position[1]), __ldg(&lt->position[2]));
+                ld = mk3(__ldg(&lt->direction[0]), __ldg(&lt->direction[1]), __ldg(&lt->direction[2]));
+                radc = mk3(__ldg(&lt->radiance[0]), __ldg(&lt->radiance[1]), __ldg(&lt->radiance[2]));
+              }
+              if (is_env) {
+                // EnvironmentLight::sample_L, uniform over the sphere: pdf = 1 / (4 pi)
+                const uint4 r4 = philox4x32_10(pix, sample, b, 1 + j, wp.k0, wp.k1);
+                const float zz = 1.0f - 2.0f * u01(r4.x);
+                float sn, cs;
+                sincos2pi(u01(r4.y), &sn, &cs);
+                const float rr2 = 1.0f - zz * zz;
+                const float rr = __fsqrt_rn(rr2 < 0.0f ? 0.0f : rr2);
+                wi = mk3(rr * cs, zz, rr * sn);
+                dist = INF_F; pdf = 0.0795774715459476679f;
+                Lr = env_lookup(sc.env, sc.env_w, sc.env_h, wi);
+              } else if (lt_kind == B2RT_LIGHT_AREA) {
                 // AreaLight::sample_L, src/static_scene/light.cpp:81-92
                 const uint4 r4 = philox4x32_10(pix, sample, b, 1 + j, wp.k0, wp.k1);
                 const float ux = u01(r4.x) - 0.5f, uy = u01(r4.y) - 0.5f;
@@ -298,7 +357,8 @@ k_shade(WaveParams wp, SceneDev sc, PathBufs pb, uint32_t b) {
               if (single) {
                 if (valid) {
                   const float wgt = __fdiv_rn(cos_in, (float)ns * pdf);
-                  const f3 f = mk3(__ldg(&mp->albedo[0]), __ldg(&mp->albedo[1]), __ldg(&mp->albedo[2])) * 0.318309886183790672f;
+                  const f3 f = (EXT && m_kind == B2RT_MAT_GLOSSY) ? glossy_f(mp, wo, mk3(dot3(wi, X), dot3(wi, Y), cos_in))
+                                                         : mk3(__ldg(&mp->albedo[0]), __ldg(&mp->albedo[1]), __ldg(&mp->albedo[2])) * 0.318309886183790672f;
                   sh_c = thr * f * Lr * wgt;
                   sh_d = make_float4(wi.x, wi.y, wi.z, dist - wp.eps);
                   sh_valid = true;
@@ -306,7 +366,8 @@ k_shade(WaveParams wp, SceneDev sc, PathBufs pb, uint32_t b) {
                 }
               } else if (valid) {
                 const float wgt = __fdiv_rn(cos_in, (float)ns * pdf);
-                const f3 f = mk3(__ldg(&mp->albedo[0]), __ldg(&mp->albedo[1]), __ldg(&mp->albedo[2])) * 0.318309886183790672f;
+                const f3 f = (EXT && m_kind == B2RT_MAT_GLOSSY) ? glossy_f(mp, wo, mk3(dot3(wi, X), dot3(wi, Y), cos_in))
+                                                       : mk3(__ldg(&mp->albedo[0]), __ldg(&mp->albedo[1]), __ldg(&mp->albedo[2])) * 0.318309886183790672f;
                 const f3 c = thr * f * Lr * wgt;
                 const float tmx = dist - wp.eps;
                 pb.s_o[q] = make_float4(P.x, P.y, P.z, wp.eps);
@@ -329,13 +390,15 @@ k_shade(WaveParams wp, SceneDev sc, PathBufs pb, uint32_t b) {
           const float u2 = u01(r4.z), u3 = u01(r4.w);
           f3 wi_l, weight;
           bool delta = false;
-          if (m_kind == B2RT_MAT_DIFFUSE) {
+          if (m_kind == B2RT_MAT_DIFFUSE || (EXT && m_kind == B2RT_MAT_GLOSSY)) {
             const float r = __fsqrt_rn(u2);
             float s, c;
             sincos2pi(u3, &s, &c);
             const float zz = 1.0f - u2;
             wi_l = mk3(r * c, r * s, __fsqrt_rn(zz < 0.0f ? 0.0f : zz));
-            weight = mk3(__ldg(&mp->albedo[0]), __ldg(&mp->albedo[1]), __ldg(&mp->albedo[2]));
+            // cosine-weighted sample, pdf = cos / pi: f * cos / pdf = f * pi (= albedo for the diffuse BSDF)
+            weight = (!EXT || m_kind == B2RT_MAT_DIFFUSE) ? mk3(__ldg(&mp->albedo[0]), __ldg(&mp->albedo[1]), __ldg(&mp->albedo[2]))
+                                                          : glossy_f(mp, wo, wi_l) * 3.14159265358979324f;
           } else if (m_kind == B2RT_MAT_MIRROR) {
             wi_l = mk3(-wo.x, -wo.y, wo.z);
             weight = mk3(__ldg(&mp->albedo[0]), __ldg(&mp->albedo[1]), __ldg(&mp->albedo[2]));
@@ -604,7 +667,7 @@ void Renderer::destroy() {
   ev_sync.clear();
   if (stream2) { cudaStreamDestroy(stream2); stream2 = nullptr; }
   release_scene();
-  free_ptr(accum); free_ptr(img_a); free_ptr(img_b); free_ptr(ldr);
+  free_ptr(accum); free_ptr(img_a); free_ptr(img_b); free_ptr(ldr); free_ptr(d_env); d_env = nullptr;
   if (host_image) { cudaFreeHost(host_image); host_image = nullptr; host_image_cap = 0; }
   if (ev_start) cudaEventDestroy(ev_start);
   if (ev_done) cudaEventDestroy(ev_done);
@@ -718,10 +781,26 @@ int Renderer::set_scene(const b2rt_scene_desc* d) {
   shadow_per_hit = 0;
   for (auto& l : hs.lights) shadow_per_hit += l.kind == B2RT_LIGHT_AREA ? std::max(1u, cfg.ns_area_light) : 1u;
   lights_host = hs.lights;
+  have_glossy = false;
+  for (auto& m : hs.materials) have_glossy = have_glossy || m.kind == B2RT_MAT_GLOSSY;
   have_scene = true;
   B2RT_CUDA_OK(cudaDeviceSynchronize());   // uploads above used the legacy stream; work runs on `stream`
   lap("scene upload");
   return B2RT_OK;
+}
+
+int Renderer::set_envmap(const float* rgb, uint32_t w, uint32_t h) {
+  RCHECK(set_device());
+  if (running) RCHECK(wait());
+  B2RT_CUDA_OK(cudaStreamSynchronize(stream));
+  free_ptr(d_env); d_env = nullptr; env_w = env_h = 0;
+  if (rgb) {
+    if (!w || !h || (uint64_t)w * h > (1ull << 28)) { set_error("invalid environment map size"); return B2RT_ERR_INVALID; }
+    B2RT_CUDA_OK(cudaMalloc(&d_env, (size_t)w * h * 12));
+    B2RT_CUDA_OK(cudaMemcpy(d_env, rgb, (size_t)w * h * 12, cudaMemcpyHostToDevice));
+    env_w = w; env_h = h;
+  }
+  return clear();
 }
 
 int Renderer::set_camera(const b2rt_camera* c) {
@@ -759,6 +838,7 @@ int Renderer::ensure_wave() {
   // shadow rays per interaction can change with the knobs
   uint32_t S = 0;
   for (auto& l : lights_host) S += l.kind == B2RT_LIGHT_AREA ? std::max(1u, cfg.ns_area_light) : 1u;
+  if (d_env) S += 1;   // the environment map is sampled like one more light
   shadow_per_hit = S;
   const uint64_t n_pix = (uint64_t)width * height;
   uint64_t cap = cfg.max_wave_paths ? cfg.max_wave_paths : (64u << 20);   // ~180 B of state per path + two schedulers: ~19 GB of the 180 GB
@@ -826,6 +906,7 @@ int Renderer::make_frame_ctx(FrameCtx* fc) {
   SceneDev& sd = fc->sd;
   sd.prim_geom = (const float4*)d_prim_geom; sd.tri_normals = d_tri_normals; sd.prim_material = d_prim_material;
   sd.materials = d_materials; sd.lights = d_lights; sd.light_area = d_light_area; sd.n_tris = n_tris; sd.n_lights = n_lights;
+  sd.env = d_env; sd.env_w = d_env ? env_w : 0u; sd.env_h = d_env ? env_h : 0u;
   PathBufs& pb = fc->pb;
   pb.lo = (float4*)l_o[0]; pb.ld = (float4*)l_d[0]; pb.lh = l_h[0]; pb.lslot = l_slot[0];
   pb.no = (float4*)l_o[1]; pb.nd = (float4*)l_d[1]; pb.nh = l_h[1]; pb.nslot = l_slot[1];
@@ -845,6 +926,7 @@ int Renderer::enqueue_wave(const FrameCtx& fc, const WaveParams& wp, uint32_t st
     pb.no = (float4*)l_o[nxt]; pb.nd = (float4*)l_d[nxt]; pb.nh = l_h[nxt]; pb.nslot = l_slot[nxt];
   };
   const uint32_t max_depth = fc.max_depth, S = fc.S;
+  const bool shade_ext = d_env != nullptr || have_glossy;
   const uint32_t n = wp.n_pix * wp.spp;
   const uint32_t g = (n + 255) / 256;
   bind_lists(0);   // k_raygen fills list 0; k_shade(b) appends the continuing paths to list (b+1)&1
@@ -861,7 +943,9 @@ int Renderer::enqueue_wave(const FrameCtx& fc, const WaveParams& wp, uint32_t st
     RCHECK(tracer.trace_sliced(stream, pb.lo, pb.ld, pb.lh, counts + ACT0 + b, n, false));
     // shade(b) adds emission to the radiance that resolve(b - 1) updates and rewrites the shadow list it reads
     if (pending_resolve) { B2RT_CUDA_OK(cudaStreamWaitEvent(stream, ev_sync[2 * (b - 1) + 1], 0)); pending_resolve = false; }
-    k_shade<<<(n + SHADE_THREADS - 1) / SHADE_THREADS, SHADE_THREADS, 0, stream>>>(wp, fc.sd, pb, b); launches++;
+    if (shade_ext) k_shade<true><<<(n + SHADE_THREADS - 1) / SHADE_THREADS, SHADE_THREADS, 0, stream>>>(wp, fc.sd, pb, b);
+    else k_shade<false><<<(n + SHADE_THREADS - 1) / SHADE_THREADS, SHADE_THREADS, 0, stream>>>(wp, fc.sd, pb, b);
+    launches++;
     if (S > 0) {
       if (ov) {
         // shadow rays of bounce b on the second stream, next to the closest-hit trace of bounce b + 1

@@ -36,10 +36,11 @@ struct Renderer {
   void* d_prim_geom = nullptr; float* d_tri_normals = nullptr; float* d_tri_normals_buf = nullptr; uint32_t* d_prim_material = nullptr;
   b2rt_material* d_materials = nullptr; b2rt_light* d_lights = nullptr; float* d_light_area = nullptr;
   std::vector<b2rt_light> lights_host;
+  float* d_env = nullptr; uint32_t env_w = 0, env_h = 0;   // environment map (b2rt_set_envmap)
   size_t cap_prims = 0, cap_normals = 0, cap_mats = 0, cap_lights = 0;   // grow-only device array capacities (elements)
   uint32_t n_tris = 0, n_lights = 0, n_wide_nodes = 0, shadow_per_hit = 0;
   double build_ms = 0;
-  bool have_scene = false, have_camera = false, running = false, bvh_stale = false;
+  bool have_scene = false, have_camera = false, running = false, bvh_stale = false, have_glossy = false;
   b2rt_camera cam{};
   // frame
   uint32_t width = 0, height = 0;
@@ -73,6 +74,7 @@ struct Renderer {
   void release_wave();
   int set_scene(const b2rt_scene_desc* d);
   int set_camera(const b2rt_camera* c);
+  int set_envmap(const float* rgb, uint32_t w, uint32_t h);
   int set_frame_size(uint32_t w, uint32_t h);
   int clear();
   int ensure_wave();

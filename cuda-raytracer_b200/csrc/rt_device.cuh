@@ -119,4 +119,42 @@ __device__ __forceinline__ void sincos2pi(float u, float* s_out, float* c_out) {
   *s_out = so; *c_out = co;
 }
 
+// atan2(y, x) / (2 pi) in [0, 1): octant reduction + the polynomial of Abramowitz & Stegun 4.4.49 in plain fp32
+// multiplies / adds and one IEEE division -- the same expression as the oracle's, so environment-map look-ups are
+// bit-identical (libm's atan2f / acosf differ between glibc and CUDA)
+__device__ __forceinline__ float atan2_turns(float y, float x) {
+  const float ax = fabsf(x), ay = fabsf(y);
+  const bool swap = ay > ax;
+  const float num = swap ? ax : ay, den = swap ? ay : ax;
+  const float a = den > 0.0f ? __fdiv_rn(num, den) : 0.0f;
+  const float a2 = a * a;
+  float p = 0.0028662257f;
+  p = p * a2 - 0.0161657367f;
+  p = p * a2 + 0.0429096138f;
+  p = p * a2 - 0.0752896400f;
+  p = p * a2 + 0.1065626393f;
+  p = p * a2 - 0.1420889944f;
+  p = p * a2 + 0.1999355085f;
+  p = p * a2 - 0.3333314528f;
+  p = p * a2 + 1.0f;
+  float r = (a * p) * 0.159154943091895336f;
+  if (swap) r = 0.25f - r;
+  if (x < 0.0f) r = 0.5f - r;
+  if (y < 0.0f) r = 1.0f - r;
+  return r >= 1.0f ? 0.0f : r;
+}
+
+__device__ __forceinline__ float powi(float b, uint32_t e) {
+  float r = 1.0f;
+  while (e) { if (e & 1u) r = r * b; b = b * b; e >>= 1; }
+  return r;
+}
+// exponent of the glossy lobe (B2RT_MAT_GLOSSY, include/b2rt.h)
+__device__ __forceinline__ uint32_t glossy_exponent(float roughness) {
+  const float r2 = roughness * roughness;
+  if (!(r2 > 4.8e-4f)) return 4096u;
+  const float e = __fdiv_rn(2.0f, r2) - 2.0f;
+  return e < 1.0f ? 1u : (e > 4096.0f ? 4096u : (uint32_t)e);
+}
+
 }  // namespace b2rt

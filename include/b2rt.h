@@ -51,7 +51,10 @@ typedef enum b2rt_material_kind {
   B2RT_MAT_MIRROR = 1,     /* MirrorBSDF    (delta) */
   B2RT_MAT_GLASS = 2,      /* GlassBSDF     (delta, Fresnel reflect/refract) */
   B2RT_MAT_EMISSION = 3,   /* EmissionBSDF  (f = 0, get_emission() = radiance) */
-  B2RT_MAT_REFRACTION = 4  /* RefractionBSDF(delta, always refract) */
+  B2RT_MAT_REFRACTION = 4, /* RefractionBSDF(delta, always refract) */
+  B2RT_MAT_GLOSSY = 5      /* GlossyBSDF(reflectance, roughness) (src/bsdf.h:143-162, commented out in the checkout):
+                              normalised Phong lobe about the mirror direction, f = albedo (n+2)/(2 pi) cos^n, with the
+                              INTEGER exponent n = clamp(int(2 / roughness^2) - 2, 1, 4096); not delta */
 } b2rt_material_kind;
 
 typedef struct b2rt_material {
@@ -60,7 +63,7 @@ typedef struct b2rt_material {
   float transmittance[3];  /* glass / refraction */
   float emission[3];       /* EmissionBSDF radiance */
   float ior;               /* glass / refraction */
-  float roughness;         /* parsed, unused (the reference ignores it too) */
+  float roughness;         /* glossy: lobe width (see B2RT_MAT_GLOSSY); parsed but unused for glass / refraction */
 } b2rt_material;
 
 typedef enum b2rt_light_kind {
@@ -248,6 +251,13 @@ int b2rt_create(const b2rt_config* cfg, b2rt_renderer** out);
 int b2rt_set_config(b2rt_renderer* r, const b2rt_config* cfg); /* ns_aa/max_ray_depth/... knobs */
 int b2rt_set_scene(b2rt_renderer* r, const b2rt_scene_desc* scene);
 int b2rt_set_camera(b2rt_renderer* r, const b2rt_camera* cam);
+/* Environment light: the `HDRImageBuffer* envmap` argument of PathTracer::PathTracer (src/pathtracer.h:57-60; CLI -e,
+ * src/main.cpp:78-105) + EnvironmentLight (src/static_scene/environment_light.h; sample_L / sample_dir are stubs in the
+ * checkout).  rgb = width*height RGB fp32 triples, index x + y*width, row 0 = the +y pole, x = azimuth
+ * atan2(d.z, d.x) / 2 pi; copied.  NULL removes it.  Rays that leave the scene see the map (bilinear look-up; counted
+ * like emitted radiance: camera rays and after delta bounces); every diffuse / glossy interaction samples it as one
+ * more light, uniformly over the sphere.  Restarts accumulation. */
+int b2rt_set_envmap(b2rt_renderer* r, const float* rgb, uint32_t width, uint32_t height);
 int b2rt_set_frame_size(b2rt_renderer* r, uint32_t width, uint32_t height);
 int b2rt_start(b2rt_renderer* r);
 int b2rt_is_done(b2rt_renderer* r);     /* 1 done, 0 running, <0 error */

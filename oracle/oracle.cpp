@@ -102,6 +102,46 @@ inline void sincos2pi(float u, float* s_out, float* c_out) {
   }
 }
 
+// atan2(y, x) / (2 pi) in [0, 1): octant reduction + the polynomial of Abramowitz & Stegun 4.4.49 (|err| <= 2e-8 on
+// [0, 1]) in plain fp32 multiplies / adds and one IEEE division, restated identically in the kernels (rt_device.cuh),
+// so that environment-map lookups are bit-identical (libm's atan2f / acosf differ between glibc and CUDA).
+inline float atan2_turns(float y, float x) {
+  const float ax = fabsf(x), ay = fabsf(y);
+  const bool swap = ay > ax;
+  const float num = swap ? ax : ay, den = swap ? ay : ax;
+  const float a = den > 0.0f ? num / den : 0.0f;
+  const float a2 = a * a;
+  float p = 0.0028662257f;
+  p = p * a2 - 0.0161657367f;
+  p = p * a2 + 0.0429096138f;
+  p = p * a2 - 0.0752896400f;
+  p = p * a2 + 0.1065626393f;
+  p = p * a2 - 0.1420889944f;
+  p = p * a2 + 0.1999355085f;
+  p = p * a2 - 0.3333314528f;
+  p = p * a2 + 1.0f;
+  float r = (a * p) * 0.159154943091895336f;   // turns
+  if (swap) r = 0.25f - r;
+  if (x < 0.0f) r = 0.5f - r;
+  if (y < 0.0f) r = 1.0f - r;
+  return r >= 1.0f ? 0.0f : r;
+}
+
+// integer power by squaring (the glossy lobe's exponent is an integer so that no pow() is involved)
+inline float powi(float b, uint32_t e) {
+  float r = 1.0f;
+  while (e) { if (e & 1u) r = r * b; b = b * b; e >>= 1; }
+  return r;
+}
+// GlossyBSDF(reflectance, roughness) (src/bsdf.h:143-162, commented out in the checkout; bodies are stubs,
+// src/bsdf.cpp:59-70): a normalised Phong lobe about the mirror direction, exponent n = clamp(int(2 / roughness^2) - 2, 1, 4096)
+inline uint32_t glossy_exponent(float roughness) {
+  const float r2 = roughness * roughness;
+  if (!(r2 > 4.8e-4f)) return 4096u;
+  const float e = 2.0f / r2 - 2.0f;
+  return e < 1.0f ? 1u : (e > 4096.0f ? 4096u : (uint32_t)e);
+}
+
 // ---- primitives -----------------------------------------------------------------------------------
 struct Prim {  // triangle: v0,e1,e2 ; sphere: v0 = centre, e1.x = radius
   V3 v0, e1, e2;
@@ -203,6 +243,9 @@ struct Scene {
   std::vector<b2rt_material> mats;
   std::vector<b2rt_light> lights;
   uint32_t n_tris = 0, n_spheres = 0;
+  // environment map (EnvironmentLight, src/static_scene/environment_light.h; PathTracer ctor argument envmap,
+  // src/pathtracer.h:57-60): RGB fp32, index x + y*w, row 0 = the +y pole, x = azimuth atan2(z, x) / 2 pi
+  std::vector<float> env; uint32_t env_w = 0, env_h = 0;
   // BVH
   std::vector<uint32_t> order;      // BVHAccel::primitives after the build (getSortedPrimitives)
   std::vector<BNode> nodes;         // pre-order, node 0 = root
@@ -407,6 +450,39 @@ inline void generate_ray(const Cam& c, float sx, float sy, V3* o, V3* d) {
   *d = normalize(w);
 }
 
+// bilinear look-up of the environment map in direction d (unit): wraps in azimuth, clamps at the poles
+inline V3 env_lookup(const Scene& sc, V3 d) {
+  const float u = atan2_turns(d.z, d.x);
+  float cy = d.y > 1.0f ? 1.0f : (d.y < -1.0f ? -1.0f : d.y);
+  float sy = 1.0f - cy * cy;
+  const float v = 2.0f * atan2_turns(sqrtf(sy < 0.0f ? 0.0f : sy), cy);   // polar angle / pi
+  const float fx = u * (float)sc.env_w - 0.5f, fy = v * (float)sc.env_h - 0.5f;
+  const float flx = floorf(fx), fly = floorf(fy);
+  const float tx = fx - flx, ty = fy - fly;
+  int x0 = (int)flx, y0 = (int)fly;
+  int x1 = x0 + 1, y1 = y0 + 1;
+  const int W = (int)sc.env_w, H = (int)sc.env_h;
+  x0 = ((x0 % W) + W) % W; x1 = ((x1 % W) + W) % W;
+  y0 = y0 < 0 ? 0 : (y0 > H - 1 ? H - 1 : y0); y1 = y1 < 0 ? 0 : (y1 > H - 1 ? H - 1 : y1);
+  auto px = [&](int x, int y) { const float* p = &sc.env[3 * ((size_t)y * W + x)]; return mk(p[0], p[1], p[2]); };
+  const V3 a = px(x0, y0) * (1.0f - tx) + px(x1, y0) * tx;
+  const V3 b = px(x0, y1) * (1.0f - tx) + px(x1, y1) * tx;
+  return a * (1.0f - ty) + b * ty;
+}
+
+// f(wo, wi) of the non-delta BSDFs in the local frame (z = normal): diffuse albedo / pi (src/bsdf.cpp:37-39); glossy
+// reflectance * (n + 2) / (2 pi) * cos^n(angle between wi and the mirror direction of wo)
+inline V3 bsdf_f(const b2rt_material& m, V3 wo, V3 wi) {
+  const V3 alb = mk(m.albedo[0], m.albedo[1], m.albedo[2]);
+  if (m.kind == B2RT_MAT_GLOSSY) {
+    const uint32_t n = glossy_exponent(m.roughness);
+    float c = dot(mk(-wo.x, -wo.y, wo.z), wi);
+    if (!(c > 0.0f)) c = 0.0f;
+    return alb * (((float)(n + 2u) * 0.159154943091895336f) * powi(c, n));
+  }
+  return alb * 0.318309886183790672f;
+}
+
 struct RenderCtx {
   const Scene* sc;
   Cam cam;
@@ -442,7 +518,11 @@ V3 trace_path(const RenderCtx& rc, uint32_t pix, uint32_t x, uint32_t y, uint32_
     Hit hit;
     if (b == 0) cn->rays_camera++; else cn->rays_bounce++;
     closest_bvh(sc, o, d, tmin, INF, &hit, cn);
-    if (hit.prim == 0xFFFFFFFFu) break;
+    if (hit.prim == 0xFFFFFFFFu) {
+      // EnvironmentLight::sample_dir (src/static_scene/environment_light.h): counted like emitted radiance
+      if (sc.env_w && count_emission) L = L + thr * env_lookup(sc, d);
+      break;
+    }
     const b2rt_material& m = sc.mats[sc.prim_mat[hit.prim]];
     if (m.kind == B2RT_MAT_EMISSION) {
       if (count_emission) L = L + thr * mk(m.emission[0], m.emission[1], m.emission[2]);
@@ -470,17 +550,31 @@ V3 trace_path(const RenderCtx& rc, uint32_t pix, uint32_t x, uint32_t y, uint32_
     V3 wo_w = neg(d);
     V3 wo = mk(dot(wo_w, X), dot(wo_w, Y), dot(wo_w, Z));
 
-    if (m.kind == B2RT_MAT_DIFFUSE) {
+    if (m.kind == B2RT_MAT_DIFFUSE || m.kind == B2RT_MAT_GLOSSY) {
       uint32_t j = 0;
-      for (size_t li = 0; li < sc.lights.size(); ++li) {
-        const b2rt_light& lt = sc.lights[li];
-        uint32_t ns = lt.kind == B2RT_LIGHT_AREA ? std::max(1u, rc.cfg.ns_area_light) : 1u;
+      const size_t n_lights = sc.lights.size() + (sc.env_w ? 1 : 0);   // the environment map is one more light
+      for (size_t li = 0; li < n_lights; ++li) {
+        const bool is_env = li == sc.lights.size();
+        static const b2rt_light no_light = {};
+        const b2rt_light& lt = is_env ? no_light : sc.lights[li];
+        uint32_t ns = (!is_env && lt.kind == B2RT_LIGHT_AREA) ? std::max(1u, rc.cfg.ns_area_light) : 1u;
         for (uint32_t k = 0; k < ns; ++k, ++j) {
           V3 wi; float dist, pdf; V3 Lr;
           V3 lp = mk(lt.position[0], lt.position[1], lt.position[2]);
           V3 ld = mk(lt.direction[0], lt.direction[1], lt.direction[2]);
           V3 rad = mk(lt.radiance[0], lt.radiance[1], lt.radiance[2]);
-          if (lt.kind == B2RT_LIGHT_AREA) {
+          if (is_env) {
+            // EnvironmentLight::sample_L, uniform over the sphere: pdf = 1 / (4 pi)
+            philox4x32_10(pix, sample, b, 1 + j, k0, k1, r4);
+            const float zz = 1.0f - 2.0f * u01(r4[0]);
+            float sn, cs;
+            sincos2pi(u01(r4[1]), &sn, &cs);
+            const float rr2 = 1.0f - zz * zz;
+            const float rr = sqrtf(rr2 < 0.0f ? 0.0f : rr2);
+            wi = mk(rr * cs, zz, rr * sn);
+            dist = INF; pdf = 0.0795774715459476679f;
+            Lr = env_lookup(sc, wi);
+          } else if (lt.kind == B2RT_LIGHT_AREA) {
             philox4x32_10(pix, sample, b, 1 + j, k0, k1, r4);
             float ux = u01(r4[0]) - 0.5f, uy = u01(r4[1]) - 0.5f;
             V3 dv = lp + mk(lt.dim_x[0], lt.dim_x[1], lt.dim_x[2]) * ux + mk(lt.dim_y[0], lt.dim_y[1], lt.dim_y[2]) * uy - P;
@@ -507,7 +601,7 @@ V3 trace_path(const RenderCtx& rc, uint32_t pix, uint32_t x, uint32_t y, uint32_
           cn->rays_shadow++;
           if (occluded_bvh(sc, P, wi, rc.eps, dist - rc.eps, cn)) continue;
           float wgt = cos_in / ((float)ns * pdf);                  // pathtracer.cpp:473
-          V3 f = mk(m.albedo[0], m.albedo[1], m.albedo[2]) * 0.318309886183790672f;  // bsdf.cpp:37-39
+          V3 f = bsdf_f(m, wo, mk(dot(wi, X), dot(wi, Y), cos_in));
           L = L + thr * f * Lr * wgt;
         }
       }
@@ -520,12 +614,13 @@ V3 trace_path(const RenderCtx& rc, uint32_t pix, uint32_t x, uint32_t y, uint32_
     float u2 = u01(r4[2]), u3 = u01(r4[3]);
     V3 wi_l, weight;
     bool delta = false;
-    if (m.kind == B2RT_MAT_DIFFUSE) {
+    if (m.kind == B2RT_MAT_DIFFUSE || m.kind == B2RT_MAT_GLOSSY) {
       float r = sqrtf(u2), s, c;
       sincos2pi(u3, &s, &c);
       float zz = 1.0f - u2;
       wi_l = mk(r * c, r * s, sqrtf(zz < 0.0f ? 0.0f : zz));
-      weight = mk(m.albedo[0], m.albedo[1], m.albedo[2]);  // f*cos/pdf = albedo
+      // cosine-weighted sample, pdf = cos / pi: f * cos / pdf = f * pi (= albedo for the diffuse BSDF)
+      weight = m.kind == B2RT_MAT_DIFFUSE ? mk(m.albedo[0], m.albedo[1], m.albedo[2]) : bsdf_f(m, wo, wi_l) * 3.14159265358979324f;
     } else if (m.kind == B2RT_MAT_MIRROR) {
       wi_l = mk(-wo.x, -wo.y, wo.z);
       weight = mk(m.albedo[0], m.albedo[1], m.albedo[2]);
@@ -620,6 +715,13 @@ void* orc_scene_create(const b2rt_scene_desc* d, uint32_t max_leaf) {
   return sc;
 }
 void orc_scene_destroy(void* s) { delete (Scene*)s; }
+// environment map for orc_render (rgb = nullptr removes it)
+void orc_set_envmap(void* s, const float* rgb, uint32_t w, uint32_t h) {
+  Scene* sc = (Scene*)s;
+  sc->env.clear(); sc->env_w = sc->env_h = 0;
+  if (rgb && w && h) { sc->env.assign(rgb, rgb + (size_t)w * h * 3); sc->env_w = w; sc->env_h = h; }
+}
+float orc_atan2_turns(float y, float x) { return atan2_turns(y, x); }
 
 // BVH structure dump for the cross-check against oracle/_ref (the reference's own builder).
 uint32_t orc_bvh_node_count(void* s) { return (uint32_t)((Scene*)s)->nodes.size(); }

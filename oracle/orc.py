@@ -37,6 +37,8 @@ def lib():
         _lib.orc_filter.argtypes = [C.c_uint32, C.c_float, C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p]
         _lib.orc_philox.argtypes = [C.c_uint32] * 6 + [C.c_void_p]
         _lib.orc_sincos2pi.argtypes = [C.c_float, C.POINTER(C.c_float), C.POINTER(C.c_float)]
+        _lib.orc_set_envmap.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32]
+        _lib.orc_atan2_turns.argtypes = [C.c_float, C.c_float]; _lib.orc_atan2_turns.restype = C.c_float
     return _lib
 
 
@@ -78,6 +80,14 @@ class OracleScene:
         self.last_counters = dict(box_tests=int(cnt[0]), prim_tests=int(cnt[1]))
         return t, prim
 
+    def set_envmap(self, rgb):
+        """float32 [h, w, 3] environment map for render() (None removes it); layout as b2rt_set_envmap."""
+        if rgb is None:
+            lib().orc_set_envmap(self._h, None, 0, 0)
+        else:
+            a = np.ascontiguousarray(rgb, np.float32)
+            lib().orc_set_envmap(self._h, a.ctypes.data, a.shape[1], a.shape[0])
+
     def render(self, cam, cfg, width, height, threads=None, tile_stride=1):
         rgb = np.zeros((height, width, 3), np.float32)
         stats = np.zeros(5, np.uint64); sec = C.c_double(0)
@@ -114,6 +124,10 @@ def philox(c, k):
     out = np.zeros(4, np.uint32)
     lib().orc_philox(*[int(x) for x in c], int(k[0]), int(k[1]), out.ctypes.data)
     return out
+
+
+def atan2_turns(y, x):
+    return float(lib().orc_atan2_turns(float(y), float(x)))
 
 
 def sincos2pi(u):

@@ -799,3 +799,60 @@ def test_ten_million_triangle_soup_against_brute_force():
         assert np.array_equal(p, p_ref), (builder, int((p != p_ref).sum()))
         assert np.array_equal(t, t_ref), builder
         bvh.close()
+
+
+def _env_gradient(w=32, h=16):
+    """A smooth HDR environment with a bright patch (so the bilinear look-up and its wrap / pole clamps all matter)."""
+    y, x = np.mgrid[0:h, 0:w].astype(np.float32)
+    env = np.stack([0.2 + 0.8 * x / w, 0.3 + 0.5 * y / h, 0.6 - 0.4 * x / w], -1).astype(np.float32)
+    env[2:5, 3:8] += np.float32(6.0)
+    return env
+
+
+@pytest.mark.parametrize("scene_name", ["CBspheres_lambertian", "CBcoil"])
+def test_environment_light_matches_oracle(scene_name):
+    """EnvironmentLight (the `envmap` argument of PathTracer::PathTracer, src/pathtracer.h:57-60): escaping rays read the
+    map, every diffuse interaction samples it as one more light.  The look-up's arctangent is the shared polynomial, so
+    the frame is expected bit-identical to the oracle's; removing the map restores the plain frame."""
+    sc = Scene.load(scene_path(scene_name))
+    w, h = 80, 60
+    cam = place_camera(sc, w, h)
+    env = _env_gradient()
+    cfg = dict(ns_aa=4, max_ray_depth=4, ns_area_light=1, seed=21)
+    pt = b2rt.PathTracer(envmap=env, **cfg)
+    pt.set_scene(sc); pt.set_camera(cam); pt.set_frame_size(w, h); pt.render()
+    img = pt.hdr()
+    o = orc.OracleScene(sc, 4); o.set_envmap(env)
+    ref = o.render(cam, Config(**cfg), w, h)
+    assert np.sqrt(np.mean((img - ref) ** 2)) <= 1e-6 and np.abs(img - ref).max() <= 1e-5
+    pt.set_envmap(None); pt.render()
+    o.set_envmap(None)
+    plain = o.render(cam, Config(**cfg), w, h)
+    assert np.sqrt(np.mean((pt.hdr() - plain) ** 2)) <= 1e-6
+    assert np.abs(img - plain).max() > 0.05                 # the environment did light the scene
+    pt.close()
+
+
+def test_glossy_bsdf_matches_oracle():
+    """GlossyBSDF(reflectance, roughness) (src/bsdf.h:143-162): Phong lobe with an integer exponent, next-event
+    estimation + cosine-weighted sampling; glossy walls and a glossy sphere in the Cornell box, with and without an
+    environment map."""
+    from b2rt.scene import MAT_DIFFUSE, MAT_GLOSSY
+    sc = Scene.load(scene_path("CBspheres_lambertian"))
+    k = 0
+    for m in sc.materials:
+        if m["kind"] == MAT_DIFFUSE:
+            m["kind"] = MAT_GLOSSY; m["roughness"] = (0.08, 0.3, 0.9)[k % 3]; k += 1
+    assert k >= 3
+    w, h = 72, 54
+    cam = place_camera(sc, w, h)
+    cfg = dict(ns_aa=4, max_ray_depth=5, ns_area_light=2, seed=31)
+    for env in (None, _env_gradient()):
+        pt = b2rt.PathTracer(envmap=env, **cfg)
+        pt.set_scene(sc); pt.set_camera(cam); pt.set_frame_size(w, h); pt.render()
+        img = pt.hdr()
+        o = orc.OracleScene(sc, 4); o.set_envmap(env)
+        ref = o.render(cam, Config(**cfg), w, h)
+        assert np.sqrt(np.mean((img - ref) ** 2)) <= 1e-6 and np.abs(img - ref).max() <= 1e-5
+        assert img.max() > 0.05
+        pt.close()

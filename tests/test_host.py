@@ -413,3 +413,20 @@ def test_comm_api_fails_cleanly_without_a_device():
     assert b2rt.Comm.version() >= 0
     with pytest.raises(b2rt.B2rtError):
         b2rt.Comm(2, 0, b"\0" * 128, device=0)
+
+
+def test_load_dae_accepts_glossy(tmp_path):
+    """<glossy> in the CMU462 profile (commented out in the reference's parser, collada.cpp:898-907) loads as
+    B2RT_MAT_GLOSSY through the C++ loader and through the independent Python converter alike."""
+    import subprocess
+    src = open(os.path.join(ROOT, "tests", "golden", "mini_scene.dae")).read()
+    assert "<mirror>" in src
+    i, j = src.index("<mirror>"), src.index("</mirror>") + len("</mirror>")
+    dae = tmp_path / "glossy.dae"
+    dae.write_text(src[:i] + "<glossy><reflectance>0.7 0.6 0.5</reflectance><roughness>0.25</roughness></glossy>" + src[j:])
+    a = b2rt.load_dae(str(dae))
+    g = [m for m in a.materials if m["kind"] == 5]
+    assert len(g) == 1 and g[0]["roughness"] == 0.25 and [round(v, 6) for v in g[0]["albedo"]] == [0.7, 0.6, 0.5]
+    out = tmp_path / "glossy.b2s"
+    subprocess.check_call([sys.executable, os.path.join(ROOT, "tools", "dae2scene.py"), str(dae), str(out)])
+    _same_scene(a, Scene.load(str(out)))

@@ -35,7 +35,7 @@ import numpy as np
 
 NS = "{http://www.collada.org/2005/11/COLLADASchema}"
 
-MAT_DIFFUSE, MAT_MIRROR, MAT_GLASS, MAT_EMISSION, MAT_REFRACTION = 0, 1, 2, 3, 4
+MAT_DIFFUSE, MAT_MIRROR, MAT_GLASS, MAT_EMISSION, MAT_REFRACTION, MAT_GLOSSY = 0, 1, 2, 3, 4, 5
 LIGHT_AREA, LIGHT_POINT, LIGHT_DIRECTIONAL = 0, 1, 2
 
 
@@ -96,6 +96,8 @@ def _material(root_ids, mat_id):
                 out.update(kind=MAT_EMISSION, emission=list(rad), albedo=[0, 0, 0])
             elif tag == "mirror":
                 out.update(kind=MAT_MIRROR, albedo=list(get("reflectance")[:3]))
+            elif tag == "glossy":       # commented out in the reference's parser (collada.cpp:898-907); accepted here
+                out.update(kind=MAT_GLOSSY, albedo=list(get("reflectance")[:3]), roughness=float(get("roughness")[0]))
             elif tag == "refraction":
                 out.update(kind=MAT_REFRACTION, transmittance=list(get("transmittance")[:3]),
                            roughness=float(get("roughness")[0]), ior=float(get("ior")[0]), albedo=[0, 0, 0])
