@@ -442,7 +442,18 @@ class Comm:
     Comm.unique_id() on rank 0 -> 128 bytes, shipped to the other ranks by any means (bench.py broadcasts them with
     torch.distributed), then Comm(n_ranks, rank, id, device) on every rank."""
 
+    @staticmethod
+    def _prefer_framework_nccl():
+        # libb2rt.so binds NCCL at run time and takes the copy the process already has.  PyTorch bundles its own
+        # (newer) libnccl.so.2; if the system copy were loaded first, a later `import torch` would resolve against it and
+        # fail.  So in a Python process the framework's copy goes first.
+        try:
+            import torch  # noqa: F401
+        except ImportError:
+            pass
+
     def __init__(self, n_ranks, rank, uid, device=-1):
+        self._prefer_framework_nccl()
         if len(uid) != 128:
             raise ValueError("unique id must be 128 bytes")
         buf = (C.c_uint8 * 128).from_buffer_copy(bytes(uid))
@@ -453,12 +464,14 @@ class Comm:
 
     @staticmethod
     def unique_id():
+        Comm._prefer_framework_nccl()
         buf = (C.c_uint8 * 128)()
         _check(lib().b2rt_comm_unique_id(buf))
         return bytes(buf)
 
     @staticmethod
     def version():
+        Comm._prefer_framework_nccl()
         return lib().b2rt_comm_version()
 
     def close(self):

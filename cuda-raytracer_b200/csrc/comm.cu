@@ -46,11 +46,12 @@ NcclApi& nccl() {
   static NcclApi api;
   static std::once_flag once;
   std::call_once(once, [] {
-    // the copy the process already has (RTLD_NOLOAD), else the system's
+    // the copy the process already has (RTLD_NOLOAD), else the system's.  A host program that also uses a framework
+    // with a bundled NCCL (PyTorch) must load the framework first: one process, one libnccl.so.2.
     const char* names[] = {"libnccl.so.2", "libnccl.so"};
-    for (const char* n : names) { api.lib = dlopen(n, RTLD_NOW | RTLD_NOLOAD | RTLD_GLOBAL); if (api.lib) break; }
+    for (const char* n : names) { api.lib = dlopen(n, RTLD_NOW | RTLD_NOLOAD); if (api.lib) break; }
     if (!api.lib)
-      for (const char* n : names) { api.lib = dlopen(n, RTLD_NOW | RTLD_GLOBAL); if (api.lib) break; }
+      for (const char* n : names) { api.lib = dlopen(n, RTLD_NOW | RTLD_LOCAL); if (api.lib) break; }
     if (!api.lib) return;
     auto sym = [&](const char* s) { return dlsym(api.lib, s); };
     api.GetUniqueId = (decltype(api.GetUniqueId))sym("ncclGetUniqueId");
