@@ -31,8 +31,20 @@ constexpr uint32_t MAX_LEVELS = 32;
 #ifndef B2RT_STACK8
 #define B2RT_STACK8 35
 #endif
-constexpr uint32_t stack_entries(uint32_t width) { return width == 8 ? (uint32_t)B2RT_STACK8 : (uint32_t)B2RT_STACK4; }
-constexpr uint32_t max_treelet_nodes(uint32_t width) { return width == 8 ? 512u : 1024u; }
+#ifndef B2RT_STACK2
+#define B2RT_STACK2 16
+#endif
+#ifndef B2RT_STACK16
+#define B2RT_STACK16 45
+#endif
+// widths 2 and 16 exist for the BVH-width sweep of BASELINE configs[4] (the reference's image7.png: W = 2 / 4 / 8 / 16);
+// 4 is the default, 8 the alternative the device builder also produces
+constexpr bool width_ok(uint32_t width) { return width == 2 || width == 4 || width == 8 || width == 16; }
+constexpr uint32_t stack_entries(uint32_t width) {
+  return width == 2 ? (uint32_t)B2RT_STACK2 : width == 8 ? (uint32_t)B2RT_STACK8 : width == 16 ? (uint32_t)B2RT_STACK16 : (uint32_t)B2RT_STACK4;
+}
+constexpr uint32_t slot_bits(uint32_t width) { return width == 2 ? 1u : width == 8 ? 3u : width == 16 ? 4u : 2u; }
+constexpr uint32_t max_treelet_nodes(uint32_t width) { return 4096u >> slot_bits(width); }   // (node, slot) fits 12 bits
 
 // Byte stride of a wide node inside a subtree blob: 32 * W bytes of rows (6 box rows + child references + 16 B spare)
 // plus B2RT_NODE_PAD.  With a stride of 128 B the same row of every node falls into the same four shared-memory banks,
@@ -42,7 +54,7 @@ constexpr uint32_t max_treelet_nodes(uint32_t width) { return width == 8 ? 512u 
 #ifndef B2RT_NODE_PAD
 #define B2RT_NODE_PAD 16
 #endif
-constexpr uint32_t node_bytes(uint32_t width) { return (width == 8 ? 256u : 128u) + (uint32_t)B2RT_NODE_PAD; }
+constexpr uint32_t node_bytes(uint32_t width) { return 32u * width + (uint32_t)B2RT_NODE_PAD; }
 
 struct TreeletDesc {      // one per subtree ("treelet"), 16 B
   uint32_t offset16;      // blob offset / 16

@@ -440,7 +440,7 @@ int make_host_scene(const b2rt_scene_desc* d, HostScene* out, bool with_geometry
 int build_wide_bvh(const HostScene& sc, uint32_t max_leaf, uint32_t width, uint32_t treelet_bytes, WideBVH* out) {
   auto t0 = std::chrono::steady_clock::now();
   if (width == 0) width = 4;
-  if (width != 4 && width != 8) { set_error("bvh width must be 4 or 8"); return B2RT_ERR_INVALID; }
+  if (!width_ok(width)) { set_error("bvh width must be 2, 4, 8 or 16"); return B2RT_ERR_INVALID; }
   if (max_leaf == 0) max_leaf = 4;
   if (max_leaf > 64) { set_error("max_leaf_size must be <= 64"); return B2RT_ERR_INVALID; }
   const uint32_t NB = node_bytes(width);

@@ -875,7 +875,7 @@ int build_wide_bvh_device(const b2rt_scene_desc* sc, uint32_t max_leaf, uint32_t
   if (sc->n_spheres && !sc->spheres) { set_error("spheres is null"); return B2RT_ERR_INVALID; }
   const uint64_t n = (uint64_t)sc->n_tris + sc->n_spheres;
   if (width == 0) width = 4;
-  if (width != 4 && width != 8) { set_error("bvh width must be 4 or 8"); return B2RT_ERR_INVALID; }
+  if (width != 4 && width != 8) { set_error("the device builder makes 4- or 8-wide trees (widths 2 and 16: host builder)"); return B2RT_ERR_INVALID; }
   if (max_leaf == 0) max_leaf = 4;
   if (max_leaf > 64) { set_error("max_leaf_size must be <= 64"); return B2RT_ERR_INVALID; }
   if (n == 0) { set_error("gpu bvh build: empty scene"); return B2RT_ERR_INVALID; }

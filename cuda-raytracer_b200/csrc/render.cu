@@ -700,6 +700,7 @@ int Renderer::set_scene(const b2rt_scene_desc* d) {
   bool on_device = cfg.bvh_builder == 2 || (cfg.bvh_builder == 0 && n_prims64 >= (1u << 14));
   if (const char* e = getenv("B2RT_BUILDER")) on_device = !strcmp(e, "gpu");
   on_device = on_device && n_prims64 > 0;
+  if (cfg.bvh_builder != 2 && cfg.bvh_width != 0 && cfg.bvh_width != 4 && cfg.bvh_width != 8) on_device = false;   // widths 2 / 16: host builder only
   HostScene hs;
   RCHECK(make_host_scene(d, &hs, !on_device));   // device build: the primitive records are made on the GPU (k_make_prims)
   lap("host scene");

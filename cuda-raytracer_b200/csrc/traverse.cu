@@ -311,16 +311,9 @@ struct TravParams {
 };
 
 template <int W>
-struct NodeView;
-template <>
-struct NodeView<4> {
-  static constexpr int BYTES = (int)node_bytes(4);
-  static constexpr int SLOT_BITS = 2;
-};
-template <>
-struct NodeView<8> {
-  static constexpr int BYTES = (int)node_bytes(8);
-  static constexpr int SLOT_BITS = 3;
+struct NodeView {
+  static constexpr int BYTES = (int)node_bytes(W);
+  static constexpr int SLOT_BITS = (int)slot_bits(W);
 };
 constexpr uint32_t STACK_TN_MASK = 0xFFFFF000u;   // stack entry: [31:12] entry distance bits, [11:0] node << SLOT_BITS | slot
 
@@ -428,7 +421,7 @@ __device__ __forceinline__ float4 ldg_stream_f4(const float4* p) {
 }
 
 template <int W, bool ANYHIT, bool STATS>
-__global__ void __launch_bounds__(TRAV_THREADS, (W == 4 ? B2RT_OCC4 : 2))
+__global__ void __launch_bounds__(TRAV_THREADS, (W <= 4 ? B2RT_OCC4 : (W == 8 ? 2 : 1)))
 k_traverse(const TravParams P) {
   extern __shared__ __align__(128) uint8_t smem[];
   __shared__ __align__(8) uint64_t s_bar;
@@ -647,28 +640,45 @@ k_traverse(const TravParams P) {
         // sign-ordered slab test: per axis the near plane row is lo (inv >= 0) or hi (inv < 0), chosen once
         // per ray (row offsets nx/ny/nz, fx/fy/fz), so a box costs 6 fma + 3 max + 3 min.  Empty slots hold
         // inverted infinite boxes (lo = +inf, hi = -inf) => t_near = +inf, t_far = -inf => never hit.
+        if (W >= 4) {
 #pragma unroll
-        for (int q = 0; q < W / 4; ++q) {
-          const float4 ax = lds_f4(na + nx + 16 * q), bx = lds_f4(na + fx + 16 * q);
-          const float4 ay = lds_f4(na + ny + 16 * q), by = lds_f4(na + fy + 16 * q);
-          const float4 az = lds_f4(na + nz + 16 * q), bz = lds_f4(na + fz + 16 * q);
-          const float axa[4] = {ax.x, ax.y, ax.z, ax.w}, aya[4] = {ay.x, ay.y, ay.z, ay.w}, aza[4] = {az.x, az.y, az.z, az.w};
-          const float bxa[4] = {bx.x, bx.y, bx.z, bx.w}, bya[4] = {by.x, by.y, by.z, by.w}, bza[4] = {bz.x, bz.y, bz.z, bz.w};
+          for (int q = 0; q < W / 4; ++q) {
+            const float4 ax = lds_f4(na + nx + 16 * q), bx = lds_f4(na + fx + 16 * q);
+            const float4 ay = lds_f4(na + ny + 16 * q), by = lds_f4(na + fy + 16 * q);
+            const float4 az = lds_f4(na + nz + 16 * q), bz = lds_f4(na + fz + 16 * q);
+            const float axa[4] = {ax.x, ax.y, ax.z, ax.w}, aya[4] = {ay.x, ay.y, ay.z, ay.w}, aza[4] = {az.x, az.y, az.z, az.w};
+            const float bxa[4] = {bx.x, bx.y, bx.z, bx.w}, bya[4] = {by.x, by.y, by.z, by.w}, bza[4] = {bz.x, bz.y, bz.z, bz.w};
 #pragma unroll
-          for (int c = 0; c < 4; ++c) {
-            const float tn = fmaxf(fmax3(__fmaf_rn(axa[c], inv.x, noi.x), __fmaf_rn(aya[c], inv.y, noi.y),
-                                         __fmaf_rn(aza[c], inv.z, noi.z)), tmin);
-            const float tf = fminf(fmin3(__fmaf_rn(bxa[c], inv.x, noi.x), __fmaf_rn(bya[c], inv.y, noi.y),
-                                         __fmaf_rn(bza[c], inv.z, noi.z)), best_t);
+            for (int c = 0; c < 4; ++c) {
+              const float tn = fmaxf(fmax3(__fmaf_rn(axa[c], inv.x, noi.x), __fmaf_rn(aya[c], inv.y, noi.y),
+                                           __fmaf_rn(aza[c], inv.z, noi.z)), tmin);
+              const float tf = fminf(fmin3(__fmaf_rn(bxa[c], inv.x, noi.x), __fmaf_rn(bya[c], inv.y, noi.y),
+                                           __fmaf_rn(bza[c], inv.z, noi.z)), best_t);
+              const bool hit = tn <= tf * 1.0000004f;
+              // key: entry distance (low byte dropped = rounded down, keeps order for t >= 0) | child slot in the low byte (one PRMT)
+              keys[(q * 4 + c) % W] = hit ? __byte_perm(__float_as_uint(tn), (uint32_t)(q * 4 + c), 0x3214) : 0xFFFFFFFFu;
+            }
+          }
+        } else {   // W == 2: 8-byte rows
+          const unsigned long long ax = lds_u64(na + nx), bx = lds_u64(na + fx), ay = lds_u64(na + ny), by = lds_u64(na + fy);
+          const unsigned long long az = lds_u64(na + nz), bz = lds_u64(na + fz);
+#pragma unroll
+          for (int c = 0; c < 2; ++c) {
+            const int sh = 32 * c;
+            const float tn = fmaxf(fmax3(__fmaf_rn(__uint_as_float((uint32_t)(ax >> sh)), inv.x, noi.x), __fmaf_rn(__uint_as_float((uint32_t)(ay >> sh)), inv.y, noi.y),
+                                         __fmaf_rn(__uint_as_float((uint32_t)(az >> sh)), inv.z, noi.z)), tmin);
+            const float tf = fminf(fmin3(__fmaf_rn(__uint_as_float((uint32_t)(bx >> sh)), inv.x, noi.x), __fmaf_rn(__uint_as_float((uint32_t)(by >> sh)), inv.y, noi.y),
+                                         __fmaf_rn(__uint_as_float((uint32_t)(bz >> sh)), inv.z, noi.z)), best_t);
             const bool hit = tn <= tf * 1.0000004f;
-            // key: entry distance (low byte dropped = rounded down, keeps order for t >= 0) | child slot in the low byte (one PRMT)
-            keys[q * 4 + c] = hit ? __byte_perm(__float_as_uint(tn), (uint32_t)(q * 4 + c), 0x3214) : 0xFFFFFFFFu;
+            keys[c % W] = hit ? __byte_perm(__float_as_uint(tn), (uint32_t)c, 0x3214) : 0xFFFFFFFFu;
           }
         }
-#define B2_CE(a, b) { const uint32_t lo_ = min(keys[a], keys[b]), hi_ = max(keys[a], keys[b]); keys[a] = lo_; keys[b] = hi_; }
-        if (W == 4) {
+#define B2_CE(a, b) { const uint32_t lo_ = min(keys[(a) % W], keys[(b) % W]), hi_ = max(keys[(a) % W], keys[(b) % W]); keys[(a) % W] = lo_; keys[(b) % W] = hi_; }
+        if (W == 2) {
+          B2_CE(0, 1)
+        } else if (W == 4) {
           B2_CE(0, 1) B2_CE(2, 3) B2_CE(0, 2) B2_CE(1, 3) B2_CE(1, 2)
-        } else {
+        } else if (W == 8) {
           B2_CE(0, 1) B2_CE(2, 3) B2_CE(4, 5) B2_CE(6, 7)
           B2_CE(0, 2) B2_CE(1, 3) B2_CE(4, 6) B2_CE(5, 7)
           B2_CE(1, 2) B2_CE(5, 6) B2_CE(0, 4) B2_CE(3, 7)
@@ -676,6 +686,23 @@ k_traverse(const TravParams P) {
           B2_CE(1, 4) B2_CE(3, 6)
           B2_CE(2, 4) B2_CE(3, 5)
           B2_CE(3, 4)
+        } else {   // W == 16: bitonic network (80 compare-exchanges), fully unrolled
+#pragma unroll
+          for (int k = 2; k <= W; k <<= 1) {
+#pragma unroll
+            for (int j = k >> 1; j > 0; j >>= 1) {
+#pragma unroll
+              for (int i = 0; i < W; ++i) {
+                const int l = i ^ j;
+                if (l > i) {
+                  const uint32_t a_ = keys[i], b_ = keys[l];
+                  const bool up = (i & k) == 0;
+                  keys[i] = up ? min(a_, b_) : max(a_, b_);
+                  keys[l] = up ? max(a_, b_) : min(a_, b_);
+                }
+              }
+            }
+          }
         }
 #undef B2_CE
         // far-to-near onto the stack; the nearest child becomes the current reference without a stack round trip.
@@ -684,7 +711,7 @@ k_traverse(const TravParams P) {
 #pragma unroll
         for (int q = W - 1; q >= 1; --q) {
           if (keys[q] != 0xFFFFFFFFu) {
-            B2_CHECK(sp < (W == 8 ? B2RT_STACK8 : B2RT_STACK4), 3, sp);
+            B2_CHECK(sp < (int)stack_entries(W), 3, sp);
             sts_u32(stack + (uint32_t)sp * (TRAV_THREADS * 4u), (keys[q] & (STACK_TN_MASK | (uint32_t)(W - 1))) | node_tag);
             ++sp;
           }
@@ -982,17 +1009,18 @@ int Tracer::init(const DeviceBVH& b, uint64_t max_rays_, uint32_t pair_factor) {
   if (const char* e = getenv("B2RT_CHUNK0_MAX")) { int v = atoi(e); if (v >= 32 && v <= (1 << 24)) chunk0_max = (uint32_t)v; }
   int occ = 1, o2 = 1, o3 = 1, o4 = 1;
   int rc;
-  if (bvh.width == 8) {
-    if ((rc = prep_kernel<8, false, false>(smem_bytes, &occ))) return rc;
-    if ((rc = prep_kernel<8, true, false>(smem_bytes, &o2))) return rc;
-    if ((rc = prep_kernel<8, false, true>(smem_bytes, &o3))) return rc;
-    if ((rc = prep_kernel<8, true, true>(smem_bytes, &o4))) return rc;
-  } else {
-    if ((rc = prep_kernel<4, false, false>(smem_bytes, &occ))) return rc;
-    if ((rc = prep_kernel<4, true, false>(smem_bytes, &o2))) return rc;
-    if ((rc = prep_kernel<4, false, true>(smem_bytes, &o3))) return rc;
-    if ((rc = prep_kernel<4, true, true>(smem_bytes, &o4))) return rc;
-  }
+#define B2_PREP(WW)                                                             \
+  do {                                                                          \
+    if ((rc = prep_kernel<WW, false, false>(smem_bytes, &occ))) return rc;      \
+    if ((rc = prep_kernel<WW, true, false>(smem_bytes, &o2))) return rc;        \
+    if ((rc = prep_kernel<WW, false, true>(smem_bytes, &o3))) return rc;        \
+    if ((rc = prep_kernel<WW, true, true>(smem_bytes, &o4))) return rc;         \
+  } while (0)
+  if (bvh.width == 2) B2_PREP(2);
+  else if (bvh.width == 8) B2_PREP(8);
+  else if (bvh.width == 16) B2_PREP(16);
+  else B2_PREP(4);
+#undef B2_PREP
   ctas_per_sm = std::max(1, std::min(std::min(occ, o2), std::min(o3, o4)));
   if (getenv("B2RT_VERBOSE"))
     fprintf(stderr, "b2rt: k_traverse W=%u: %d threads, %zu B dynamic smem (subtree %u + stacks %zu + ring %u), %d CTAs/SM x %d SMs\n",
@@ -1116,7 +1144,9 @@ int Tracer::trace(cudaStream_t s, const float4* ray_o, const float4* ray_d, unsi
       ev_deeper.push_back(L ? 1 : 0);
       cudaEventRecord(e0, s);
     }
-    if (bvh.width == 8) launch_traverse<8>(*this, s, P, any_hit, collect_stats);
+    if (bvh.width == 2) launch_traverse<2>(*this, s, P, any_hit, collect_stats);
+    else if (bvh.width == 8) launch_traverse<8>(*this, s, P, any_hit, collect_stats);
+    else if (bvh.width == 16) launch_traverse<16>(*this, s, P, any_hit, collect_stats);
     else launch_traverse<4>(*this, s, P, any_hit, collect_stats);
     if (time_kernels) cudaEventRecord(e1, s);
     launches++; traverse_launches++; if (L == 0) traverse_launches_l0++;

@@ -60,7 +60,8 @@ def test_closest_hit_bit_exact_mid_sized_batches(n_random, w, h):
 
 @pytest.mark.parametrize("name", ["CBbunny", "CBcoil", "CBgems", "CBspheres_lambertian", "CBspheres", "CBempty", "trigs10",
                                   "sphere_diffuse", "plane1024", "floating"])
-@pytest.mark.parametrize("width,treelet_bytes,max_leaf", [(4, 0, 4), (8, 0, 4), (4, 8192, 2), (8, 100000, 8)])
+@pytest.mark.parametrize("width,treelet_bytes,max_leaf", [(4, 0, 4), (8, 0, 4), (4, 8192, 2), (8, 100000, 8), (2, 0, 4), (16, 0, 8),
+                                                          (2, 8192, 16), (16, 65536, 32)])
 def test_closest_hit_bit_exact(name, width, treelet_bytes, max_leaf):
     sc = Scene.load(scene_path(name))
     o = orc.OracleScene(sc, 4)

@@ -62,7 +62,7 @@ def test_product_does_not_link_oracle():
 
 @pytest.mark.parametrize("name", ["CBbunny", "CBcoil", "CBgems", "CBspheres_lambertian", "CBempty", "trigs1", "sphere_diffuse",
                                   "plane1024"])
-@pytest.mark.parametrize("width", [4, 8])
+@pytest.mark.parametrize("width", [2, 4, 8, 16])
 def test_bvh_blob_structure(name, width):
     sc = Scene.load(scene_path(name))
     for tb in (0, 8192, 150000):
@@ -86,7 +86,7 @@ def test_bvh_blob_structure_soup_and_degenerate():
 def test_invalid_arguments():
     sc = Scene.load(scene_path("trigs1"))
     with pytest.raises(b2rt.B2rtError):
-        b2rt.validate_bvh_host(sc, 4, 5, 0)          # width must be 4 or 8
+        b2rt.validate_bvh_host(sc, 4, 5, 0)          # width must be 2, 4, 8 or 16
     with pytest.raises(b2rt.B2rtError):
         b2rt.validate_bvh_host(sc, 100, 4, 0)        # leaf size limit
     bad = Scene(sc.tri_verts, None, np.array([7], np.uint32))
