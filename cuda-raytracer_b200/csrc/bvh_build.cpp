@@ -430,6 +430,9 @@ int make_host_scene(const b2rt_scene_desc* d, HostScene* out, bool with_geometry
     m.kind = B2RT_MAT_DIFFUSE; m.albedo[0] = m.albedo[1] = m.albedo[2] = 0.5f; m.ior = 1.f;
     out->materials.assign(1, m);
   }
+  if (out->materials.size() >= (1u << 28)) { set_error("too many materials"); return B2RT_ERR_INVALID; }
+  for (const b2rt_material& m : out->materials)
+    if (m.kind < B2RT_MAT_DIFFUSE || m.kind > B2RT_MAT_GLOSSY) { set_error("unknown material kind"); return B2RT_ERR_INVALID; }
   for (uint32_t i = 0; i < n; ++i)
     if (out->prim_material[i] >= out->materials.size()) { set_error("material index out of range"); return B2RT_ERR_INVALID; }
   if (d->n_lights && d->lights) out->lights.assign(d->lights, d->lights + d->n_lights);

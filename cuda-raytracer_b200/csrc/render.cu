@@ -29,7 +29,9 @@ namespace b2rt {
 namespace {
 
 constexpr float INF_F = __builtin_huge_valf();
-constexpr uint32_t MAX_DEPTH = 96, ACT0 = 8, SH0 = ACT0 + MAX_DEPTH + 8, SHV0 = SH0 + MAX_DEPTH + 8, N_COUNTS = 512;
+constexpr uint32_t MAX_DEPTH = 96, ACT0 = 8, SH0 = ACT0 + MAX_DEPTH + 8, SHV0 = SH0 + MAX_DEPTH + 8, REAL0 = SHV0 + MAX_DEPTH + 8,
+                   BLKA0 = REAL0 + MAX_DEPTH + 8, BLKS0 = BLKA0 + MAX_DEPTH + 8, N_COUNTS = 1024;
+static_assert(BLKS0 + MAX_DEPTH + 8 <= N_COUNTS, "counter table");
 
 struct CamDev { f3 pos, cx, cy, cz; float tan_h, tan_v; };
 
@@ -59,9 +61,11 @@ struct PathBufs {
   // (one per light sample; samples that cannot contribute are null rays the any-hit traversal skips)
   float4* s_o; float4* s_d; unsigned long long* s_hits; float4* s_contrib;
   uint32_t* s_q0;    // [slot] first shadow-list entry of the path's block, 0xFFFFFFFF = none
-  // [3] = cancel flag; [ACT0 + b] = active paths at bounce b; [SH0 + b] = shadow-list entries of bounce b;
-  // [SHV0 + b] = of which real shadow rays
+  // [3] = cancel flag; [ACT0 + b] = entries of bounce b's path list (of which [REAL0 + b] are paths, the rest null
+  // entries, see k_shade); [SH0 + b] = shadow-list entries of bounce b; [SHV0 + b] = of which real shadow rays;
+  // [BLKA0 + b] / [BLKS0 + b] = reservation blocks handed out of the two lists
   uint32_t* counts;
+  uint32_t inc_bound;   // 0xFFFFFFFF (see next_block)
 };
 
 __global__ void __launch_bounds__(256)
@@ -72,6 +76,9 @@ k_raygen(WaveParams wp, CamDev cam, PathBufs pb) {
     pb.counts[ACT0 + threadIdx.x] = (threadIdx.x == 0) ? (pb.counts[3] ? 0u : n) : 0u;
     pb.counts[SH0 + threadIdx.x] = 0u;
     pb.counts[SHV0 + threadIdx.x] = 0u;
+    pb.counts[REAL0 + threadIdx.x] = 0u;
+    pb.counts[BLKA0 + threadIdx.x] = 0u;
+    pb.counts[BLKS0 + threadIdx.x] = 0u;
   }
   if (slot >= n) return;
   const uint32_t pix = wp.pix0 + slot / wp.spp;
@@ -195,41 +202,134 @@ __device__ __forceinline__ uint2 block_append2(uint32_t* counter_a, bool pred_a,
   return pos;
 }
 
+// A warp's private piece of a dense output list.  Warps reserve blocks of `blk` entries from the list's block counter
+// (one atomic per block instead of one per tile; the next block is reserved a tile ahead, so nobody waits for the
+// atomic's round trip) and append into their piece with ballots only -- no shared memory, no barrier.  What a warp has
+// reserved but not filled when it runs out of input becomes NULL entries (see k_shade).
+struct OutRange {
+  uint32_t next = 0, end = 0;   // warp-uniform: unused entries [next, end) of the current block
+  uint32_t spare = 0;           // lane 0 only: index of the block reserved ahead
+  uint32_t blocks = 0;          // warp-uniform: blocks this warp has reserved
+  bool has = false;             // warp-uniform: a block is reserved ahead
+};
+// The block counter is bumped with atom.inc and a bound (0xFFFFFFFF) that arrives as a kernel argument.  A plain
+// atom.add here is rewritten by ptxas into its warp-aggregated form -- vote, leader, ATOMG, SHFL of the result to every
+// participant -- and that SHFL sits right behind the atomic and waits for the round trip this scheme exists to hide
+// (13 % of the kernel's stall samples); an inc with a run-time bound is left alone.
+__device__ __forceinline__ uint32_t next_block(uint32_t* block_counter, uint32_t bound) {
+  uint32_t old;
+  asm volatile("atom.global.inc.u32 %0, [%1], %2;" : "=r"(old) : "l"(block_counter), "r"(bound) : "memory");
+  return old;
+}
+__device__ __forceinline__ void reserve_ahead(OutRange& r, uint32_t* block_counter, uint32_t bound, uint32_t need, uint32_t lane) {
+  if (!r.has && r.end - r.next < need) {
+    if (lane == 0) r.spare = next_block(block_counter, bound);
+    r.has = true; r.blocks++;
+  }
+}
+// position of this lane's run of `per` entries (garbage when pred == false); blk_entries >= 32 * per
+__device__ __forceinline__ uint32_t warp_append(OutRange& r, uint32_t* block_counter, uint32_t bound, bool pred, uint32_t per,
+                                                uint32_t blk_entries, uint32_t lane, uint32_t lane_lt) {
+  const uint32_t m = __ballot_sync(0xffffffffu, pred);
+  const uint32_t cnt = (uint32_t)__popc(m) * per, rank = (uint32_t)__popc(m & lane_lt) * per;
+  const uint32_t avail = r.end - r.next;
+  uint32_t pos;
+  if (cnt > avail) {   // warp-uniform: the block is full, the rest goes to the head of the next one
+    if (!r.has) { if (lane == 0) r.spare = next_block(block_counter, bound); r.blocks++; }
+    const uint32_t base = __shfl_sync(0xffffffffu, r.spare, 0) * blk_entries;
+    pos = rank < avail ? r.next + rank : base + (rank - avail);
+    r.next = base + (cnt - avail); r.end = base + blk_entries; r.has = false;
+  } else {
+    pos = r.next + rank;
+    r.next += cnt;
+  }
+  return pos;
+}
+
 // One surface interaction for every active path (bounce index b).
-// 128-thread CTAs, 8 per SM: the two list appends end in CTA-wide barriers, where every warp waits for the slowest
-// one's dependent loads; four warps per barrier wait less than eight (cfg2 / cfg3 frame -1.8 % / -1.5 %, gpurun_out/r2_ab11)
+// PERSISTENT warps: the launch has a fixed number of warps; warp w takes the 32-entry tiles w, w + stride, ... of the
+// bounce's path list, loads the next tile's list entries before it works on the current one, and appends the continuing
+// paths and the shadow rays to warp-private pieces of the output lists (OutRange).  Round 1 ran one thread per entry
+// with two CTA-aggregated appends; their barriers -- every warp of the CTA waiting for the one global atomic behind
+// the slowest warp's dependent loads -- were 35 % of the kernel's warp samples (profiles/r01_shade_ncu.md).
+// NULL entries: the unfilled rest of a warp's last block.  Path list: slot 0xFFFFFFFF, hit word (t = -1, prim 0);
+// shadow list: contribution 0, hit word (t = -1, prim 0).  The traversal retires a ray whose interval is empty without
+// a node visit, k_shade / k_resolve_shadow skip entries without a slot.  A list is at most
+// shade_slack() entries longer than the paths it holds.
 #ifndef B2RT_SHADE_OCC
-#define B2RT_SHADE_OCC 8
+#define B2RT_SHADE_OCC 5
 #endif
 #ifndef B2RT_SHADE_THREADS
 #define B2RT_SHADE_THREADS 128
 #endif
-constexpr int SHADE_THREADS = B2RT_SHADE_THREADS;   // <= 256 (block_append's scratch holds 8 warp counts)
+constexpr int SHADE_THREADS = B2RT_SHADE_THREADS;
+constexpr uint32_t SHADE_BLK_MAX = 128;   // largest reservation block, in list items
+constexpr unsigned long long NULL_HIT = 0xBF80000000000000ull;   // (t = -1.0f, prim 0): an empty interval, "occluded"
 // EXT = the scene has an environment map or a glossy material; the common instantiation carries neither (their
 // look-up / lobe calls cost registers the 64-register kernel does not have to spare)
 template <bool EXT>
 __global__ void __launch_bounds__(SHADE_THREADS, B2RT_SHADE_OCC)
 k_shade(WaveParams wp, SceneDev sc, PathBufs pb, uint32_t b) {
   const uint32_t n = pb.counts[ACT0 + b];
-  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-  bool cont = false;
-  uint32_t slot = 0;
-  float4 next_o = make_float4(0.f, 0.f, 0.f, 0.f), next_d = make_float4(0.f, 0.f, 1.f, 0.f);
+  const uint32_t lane = threadIdx.x & 31, lane_lt = (1u << lane) - 1u;
+  const uint32_t n_tiles = (n + 31u) >> 5;
+  // short lists use fewer warps (>= 8 tiles each), so that the null entries stay a small part of the output
+  const uint32_t stride = min((gridDim.x * (uint32_t)SHADE_THREADS) >> 5, max(1u, n_tiles >> 3));
+  const uint32_t gw = (blockIdx.x * (uint32_t)SHADE_THREADS + threadIdx.x) >> 5;
+  if (gw >= stride) return;
+  const uint32_t tiles_per_warp = n_tiles / stride;
+  const uint32_t blk = tiles_per_warp < 32u ? 32u : (tiles_per_warp < 128u ? 64u : SHADE_BLK_MAX);
   const uint32_t S = wp.S;
-  unsigned long long h = 0;
+  const bool single = S == 1;
+  const uint32_t blk_sh = blk * max(S, 1u);
+  OutRange out_a, out_s;
+  uint32_t real_a = 0, real_s = 0;   // per-lane counts of the paths / real shadow rays this lane appended
+  // the next tile's list entries, loaded one tile ahead
+  uint32_t p_slot = 0xFFFFFFFFu;
+  unsigned long long p_h = 0;
+  float4 p_o = make_float4(0.f, 0.f, 0.f, 0.f), p_d = make_float4(0.f, 0.f, 1.f, 0.f);
+  {
+    const uint32_t i = gw * 32u + lane;
+    if (i < n) { p_slot = pb.lslot[i]; p_h = pb.lh[i]; p_o = pb.lo[i]; p_d = pb.ld[i]; }
+  }
+  for (uint32_t tile = gw; tile < n_tiles; tile += stride) {
+  const uint32_t slot = p_slot;
+  const unsigned long long h = p_h;
+  const float4 ro = p_o, rd = p_d;
+  const bool active = slot != 0xFFFFFFFFu;   // not past the end of the list, not a null entry
+  p_slot = 0xFFFFFFFFu;
+  {
+    const uint32_t i = (tile + stride) * 32u + lane;
+    if (tile + stride < n_tiles && i < n) { p_slot = pb.lslot[i]; p_h = pb.lh[i]; p_o = pb.lo[i]; p_d = pb.ld[i]; }
+  }
+  reserve_ahead(out_a, &pb.counts[BLKA0 + b + 1], pb.inc_bound, 32u, lane);
+  if (S > 0) reserve_ahead(out_s, &pb.counts[BLKS0 + b], pb.inc_bound, 32u * S, lane);
+  bool cont = false;
+  float4 next_o = make_float4(0.f, 0.f, 0.f, 0.f), next_d = make_float4(0.f, 0.f, 1.f, 0.f);
   uint32_t prim = 0xFFFFFFFFu;
   // the material is read field by field where it is used (the table is a few cache lines); holding the 48-byte record
   // and the 64-byte light record in registers across the kernel was the main source of spills at 64 registers
   const b2rt_material* mp = sc.materials;
   int32_t m_kind = -1;
-  float4 ro = make_float4(0.f, 0.f, 0.f, 0.f), rd = make_float4(0.f, 0.f, 1.f, 0.f), thr4 = make_float4(0.f, 0.f, 0.f, 0.f);
-  if (i < n) {
-    slot = pb.lslot[i];
-    h = pb.lh[i];
-    // independent of the hit word: issued together with it instead of behind the material lookup (shorter dependent chain)
-    ro = pb.lo[i]; rd = pb.ld[i]; thr4 = pb.thr[slot];
+  float4 thr4 = make_float4(0.f, 0.f, 0.f, 0.f);
+  PrimRec pr;
+  pr.a = pr.b = pr.c = make_float4(0.f, 0.f, 0.f, 0.f);
+  float vn[9] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  if (active) {
+    thr4 = pb.thr[slot];
     prim = (uint32_t)h;
-    if (prim != 0xFFFFFFFFu) { mp = sc.materials + sc.prim_material[prim]; m_kind = __ldg(&mp->kind); }
+    if (prim != 0xFFFFFFFFu) {
+      // everything that depends on the primitive index alone is requested at once: the material word (index | kind << 28,
+      // k_tag_material), the primitive record, the vertex normals
+      const uint32_t pm = __ldg(sc.prim_material + prim);
+      pr.a = __ldg(sc.prim_geom + (size_t)prim * 3); pr.b = __ldg(sc.prim_geom + (size_t)prim * 3 + 1); pr.c = __ldg(sc.prim_geom + (size_t)prim * 3 + 2);
+      if (sc.tri_normals && prim < sc.n_tris) {
+        const float* nn = sc.tri_normals + (size_t)prim * 9;
+#pragma unroll
+        for (int k = 0; k < 9; ++k) vn[k] = __ldg(nn + k);
+      }
+      mp = sc.materials + (pm & 0x0FFFFFFFu); m_kind = (int32_t)(pm >> 28);
+    }
   }
   // every diffuse hit reserves S consecutive entries of the bounce's shadow-ray list: one atomic per warp, blocks in
   // lane order, so the list stays coalesced against the path list
@@ -239,18 +339,16 @@ k_shade(WaveParams wp, SceneDev sc, PathBufs pb, uint32_t b) {
   // box scenes 45 % of the light samples lie behind the surface, and null rays cost the any-hit traversal a list
   // entry each (stream + retire).
   const bool wants_shadow = prim != 0xFFFFFFFFu && (m_kind == B2RT_MAT_DIFFUSE || (EXT && m_kind == B2RT_MAT_GLOSSY)) && S > 0;
-  const bool single = S == 1;
-  __shared__ uint32_t s_app[10];
   uint32_t q0 = 0xFFFFFFFFu;
-  if (!single) {
-    q0 = block_append(&pb.counts[SH0 + b], wants_shadow, S, s_app);
+  if (!single && S > 0) {
+    q0 = warp_append(out_s, &pb.counts[BLKS0 + b], pb.inc_bound, wants_shadow, S, blk_sh, lane, lane_lt);
     if (!wants_shadow) q0 = 0xFFFFFFFFu;
   }
   uint32_t n_valid = 0;
   bool sh_valid = false;
   float4 sh_d = make_float4(0.f, 0.f, 1.f, -1.f);
   f3 sh_c = mk3(0.f, 0.f, 0.f);
-  if (i < n) {
+  if (active) {
     if (!single) pb.s_q0[slot] = q0;
     if (prim == 0xFFFFFFFFu) {
       // the ray left the scene: EnvironmentLight::sample_dir, counted like emitted radiance (camera rays, delta bounces)
@@ -276,8 +374,6 @@ k_shade(WaveParams wp, SceneDev sc, PathBufs pb, uint32_t b) {
         const f3 o = mk3(ro.x, ro.y, ro.z), d = mk3(rd.x, rd.y, rd.z);
         const f3 P = o + d * t;
         next_o = make_float4(P.x, P.y, P.z, wp.eps);   // origin of the shadow ray and of the continuing ray
-        PrimRec pr;
-        pr.a = sc.prim_geom[(size_t)prim * 3]; pr.b = sc.prim_geom[(size_t)prim * 3 + 1]; pr.c = sc.prim_geom[(size_t)prim * 3 + 2];
         const bool is_sphere = prim >= sc.n_tris;
         f3 nrm;
         bool backface = false;
@@ -287,9 +383,8 @@ k_shade(WaveParams wp, SceneDev sc, PathBufs pb, uint32_t b) {
           // recover (u,v) with the same arithmetic as the traversal test
           float tt, u = 0.f, v = 0.f;
           hit_triangle(pr, o, d, ro.w, INF_F, &tt, &u, &v);
-          const float* nn = sc.tri_normals + (size_t)prim * 9;
           const float w0 = 1.0f - u - v;
-          nrm = mk3(nn[3], nn[4], nn[5]) * u + mk3(nn[6], nn[7], nn[8]) * v + mk3(nn[0], nn[1], nn[2]) * w0;
+          nrm = mk3(vn[3], vn[4], vn[5]) * u + mk3(vn[6], vn[7], vn[8]) * v + mk3(vn[0], vn[1], vn[2]) * w0;
         } else {
           nrm = cross3(mk3(pr.a.w, pr.b.x, pr.b.y), mk3(pr.b.z, pr.b.w, pr.c.x));
         }
@@ -440,20 +535,48 @@ k_shade(WaveParams wp, SceneDev sc, PathBufs pb, uint32_t b) {
     }
   }
   // the continuing paths form the next bounce's dense ray list
-  uint32_t p;
+  const uint32_t p = warp_append(out_a, &pb.counts[BLKA0 + b + 1], pb.inc_bound, cont, 1, blk, lane, lane_lt);
   if (single) {
-    const uint2 pq = block_append2(&pb.counts[ACT0 + b + 1], cont, &pb.counts[SH0 + b], sh_valid, s_app, n_valid, &pb.counts[SHV0 + b]);
-    p = pq.x;
-    if (i < n) pb.s_q0[slot] = sh_valid ? pq.y : 0xFFFFFFFFu;
+    const uint32_t q = warp_append(out_s, &pb.counts[BLKS0 + b], pb.inc_bound, sh_valid, 1, blk_sh, lane, lane_lt);
+    if (active) pb.s_q0[slot] = sh_valid ? q : 0xFFFFFFFFu;
     if (sh_valid) {
-      pb.s_o[pq.y] = next_o; pb.s_d[pq.y] = sh_d; pb.s_hits[pq.y] = pack_hit(sh_d.w, 0xFFFFFFFFu);
-      pb.s_contrib[pq.y] = make_float4(sh_c.x, sh_c.y, sh_c.z, 1.f);
+      pb.s_o[q] = next_o; pb.s_d[q] = sh_d; pb.s_hits[q] = pack_hit(sh_d.w, 0xFFFFFFFFu);
+      pb.s_contrib[q] = make_float4(sh_c.x, sh_c.y, sh_c.z, 1.f);
     }
-  } else {
-    p = block_append(&pb.counts[ACT0 + b + 1], cont, 1, s_app, n_valid, &pb.counts[SHV0 + b]);
   }
+  real_s += n_valid;
   if (cont) {
     pb.no[p] = next_o; pb.nd[p] = next_d; pb.nh[p] = pack_hit(INF_F, 0xFFFFFFFFu); pb.nslot[p] = slot;
+    real_a++;
+  }
+  }   // tiles
+  // null entries for what this warp reserved and did not fill
+  for (int k = 0; k < 2; ++k) {
+    const uint32_t spare = __shfl_sync(0xffffffffu, out_a.spare, 0) * blk;
+    const uint32_t lo = k ? spare : out_a.next, hi = k ? spare + blk : out_a.end;
+    if (k && !out_a.has) break;
+    for (uint32_t q = lo + lane; q < hi; q += 32u) {
+      pb.no[q] = make_float4(0.f, 0.f, 0.f, 0.f); pb.nd[q] = make_float4(0.f, 0.f, 1.f, -1.f);
+      pb.nh[q] = NULL_HIT; pb.nslot[q] = 0xFFFFFFFFu;
+    }
+  }
+  for (int k = 0; k < 2; ++k) {
+    const uint32_t spare = __shfl_sync(0xffffffffu, out_s.spare, 0) * blk_sh;
+    const uint32_t lo = k ? spare : out_s.next, hi = k ? spare + blk_sh : out_s.end;
+    if (k && !out_s.has) break;
+    for (uint32_t q = lo + lane; q < hi; q += 32u) {
+      pb.s_o[q] = make_float4(0.f, 0.f, 0.f, 0.f); pb.s_d[q] = make_float4(0.f, 0.f, 1.f, -1.f);
+      pb.s_hits[q] = NULL_HIT; pb.s_contrib[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+  }
+  real_a = __reduce_add_sync(0xffffffffu, real_a);
+  real_s = __reduce_add_sync(0xffffffffu, real_s);
+  if (lane == 0) {
+    // the lists' lengths in entries (what the traversal and the next bounce read) and the real rays among them
+    if (out_a.blocks) atomicAdd(&pb.counts[ACT0 + b + 1], out_a.blocks * blk);
+    if (out_s.blocks) atomicAdd(&pb.counts[SH0 + b], out_s.blocks * blk_sh);
+    if (real_a) atomicAdd(&pb.counts[REAL0 + b + 1], real_a);
+    if (real_s) atomicAdd(&pb.counts[SHV0 + b], real_s);
   }
 }
 
@@ -464,6 +587,7 @@ k_resolve_shadow(WaveParams wp, PathBufs pb, uint32_t b) {
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const uint32_t slot = pb.lslot[i];
+  if (slot == 0xFFFFFFFFu) return;   // null entry (k_shade)
   const uint32_t S = wp.S;
   const uint32_t q0 = pb.s_q0[slot];
   if (q0 == 0xFFFFFFFFu) return;
@@ -491,7 +615,7 @@ __global__ void k_wave_end(PathBufs pb, uint32_t max_depth, unsigned long long* 
   *status = st;
   if (st != 1u) return;
   unsigned long long nb = 0, ns = 0;
-  for (uint32_t b = 0; b < max_depth; ++b) { if (b) nb += pb.counts[ACT0 + b]; ns += pb.counts[SHV0 + b]; }
+  for (uint32_t b = 0; b < max_depth; ++b) { if (b) nb += pb.counts[REAL0 + b]; ns += pb.counts[SHV0 + b]; }
   totals[0] += nb; totals[1] += ns; totals[2] += n_paths;
 }
 
@@ -607,6 +731,15 @@ k_tonemap(const float4* __restrict__ img, uint32_t* __restrict__ out, uint32_t n
 }
 
 __global__ void k_fill_u32(uint32_t* p, uint32_t v) { *p = v; }
+// material index -> index | kind << 28: k_shade learns the kind of surface from the word it loads anyway instead of
+// from a second, dependent load
+__global__ void __launch_bounds__(256)
+k_tag_material(uint32_t* __restrict__ prim_material, const b2rt_material* __restrict__ materials, uint32_t n) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const uint32_t m = prim_material[i];
+  prim_material[i] = m | ((uint32_t)materials[m].kind << 28);
+}
 
 }  // namespace
 
@@ -755,6 +888,10 @@ int Renderer::set_scene(const b2rt_scene_desc* d) {
     B2RT_CUDA_OK(cudaMemcpy(d_prim_material, hs.prim_material.data(), (size_t)hs.n_prims() * 4, cudaMemcpyHostToDevice));
   }
   B2RT_CUDA_OK(cudaMemcpy(d_materials, hs.materials.data(), hs.materials.size() * sizeof(b2rt_material), cudaMemcpyHostToDevice));
+  if (hs.n_prims()) {
+    k_tag_material<<<(uint32_t)((hs.n_prims() + 255) / 256), 256, 0, stream>>>(d_prim_material, d_materials, (uint32_t)hs.n_prims());
+    B2RT_CUDA_OK(cudaGetLastError());
+  }
   if (d->tri_normals && d->n_tris) {   // straight from the caller's array
     const size_t nn = (size_t)d->n_tris * 9;
     if (cap_normals < nn) {
@@ -846,6 +983,14 @@ int Renderer::ensure_wave() {
   cap = std::max<uint64_t>(cap, 1024);
   const uint64_t want = std::min<uint64_t>(cap, n_pix * std::max(1u, cfg.ns_aa));
   const uint32_t Salloc = std::max(1u, S);
+  if (!shade_ctas) {
+    int sms = 0;
+    B2RT_CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
+    shade_ctas = (uint32_t)sms * B2RT_SHADE_OCC;
+  }
+  // k_shade's null entries: every warp may leave up to two reservation blocks unfilled per list and bounce
+  const uint64_t slack = (uint64_t)shade_ctas * (SHADE_THREADS / 32) * 2 * SHADE_BLK_MAX;
+  list_slack = (uint32_t)slack;
   // Two schedulers on two streams (default; B2RT_OVERLAP=0 turns it off): see start().
   overlap = getenv("B2RT_OVERLAP") ? atoi(getenv("B2RT_OVERLAP")) != 0 : true;
   if (overlap && !stream2) {
@@ -853,7 +998,7 @@ int Renderer::ensure_wave() {
     ev_sync.resize(2 * MAX_DEPTH);
     for (auto& e : ev_sync) B2RT_CUDA_OK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
   }
-  if (wave_cap >= want && wave_S >= Salloc && tracer.max_rays >= want * Salloc && (!overlap || tracer2.max_rays >= want * Salloc)) {
+  if (wave_cap >= want && wave_S >= Salloc && tracer.max_rays >= (want + slack) * Salloc && (!overlap || tracer2.max_rays >= (want + slack) * Salloc)) {
     if (bvh_stale) {
       RCHECK(tracer.init(dbvh, tracer.max_rays, 4));
       if (overlap) RCHECK(tracer2.init(dbvh, tracer2.max_rays, 4));
@@ -867,24 +1012,24 @@ int Renderer::ensure_wave() {
   wave_cap = want; wave_S = Salloc;
   // (+16 entries: the traversal copies ray tiles in 16-byte units and may read up to 3 entries past a list's end)
   for (int k = 0; k < 2; ++k) {
-    B2RT_CUDA_OK(cudaMalloc(&l_o[k], (wave_cap + 16) * sizeof(float4)));
-    B2RT_CUDA_OK(cudaMalloc(&l_d[k], (wave_cap + 16) * sizeof(float4)));
-    B2RT_CUDA_OK(cudaMalloc(&l_h[k], (wave_cap + 16) * 8));
-    B2RT_CUDA_OK(cudaMalloc(&l_slot[k], (wave_cap + 16) * 4));
+    B2RT_CUDA_OK(cudaMalloc(&l_o[k], (wave_cap + slack + 16) * sizeof(float4)));
+    B2RT_CUDA_OK(cudaMalloc(&l_d[k], (wave_cap + slack + 16) * sizeof(float4)));
+    B2RT_CUDA_OK(cudaMalloc(&l_h[k], (wave_cap + slack + 16) * 8));
+    B2RT_CUDA_OK(cudaMalloc(&l_slot[k], (wave_cap + slack + 16) * 4));
   }
   B2RT_CUDA_OK(cudaMalloc(&thr, wave_cap * sizeof(float4)));
   B2RT_CUDA_OK(cudaMalloc(&rad, wave_cap * sizeof(float4)));
-  B2RT_CUDA_OK(cudaMalloc(&s_o, (wave_cap * Salloc + 16) * sizeof(float4)));
-  B2RT_CUDA_OK(cudaMalloc(&s_d, (wave_cap * Salloc + 16) * sizeof(float4)));
-  B2RT_CUDA_OK(cudaMalloc(&s_hits, (wave_cap * Salloc + 16) * 8));
-  B2RT_CUDA_OK(cudaMalloc(&s_contrib, wave_cap * Salloc * sizeof(float4)));
+  B2RT_CUDA_OK(cudaMalloc(&s_o, ((wave_cap + slack) * Salloc + 16) * sizeof(float4)));
+  B2RT_CUDA_OK(cudaMalloc(&s_d, ((wave_cap + slack) * Salloc + 16) * sizeof(float4)));
+  B2RT_CUDA_OK(cudaMalloc(&s_hits, ((wave_cap + slack) * Salloc + 16) * 8));
+  B2RT_CUDA_OK(cudaMalloc(&s_contrib, (wave_cap + slack) * Salloc * sizeof(float4)));
   B2RT_CUDA_OK(cudaMalloc(&s_q0, wave_cap * 4));
   B2RT_CUDA_OK(cudaMalloc(&counts, N_COUNTS * 4));
   B2RT_CUDA_OK(cudaMalloc(&totals, 8 * 8));
   B2RT_CUDA_OK(cudaMemset(counts, 0, N_COUNTS * 4));
   B2RT_CUDA_OK(cudaMemset(totals, 0, 8 * 8));
-  RCHECK(tracer.init(dbvh, wave_cap * Salloc, 4));
-  if (overlap) RCHECK(tracer2.init(dbvh, wave_cap * Salloc, 4));
+  RCHECK(tracer.init(dbvh, (wave_cap + slack) * Salloc, 4));
+  if (overlap) RCHECK(tracer2.init(dbvh, (wave_cap + slack) * Salloc, 4));
   bvh_stale = false;
   return B2RT_OK;
 }
@@ -913,7 +1058,7 @@ int Renderer::make_frame_ctx(FrameCtx* fc) {
   pb.no = (float4*)l_o[1]; pb.nd = (float4*)l_d[1]; pb.nh = l_h[1]; pb.nslot = l_slot[1];
   pb.thr = (float4*)thr; pb.rad = (float4*)rad;
   pb.s_o = (float4*)s_o; pb.s_d = (float4*)s_d; pb.s_hits = s_hits; pb.s_contrib = (float4*)s_contrib;
-  pb.s_q0 = s_q0; pb.counts = counts;
+  pb.s_q0 = s_q0; pb.counts = counts; pb.inc_bound = 0xFFFFFFFFu;
   return B2RT_OK;
 }
 
@@ -930,6 +1075,8 @@ int Renderer::enqueue_wave(const FrameCtx& fc, const WaveParams& wp, uint32_t st
   const bool shade_ext = d_env != nullptr || have_glossy;
   const uint32_t n = wp.n_pix * wp.spp;
   const uint32_t g = (n + 255) / 256;
+  const uint64_t n_list = (uint64_t)n + list_slack;       // longest list of the wave, null entries included
+  const uint32_t g_list = (uint32_t)((n_list + 255) / 256);
   bind_lists(0);   // k_raygen fills list 0; k_shade(b) appends the continuing paths to list (b+1)&1
   k_raygen<<<g, 256, 0, stream>>>(wp, fc.cd, pb); launches++;
   // The shadow rays of bounce b and the continuing rays of bounce b + 1 both come out of k_shade(b) and do not
@@ -941,24 +1088,24 @@ int Renderer::enqueue_wave(const FrameCtx& fc, const WaveParams& wp, uint32_t st
   bool pending_resolve = false;
   for (uint32_t b = 0; b < max_depth; ++b) {
     bind_lists(b & 1u);
-    RCHECK(tracer.trace_sliced(stream, pb.lo, pb.ld, pb.lh, counts + ACT0 + b, n, false));
+    RCHECK(tracer.trace_sliced(stream, pb.lo, pb.ld, pb.lh, counts + ACT0 + b, n_list, false));
     // shade(b) adds emission to the radiance that resolve(b - 1) updates and rewrites the shadow list it reads
     if (pending_resolve) { B2RT_CUDA_OK(cudaStreamWaitEvent(stream, ev_sync[2 * (b - 1) + 1], 0)); pending_resolve = false; }
-    if (shade_ext) k_shade<true><<<(n + SHADE_THREADS - 1) / SHADE_THREADS, SHADE_THREADS, 0, stream>>>(wp, fc.sd, pb, b);
-    else k_shade<false><<<(n + SHADE_THREADS - 1) / SHADE_THREADS, SHADE_THREADS, 0, stream>>>(wp, fc.sd, pb, b);
+    if (shade_ext) k_shade<true><<<shade_ctas, SHADE_THREADS, 0, stream>>>(wp, fc.sd, pb, b);
+    else k_shade<false><<<shade_ctas, SHADE_THREADS, 0, stream>>>(wp, fc.sd, pb, b);
     launches++;
     if (S > 0) {
       if (ov) {
         // shadow rays of bounce b on the second stream, next to the closest-hit trace of bounce b + 1
         B2RT_CUDA_OK(cudaEventRecord(ev_sync[2 * b], stream));
         B2RT_CUDA_OK(cudaStreamWaitEvent(stream2, ev_sync[2 * b], 0));
-        RCHECK(tracer2.trace_sliced(stream2, pb.s_o, pb.s_d, pb.s_hits, counts + SH0 + b, (uint64_t)n * S, true));
-        k_resolve_shadow<<<g, 256, 0, stream2>>>(wp, pb, b); launches++;
+        RCHECK(tracer2.trace_sliced(stream2, pb.s_o, pb.s_d, pb.s_hits, counts + SH0 + b, n_list * S, true));
+        k_resolve_shadow<<<g_list, 256, 0, stream2>>>(wp, pb, b); launches++;
         B2RT_CUDA_OK(cudaEventRecord(ev_sync[2 * b + 1], stream2));
         pending_resolve = true;
       } else {
-        RCHECK(tracer.trace_sliced(stream, pb.s_o, pb.s_d, pb.s_hits, counts + SH0 + b, (uint64_t)n * S, true));
-        k_resolve_shadow<<<g, 256, 0, stream>>>(wp, pb, b); launches++;
+        RCHECK(tracer.trace_sliced(stream, pb.s_o, pb.s_d, pb.s_hits, counts + SH0 + b, n_list * S, true));
+        k_resolve_shadow<<<g_list, 256, 0, stream>>>(wp, pb, b); launches++;
       }
     }
   }

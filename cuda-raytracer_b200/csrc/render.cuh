@@ -55,6 +55,7 @@ struct Renderer {
   uint64_t waves_retried = 0;
   // wave buffers
   uint64_t wave_cap = 0; uint32_t wave_S = 0;
+  uint32_t shade_ctas = 0, list_slack = 0;   // k_shade's fixed grid; null entries a list can hold on top of its paths
   void *l_o[2] = {nullptr, nullptr}, *l_d[2] = {nullptr, nullptr};           // dense ray lists (double-buffered by bounce)
   unsigned long long *l_h[2] = {nullptr, nullptr};
   uint32_t *l_slot[2] = {nullptr, nullptr};

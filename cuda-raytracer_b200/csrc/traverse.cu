@@ -623,7 +623,8 @@ k_traverse(const TravParams P) {
           ny = inv.y >= 0.f ? 4u * W : 16u * W;
           nz = inv.z >= 0.f ? 8u * W : 20u * W;
           have = true; sp = 0;
-          const bool skip = ANYHIT && h0_id != 0xFFFFFFFFu;
+          // not traced: an any-hit ray that is already occluded; a ray whose interval is empty (the renderer's null entries)
+          const bool skip = ANYHIT ? h0_id != 0xFFFFFFFFu : best_t < tmin;
           cur = skip ? REF_NONE : 0u;   // INTERNAL node 0 = subtree root
           if (STATS) st_visits++;
         }
@@ -867,7 +868,7 @@ k_slice_init(const uint32_t* n_dev, const float4* __restrict__ ray_o, const floa
       t_enter = t_enter - box.margin - 1e-4f * fabsf(t_enter);
       // dropped only when the comparison is TRUE (a NaN keeps the ray): the ray misses the padded box, the box is
       // behind tmin, or beyond tmax
-      const bool miss = (t_enter > t_exit) || (t_exit < o.w) || (t_enter > d.w);
+      const bool miss = (t_enter > t_exit) || (t_exit < o.w) || (t_enter > d.w) || (d.w < o.w);
       const bool done = any_hit && (uint32_t)hits[i] != 0xFFFFFFFFu;
       keep = !miss && !done;
       t_end = fminf(d.w, fmaxf(o.w, t_enter) + first);
