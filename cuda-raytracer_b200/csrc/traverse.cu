@@ -136,7 +136,15 @@ __device__ __forceinline__ void block_excl_scan2(uint32_t a, uint32_t b, uint32_
 __global__ void __launch_bounds__(1024, 1)
 k_schedule_level(uint32_t* __restrict__ cnt, uint32_t* __restrict__ seg_off, uint32_t* __restrict__ cursor,
                  uint4* __restrict__ chunks, uint32_t* __restrict__ ctrl, uint32_t first, uint32_t n, uint32_t chunk_rays,
-                 uint32_t chunk_cap, uint32_t level) {
+                 uint32_t chunk_cap, uint32_t level, uint32_t pair_cap, uint32_t want_chunks, uint32_t chunk_min) {
+  // A level with few rays gets smaller chunks, so that the launch still has `want_chunks` of them (a few per resident
+  // CTA): with 1024-ray chunks a launch of 1 M rays is 1000 chunks for 592 CTAs and its second round runs on a
+  // half-empty GPU.  The level's ray count is the pair count of the level above.
+  {
+    const uint32_t total = min(ctrl[(level - 1u) & 1u], pair_cap);
+    const uint32_t fit = (total / max(want_chunks, 1u) + 127u) & ~127u;
+    chunk_rays = min(chunk_rays, max(chunk_min, fit));
+  }
   __shared__ uint32_t sh[66];
   __shared__ uint4 big[1024];   // (subtree, seg offset, count, chunk base) of subtrees with many chunks
   __shared__ uint32_t n_big;
@@ -1001,13 +1009,15 @@ int Tracer::init(const DeviceBVH& b, uint64_t max_rays_, uint32_t pair_factor) {
   }
   // BVH dependent part (small, grow-only)
   bvh = b;
-  chunk_cap = pair_cap / chunk_rays + (uint64_t)bvh.n_treelets + 1024;
   // dynamic shared memory: the staged subtree blob, then the per-thread traversal stacks
   stack_off = (std::max<size_t>(bvh.max_treelet_bytes, 1024) + 127) & ~(size_t)127;
   ring_off = 0;
   smem_bytes = stack_off + stack_bytes(bvh.width);
   if (const char* e = getenv("B2RT_CHUNK_RAYS")) { int v = atoi(e); if (v >= 32 && v <= (1 << 20)) chunk_rays = (uint32_t)v; }
+  if (const char* e = getenv("B2RT_CHUNK_MIN")) { int v = atoi(e); if (v >= 32 && v <= (1 << 20)) chunk_min = (uint32_t)v; }
+  if (const char* e = getenv("B2RT_CHUNKS_PER_CTA")) { int v = atoi(e); if (v >= 0 && v <= 64) chunks_per_cta = (uint32_t)v; }
   if (const char* e = getenv("B2RT_CHUNK0_MAX")) { int v = atoi(e); if (v >= 32 && v <= (1 << 24)) chunk0_max = (uint32_t)v; }
+  chunk_cap = pair_cap / std::min(chunk_rays, chunk_min) + (uint64_t)bvh.n_treelets + 1024;
   int occ = 1, o2 = 1, o3 = 1, o4 = 1;
   int rc;
 #define B2_PREP(WW)                                                             \
@@ -1119,7 +1129,7 @@ int Tracer::trace(cudaStream_t s, const float4* ray_o, const float4* ray_d, unsi
         k_count<<<num_sms * 8, 256, 0, s>>>(pairs, &ctrl[(L - 1) & 1], cnt, (uint32_t)pair_cap);
       }
       k_schedule_level<<<1, 1024, 0, s>>>(cnt, seg_off, cursor, chunks, ctrl, lr.first, lr.count, chunk_rays,
-                                          (uint32_t)chunk_cap, L);
+                                          (uint32_t)chunk_cap, L, (uint32_t)pair_cap, num_sms * ctas_per_sm * chunks_per_cta, chunk_min);
       launches += 2;
     }
     if (L > 0) {
