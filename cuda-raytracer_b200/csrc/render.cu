@@ -66,6 +66,7 @@ struct PathBufs {
   // [BLKA0 + b] / [BLKS0 + b] = reservation blocks handed out of the two lists
   uint32_t* counts;
   uint32_t inc_bound;   // 0xFFFFFFFF (see next_block)
+  uint32_t list_cap, shadow_cap;   // entries allocated per path list / for the shadow list (checked in B2RT_CHECKS builds)
 };
 
 __global__ void __launch_bounds__(256)
@@ -545,6 +546,9 @@ k_shade(WaveParams wp, SceneDev sc, PathBufs pb, uint32_t b) {
     }
   }
   real_s += n_valid;
+#ifdef B2RT_CHECKS
+  if ((cont && p >= pb.list_cap) || out_a.end > pb.list_cap || out_s.end > pb.shadow_cap) __trap();
+#endif
   if (cont) {
     pb.no[p] = next_o; pb.nd[p] = next_d; pb.nh[p] = pack_hit(INF_F, 0xFFFFFFFFu); pb.nslot[p] = slot;
     real_a++;
@@ -1059,6 +1063,8 @@ int Renderer::make_frame_ctx(FrameCtx* fc) {
   pb.thr = (float4*)thr; pb.rad = (float4*)rad;
   pb.s_o = (float4*)s_o; pb.s_d = (float4*)s_d; pb.s_hits = s_hits; pb.s_contrib = (float4*)s_contrib;
   pb.s_q0 = s_q0; pb.counts = counts; pb.inc_bound = 0xFFFFFFFFu;
+  pb.list_cap = (uint32_t)std::min<uint64_t>(wave_cap + list_slack, 0xFFFFFFFFull);
+  pb.shadow_cap = (uint32_t)std::min<uint64_t>((wave_cap + list_slack) * std::max(1u, wave_S), 0xFFFFFFFFull);
   return B2RT_OK;
 }
 

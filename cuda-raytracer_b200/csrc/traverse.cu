@@ -428,6 +428,7 @@ __device__ __forceinline__ float4 ldg_stream_f4(const float4* p) {
   return v;
 }
 
+template <int W> constexpr int STACK_ENTRIES_V = (int)stack_entries(W);   // (a constant the device code may name)
 template <int W, bool ANYHIT, bool STATS>
 __global__ void __launch_bounds__(TRAV_THREADS, (W <= 4 ? B2RT_OCC4 : (W == 8 ? 2 : 1)))
 k_traverse(const TravParams P) {
@@ -720,7 +721,7 @@ k_traverse(const TravParams P) {
 #pragma unroll
         for (int q = W - 1; q >= 1; --q) {
           if (keys[q] != 0xFFFFFFFFu) {
-            B2_CHECK(sp < (int)stack_entries(W), 3, sp);
+            B2_CHECK(sp < STACK_ENTRIES_V<W>, 3, sp);
             sts_u32(stack + (uint32_t)sp * (TRAV_THREADS * 4u), (keys[q] & (STACK_TN_MASK | (uint32_t)(W - 1))) | node_tag);
             ++sp;
           }
