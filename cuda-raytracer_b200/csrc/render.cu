@@ -539,10 +539,10 @@ k_shade(WaveParams wp, SceneDev sc, PathBufs pb, uint32_t b) {
   const uint32_t p = warp_append(out_a, &pb.counts[BLKA0 + b + 1], pb.inc_bound, cont, 1, blk, lane, lane_lt);
   if (single) {
     const uint32_t q = warp_append(out_s, &pb.counts[BLKS0 + b], pb.inc_bound, sh_valid, 1, blk_sh, lane, lane_lt);
-    if (active) pb.s_q0[slot] = sh_valid ? q : 0xFFFFFFFFu;
     if (sh_valid) {
+      // the entry names its path (w = slot bits): k_resolve_shadow1 walks the shadow list itself
       pb.s_o[q] = next_o; pb.s_d[q] = sh_d; pb.s_hits[q] = pack_hit(sh_d.w, 0xFFFFFFFFu);
-      pb.s_contrib[q] = make_float4(sh_c.x, sh_c.y, sh_c.z, 1.f);
+      pb.s_contrib[q] = make_float4(sh_c.x, sh_c.y, sh_c.z, __uint_as_float(slot));
     }
   }
   real_s += n_valid;
@@ -570,7 +570,7 @@ k_shade(WaveParams wp, SceneDev sc, PathBufs pb, uint32_t b) {
     if (k && !out_s.has) break;
     for (uint32_t q = lo + lane; q < hi; q += 32u) {
       pb.s_o[q] = make_float4(0.f, 0.f, 0.f, 0.f); pb.s_d[q] = make_float4(0.f, 0.f, 1.f, -1.f);
-      pb.s_hits[q] = NULL_HIT; pb.s_contrib[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+      pb.s_hits[q] = NULL_HIT; pb.s_contrib[q] = make_float4(0.f, 0.f, 0.f, single ? __uint_as_float(0xFFFFFFFFu) : 0.f);
     }
   }
   real_a = __reduce_add_sync(0xffffffffu, real_a);
@@ -605,6 +605,22 @@ k_resolve_shadow(WaveParams wp, PathBufs pb, uint32_t b) {
     }
   }
   if (any) pb.rad[slot] = L;
+}
+
+// S == 1 (one light sample per interaction): one thread per SHADOW-list entry; the entry carries its path's slot, a path
+// has at most one entry per bounce, so the sum needs no order.  (The path-list walk above reads 8 B per path to find
+// the ~55 % of them that own a shadow ray.)
+__global__ void __launch_bounds__(256)
+k_resolve_shadow1(PathBufs pb, uint32_t b) {
+  const uint32_t n = pb.counts[SH0 + b];
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float4 c = pb.s_contrib[i];
+  const uint32_t slot = __float_as_uint(c.w);
+  if (slot == 0xFFFFFFFFu || (uint32_t)pb.s_hits[i] != 0xFFFFFFFFu) return;   // null entry / occluded
+  float4 L = pb.rad[slot];
+  L.x = L.x + c.x; L.y = L.y + c.y; L.z = L.z + c.z;
+  pb.rad[slot] = L;
 }
 
 // Closes a wave: status 1 = complete, 2 = a ray queue overflowed while it was traced (its paths are incomplete: the
@@ -1106,12 +1122,16 @@ int Renderer::enqueue_wave(const FrameCtx& fc, const WaveParams& wp, uint32_t st
         B2RT_CUDA_OK(cudaEventRecord(ev_sync[2 * b], stream));
         B2RT_CUDA_OK(cudaStreamWaitEvent(stream2, ev_sync[2 * b], 0));
         RCHECK(tracer2.trace_sliced(stream2, pb.s_o, pb.s_d, pb.s_hits, counts + SH0 + b, n_list * S, true));
-        k_resolve_shadow<<<g_list, 256, 0, stream2>>>(wp, pb, b); launches++;
+        if (S == 1) k_resolve_shadow1<<<g_list, 256, 0, stream2>>>(pb, b);
+        else k_resolve_shadow<<<g_list, 256, 0, stream2>>>(wp, pb, b);
+        launches++;
         B2RT_CUDA_OK(cudaEventRecord(ev_sync[2 * b + 1], stream2));
         pending_resolve = true;
       } else {
         RCHECK(tracer.trace_sliced(stream, pb.s_o, pb.s_d, pb.s_hits, counts + SH0 + b, n_list * S, true));
-        k_resolve_shadow<<<g_list, 256, 0, stream>>>(wp, pb, b); launches++;
+        if (S == 1) k_resolve_shadow1<<<g_list, 256, 0, stream>>>(pb, b);
+        else k_resolve_shadow<<<g_list, 256, 0, stream>>>(wp, pb, b);
+        launches++;
       }
     }
   }
