@@ -27,7 +27,7 @@ struct Tracer {
   DeviceBVH bvh;
   uint64_t max_rays = 0, pair_cap = 0, chunk_cap = 0;
   uint64_t nt_cap = 0, chunk_alloc = 0;     // grow-only capacities of the per-subtree arrays / chunk list
-  uint32_t chunk_rays = 1024;      // rays per work item of a level >= 1 subtree queue (upper bound)
+  uint32_t chunk_rays = 2048;      // rays per work item of a level >= 1 subtree queue (upper bound)
   uint32_t chunk_min = 256;        // ... shrunk down to this when the level has fewer than chunks_per_cta chunks per resident CTA
   uint32_t chunks_per_cta = 2;
   uint32_t chunk0_max = 8192;      // level 0 (one subtree, every ray): chunks grow up to this
