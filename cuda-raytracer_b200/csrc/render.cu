@@ -47,9 +47,9 @@ struct SceneDev {
   uint32_t env_w, env_h;
 };
 
-// Rays live in DENSE lists (what the traversal streams with TMA): entry i of the bounce-b list is the ray of path
-// `lslot[i]`; shading appends the continuing paths to the other list, so no list ever has holes.  Per-path state
-// (throughput, radiance) is indexed by the path's slot.
+// Rays live in DENSE lists (what level 0 of the traversal streams): entry i of the bounce-b list is the ray of path
+// `lslot[i]`; shading appends the continuing paths to the other list in warp-private blocks, whose unfilled tails are
+// null entries (slot 0xFFFFFFFF, empty interval).  Per-path state (throughput, radiance) is indexed by the path's slot.
 struct PathBufs {
   // current bounce's list (read) and the next bounce's (appended to); the host swaps them per bounce -- plain
   // pointers, not an indexed array: a dynamically indexed kernel parameter would be copied to local memory
@@ -141,66 +141,6 @@ __device__ __forceinline__ void make_coord_space(f3 n, f3* X, f3* Y, f3* Z) {
   f3 y = normalize3(cross3(h, z));
   f3 x = normalize3(cross3(z, y));
   *X = x; *Y = y; *Z = z;
-}
-
-// warp-aggregated append: position of this thread's element in a dense list (callers with pred == false get
-// garbage).  Works on whatever subset of the warp is converged at the call site.
-__device__ __forceinline__ uint32_t append_pos(uint32_t* counter, bool pred) {
-  const uint32_t m = __ballot_sync(__activemask(), pred);
-  if (!pred) return 0xFFFFFFFFu;
-  const uint32_t lane = threadIdx.x & 31;
-  const uint32_t leader = __ffs(m) - 1;
-  uint32_t base = 0;
-  if (lane == leader) base = atomicAdd(counter, (uint32_t)__popc(m));
-  base = __shfl_sync(m, base, leader);
-  return base + __popc(m & ((1u << lane) - 1u));
-}
-
-// CTA-aggregated append: position of this thread's run of `per_item` consecutive elements in a dense list (garbage
-// when pred == false).  One global atomic per CTA -- the per-bounce list counters are single addresses, and L2
-// serialises same-address atomics, so one atomic per warp made the shading kernel atomic-bound.  Must be called by
-// every thread of a 256-thread CTA.  `extra` is a second per-thread value summed over the CTA into *extra_counter.
-__device__ __forceinline__ uint32_t block_append(uint32_t* counter, bool pred, uint32_t per_item, uint32_t* sh /* 10 words */,
-                                                 uint32_t extra = 0, uint32_t* extra_counter = nullptr) {
-  const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const uint32_t m = __ballot_sync(0xffffffffu, pred);
-  const uint32_t ex = extra_counter ? __reduce_add_sync(0xffffffffu, extra) : 0u;
-  if (lane == 0) sh[warp] = (uint32_t)__popc(m) | (ex << 8);   // <= 32 items, extra < 2^24 per warp
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    uint32_t tot = 0, tex = 0;
-    const uint32_t nw = blockDim.x >> 5;
-    for (uint32_t w = 0; w < nw; ++w) { const uint32_t v = sh[w]; sh[w] = tot; tot += v & 0xFFu; tex += v >> 8; }
-    sh[8] = tot ? atomicAdd(counter, tot * per_item) : 0u;
-    if (tex) atomicAdd(extra_counter, tex);
-  }
-  __syncthreads();
-  const uint32_t pos = sh[8] + (sh[warp] + (uint32_t)__popc(m & ((1u << lane) - 1u))) * per_item;
-  __syncthreads();   // sh is reused by the next call
-  return pos;
-}
-
-// Two CTA-aggregated appends (one element per flagged thread each) behind ONE barrier sequence; `extra` as above.
-__device__ __forceinline__ uint2 block_append2(uint32_t* counter_a, bool pred_a, uint32_t* counter_b, bool pred_b, uint32_t* sh /* 10 words */,
-                                               uint32_t extra, uint32_t* extra_counter) {
-  const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const uint32_t ma = __ballot_sync(0xffffffffu, pred_a), mb = __ballot_sync(0xffffffffu, pred_b);
-  const uint32_t ex = __reduce_add_sync(0xffffffffu, extra);
-  if (lane == 0) sh[warp] = (uint32_t)__popc(ma) | ((uint32_t)__popc(mb) << 8) | (ex << 16);   // each <= 32 per warp
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    uint32_t ta = 0, tb = 0, tex = 0;
-    const uint32_t nw = blockDim.x >> 5;
-    for (uint32_t w = 0; w < nw; ++w) { const uint32_t v = sh[w]; sh[w] = ta | (tb << 16); ta += v & 0xFFu; tb += (v >> 8) & 0xFFu; tex += v >> 16; }
-    sh[8] = ta ? atomicAdd(counter_a, ta) : 0u;
-    sh[9] = tb ? atomicAdd(counter_b, tb) : 0u;
-    if (tex) atomicAdd(extra_counter, tex);
-  }
-  __syncthreads();
-  const uint32_t lt = (1u << lane) - 1u;
-  const uint2 pos = make_uint2(sh[8] + (sh[warp] & 0xFFFFu) + (uint32_t)__popc(ma & lt), sh[9] + (sh[warp] >> 16) + (uint32_t)__popc(mb & lt));
-  __syncthreads();
-  return pos;
 }
 
 // A warp's private piece of a dense output list.  Warps reserve blocks of `blk` entries from the list's block counter
