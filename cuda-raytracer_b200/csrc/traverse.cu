@@ -1015,6 +1015,8 @@ int Tracer::init(const DeviceBVH& b, uint64_t max_rays_, uint32_t pair_factor) {
   ring_off = 0;
   smem_bytes = stack_off + stack_bytes(bvh.width);
   if (const char* e = getenv("B2RT_CHUNK_RAYS")) { int v = atoi(e); if (v >= 32 && v <= (1 << 20)) chunk_rays = (uint32_t)v; }
+  if (const char* e = getenv("B2RT_COUNT_CTAS")) { int v = atoi(e); if (v >= 1 && v <= 32) count_ctas = (uint32_t)v; }
+  if (const char* e = getenv("B2RT_SCATTER_CTAS")) { int v = atoi(e); if (v >= 1 && v <= 32) scatter_ctas = (uint32_t)v; }
   if (const char* e = getenv("B2RT_CHUNK_MIN")) { int v = atoi(e); if (v >= 32 && v <= (1 << 20)) chunk_min = (uint32_t)v; }
   if (const char* e = getenv("B2RT_CHUNKS_PER_CTA")) { int v = atoi(e); if (v >= 0 && v <= 64) chunks_per_cta = (uint32_t)v; }
   if (const char* e = getenv("B2RT_CHUNK0_MAX")) { int v = atoi(e); if (v >= 32 && v <= (1 << 24)) chunk0_max = (uint32_t)v; }
@@ -1125,7 +1127,7 @@ int Tracer::trace(cudaStream_t s, const float4* ray_o, const float4* ray_d, unsi
     const LevelRange lr = bvh.levels[L];
     if (L > 0) {
       if (lr.count <= 12288) {
-        k_count_tiled<<<num_sms * 4, 256, (size_t)lr.count * 4, s>>>(pairs, &ctrl[(L - 1) & 1], cnt, (uint32_t)pair_cap, lr.first, lr.count);
+        k_count_tiled<<<num_sms * count_ctas, 256, (size_t)lr.count * 4, s>>>(pairs, &ctrl[(L - 1) & 1], cnt, (uint32_t)pair_cap, lr.first, lr.count);
       } else {
         k_count<<<num_sms * 8, 256, 0, s>>>(pairs, &ctrl[(L - 1) & 1], cnt, (uint32_t)pair_cap);
       }
@@ -1135,7 +1137,7 @@ int Tracer::trace(cudaStream_t s, const float4* ray_o, const float4* ray_d, unsi
     }
     if (L > 0) {
       if (lr.count <= 12288) {
-        k_scatter_tiled<<<num_sms * 4, 256, (size_t)lr.count * 8, s>>>(pairs, &ctrl[(L - 1) & 1], seg_off, cursor, ids_sorted,
+        k_scatter_tiled<<<num_sms * scatter_ctas, 256, (size_t)lr.count * 8, s>>>(pairs, &ctrl[(L - 1) & 1], seg_off, cursor, ids_sorted,
                                                                         (uint32_t)pair_cap, lr.first, lr.count);
       } else {
         k_scatter<<<num_sms * 8, 256, 0, s>>>(pairs, &ctrl[(L - 1) & 1], seg_off, cursor, ids_sorted, (uint32_t)pair_cap);

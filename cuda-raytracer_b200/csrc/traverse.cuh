@@ -30,6 +30,7 @@ struct Tracer {
   uint32_t chunk_rays = 2048;      // rays per work item of a level >= 1 subtree queue (upper bound)
   uint32_t chunk_min = 256;        // ... shrunk down to this when the level has fewer than chunks_per_cta chunks per resident CTA
   uint32_t chunks_per_cta = 2;
+  uint32_t count_ctas = 4, scatter_ctas = 6;   // CTAs per SM of k_count_tiled / k_scatter_tiled
   uint32_t chunk0_max = 8192;      // level 0 (one subtree, every ray): chunks grow up to this
   size_t stack_off = 0;            // offset of the traversal stacks in dynamic shared memory
   size_t ring_off = 0;             // offset of the ray ring
