@@ -207,9 +207,13 @@ k_count_tiled(const uint2* __restrict__ pairs, const uint32_t* __restrict__ pair
   const uint32_t n = min(*pair_count, pair_cap);
   for (uint32_t i = threadIdx.x; i < K; i += 256) s_hist[i] = 0;
   __syncthreads();
-  for (uint32_t i = blockIdx.x * 256 + threadIdx.x; i < n; i += gridDim.x * 256) {
-    const uint32_t t = pairs[i].x;
-    if (t != 0xFFFFFFFFu) atomicAdd(&s_hist[t - first], 1u);
+  // four pairs per thread and iteration, their loads in flight together
+  for (uint32_t i0 = blockIdx.x * 1024 + threadIdx.x; i0 < n; i0 += gridDim.x * 1024) {
+    uint32_t t[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) { const uint32_t i = i0 + (uint32_t)k * 256u; t[k] = i < n ? pairs[i].x : 0xFFFFFFFFu; }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) if (t[k] != 0xFFFFFFFFu) atomicAdd(&s_hist[t[k] - first], 1u);
   }
   __syncthreads();
   for (uint32_t i = threadIdx.x; i < K; i += 256) {
