@@ -266,7 +266,10 @@ k_scatter(const uint2* __restrict__ pairs, const uint32_t* __restrict__ pair_cou
 // Tiled variant: a CTA ranks a tile of pairs in a shared-memory histogram over the level's subtrees and then
 // reserves ONE global cursor range per (tile, subtree) instead of one per warp-group -- the global atomics on the
 // few hot cursors of a small level (CBbunny: 119 subtrees) were the cost of the plain kernel.
-constexpr int SCATTER_TILE = 2048;   // pairs per CTA iteration (8 per thread)
+#ifndef B2RT_SCATTER_TILE
+#define B2RT_SCATTER_TILE 2048
+#endif
+constexpr int SCATTER_TILE = B2RT_SCATTER_TILE;   // pairs per CTA iteration (8 per thread)
 __global__ void __launch_bounds__(256)
 k_scatter_tiled(const uint2* __restrict__ pairs, const uint32_t* __restrict__ pair_count, const uint32_t* __restrict__ seg_off,
                 uint32_t* __restrict__ cursor, uint32_t* __restrict__ ids_sorted, uint32_t pair_cap, uint32_t first, uint32_t K) {
