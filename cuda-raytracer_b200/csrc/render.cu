@@ -979,8 +979,8 @@ int Renderer::ensure_wave() {
   }
   if (wave_cap >= want && wave_S >= Salloc && tracer.max_rays >= (want + slack) * Salloc && (!overlap || tracer2.max_rays >= (want + slack) * Salloc)) {
     if (bvh_stale) {
-      RCHECK(tracer.init(dbvh, tracer.max_rays, 4));
-      if (overlap) RCHECK(tracer2.init(dbvh, tracer2.max_rays, 4));
+      RCHECK(tracer.init(dbvh, tracer.max_rays, pair_factor));
+      if (overlap) RCHECK(tracer2.init(dbvh, tracer2.max_rays, pair_factor));
       bvh_stale = false;
     }
     return B2RT_OK;
@@ -1007,8 +1007,12 @@ int Renderer::ensure_wave() {
   B2RT_CUDA_OK(cudaMalloc(&totals, 8 * 8));
   B2RT_CUDA_OK(cudaMemset(counts, 0, N_COUNTS * 4));
   B2RT_CUDA_OK(cudaMemset(totals, 0, 8 * 8));
-  RCHECK(tracer.init(dbvh, (wave_cap + slack) * Salloc, 4));
-  if (overlap) RCHECK(tracer2.init(dbvh, (wave_cap + slack) * Salloc, 4));
+  if (const char* e = getenv("B2RT_PAIR_FACTOR")) {   // starting value (tests: 1 forces the growth path on a push-heavy scene)
+    int v = atoi(e);
+    if (v >= 1 && v <= 64 && !pair_factor_from_env) { pair_factor = (uint32_t)v; pair_factor_from_env = true; }
+  }
+  RCHECK(tracer.init(dbvh, (wave_cap + slack) * Salloc, pair_factor));
+  if (overlap) RCHECK(tracer2.init(dbvh, (wave_cap + slack) * Salloc, pair_factor));
   bvh_stale = false;
   return B2RT_OK;
 }
@@ -1207,14 +1211,34 @@ int Renderer::wait() {
   std::vector<uint32_t> st(waves.size());
   if (!st.empty()) B2RT_CUDA_OK(cudaMemcpy(st.data(), wave_status, st.size() * 4, cudaMemcpyDeviceToHost));
   bool cancelled = false;
-  waves_retried = 0;
+  waves_retried = 0; queues_grown = 0;
   FrameCtx fc;
   bool have_fc = false;
   for (size_t w = 0; w < st.size(); ++w) {
     if (st[w] == 3u) cancelled = true;
     if (st[w] != 2u) continue;
     if (!have_fc) { RCHECK(make_frame_ctx(&fc)); have_fc = true; }
-    RCHECK(retry_wave(fc, waves[w], 0));
+    // The queues were sized for pair_factor pushes per ray and level (4 covers the box scenes' 0.3-0.5 and the soup's
+    // 2-3).  A scene that pushes more gets larger queues -- for this wave and every later frame -- before anything is
+    // split: the stream is idle here, so the schedulers can be re-initialised in place.
+    uint32_t st_w = 2u;
+    while (st_w == 2u && pair_factor < 32 && !getenv("B2RT_DEBUG_PAIR_CAP")) {
+      pair_factor *= 2;
+      if (tracer.init(dbvh, tracer.max_rays, pair_factor) != B2RT_OK || (overlap && tracer2.init(dbvh, tracer2.max_rays, pair_factor) != B2RT_OK)) {
+        // no memory for larger queues: go back and split the wave instead
+        pair_factor /= 2;
+        RCHECK(tracer.init(dbvh, tracer.max_rays, pair_factor));
+        if (overlap) RCHECK(tracer2.init(dbvh, tracer2.max_rays, pair_factor));
+        break;
+      }
+      queues_grown++;
+      const uint32_t scratch = (uint32_t)waves.size();
+      RCHECK(enqueue_wave(fc, waves[w], scratch));
+      B2RT_CUDA_OK(cudaMemcpyAsync(&st_w, wave_status + scratch, 4, cudaMemcpyDeviceToHost, stream));
+      B2RT_CUDA_OK(cudaStreamSynchronize(stream));
+      if (st_w == 1u) waves_retried++;
+    }
+    if (st_w == 2u) RCHECK(retry_wave(fc, waves[w], 0));
   }
   unsigned long long t[8];
   B2RT_CUDA_OK(cudaMemcpy(t, totals, sizeof t, cudaMemcpyDeviceToHost));
@@ -1238,6 +1262,7 @@ int Renderer::wait() {
     last.node_visits_l0 += t20.node_visits; last.leaf_prim_tests_l0 += t20.prim_tests; last.queue_pushes_l0 += t20.pushes;
     last.staged_bytes_l0 += t20.staged_bytes; last.hit_updates_l0 += t20.hit_updates;
   }
+  last.waves_retried = waves_retried; last.queues_grown = queues_grown;
   last.kernel_launches = launches + tracer.launches + tracer2.launches;
   last.traverse_launches = tracer.traverse_launches + tracer2.traverse_launches;
   last.traverse_launches_l0 = tracer.traverse_launches_l0 + tracer2.traverse_launches_l0;

@@ -52,7 +52,9 @@ struct Renderer {
   struct FrameCtx;
   std::vector<WaveParams> waves;
   uint32_t* wave_status = nullptr; size_t wave_status_cap = 0;
-  uint64_t waves_retried = 0;
+  uint64_t waves_retried = 0, queues_grown = 0;
+  bool pair_factor_from_env = false;
+  uint32_t pair_factor = 4;   // scheduler queue capacity in pushes per ray and level; doubled by wait() after an overflow
   // wave buffers
   uint64_t wave_cap = 0; uint32_t wave_S = 0;
   uint32_t shade_ctas = 0, list_slack = 0;   // k_shade's fixed grid; null entries a list can hold on top of its paths

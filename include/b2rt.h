@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define B2RT_ABI_VERSION 2   /* 2: b2rt_stats grew the level-0 fields, b2rt_comm_*, b2rt_write_*, b2rt_bench_fp32 */
+#define B2RT_ABI_VERSION 2   /* 2: b2rt_stats grew the level-0 fields and the overflow counters, b2rt_comm_*, b2rt_write_*, b2rt_bench_fp32 */
 
 typedef enum b2rt_status {
   B2RT_OK = 0,
@@ -166,6 +166,10 @@ typedef struct b2rt_stats {
   uint64_t hit_updates_l0;
   uint64_t traverse_launches_l0;
   double ms_traverse_l0;
+  /* ray-queue overflows of the last render call (b2rt_wait recovers from them, the frame is complete either way):
+     waves rendered again, and how often the queues were enlarged (x2 per step, kept for later frames) */
+  uint64_t waves_retried;
+  uint64_t queues_grown;
 } b2rt_stats;
 
 const char* b2rt_last_error(void);

@@ -607,6 +607,33 @@ def test_renderer_splits_waves_on_queue_overflow(monkeypatch):
     pt.close()
 
 
+def test_renderer_grows_queues_on_overflow(monkeypatch):
+    """A scene that pushes more rays per level than the queues were sized for: b2rt_wait enlarges the queues (kept for
+    later frames) and renders the wave again whole; the frame is the one a renderer with large queues produces, bit for
+    bit (one wave, so the order of the sample sums does not change)."""
+    soup = random_soup(120000, size=0.05)
+    sc = Scene(soup.tri_verts, materials=[dict(kind=0, albedo=(0.7, 0.6, 0.5))],
+               lights=[dict(kind=1, radiance=(3.0, 3.0, 3.0), position=(0.5, 0.6, 2.0))], cam_dir=(0, 0, 1))
+    w, h = 640, 480
+    cam = place_camera(sc, w, h)
+    cfg = dict(ns_aa=4, max_ray_depth=2, ns_area_light=1, seed=4, treelet_bytes=8192)
+    monkeypatch.setenv("B2RT_RENDER_SLICE", "0")           # no distance slices: every ray is queued at every subtree it overlaps
+    good = b2rt.PathTracer(**cfg)
+    good.set_scene(sc); good.set_camera(cam); good.set_frame_size(w, h); good.render()
+    ref = good.hdr(); st_ref = good.stats(); good.close()
+    assert st_ref["queues_grown"] == 0 and st_ref["waves_retried"] == 0
+    monkeypatch.setenv("B2RT_PAIR_FACTOR", "1")            # queues for one push per ray and level
+    pt = b2rt.PathTracer(**cfg)
+    pt.set_scene(sc); pt.set_camera(cam); pt.set_frame_size(w, h); pt.render()
+    st = pt.stats()
+    assert st["queues_grown"] >= 1 and st["waves_retried"] >= 1, st
+    assert np.array_equal(pt.hdr(), ref)
+    pt.render()                                            # the next frame runs on the enlarged queues
+    st2 = pt.stats()
+    assert st2["queues_grown"] == 0 and st2["waves_retried"] == 0
+    pt.close()
+
+
 def test_image_writers_and_one_rank_reduce(tmp_path):
     """b2rt_write_png / b2rt_write_exr store exactly what b2rt_read_ldr / b2rt_read_hdr return (top row first), and a
     one-rank NCCL reduce through the C ABI (b2rt_comm_* + b2rt_reduce_accum) leaves the accumulation buffer as it was."""
