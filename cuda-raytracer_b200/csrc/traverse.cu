@@ -133,10 +133,16 @@ __device__ __forceinline__ void block_excl_scan2(uint32_t a, uint32_t b, uint32_
   __syncthreads();
 }
 
+// One CTA per tile of 1024 subtrees; the tiles' running totals are chained through global memory (tile t waits for the
+// inclusive prefix of tile t - 1, adds its own totals, publishes): a level of 45 K subtrees is 45 hops of about a
+// microsecond instead of 45 iterations of one CTA (528 us on the 10 M-triangle soup, round 1).  Tiles are handed out by
+// a ticket, so a CTA only ever waits for one that is already running; flags carry the launch's epoch, so nothing has
+// to be cleared between launches.  scratch: [0] ticket, [1 + 3 t ...] = (flag, ray prefix, chunk prefix) of tile t.
 __global__ void __launch_bounds__(1024, 1)
 k_schedule_level(uint32_t* __restrict__ cnt, uint32_t* __restrict__ seg_off, uint32_t* __restrict__ cursor,
                  uint4* __restrict__ chunks, uint32_t* __restrict__ ctrl, uint32_t first, uint32_t n, uint32_t chunk_rays,
-                 uint32_t chunk_cap, uint32_t level, uint32_t pair_cap, uint32_t want_chunks, uint32_t chunk_min) {
+                 uint32_t chunk_cap, uint32_t level, uint32_t pair_cap, uint32_t want_chunks, uint32_t chunk_min,
+                 uint32_t* __restrict__ scratch, uint32_t epoch) {
   // A level with few rays gets smaller chunks, so that the launch still has `want_chunks` of them (a few per resident
   // CTA): with 1024-ray chunks a launch of 1 M rays is 1000 chunks for 592 CTAs and its second round runs on a
   // half-empty GPU.  The level's ray count is the pair count of the level above.
@@ -147,50 +153,59 @@ k_schedule_level(uint32_t* __restrict__ cnt, uint32_t* __restrict__ seg_off, uin
   }
   __shared__ uint32_t sh[66];
   __shared__ uint4 big[1024];   // (subtree, seg offset, count, chunk base) of subtrees with many chunks
-  __shared__ uint32_t n_big;
-  if (threadIdx.x == 0) n_big = 0;
+  __shared__ uint32_t n_big, s_tile, s_run_off, s_run_chunks;
+  if (threadIdx.x == 0) { n_big = 0; s_tile = atomicAdd(&scratch[0], 1u); }
   __syncthreads();
-  uint32_t run_off = 0, run_chunks = 0;
-  for (uint32_t base = 0; base < n; base += blockDim.x) {
-    uint32_t i = base + threadIdx.x;
-    uint32_t t = first + i;
-    uint32_t c = i < n ? cnt[t] : 0u;
-    if (i < n) cnt[t] = 0;   // self-cleaning: every level >= 1 is scheduled exactly once per trace
-    uint32_t nch = (c + chunk_rays - 1) / chunk_rays;
-    uint32_t eo, ec, to, tc;
-    block_excl_scan2(c, nch, &eo, &ec, &to, &tc, sh);
-    if (i < n) {
-      uint32_t off = run_off + eo, cb = run_chunks + ec;
-      seg_off[t] = off; cursor[t] = 0;
-      if (nch <= 4) {
-        for (uint32_t k = 0; k < nch; ++k)
-          if (cb + k < chunk_cap) chunks[cb + k] = make_uint4(t, off + k * chunk_rays, min(chunk_rays, c - k * chunk_rays), 0);
-      } else {
-        uint32_t slot = atomicAdd(&n_big, 1u);
-        if (slot < 1024) big[slot] = make_uint4(t, off, c, cb);
-        else  // cannot happen for blockDim 1024 per tile, kept for safety: write serially
-          for (uint32_t k = 0; k < nch; ++k)
-            if (cb + k < chunk_cap) chunks[cb + k] = make_uint4(t, off + k * chunk_rays, min(chunk_rays, c - k * chunk_rays), 0);
-      }
-    }
-    __syncthreads();
-    uint32_t nb = min(n_big, 1024u);
-    for (uint32_t b = threadIdx.x >> 5; b < nb; b += blockDim.x >> 5) {   // one warp per subtree with many chunks
-      uint4 e = big[b];
-      uint32_t nch_b = (e.z + chunk_rays - 1) / chunk_rays;
-      for (uint32_t k = threadIdx.x & 31; k < nch_b; k += 32)
-        if (e.w + k < chunk_cap) chunks[e.w + k] = make_uint4(e.x, e.y + k * chunk_rays, min(chunk_rays, e.z - k * chunk_rays), 0);
-    }
-    __syncthreads();
-    if (threadIdx.x == 0) n_big = 0;
-    run_off += to; run_chunks += tc;
-    __syncthreads();
-  }
+  const uint32_t tile = s_tile, n_tiles = gridDim.x;
+  const uint32_t i = tile * 1024u + threadIdx.x;
+  const uint32_t t = first + i;
+  const uint32_t c = i < n ? cnt[t] : 0u;
+  if (i < n) cnt[t] = 0;   // self-cleaning: every level >= 1 is scheduled exactly once per trace
+  const uint32_t nch = (c + chunk_rays - 1) / chunk_rays;
+  uint32_t eo, ec, to, tc;
+  block_excl_scan2(c, nch, &eo, &ec, &to, &tc, sh);
   if (threadIdx.x == 0) {
-    if (run_chunks > chunk_cap) { run_chunks = chunk_cap; ctrl[CTRL_OVERFLOW] = 1; }
-    ctrl[CTRL_NCHUNKS] = run_chunks;
-    ctrl[CTRL_NEXT0 + (level & 1)] = 0;   // chunk cursor of THIS level's traversal
-    ctrl[level & 1] = 0;                  // pair counter the traversal of THIS level appends to
+    uint32_t ro = 0, rc = 0;
+    if (tile > 0) {
+      volatile uint32_t* prev = scratch + 1 + 3 * (tile - 1);
+      while (prev[0] != epoch) { }
+      __threadfence();
+      ro = prev[1]; rc = prev[2];
+    }
+    volatile uint32_t* mine = scratch + 1 + 3 * tile;
+    mine[1] = ro + to; mine[2] = rc + tc;
+    __threadfence();
+    mine[0] = epoch;
+    s_run_off = ro; s_run_chunks = rc;
+    if (tile + 1 == n_tiles) {   // the last ticket: every tile has one, so the counter can go back to zero
+      scratch[0] = 0;
+      uint32_t run_chunks = rc + tc;
+      if (run_chunks > chunk_cap) { run_chunks = chunk_cap; ctrl[CTRL_OVERFLOW] = 1; }
+      ctrl[CTRL_NCHUNKS] = run_chunks;
+      ctrl[CTRL_NEXT0 + (level & 1)] = 0;   // chunk cursor of THIS level's traversal
+      ctrl[level & 1] = 0;                  // pair counter the traversal of THIS level appends to
+    }
+  }
+  __syncthreads();
+  const uint32_t run_off = s_run_off, run_chunks = s_run_chunks;
+  if (i < n) {
+    const uint32_t off = run_off + eo, cb = run_chunks + ec;
+    seg_off[t] = off; cursor[t] = 0;
+    if (nch <= 4) {
+      for (uint32_t k = 0; k < nch; ++k)
+        if (cb + k < chunk_cap) chunks[cb + k] = make_uint4(t, off + k * chunk_rays, min(chunk_rays, c - k * chunk_rays), 0);
+    } else {
+      const uint32_t slot = atomicAdd(&n_big, 1u);
+      big[slot] = make_uint4(t, off, c, cb);   // at most 1024 subtrees per tile
+    }
+  }
+  __syncthreads();
+  const uint32_t nb = min(n_big, 1024u);
+  for (uint32_t b = threadIdx.x >> 5; b < nb; b += blockDim.x >> 5) {   // one warp per subtree with many chunks
+    const uint4 e = big[b];
+    const uint32_t nch_b = (e.z + chunk_rays - 1) / chunk_rays;
+    for (uint32_t k = threadIdx.x & 31; k < nch_b; k += 32)
+      if (e.w + k < chunk_cap) chunks[e.w + k] = make_uint4(e.x, e.y + k * chunk_rays, min(chunk_rays, e.z - k * chunk_rays), 0);
   }
 }
 
@@ -1056,6 +1071,10 @@ int Tracer::init(const DeviceBVH& b, uint64_t max_rays_, uint32_t pair_factor) {
     B2RT_CUDA_OK(cudaMalloc(&cnt, nt_cap * 4));
     B2RT_CUDA_OK(cudaMalloc(&seg_off, nt_cap * 4));
     B2RT_CUDA_OK(cudaMalloc(&cursor, nt_cap * 4));
+    cudaFree(sched_scratch); sched_scratch = nullptr;
+    B2RT_CUDA_OK(cudaMalloc(&sched_scratch, (4 + 3 * (nt_cap / 1024 + 2)) * 4));
+    B2RT_CUDA_OK(cudaMemset(sched_scratch, 0, (4 + 3 * (nt_cap / 1024 + 2)) * 4));
+    sched_epoch = 0;
   }
   if (chunk_alloc < chunk_cap) {
     cudaFree(chunks); chunks = nullptr;
@@ -1101,7 +1120,7 @@ int Tracer::reset_counters(cudaStream_t s) {
 }
 
 void Tracer::release() {
-  cudaFree(cnt); cudaFree(seg_off); cudaFree(cursor); cudaFree(pairs); cudaFree(ids_sorted); cudaFree(chunks);
+  cudaFree(cnt); cudaFree(seg_off); cudaFree(cursor); cudaFree(pairs); cudaFree(ids_sorted); cudaFree(chunks); cudaFree(sched_scratch); sched_scratch = nullptr;
   cudaFree(ctrl); cudaFree(counters);
   cnt = seg_off = cursor = ids_sorted = ctrl = nullptr; pairs = nullptr; chunks = nullptr; counters = nullptr;
   pair_cap = 0; max_rays = 0; nt_cap = 0; chunk_alloc = 0;
@@ -1138,8 +1157,9 @@ int Tracer::trace(cudaStream_t s, const float4* ray_o, const float4* ray_d, unsi
       } else {
         k_count<<<num_sms * 8, 256, 0, s>>>(pairs, &ctrl[(L - 1) & 1], cnt, (uint32_t)pair_cap);
       }
-      k_schedule_level<<<1, 1024, 0, s>>>(cnt, seg_off, cursor, chunks, ctrl, lr.first, lr.count, chunk_rays,
-                                          (uint32_t)chunk_cap, L, (uint32_t)pair_cap, num_sms * ctas_per_sm * chunks_per_cta, chunk_min);
+      k_schedule_level<<<std::max(1u, (lr.count + 1023) / 1024), 1024, 0, s>>>(cnt, seg_off, cursor, chunks, ctrl, lr.first, lr.count, chunk_rays,
+                                          (uint32_t)chunk_cap, L, (uint32_t)pair_cap, num_sms * ctas_per_sm * chunks_per_cta, chunk_min,
+                                          sched_scratch, ++sched_epoch);
       launches += 2;
     }
     if (L > 0) {
