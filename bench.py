@@ -41,6 +41,10 @@ WORKLOADS = {
     "cfg3": ("cfg3_standin", 1920, 1080, 256, 8, 1, "strong"),
     "cfg4": ("cfg4_standin", 3840, 2160, 1024, 8, 1, "strong"),
 }
+# what the frames are made of: no data set is read; the geometry is a scene FILE of the reference checkout, converted offline
+DATA_NOTE = ("synthetic workload, no data set: geometry = the reference checkout's CBbunny.dae converted to scenes/CBbunny.b2s "
+             "(cfg3 / cfg4: bunny mesh subdivided once as the stand-in for the missing CBdragon / CBlucy assets); "
+             "camera rays and samples generated on the device (Philox4x32-10)")
 BASELINE_INDEX = {"cfg1": 0, "cfg2": 1, "cfg3": 2, "cfg4": 3}
 
 
@@ -98,9 +102,12 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append(line.strip())
+            self.rows.append((time.monotonic(), line.strip()))
 
-    def stop(self):
+    def stop(self, since=None):
+        """Samples that arrived after `since` (the start of the timed region).  nvidia-smi needs ~100 ms to deliver its
+        first line, so the sampler is started before the warm-up steps; a timed region too short to catch a sample of
+        its own falls back to the samples of the warm-up steps right before it (same load) and says so."""
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
@@ -110,7 +117,12 @@ class ClockSampler:
             self.proc.kill()
         sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
+        window = "timed region"
+        rows = [r for t, r in self.rows if since is None or t >= since]
+        if not rows:
+            rows = [r for _, r in self.rows]
+            window = "warm-up steps + timed region (timed region shorter than the sampling period)"
+        for r in rows:
             p = [x.strip() for x in r.split(",")]
             if len(p) < 7:
                 continue
@@ -122,10 +134,10 @@ class ClockSampler:
                 if v.lower().startswith("active"):
                     reasons.add(n)
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "samples": len(sm), "reasons": sorted(reasons)}
+                "samples": len(sm), "reasons": sorted(reasons), "window": window}
 
 
-def cpu_arm(args, sc, cam, wl, spp_sample, steps, warmup):
+def cpu_arm(args, sc, cam, wl, spp_sample, steps, warmup, target_seconds=0.0):
     """The reference's CPU implementation of the path on the host cores: the oracle port (the checkout's own
     CPU traversal / integrator bodies are stubs), all host threads, bounded sample."""
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
@@ -138,11 +150,14 @@ def cpu_arm(args, sc, cam, wl, spp_sample, steps, warmup):
         o.render(cam, cfg, wl["width"], wl["height"], threads=threads, tile_stride=8)
     rays = 0
     secs = 0.0
-    for _ in range(steps):
+    done = 0
+    while done < steps or (target_seconds and secs < target_seconds and done < 24):
         o.render(cam, cfg, wl["width"], wl["height"], threads=threads)
         st = o.last_stats
         rays += st["rays_camera"] + st["rays_bounce"] + st["rays_shadow"]
         secs += st["seconds"]
+        done += 1
+    steps = done
     return dict(value=rays / secs / 1e6, unit="Mrays/s", cores=threads, kind="port",
                 sample=f"{wl['scene']} {wl['width']}x{wl['height']}, {spp_sample} of {wl['spp']} spp, depth {wl['depth']}, "
                        f"{steps} frame(s), {threads} threads, oracle binary-SAH BVH (max_leaf 4)",
@@ -185,7 +200,7 @@ def main():
         cb = cpu_arm(args, sc, cam, wl, spp_s, args.steps, args.warmup)
         line = {"impl": "reference", "metric": metric, "value": cb["value"], "unit": "Mrays/s", "n_gpus": args.gpus,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": cb["seconds"] / args.steps * 1e3,
-                "higher_is_better": True, "scaling": wl["scaling"], "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "higher_is_better": True, "scaling": wl["scaling"], "vs_baseline": None, "dtype": "f32", "data": DATA_NOTE,
                 "config": config,
                 "cpu_baseline": {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")},
                 "e2e": {"value": cb["value"], "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
@@ -226,14 +241,15 @@ def main():
     frame()
     cst = pt.stats()
     pt.set_profiling(counters=False, time_kernels=False)
+    clocks = ClockSampler(local_rank)
+    if rank == 0:
+        clocks.start()            # before the warm-up steps: see ClockSampler.stop
     for _ in range(args.warmup):
         frame()
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
-    clocks = ClockSampler(local_rank)
-    if rank == 0:
-        clocks.start()
+    t_timed = time.monotonic()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     rays = 0
     launches = 0
@@ -247,7 +263,7 @@ def main():
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
-    clk = clocks.stop() if rank == 0 else None
+    clk = clocks.stop(since=t_timed) if rank == 0 else None
     ms = ev0.elapsed_time(ev1)
     # Per-launch timing of k_traverse (roofline): the SAME K frames again with CUDA events around every traversal launch.
     # In the timed region above the renderer runs the shadow-ray trace of bounce b on a second stream next to the
@@ -387,12 +403,12 @@ def main():
 
     cpu_baseline = None
     if world == 1 and not args.no_cpu:
-        cb = cpu_arm(args, sc, cam, wl, args.cpu_spp or 4, 1, 1)
+        cb = cpu_arm(args, sc, cam, wl, args.cpu_spp or 4, 2, 1, target_seconds=10.0)   # >= 2 frames, about 10 s of CPU work
         cpu_baseline = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample", "s_per_frame_scaled")}
 
     line = {"metric": metric, "value": value, "unit": "Mrays/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms / args.steps, "s_per_frame": ms / args.steps / 1e3, "higher_is_better": True, "scaling": wl["scaling"],
-            "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config, "clocks": clk, "e2e": e2e,
+            "vs_baseline": None, "dtype": "f32", "data": DATA_NOTE, "config": config, "clocks": clk, "e2e": e2e,
             "collective": ("b2rt_reduce_accum: one ncclReduce (fp32 sum) of the accumulation buffers per frame, issued by libb2rt.so "
                            f"(NCCL {b2rt.Comm.version()})" if world > 1 else None),
             "gpu_launches": launches_total, "roofline": roofline, "cpu_baseline": cpu_baseline,
