@@ -432,6 +432,26 @@ def test_cfg4_standin_material_mix_parity():
     pt.close()
 
 
+def test_cfg4_standin_full_mesh_parity():
+    """BASELINE configs[3] stand-in with the mesh at its FULL size (bunny subdivided twice, 457,228 glass triangles, two
+    mirror spheres; device-built BVH) at a small frame: HDR frame identical to the oracle's (own binary SAH BVH)."""
+    from b2rt.scene import cfg4_standin
+    sc = cfg4_standin(Scene.load(scene_path("CBbunny")), levels=2)
+    assert sc.n_tris > 450000
+    w, h = 96, 72
+    cam = place_camera(sc, w, h)
+    cfg = dict(ns_aa=2, max_ray_depth=8, ns_area_light=1, seed=13)
+    pt = b2rt.PathTracer(**cfg)
+    pt.set_scene(sc); pt.set_camera(cam); pt.set_frame_size(w, h)
+    pt.render()
+    img = pt.hdr()
+    ref = orc.OracleScene(sc, 4).render(cam, Config(**cfg), w, h)
+    assert np.isfinite(img).all() and img.max() > 0
+    rmse = float(np.sqrt(np.mean((img - ref) ** 2)))
+    assert rmse <= 1e-6 and float(np.abs(img - ref).max()) <= 1e-5, rmse
+    pt.close()
+
+
 def test_median_filter_and_progressive_renderer():
     sc = Scene.load(scene_path("CBspheres_lambertian"))
     w, h = 100, 75
