@@ -237,8 +237,9 @@ constexpr int PLOC_RADIUS = 16;
 struct PlocClusters { uint32_t* id; float4* lo; float4* hi; };
 
 __global__ void __launch_bounds__(256) k_ploc_init(BinTree T, const float4* __restrict__ geom, const uint32_t* __restrict__ sorted,
-                                                   uint32_t n_tris, float pad, PlocClusters C, uint32_t* size) {
+                                                   uint32_t n_tris, float pad, PlocClusters C, uint32_t* size, uint32_t* c_dev) {
   const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j == 0) c_dev[0] = T.n;   // cluster count of round 0 (the later rounds' counts are written by k_ploc_compact)
   if (j >= T.n) return;
   float l[3], h[3];
   prim_box(geom, sorted[j], n_tris, l, h);
@@ -250,7 +251,10 @@ __global__ void __launch_bounds__(256) k_ploc_init(BinTree T, const float4* __re
   C.id[j] = id; C.lo[j] = lo; C.hi[j] = hi;
 }
 
-__global__ void __launch_bounds__(256) k_ploc_nn(PlocClusters C, uint32_t c, uint32_t* nn) {
+// The clustering kernels read the round's cluster count from device memory (c_dev) and are launched with a grid sized
+// for an UPPER bound of it, so that several rounds can be enqueued back to back without the host reading the count.
+__global__ void __launch_bounds__(256) k_ploc_nn(PlocClusters C, const uint32_t* __restrict__ c_dev, uint32_t* nn) {
+  const uint32_t c = *c_dev;
   __shared__ float4 s_lo[256 + 2 * PLOC_RADIUS], s_hi[256 + 2 * PLOC_RADIUS];
   const int base = (int)(blockIdx.x * 256) - PLOC_RADIUS;
   for (int k = threadIdx.x; k < 256 + 2 * PLOC_RADIUS; k += 256) {
@@ -275,10 +279,11 @@ __global__ void __launch_bounds__(256) k_ploc_nn(PlocClusters C, uint32_t c, uin
 }
 
 // mutual nearest neighbours merge into a new internal node at the lower position; valid[i] = 1 for positions that stay
-__global__ void __launch_bounds__(256) k_ploc_merge(BinTree T, PlocClusters C, uint32_t c, const uint32_t* __restrict__ nn,
-                                                    uint32_t* size, uint32_t* merges, uint32_t* valid) {
+__global__ void __launch_bounds__(256) k_ploc_merge(BinTree T, PlocClusters C, const uint32_t* __restrict__ c_dev, uint32_t c_upper,
+                                                    const uint32_t* __restrict__ nn, uint32_t* size, uint32_t* merges, uint32_t* valid) {
+  const uint32_t c = *c_dev;
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= c) return;
+  if (i >= c) { if (i < c_upper) valid[i] = 0u; return; }   // (the compaction's scan runs over c_upper positions)
   const uint32_t j = nn[i];
   uint32_t keep = 1u;
   if (j != 0xFFFFFFFFu && nn[j] == i) {
@@ -299,9 +304,12 @@ __global__ void __launch_bounds__(256) k_ploc_merge(BinTree T, PlocClusters C, u
   valid[i] = keep;
 }
 
-__global__ void __launch_bounds__(256) k_ploc_compact(PlocClusters in, uint32_t c, const uint32_t* __restrict__ valid,
-                                                      const uint32_t* __restrict__ pos, PlocClusters out) {
+__global__ void __launch_bounds__(256) k_ploc_compact(PlocClusters in, const uint32_t* __restrict__ c_dev, const uint32_t* __restrict__ valid,
+                                                      const uint32_t* __restrict__ pos, PlocClusters out, uint32_t n,
+                                                      const uint32_t* __restrict__ merges, uint32_t* c_next) {
+  const uint32_t c = *c_dev;
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i == 0) *c_next = n - *merges;   // every merge of this round is counted: k_ploc_merge has finished
   if (i >= c || !valid[i]) return;
   const uint32_t p = pos[i];
   out.id[p] = in.id[i]; out.lo[p] = in.lo[i]; out.hi[p] = in.hi[i];
@@ -729,32 +737,40 @@ static int build_device_w(const b2rt_scene_desc& sc, uint32_t max_leaf, uint32_t
     uint8_t* scan_tmp = nullptr;
     B2RT_CUDA_OK(buf.alloc(&scan_tmp, scan_bytes));
     B2RT_CUDA_OK(cudaMemsetAsync(merges, 0, 4, s));
-    k_ploc_init<<<(n + 255) / 256, 256, 0, s>>>(T, geom, sorted, sc.n_tris, pad, C[0], size);
-    uint32_t c = n, done = 0;
-    int cur = 0, iters = 0;
+    constexpr int ROUNDS_PER_SYNC = 6, MAX_ROUNDS = 8192;
+    uint32_t* c_dev = nullptr;
+    B2RT_CUDA_OK(buf.alloc(&c_dev, (size_t)MAX_ROUNDS + ROUNDS_PER_SYNC + 1));
+    k_ploc_init<<<(n + 255) / 256, 256, 0, s>>>(T, geom, sorted, sc.n_tris, pad, C[0], size, c_dev);
+    uint32_t c = n, done = 0;   // c: the exact cluster count at the last read-back = an upper bound for the rounds after it
+    int cur = 0, iters = 0, syncs = 0;
     while (c > 1) {
       if (c <= PLOC_TAIL) {   // the remaining rounds in one CTA, no host round trips
         k_ploc_tail<<<1, 1024, 0, s>>>(T, C[cur], C[cur ^ 1], c, size, merges, nn);
         ++iters;
         break;
       }
+      // a batch of rounds between two read-backs of the count (a read-back costs more than a round of a mid-sized scene)
       const uint32_t g = (c + 255) / 256;
-      k_ploc_nn<<<g, 256, 0, s>>>(C[cur], c, nn);
-      k_ploc_merge<<<g, 256, 0, s>>>(T, C[cur], c, nn, size, merges, valid);
-      B2RT_CUDA_OK(cub::DeviceScan::ExclusiveSum(scan_tmp, scan_bytes, valid, pos, (int)c, s));
-      k_ploc_compact<<<g, 256, 0, s>>>(C[cur], c, valid, pos, C[cur ^ 1]);
+      for (int r = 0; r < ROUNDS_PER_SYNC; ++r, ++iters) {
+        k_ploc_nn<<<g, 256, 0, s>>>(C[cur], c_dev + iters, nn);
+        k_ploc_merge<<<g, 256, 0, s>>>(T, C[cur], c_dev + iters, c, nn, size, merges, valid);
+        B2RT_CUDA_OK(cub::DeviceScan::ExclusiveSum(scan_tmp, scan_bytes, valid, pos, (int)c, s));
+        k_ploc_compact<<<g, 256, 0, s>>>(C[cur], c_dev + iters, valid, pos, C[cur ^ 1], n, merges, c_dev + iters + 1);
+        cur ^= 1;
+      }
       B2RT_CUDA_OK(cudaMemcpyAsync(&done, merges, 4, cudaMemcpyDeviceToHost, s));
       B2RT_CUDA_OK(cudaStreamSynchronize(s));
+      ++syncs;
       if (n - done >= c) { set_error("gpu bvh build: PLOC made no progress"); return B2RT_ERR_INVALID; }
-      c = n - done; cur ^= 1;
-      if (++iters > 4096) { set_error("gpu bvh build: PLOC did not converge"); return B2RT_ERR_INVALID; }
+      c = n - done;
+      if (iters > MAX_ROUNDS) { set_error("gpu bvh build: PLOC did not converge"); return B2RT_ERR_INVALID; }
     }
     const uint32_t n_all = 2 * n - 1;
     k_ploc_first<<<(n_all + 255) / 256, 256, 0, s>>>(T, size, first_of);
     k_ploc_finish<<<(n_all + 255) / 256, 256, 0, s>>>(T, size, first_of, sorted, sorted2, leaf_lo, leaf_hi);
     k_ploc_leaf_boxes<<<(n + 255) / 256, 256, 0, s>>>(T, leaf_lo, leaf_hi);
     sorted = sorted2;
-    if (verbose) fprintf(stderr, "b2rt: gpu build PLOC: %d rounds with a host read-back (the last one finishes in one CTA)\n", iters);
+    if (verbose) fprintf(stderr, "b2rt: gpu build PLOC: %d rounds, %d host read-backs of the cluster count (the last round finishes in one CTA)\n", iters, syncs);
     lap("ploc tree");
   }
   // 6. wide collapse, one launch per wide level
