@@ -2,7 +2,7 @@
 // src/bvh.cpp:339-365, 275-337, 234-273, for scenes where the host build dominates set-up: the 10 M triangle soup
 // takes seconds on the host and tens of milliseconds here).
 //
-// Pipeline, everything on the device, one host read-back per tree level (a 4-byte count):
+// Pipeline, everything on the device; the host reads back a 4-byte count per wide-tree level and per six PLOC rounds:
 //   1. k_bounds          primitive boxes -> scene box + summed projected area (block reduction + ordered-int atomics)
 //   2. k_morton          63-bit Morton code of the box centre            3. cub::DeviceRadixSort (key, primitive)
 //   4. k_ploc_*          binary tree by parallel locally-ordered clustering over the Morton order (Meister & Bittner 2018;
