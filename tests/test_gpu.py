@@ -452,6 +452,18 @@ def test_cfg4_standin_full_mesh_parity():
     pt.close()
 
 
+def test_random_scenes_and_configurations_match_oracle():
+    """tools/fuzz_frames.py: random scenes (all material kinds, vertex normals, spheres, the three light kinds, optional
+    environment map) x random renderer configurations (spp, depth, light samples, wave size, BVH width / leaf / subtree
+    budget, host or device builder): every HDR frame identical to the oracle's."""
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, "tools", "fuzz_frames.py"), "12", "77"], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
+    assert "mismatches: 0" in r.stdout
+
+
 def test_median_filter_and_progressive_renderer():
     sc = Scene.load(scene_path("CBspheres_lambertian"))
     w, h = 100, 75
