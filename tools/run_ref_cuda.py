@@ -3,7 +3,7 @@
 sm_100a by oracle/build_ref.sh, driven headless by oracle/ref_cuda_driver.cpp) on the same B200, next to this repo's
 renderer at the reference's operating point: 512 x 512, 2 samples per pixel per frame, 3 surface interactions with
 next-event estimation at each (the reference traces a fixed script of 8 passes: 3 closest-hit + 5 shadow; here
-max_ray_depth 3, ns_area_light 2 = 3 closest-hit + up to 6 shadow rays per path).  Writes gpurun_out/ref_cuda_r01.json."""
+max_ray_depth 3, ns_area_light 2 = 3 closest-hit + up to 6 shadow rays per path).  Writes gpurun_out/ref_cuda_r01.json (copied to profiles/r0N_reference_cuda.json)."""
 import json
 import os
 import re
