@@ -50,7 +50,7 @@ class Stats(C.Structure):
                 ("bvh_bytes", C.c_uint64), ("node_visits_l0", C.c_uint64), ("leaf_prim_tests_l0", C.c_uint64),
                 ("queue_pushes_l0", C.c_uint64), ("staged_bytes_l0", C.c_uint64), ("hit_updates_l0", C.c_uint64),
                 ("traverse_launches_l0", C.c_uint64), ("ms_traverse_l0", C.c_double),
-                ("waves_retried", C.c_uint64), ("queues_grown", C.c_uint64)]
+                ("waves_retried", C.c_uint64), ("queues_grown", C.c_uint64), ("graph_replays", C.c_uint64)]
 
     def as_dict(self):
         return {n: getattr(self, n) for n, _ in self._fields_}

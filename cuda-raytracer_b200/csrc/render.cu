@@ -83,7 +83,7 @@ k_raygen(WaveParams wp, CamDev cam, PathBufs pb) {
   }
   if (slot >= n) return;
   const uint32_t pix = wp.pix0 + slot / wp.spp;
-  const uint32_t sample = wp.sample0 + (slot % wp.spp) * wp.sample_stride;
+  const uint32_t sample = __ldg(wp.sample_base) + wp.sample0 + (slot % wp.spp) * wp.sample_stride;
   const uint32_t x = pix % wp.width, y = pix / wp.width;
   const uint4 r = philox4x32_10(pix, sample, 0, 0, wp.k0, wp.k1);
   float jx = 0.5f, jy = 0.5f;
@@ -336,7 +336,7 @@ k_shade(WaveParams wp, SceneDev sc, PathBufs pb, uint32_t b) {
         const f3 wo_w = neg3(d);
         const f3 wo = mk3(dot3(wo_w, X), dot3(wo_w, Y), dot3(wo_w, Z));
         const uint32_t pix = wp.pix0 + slot / wp.spp;
-        const uint32_t sample = wp.sample0 + (slot % wp.spp) * wp.sample_stride;
+        const uint32_t sample = __ldg(wp.sample_base) + wp.sample0 + (slot % wp.spp) * wp.sample_stride;
 
         if (m_kind == B2RT_MAT_DIFFUSE || (EXT && m_kind == B2RT_MAT_GLOSSY)) {
           // direct lighting: src/pathtracer.cpp:439-478 + shadow ray (Task 4); the environment map is one more light
@@ -747,6 +747,9 @@ int Renderer::create(const b2rt_config* c) {
   stream = own_stream;
   B2RT_CUDA_OK(cudaEventCreate(&ev_start));
   B2RT_CUDA_OK(cudaEventCreate(&ev_done));
+  B2RT_CUDA_OK(cudaMalloc(&d_sample_base, 4));
+  B2RT_CUDA_OK(cudaHostAlloc(&h_sample_base, 4, cudaHostAllocDefault));
+  if (const char* e = getenv("B2RT_GRAPH")) graph_off = atoi(e) == 0;
   return B2RT_OK;
 }
 
@@ -772,6 +775,9 @@ void Renderer::release_wave() {
 
 void Renderer::destroy() {
   if (stream) cudaStreamSynchronize(stream);
+  if (graph_exec) { cudaGraphExecDestroy(graph_exec); graph_exec = nullptr; }
+  free_ptr(d_sample_base); d_sample_base = nullptr;
+  if (h_sample_base) { cudaFreeHost(h_sample_base); h_sample_base = nullptr; }
   release_wave();
   tracer.release();
   tracer2.release();
@@ -1140,7 +1146,7 @@ int Renderer::start() {
     for (uint64_t p0 = 0; p0 < n_pix; p0 += pix_chunk) {
       WaveParams wp;
       wp.pix0 = (uint32_t)p0; wp.n_pix = (uint32_t)std::min<uint64_t>(pix_chunk, n_pix - p0);
-      wp.spp = spp; wp.sample0 = cfg.sample_first + s0 * stride; wp.sample_stride = stride;
+      wp.spp = spp; wp.sample0 = s0 * stride; wp.sample_base = d_sample_base; wp.sample_stride = stride;
       wp.width = width; wp.height = height;
       wp.jitter = (cfg.ns_aa * stride) > 1 ? 1u : 0u;
       wp.k0 = (uint32_t)cfg.seed; wp.k1 = (uint32_t)(cfg.seed >> 32);
@@ -1156,11 +1162,87 @@ int Renderer::start() {
     B2RT_CUDA_OK(cudaMalloc(&wave_status, wave_status_cap * 4));
   }
   B2RT_CUDA_OK(cudaMemsetAsync(wave_status, 0, (waves.size() + 1) * 4, stream));
-  for (size_t w = 0; w < waves.size(); ++w) RCHECK(enqueue_wave(fc, waves[w], (uint32_t)w));
+  *h_sample_base = cfg.sample_first;
+  B2RT_CUDA_OK(cudaMemcpyAsync(d_sample_base, h_sample_base, 4, cudaMemcpyHostToDevice, stream));
+  // eager, capture or replay (see render.cuh)
+  const bool may_graph = !graph_off && !tracer.time_kernels;
+  const uint64_t sig = may_graph ? frame_signature(fc) : 0;
+  if (may_graph && graph_exec && sig == graph_sig) {
+    B2RT_CUDA_OK(cudaGraphLaunch(graph_exec, stream));
+    launches = g_launches;
+    tracer.launches = g_t1[0]; tracer.traverse_launches = g_t1[1]; tracer.traverse_launches_l0 = g_t1[2];
+    tracer2.launches = g_t2[0]; tracer2.traverse_launches = g_t2[1]; tracer2.traverse_launches_l0 = g_t2[2];
+    graph_replays++;
+  } else if (may_graph && sig == last_sig) {
+    // second identical frame in a row: capture it (every buffer it needs exists since the first one), then launch it
+    if (graph_exec) { cudaGraphExecDestroy(graph_exec); graph_exec = nullptr; }
+    cudaGraph_t g = nullptr;
+    int rc = B2RT_OK;
+    if (cudaStreamBeginCapture(stream, cudaStreamCaptureModeThreadLocal) == cudaSuccess) {
+      for (size_t w = 0; w < waves.size() && rc == B2RT_OK; ++w) rc = enqueue_wave(fc, waves[w], (uint32_t)w);
+      const cudaError_t ce = cudaStreamEndCapture(stream, &g);
+      if (rc == B2RT_OK && ce == cudaSuccess && g && cudaGraphInstantiate(&graph_exec, g, 0) == cudaSuccess) {
+        graph_sig = sig;
+        g_launches = launches;
+        g_t1[0] = tracer.launches; g_t1[1] = tracer.traverse_launches; g_t1[2] = tracer.traverse_launches_l0;
+        g_t2[0] = tracer2.launches; g_t2[1] = tracer2.traverse_launches; g_t2[2] = tracer2.traverse_launches_l0;
+      } else {
+        graph_exec = nullptr;
+      }
+      if (g) cudaGraphDestroy(g);
+    }
+    cudaGetLastError();   // (a failed capture leaves a sticky-looking error code behind; the eager path below is the answer to it)
+    if (graph_exec) {
+      B2RT_CUDA_OK(cudaGraphLaunch(graph_exec, stream));
+    } else {
+      graph_off = true;   // this renderer's frames cannot be captured: stay eager
+      launches = 0;
+      tracer.launches = tracer.traverse_launches = tracer.traverse_launches_l0 = 0;
+      tracer2.launches = tracer2.traverse_launches = tracer2.traverse_launches_l0 = 0;
+      for (size_t w = 0; w < waves.size(); ++w) RCHECK(enqueue_wave(fc, waves[w], (uint32_t)w));
+    }
+  } else {
+    for (size_t w = 0; w < waves.size(); ++w) RCHECK(enqueue_wave(fc, waves[w], (uint32_t)w));
+  }
+  last_sig = sig;
   B2RT_CUDA_OK(cudaGetLastError());
   B2RT_CUDA_OK(cudaEventRecord(ev_done, stream));
   running = true;
   return B2RT_OK;
+}
+
+// Everything a frame's launch sequence depends on besides the contents of device memory: the frame context (camera, scene
+// and list pointers, counts), the waves, both schedulers' buffers and launch shapes, the subtree levels, the mode flags.
+uint64_t Renderer::frame_signature(const FrameCtx& fc) const {
+  uint64_t h = 1469598103934665603ull;
+  auto mix = [&](const void* p, size_t n) { const uint8_t* b = (const uint8_t*)p; for (size_t i = 0; i < n; ++i) { h ^= b[i]; h *= 1099511628211ull; } };
+  auto mixv = [&](uint64_t v) { mix(&v, 8); };
+  // (struct padding is not hashed: field by field)
+  mix(&fc.cd.pos, sizeof fc.cd.pos); mix(&fc.cd.cx, sizeof fc.cd.cx); mix(&fc.cd.cy, sizeof fc.cd.cy); mix(&fc.cd.cz, sizeof fc.cd.cz);
+  mix(&fc.cd.tan_h, 4); mix(&fc.cd.tan_v, 4);
+  const SceneDev& sd = fc.sd;
+  mixv((uint64_t)sd.prim_geom); mixv((uint64_t)sd.tri_normals); mixv((uint64_t)sd.prim_material); mixv((uint64_t)sd.materials);
+  mixv((uint64_t)sd.lights); mixv((uint64_t)sd.light_area); mixv(sd.n_tris); mixv(sd.n_lights); mixv((uint64_t)sd.env); mixv(sd.env_w); mixv(sd.env_h);
+  const PathBufs& pb = fc.pb;
+  const void* ptrs[] = {pb.lo, pb.ld, pb.lh, pb.lslot, pb.no, pb.nd, pb.nh, pb.nslot, pb.thr, pb.rad, pb.s_o, pb.s_d, pb.s_hits, pb.s_contrib,
+                        pb.s_q0, pb.counts, accum, wave_status, totals, d_sample_base, (const void*)stream, (const void*)stream2};
+  for (const void* q : ptrs) mixv((uint64_t)q);
+  mixv(pb.list_cap); mixv(pb.shadow_cap); mixv(fc.max_depth); mixv(fc.S); mixv(overlap); mixv(have_glossy); mixv(shade_ctas); mixv(list_slack);
+  for (const WaveParams& w : waves) {
+    const uint32_t v[] = {w.pix0, w.n_pix, w.spp, w.sample0, w.sample_stride, w.width, w.height, w.jitter, w.k0, w.k1, w.max_depth, w.ns_area_light, w.S};
+    mix(v, sizeof v); mix(&w.eps, 4);
+  }
+  for (const Tracer* t : {&tracer, &tracer2}) {
+    const void* tp[] = {t->bvh.blob, t->bvh.treelets, t->cnt, t->seg_off, t->cursor, t->pairs, t->ids_sorted, t->chunks, t->ctrl, t->counters,
+                        t->sched_scratch, t->sl_n, t->sl_o[0], t->sl_o[1]};
+    for (const void* q : tp) mixv((uint64_t)q);
+    mixv(t->pair_cap); mixv(t->max_rays); mixv(t->chunk_cap); mixv(t->chunk_rays); mixv(t->chunk_min); mixv(t->chunks_per_cta); mixv(t->chunk0_max);
+    mixv(t->smem_bytes); mixv(t->stack_off); mixv(t->ctas_per_sm); mixv(t->num_sms); mixv(t->count_ctas); mixv(t->scatter_ctas);
+    mixv(t->collect_stats); mixv(t->time_kernels); mixv(t->slice_passes); mix(&t->slice_first, 4); mix(&t->slice_growth, 4); mix(t->slice_bbox, sizeof t->slice_bbox);
+    mixv(t->bvh.n_treelets); mixv(t->bvh.n_levels); mixv(t->bvh.width); mixv(t->bvh.max_treelet_bytes);
+    for (uint32_t L = 0; L < t->bvh.n_levels; ++L) { mixv(t->bvh.levels[L].first); mixv(t->bvh.levels[L].count); }
+  }
+  return h ? h : 1;
 }
 
 int Renderer::is_done() {
@@ -1262,7 +1344,7 @@ int Renderer::wait() {
     last.node_visits_l0 += t20.node_visits; last.leaf_prim_tests_l0 += t20.prim_tests; last.queue_pushes_l0 += t20.pushes;
     last.staged_bytes_l0 += t20.staged_bytes; last.hit_updates_l0 += t20.hit_updates;
   }
-  last.waves_retried = waves_retried; last.queues_grown = queues_grown;
+  last.waves_retried = waves_retried; last.queues_grown = queues_grown; last.graph_replays = graph_replays;
   last.kernel_launches = launches + tracer.launches + tracer2.launches;
   last.traverse_launches = tracer.traverse_launches + tracer2.traverse_launches;
   last.traverse_launches_l0 = tracer.traverse_launches_l0 + tracer2.traverse_launches_l0;

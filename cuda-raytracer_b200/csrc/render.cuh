@@ -10,7 +10,9 @@ namespace b2rt {
 struct WaveParams {
   uint32_t pix0, n_pix;       // pixel range of this wave
   uint32_t spp;               // samples per pixel in this wave
-  uint32_t sample0;           // global index of the wave's first sample
+  uint32_t sample0;           // index of the wave's first sample, relative to *sample_base
+  const uint32_t* sample_base;  // device word: the frame's first global sample (cfg.sample_first); behind a pointer so
+                              // that a captured frame (CUDA graph) can be replayed for the next samples
   uint32_t sample_stride;
   uint32_t width, height;
   uint32_t jitter;            // 0 -> pixel centre
@@ -53,6 +55,17 @@ struct Renderer {
   std::vector<WaveParams> waves;
   uint32_t* wave_status = nullptr; size_t wave_status_cap = 0;
   uint64_t waves_retried = 0, queues_grown = 0;
+  // A frame whose launch sequence is identical to the previous one (same scene buffers, camera, waves, schedulers) is
+  // captured into a CUDA graph on its second occurrence and replayed from the third on: at the reference's operating point
+  // (2 samples of a 512 x 512 frame per render() call) the frame is ~70 launches of a few microseconds each and the
+  // launch gaps are most of its time.  B2RT_GRAPH=0 turns it off; per-launch timing (b2rt_set_profiling) never uses it.
+  cudaGraphExec_t graph_exec = nullptr;
+  uint64_t graph_sig = 0, last_sig = 0;
+  bool graph_off = false;
+  uint64_t g_launches = 0, g_t1[3] = {0, 0, 0}, g_t2[3] = {0, 0, 0};   // launch counts of the captured frame
+  uint64_t graph_replays = 0;
+  uint32_t* d_sample_base = nullptr; uint32_t* h_sample_base = nullptr;   // device word + its page-locked source
+  uint64_t frame_signature(const FrameCtx& fc) const;
   bool pair_factor_from_env = false;
   uint32_t pair_factor = 4;   // scheduler queue capacity in pushes per ray and level; doubled by wait() after an overflow
   // wave buffers

@@ -136,13 +136,15 @@ __device__ __forceinline__ void block_excl_scan2(uint32_t a, uint32_t b, uint32_
 // One CTA per tile of 1024 subtrees; the tiles' running totals are chained through global memory (tile t waits for the
 // inclusive prefix of tile t - 1, adds its own totals, publishes): a level of 45 K subtrees is 45 hops of about a
 // microsecond instead of 45 iterations of one CTA (528 us on the 10 M-triangle soup, round 1).  Tiles are handed out by
-// a ticket, so a CTA only ever waits for one that is already running; flags carry the launch's epoch, so nothing has
-// to be cleared between launches.  scratch: [0] ticket, [1 + 3 t ...] = (flag, ray prefix, chunk prefix) of tile t.
+// a ticket, so a CTA only ever waits for one that is already running.  The last tile clears the flags again: when it
+// has seen its predecessor's flag, every earlier flag has been read by ITS successor, so the launch leaves the scratch
+// area as it found it (no per-launch argument: the launch can be replayed from a CUDA graph).
+// scratch: [0] ticket, [1 + 3 t ...] = (flag, ray prefix, chunk prefix) of tile t.
 __global__ void __launch_bounds__(1024, 1)
 k_schedule_level(uint32_t* __restrict__ cnt, uint32_t* __restrict__ seg_off, uint32_t* __restrict__ cursor,
                  uint4* __restrict__ chunks, uint32_t* __restrict__ ctrl, uint32_t first, uint32_t n, uint32_t chunk_rays,
                  uint32_t chunk_cap, uint32_t level, uint32_t pair_cap, uint32_t want_chunks, uint32_t chunk_min,
-                 uint32_t* __restrict__ scratch, uint32_t epoch) {
+                 uint32_t* __restrict__ scratch) {
   // A level with few rays gets smaller chunks, so that the launch still has `want_chunks` of them (a few per resident
   // CTA): with 1024-ray chunks a launch of 1 M rays is 1000 chunks for 592 CTAs and its second round runs on a
   // half-empty GPU.  The level's ray count is the pair count of the level above.
@@ -168,17 +170,18 @@ k_schedule_level(uint32_t* __restrict__ cnt, uint32_t* __restrict__ seg_off, uin
     uint32_t ro = 0, rc = 0;
     if (tile > 0) {
       volatile uint32_t* prev = scratch + 1 + 3 * (tile - 1);
-      while (prev[0] != epoch) { }
+      while (prev[0] == 0u) { }
       __threadfence();
       ro = prev[1]; rc = prev[2];
     }
     volatile uint32_t* mine = scratch + 1 + 3 * tile;
     mine[1] = ro + to; mine[2] = rc + tc;
     __threadfence();
-    mine[0] = epoch;
+    if (tile + 1 < n_tiles) mine[0] = 1u;
     s_run_off = ro; s_run_chunks = rc;
     if (tile + 1 == n_tiles) {   // the last ticket: every tile has one, so the counter can go back to zero
       scratch[0] = 0;
+      for (uint32_t k = 0; k + 1 < n_tiles; ++k) scratch[1 + 3 * k] = 0u;
       uint32_t run_chunks = rc + tc;
       if (run_chunks > chunk_cap) { run_chunks = chunk_cap; ctrl[CTRL_OVERFLOW] = 1; }
       ctrl[CTRL_NCHUNKS] = run_chunks;
@@ -1074,7 +1077,6 @@ int Tracer::init(const DeviceBVH& b, uint64_t max_rays_, uint32_t pair_factor) {
     cudaFree(sched_scratch); sched_scratch = nullptr;
     B2RT_CUDA_OK(cudaMalloc(&sched_scratch, (4 + 3 * (nt_cap / 1024 + 2)) * 4));
     B2RT_CUDA_OK(cudaMemset(sched_scratch, 0, (4 + 3 * (nt_cap / 1024 + 2)) * 4));
-    sched_epoch = 0;
   }
   if (chunk_alloc < chunk_cap) {
     cudaFree(chunks); chunks = nullptr;
@@ -1159,7 +1161,7 @@ int Tracer::trace(cudaStream_t s, const float4* ray_o, const float4* ray_d, unsi
       }
       k_schedule_level<<<std::max(1u, (lr.count + 1023) / 1024), 1024, 0, s>>>(cnt, seg_off, cursor, chunks, ctrl, lr.first, lr.count, chunk_rays,
                                           (uint32_t)chunk_cap, L, (uint32_t)pair_cap, num_sms * ctas_per_sm * chunks_per_cta, chunk_min,
-                                          sched_scratch, ++sched_epoch);
+                                          sched_scratch);
       launches += 2;
     }
     if (L > 0) {

@@ -40,7 +40,7 @@ struct Tracer {
   uint32_t* cnt = nullptr;        // [n_treelets] rays queued per subtree
   uint32_t* seg_off = nullptr;    // [n_treelets]
   uint32_t* cursor = nullptr;     // [n_treelets]
-  uint32_t* sched_scratch = nullptr; uint32_t sched_epoch = 0;   // k_schedule_level: ticket + per-tile (flag, prefixes)
+  uint32_t* sched_scratch = nullptr;   // k_schedule_level: ticket + per-tile (flag, prefixes)
   uint2* pairs = nullptr;         // [pair_cap] (subtree id, ray id)
   uint32_t* ids_sorted = nullptr; // [pair_cap] ray ids grouped by subtree (levels >= 1)
   uint4* chunks = nullptr;        // [chunk_cap] (subtree, first, count, -)

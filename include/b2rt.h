@@ -170,6 +170,9 @@ typedef struct b2rt_stats {
      waves rendered again, and how often the queues were enlarged (x2 per step, kept for later frames) */
   uint64_t waves_retried;
   uint64_t queues_grown;
+  /* frames of this renderer that were replayed from a captured CUDA graph so far (a frame whose launch sequence equals
+     the previous one's is captured on its second occurrence; B2RT_GRAPH=0 disables it) */
+  uint64_t graph_replays;
 } b2rt_stats;
 
 const char* b2rt_last_error(void);

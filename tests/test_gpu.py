@@ -452,6 +452,31 @@ def test_cfg4_standin_full_mesh_parity():
     pt.close()
 
 
+def test_progressive_frames_replayed_from_a_graph_match_oracle(monkeypatch):
+    """CudaRenderer.render() adds samples_per_frame samples per call; from the third call on the frame is replayed from a
+    captured CUDA graph with only the first sample index changed (a device word).  Five calls = the oracle's 10-spp
+    frame, and the same with graphs disabled, bit for bit."""
+    sc = Scene.load(scene_path("CBspheres_lambertian"))
+    w, h = 96, 72
+    cam = place_camera(sc, w, h)
+    imgs = []
+    for graphs in (True, False):
+        if not graphs:
+            monkeypatch.setenv("B2RT_GRAPH", "0")
+        r = b2rt.CudaRenderer(samples_per_frame=2, max_ray_depth=4, ns_area_light=1, median_threshold=0, seed=21)
+        r.allocOutputImage(w, h); r.loadScene(sc); r.setViewpoint(cam)
+        for _ in range(5):
+            r.render()
+        st = r.pt.stats()
+        assert (st["graph_replays"] == 3) if graphs else (st["graph_replays"] == 0), st
+        imgs.append(r.pt.hdr())
+        r.pt.close()
+    ref = orc.OracleScene(sc, 4).render(cam, Config(ns_aa=10, max_ray_depth=4, ns_area_light=1, seed=21), w, h)
+    assert np.array_equal(imgs[0], imgs[1])
+    rmse = float(np.sqrt(np.mean((imgs[0] - ref) ** 2)))
+    assert rmse <= 1e-6 and float(np.abs(imgs[0] - ref).max()) <= 1e-5, rmse
+
+
 def test_random_scenes_and_configurations_match_oracle():
     """tools/fuzz_frames.py: random scenes (all material kinds, vertex normals, spheres, the three light kinds, optional
     environment map) x random renderer configurations (spp, depth, light samples, wave size, BVH width / leaf / subtree
