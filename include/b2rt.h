@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define B2RT_ABI_VERSION 2   /* 2: b2rt_stats grew the level-0 fields and the overflow counters, b2rt_comm_*, b2rt_write_*, b2rt_bench_fp32 */
+#define B2RT_ABI_VERSION 2   /* 2: b2rt_stats grew the level-0 fields, the overflow counters and graph_replays; b2rt_comm_*, b2rt_write_*, b2rt_bench_fp32 */
 
 typedef enum b2rt_status {
   B2RT_OK = 0,
