@@ -73,6 +73,16 @@ def test_closest_hit_bit_exact(name, width, treelet_bytes, max_leaf):
     assert np.array_equal(t, tr)
     st = bvh.stats()
     assert st["kernel_launches"] >= 1 and st["subtree_visits"] >= len(org)
+    # any hit on every scene / width / subtree budget: occluded inside a random window <=> the oracle's closest hit
+    # restricted to that window exists
+    rng = np.random.default_rng(17)
+    bb = bvh.get_bbox()
+    diag = float(np.linalg.norm(bb[3:] - bb[:3]))
+    tmin = (rng.random(len(org)) * 0.1 * diag).astype(np.float32)
+    tmax = (tmin + rng.random(len(org)) * 0.6 * diag).astype(np.float32)
+    occ = bvh.occluded(org, dirs, tmin, tmax)
+    _, pw = o.intersect(org, dirs, tmin, tmax)
+    assert np.array_equal(occ, pw != MISS), f"{int(np.sum(occ != (pw != MISS)))} any-hit flags differ"
     bvh.close()
 
 
@@ -366,6 +376,38 @@ def test_dragon_class_standin_parity():
     pt.set_scene(sc); pt.set_camera(cam); pt.set_frame_size(w, h); pt.render()
     ref = o.render(cam, Config(ns_aa=2, max_ray_depth=8, ns_area_light=1, seed=4), w, h)
     assert float(np.sqrt(np.mean((pt.hdr() - ref) ** 2))) <= 1e-6
+
+
+def test_full_size_properties_cfg3():
+    """BASELINE configs[2] at full size (the dragon-class stand-in, 1920x1080, 256 spp, depth 8 -- bench.py's default
+    workload, BVH built on the device like there): determinism, linearity over two sample shards (the multi-GPU
+    decomposition), a one-sample shard of the same global stream against the oracle at full resolution, ray-count
+    conservation; the third frame of the same signature is replayed from a CUDA graph and must not change a bit."""
+    from b2rt.scene import cfg3_standin
+    sc = cfg3_standin(Scene.load(scene_path("CBbunny")))
+    w, h, spp, depth = 1920, 1080, 256, 8
+    cam = place_camera(sc, w, h)
+    pt = b2rt.PathTracer(ns_aa=spp, max_ray_depth=depth, ns_area_light=1, seed=1)
+    pt.set_scene(sc); pt.set_camera(cam); pt.set_frame_size(w, h)
+    pt.render(); full = pt.hdr(); st = pt.stats()
+    assert st["rays_camera"] == w * h * spp
+    assert st["rays_bounce"] < st["rays_camera"] * (depth - 1) and st["rays_shadow"] < st["rays_camera"] * depth
+    for _ in range(2):
+        pt.clear(); pt.render()
+        assert np.array_equal(pt.hdr(), full)                              # deterministic, eager and replayed
+    assert pt.stats()["graph_replays"] >= 1
+    halves = []
+    for r in range(2):
+        pt.set_config(ns_aa=spp // 2, sample_first=r, sample_stride=2)
+        pt.clear(); pt.render(); halves.append(pt.hdr())
+    np.testing.assert_allclose(0.5 * (halves[0] + halves[1]), full, rtol=1e-4, atol=1e-5)
+    pt.set_config(ns_aa=1, sample_first=201, sample_stride=256)
+    pt.clear(); pt.render(); one = pt.hdr()
+    ref = orc.OracleScene(sc, 4).render(cam, Config(ns_aa=1, max_ray_depth=depth, ns_area_light=1, seed=1, sample_first=201,
+                                                    sample_stride=256), w, h)
+    assert float(np.sqrt(np.mean((one - ref) ** 2))) <= 1e-6
+    assert float(np.abs(one - ref).max()) <= 1e-5
+    pt.close()
 
 
 @pytest.mark.parametrize("name", ["CBbunny", "CBspheres", "CBcoil"])
