@@ -529,73 +529,125 @@ struct PartParams {
   uint32_t* overflow;
 };
 
+// One WARP per subtree root.  The packing itself is sequential (every decision moves the running byte / node counts),
+// but what made the one-thread version slow was three dependent global-memory latencies per node (queue entry -> child
+// references -> the children's subtree sizes): 286 us per launch on the cfg3 stand-in whatever the number of roots.
+// Here the breadth-first queue lives in shared memory and a batch of 32 / W queue nodes is loaded at once, one lane per
+// (node, child); the decisions then run over the batch in the same order as before with the lanes' values fetched by
+// shuffles (every lane keeps the same running state), the primitives of a leaf child are placed by all lanes, and the
+// batch's exits take ONE atomic.  Same decisions in the same order, so the slabs are byte-identical to the old kernel's.
+constexpr int PART_WARPS = 2;
+template <int W> constexpr uint32_t PART_QUEUE_V = max_treelet_nodes(W);
 template <int W>
-__global__ void __launch_bounds__(64) k_partition(BinTree T, WideTmp Wt, PartParams P) {
-  const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
-  if (k >= P.n_roots) return;
+__global__ void __launch_bounds__(PART_WARPS * 32) k_partition(BinTree T, WideTmp Wt, PartParams P) {
   constexpr uint32_t NB = 32u * W + (uint32_t)B2RT_NODE_PAD;   // = node_bytes(W)
-  constexpr uint32_t PAD = 28 * W;            // byte offset of a node's unused tail (queue bookkeeping while building)
+  constexpr uint32_t PAD = 28 * W;            // byte offset of a node's unused tail
+  constexpr uint32_t NPB = 32 / W;            // queue nodes per batch
+  constexpr uint32_t ROWS16 = 24 * W / 16;    // 16-byte words of a node's box rows
+  constexpr uint32_t FULL = 0xffffffffu;
+  __shared__ uint2 s_queue[PART_WARPS][PART_QUEUE_V<W>];   // (wide index, depth | whole << 8)
+  __shared__ uint2 s_exit[PART_WARPS][32];                      // this batch's exits: (slab byte offset of the reference, wide index)
+  const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t k = blockIdx.x * PART_WARPS + warp;
+  if (k >= P.n_roots) return;
   const uint32_t tid = P.first_id + k;
   uint8_t* slab = P.slabs + (size_t)tid * P.stride;
-  // the slab's node array doubles as the breadth-first queue: node q's tail holds (wide index, depth | whole << 8)
+  uint2* Q = s_queue[warp];
+  uint2* X = s_exit[warp];
+  const uint32_t root = P.roots[k];
   uint32_t n_nodes = 1, committed = 1, n_prims = 0;
-  uint64_t used = NB + (uint64_t)Wt.own_prims[P.roots[k]] * PRIM_BYTES;
-  { uint32_t* tail = reinterpret_cast<uint32_t*>(slab + PAD); tail[0] = P.roots[k]; tail[1] = 1u; }
-  for (uint32_t q = 0; q < n_nodes; ++q) {
-    uint8_t* node = slab + (size_t)q * NB;
-    uint32_t* tail = reinterpret_cast<uint32_t*>(node + PAD);
-    const uint32_t widx = tail[0], depth = tail[1] & 0xFFu; const bool whole = (tail[1] >> 8) != 0;
-    const uint4* src = reinterpret_cast<const uint4*>(Wt.nodes + (size_t)widx * NB);
-    uint4* dst = reinterpret_cast<uint4*>(node);
-#pragma unroll
-    for (int v = 0; v < (int)(24 * W / 16); ++v) dst[v] = src[v];
-    const uint32_t* srefs = reinterpret_cast<const uint32_t*>(Wt.nodes + (size_t)widx * NB + 24 * W);
-    uint32_t* drefs = reinterpret_cast<uint32_t*>(node + 24 * W);
-    tail[0] = 0; tail[1] = 0;
-    for (int c = 0; c < W; ++c) {
-      const uint32_t r = srefs[c];
-      if (r == REF_EMPTY_WORD) { drefs[c] = r; continue; }
+  uint64_t used = NB + (uint64_t)Wt.own_prims[root] * PRIM_BYTES;
+  if (lane == 0) Q[0] = make_uint2(root, 1u);
+  __syncwarp();
+  for (uint32_t q0 = 0, nb = 0; q0 < n_nodes; q0 += nb) {
+    nb = min(NPB, n_nodes - q0);   // the queue grows while the batch is decided; the next batch starts where this one ends
+    // ---- load phase: lane (j, c) reads child c of queue node q0 + j and what the decision needs to know about it
+    const uint32_t j = lane / W, c = lane % W;
+    const bool valid = j < nb;
+    const uint2 qe = valid ? Q[q0 + j] : make_uint2(0u, 0u);
+    uint32_t r = REF_EMPTY_WORD, m0 = 0, m1 = 0, m2 = 0, m3 = 0;
+    if (valid) r = reinterpret_cast<const uint32_t*>(Wt.nodes + (size_t)qe.x * NB + 24 * W)[c];
+    if (r != REF_EMPTY_WORD) {
       const uint32_t pay = r & 0x3FFFFFFFu;
       if ((r >> 30) == REF_LEAF) {
-        const uint32_t first = pay >= T.n - 1 ? pay - (T.n - 1) : T.first[pay];
-        const uint32_t cnt = pay >= T.n - 1 ? 1u : T.last[pay] - first + 1u;
-        drefs[c] = (REF_LEAF << 30) | ((cnt - 1u) << 24) | n_prims;
-        for (uint32_t p = 0; p < cnt; ++p) P.prim_dest[first + p] = make_uint2(tid, n_prims + p);
-        n_prims += cnt;
-        continue;
-      }
-      // internal child: whole subtree / partial / exit (host builder's rules, breadth-first instead of by area)
-      const uint32_t sb = Wt.sub_bytes[pay], sn = Wt.sub_nodes[pay], sh = Wt.height[pay];
-      bool take = whole, take_whole = whole;
-      if (!take) {
-        if (used + sb <= P.budget && depth + sh <= P.depth_limit && (uint64_t)committed + sn <= P.node_limit) {
-          take = take_whole = true; used += sb; committed += sn;
-        } else {
-          const bool fits_alone = sb <= P.budget && sh <= P.depth_limit && sn <= P.node_limit;
-          const uint64_t own = NB + (uint64_t)Wt.own_prims[pay] * PRIM_BYTES;
-          if (!fits_alone && used + own <= P.budget && depth + 1 <= P.depth_limit && committed < P.node_limit) {
-            take = true; used += own; committed += 1;
-          }
-        }
-      }
-      if (take) {
-        uint32_t* ct = reinterpret_cast<uint32_t*>(slab + (size_t)n_nodes * NB + PAD);
-        ct[0] = pay; ct[1] = (depth + 1u) | (take_whole ? 0x100u : 0u);
-        drefs[c] = (REF_INTERNAL << 30) | n_nodes;
-        ++n_nodes;
+        m0 = pay >= T.n - 1 ? pay - (T.n - 1) : T.first[pay];                // first sorted position
+        m1 = pay >= T.n - 1 ? 1u : T.last[pay] - m0 + 1u;                    // primitive count
       } else {
-        const uint32_t e = atomicAdd(P.next_count, 1u);
-        if (P.next_first_id + e >= P.cap_subtrees) { *P.overflow = 2; drefs[c] = REF_EMPTY_WORD; continue; }
-        P.next_roots[e] = pay;
-        drefs[c] = (REF_EXIT << 30) | (P.next_first_id + e);
+        m0 = Wt.sub_bytes[pay]; m1 = Wt.sub_nodes[pay]; m2 = Wt.height[pay]; m3 = Wt.own_prims[pay];
       }
     }
+    // box rows of the batch's nodes, tails cleared
+    for (uint32_t i = lane; i < nb * ROWS16; i += 32) {
+      const uint32_t jj = i / ROWS16, v = i % ROWS16;
+      reinterpret_cast<uint4*>(slab + (size_t)(q0 + jj) * NB)[v] = reinterpret_cast<const uint4*>(Wt.nodes + (size_t)Q[q0 + jj].x * NB)[v];
+    }
+    if (lane < nb) { uint32_t* tail = reinterpret_cast<uint32_t*>(slab + (size_t)(q0 + lane) * NB + PAD); tail[0] = 0; tail[1] = 0; }
+    // ---- decisions, in queue / child order
+    uint32_t n_ex = 0;
+    for (uint32_t jj = 0; jj < nb; ++jj) {
+      const uint32_t dw = __shfl_sync(FULL, qe.y, jj * W);
+      const uint32_t depth = dw & 0xFFu; const bool whole = (dw >> 8) != 0;
+      const uint32_t ref_off = (q0 + jj) * NB + 24 * W;   // slab byte offset of the node's child references
+#pragma unroll
+      for (uint32_t cc = 0; cc < (uint32_t)W; ++cc) {
+        const uint32_t src = jj * W + cc;
+        const uint32_t rr = __shfl_sync(FULL, r, src);
+        const uint32_t a0 = __shfl_sync(FULL, m0, src), a1 = __shfl_sync(FULL, m1, src);
+        const uint32_t a2 = __shfl_sync(FULL, m2, src), a3 = __shfl_sync(FULL, m3, src);
+        uint32_t* dref = reinterpret_cast<uint32_t*>(slab + ref_off) + cc;
+        if (rr == REF_EMPTY_WORD) { if (lane == 0) *dref = rr; continue; }
+        const uint32_t pay = rr & 0x3FFFFFFFu;
+        if ((rr >> 30) == REF_LEAF) {
+          if (lane == 0) *dref = (REF_LEAF << 30) | ((a1 - 1u) << 24) | n_prims;
+          for (uint32_t p = lane; p < a1; p += 32) P.prim_dest[a0 + p] = make_uint2(tid, n_prims + p);
+          n_prims += a1;
+          continue;
+        }
+        // internal child: whole subtree / partial / exit (host builder's rules, breadth-first instead of by area)
+        const uint32_t sb = a0, sn = a1, sh = a2;
+        bool take = whole, take_whole = whole;
+        if (!take) {
+          if (used + sb <= P.budget && depth + sh <= P.depth_limit && (uint64_t)committed + sn <= P.node_limit) {
+            take = take_whole = true; used += sb; committed += sn;
+          } else {
+            const bool fits_alone = sb <= P.budget && sh <= P.depth_limit && sn <= P.node_limit;
+            const uint64_t own = NB + (uint64_t)a3 * PRIM_BYTES;
+            if (!fits_alone && used + own <= P.budget && depth + 1 <= P.depth_limit && committed < P.node_limit) {
+              take = true; used += own; committed += 1;
+            }
+          }
+        }
+        if (take) {
+          if (lane == 0) { Q[n_nodes] = make_uint2(pay, (depth + 1u) | (take_whole ? 0x100u : 0u)); *dref = (REF_INTERNAL << 30) | n_nodes; }
+          ++n_nodes;
+        } else {
+          if (lane == 0) X[n_ex] = make_uint2(ref_off + cc * 4u, pay);
+          ++n_ex;
+        }
+      }
+    }
+    __syncwarp();
+    // ---- the batch's exits become subtree roots of the next level: one reservation
+    if (n_ex) {
+      uint32_t e0 = 0;
+      if (lane == 0) e0 = atomicAdd(P.next_count, n_ex);
+      e0 = __shfl_sync(FULL, e0, 0);
+      if (lane < n_ex) {
+        const uint2 x = X[lane];
+        uint32_t* dref = reinterpret_cast<uint32_t*>(slab + x.x);
+        if (P.next_first_id + e0 + lane >= P.cap_subtrees) { *P.overflow = 2; *dref = REF_EMPTY_WORD; }
+        else { P.next_roots[e0 + lane] = x.y; *dref = (REF_EXIT << 30) | (P.next_first_id + e0 + lane); }
+      }
+      __syncwarp();
+    }
   }
-  TreeletDesc d;
-  d.offset16 = 0;   // assigned by the compaction
-  d.bytes = (uint32_t)(((uint64_t)n_nodes * NB + (uint64_t)n_prims * PRIM_BYTES + 15u) & ~15ull);
-  d.n_nodes = n_nodes; d.n_prims = n_prims;
-  P.descs[tid] = d;
+  if (lane == 0) {
+    TreeletDesc d;
+    d.offset16 = 0;   // assigned by the compaction
+    d.bytes = (uint32_t)(((uint64_t)n_nodes * NB + (uint64_t)n_prims * PRIM_BYTES + 15u) & ~15ull);
+    d.n_nodes = n_nodes; d.n_prims = n_prims;
+    P.descs[tid] = d;
+  }
 }
 
 // slabs -> dense blob (one CTA per subtree, node part only; primitives are gathered by k_copy_prims)
@@ -835,7 +887,7 @@ static int build_device_w(const b2rt_scene_desc& sc, uint32_t max_leaf, uint32_t
     P.slabs = slabs; P.stride = stride; P.descs = descs_tmp; P.roots = r_a; P.n_roots = n_roots; P.first_id = first_id;
     P.next_roots = r_b; P.next_count = ctr + 2; P.next_first_id = first_id + n_roots; P.cap_subtrees = cap_subtrees;
     P.prim_dest = prim_dest; P.budget = treelet_bytes; P.depth_limit = depth_limit; P.node_limit = node_limit; P.overflow = ctr + 1;
-    k_partition<W><<<(n_roots + 63) / 64, 64, 0, s>>>(T, Wt, P);
+    k_partition<W><<<(n_roots + PART_WARPS - 1) / PART_WARPS, PART_WARPS * 32, 0, s>>>(T, Wt, P);
     uint32_t h[2];
     B2RT_CUDA_OK(cudaMemcpyAsync(h, ctr + 1, 8, cudaMemcpyDeviceToHost, s));
     B2RT_CUDA_OK(cudaStreamSynchronize(s));
