@@ -268,7 +268,7 @@ int b2rt_bvh_build_device(const b2rt_scene_desc* scene, uint32_t max_leaf_size, 
   B2RT_BVH_OK(cudaStreamCreateWithFlags(&b->stream, cudaStreamNonBlocking));
   int rc = build_wide_bvh_device(scene, max_leaf_size, width, treelet_bytes, b->stream, &b->dbvh, &b->host_meta);
   if (rc) { b2rt_bvh_destroy(b); return rc; }
-  b->max_leaf = max_leaf_size ? max_leaf_size : 4; b->treelet_budget = treelet_bytes;
+  b->max_leaf = max_leaf_size ? max_leaf_size : 3; b->treelet_budget = treelet_bytes;
   B2RT_BVH_OK(cudaMalloc(&b->n_dev, 4));
   b->tracer.bvh = b->dbvh;
   b->tracer.collect_stats = true;

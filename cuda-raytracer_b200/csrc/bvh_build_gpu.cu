@@ -944,7 +944,10 @@ int build_wide_bvh_device(const b2rt_scene_desc* sc, uint32_t max_leaf, uint32_t
   const uint64_t n = (uint64_t)sc->n_tris + sc->n_spheres;
   if (width == 0) width = 4;
   if (width != 4 && width != 8) { set_error("the device builder makes 4- or 8-wide trees (widths 2 and 16: host builder)"); return B2RT_ERR_INVALID; }
-  if (max_leaf == 0) max_leaf = 4;
+  // default leaf size of the device builder: 3 (measured against 2 / 4 / 6 / 8 and against the host builder's SAH-cost leaf
+  // termination applied to the PLOC tree's own splits, on cfg2, the cfg3 / cfg4 stand-ins and the 10 M soup:
+  // profiles/r02_sweep_device_leaf.txt)
+  if (max_leaf == 0) max_leaf = 3;
   if (max_leaf > 64) { set_error("max_leaf_size must be <= 64"); return B2RT_ERR_INVALID; }
   if (n == 0) { set_error("gpu bvh build: empty scene"); return B2RT_ERR_INVALID; }
   if (n >= (1u << 29)) { set_error("gpu bvh build: too many primitives"); return B2RT_ERR_INVALID; }

@@ -115,7 +115,7 @@ typedef struct b2rt_config {
   uint64_t seed;             /* counter-based RNG key; stream = (pixel, sample, bounce) */
   float ray_eps;             /* t_min offset of secondary rays; 0 -> 1e-4 */
   uint32_t bvh_width;        /* 2, 4, 8 or 16 (2 and 16: host builder only; they exist for the width sweep); 0 -> default (4) */
-  uint32_t max_leaf_size;    /* BVHAccel max_leaf_size (src/bvh.h:111); 0 -> default (4) */
+  uint32_t max_leaf_size;    /* BVHAccel max_leaf_size (src/bvh.h:111); 0 -> default (host builder: 4, ended earlier by SAH cost; device builder: 3) */
   uint32_t treelet_bytes;    /* shared-memory subtree budget; 0 -> default */
   uint32_t max_wave_paths;   /* paths in flight per wave; 0 -> default */
   uint32_t median_threshold; /* 3x3 median when total spp < this (POST_PROCESS_THRESHOLD,
