@@ -232,7 +232,10 @@ __global__ void __launch_bounds__(256) k_refit(BinTree T, const float4* __restri
 // (internal i in [0, n-1), leaves n-1+j; merge k gets id n-2-k, so the root -- the last merge -- is 0); afterwards the
 // leaves are renumbered in depth-first order so that every subtree covers a contiguous primitive range (first / last),
 // which is what the collapse / partition kernels read.
-constexpr int PLOC_RADIUS = 16;
+#ifndef B2RT_PLOC_RADIUS
+#define B2RT_PLOC_RADIUS 8
+#endif
+constexpr int PLOC_RADIUS = B2RT_PLOC_RADIUS;
 
 struct PlocClusters { uint32_t* id; float4* lo; float4* hi; };
 
