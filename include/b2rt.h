@@ -198,7 +198,8 @@ int b2rt_bvh_build(const b2rt_scene_desc* scene, uint32_t max_leaf_size, uint32_
  * tree, bottom-up boxes, wide collapse, subtree packing and serialisation all as CUDA kernels).
  * Replaces the same reference functions as b2rt_bvh_build; meant for scenes whose host build
  * dominates set-up.  The binary tree is built by parallel locally-ordered clustering (PLOC) over the Morton
- * order; rays trace 1-4 % slower than on the host builder's SAH tree (10 M soup: 6-9 %). */
+ * order (search radius 8, leaves of at most 3 primitives by default); rays trace as fast as on the host builder's
+ * SAH tree (cfg2 equal, cfg3 stand-in 2-3 % faster, 10 M soup equal / 10 % faster). */
 int b2rt_bvh_build_device(const b2rt_scene_desc* scene, uint32_t max_leaf_size, uint32_t width,
                           uint32_t treelet_bytes, int32_t device, b2rt_bvh** out);
 /* Structural check of the BVH a handle holds (either builder): the subtree blobs are read back
