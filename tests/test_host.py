@@ -430,3 +430,41 @@ def test_load_dae_accepts_glossy(tmp_path):
     out = tmp_path / "glossy.b2s"
     subprocess.check_call([sys.executable, os.path.join(ROOT, "tools", "dae2scene.py"), str(dae), str(out)])
     _same_scene(a, Scene.load(str(out)))
+
+
+def test_ctypes_mirror_matches_the_header_layout(tmp_path):
+    """b2rt/_abi.py restates the structs of include/b2rt.h by hand: every field's name, offset and size is compared with
+    what the C compiler makes of the header (a field added on one side only shifts everything behind it silently)."""
+    import ctypes as C
+    import re
+    import subprocess
+    from b2rt import _abi
+    pairs = [("b2rt_material", _abi.Material), ("b2rt_light", _abi.Light), ("b2rt_scene_desc", _abi.SceneDesc),
+             ("b2rt_camera", _abi.Camera), ("b2rt_config", _abi.Config), ("b2rt_stats", _abi.Stats),
+             ("b2rt_scene_file", _abi.SceneFile)]
+    header = open(os.path.join(ROOT, "include", "b2rt.h")).read()
+    lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "b2rt.h"', 'int main(void) {']
+    for cname, cls in pairs:
+        body = re.search(r"typedef struct %s \{(.*?)\} %s;" % (cname, cname), header, re.S).group(1)
+        body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
+        c_fields = []
+        for decl in body.split(";"):
+            if decl.strip():   # "float a[3], b" -> a, b
+                parts = decl.split(",")
+                names = [parts[0].strip().split()[-1]] + [q.strip() for q in parts[1:]]
+                c_fields += [re.sub(r"\[.*\]", "", q).lstrip("*").strip() for q in names]
+        assert c_fields == [n for n, _ in cls._fields_], (cname, c_fields)
+        lines.append(f'  printf("{cname} %zu\\n", sizeof({cname}));')
+        for f in c_fields:
+            lines.append(f'  printf("{cname}.{f} %zu %zu\\n", offsetof({cname}, {f}), sizeof((({cname}*)0)->{f}));')
+    lines += ['  return 0;', '}']
+    src = tmp_path / "layout.c"
+    src.write_text("\n".join(lines))
+    exe = tmp_path / "layout"
+    subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), "-o", str(exe), str(src)])
+    got = dict((ln.split()[0], [int(x) for x in ln.split()[1:]]) for ln in subprocess.check_output([str(exe)], text=True).splitlines())
+    for cname, cls in pairs:
+        assert got[cname] == [C.sizeof(cls)], (cname, got[cname], C.sizeof(cls))
+        for n, _ in cls._fields_:
+            fd = getattr(cls, n)
+            assert got[f"{cname}.{n}"] == [fd.offset, fd.size], (cname, n, got[f"{cname}.{n}"], fd.offset, fd.size)
