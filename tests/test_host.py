@@ -468,3 +468,22 @@ def test_ctypes_mirror_matches_the_header_layout(tmp_path):
         for n, _ in cls._fields_:
             fd = getattr(cls, n)
             assert got[f"{cname}.{n}"] == [fd.offset, fd.size], (cname, n, got[f"{cname}.{n}"], fd.offset, fd.size)
+
+
+def test_bench_reference_arm_prints_the_contract_line():
+    """`bench.py --impl reference` (the CPU arm the driver runs beside the GPU arm): one JSON line on stdout with the
+    GPU arm's metric / unit / config keys, `impl: reference`, a `cpu_baseline` describing the run and a zero-copy `e2e`."""
+    import json
+    import subprocess
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--workload", "cfg2", "--cpu-spp", "1",
+                          "--steps", "1", "--warmup", "0"], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [ln for ln in out.stdout.splitlines() if ln.strip()]
+    assert len(lines) == 1, out.stdout
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["metric"] == "Mrays/s (all bounces)" and d["unit"] == "Mrays/s"
+    assert d["higher_is_better"] is True and d["n_gpus"] == 1 and d["steps"] == 1 and d["value"] > 0
+    assert "CBbunny" in d["config"]["workload"] and "BASELINE configs[1]" in d["config"]["workload"]
+    cb = d["cpu_baseline"]
+    assert cb["kind"] == "port" and cb["cores"] == (os.cpu_count() or 1) and "1 of 64 spp" in cb["sample"] and cb["value"] == d["value"]
+    assert d["e2e"]["value"] == d["value"] and d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
