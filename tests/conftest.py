@@ -11,6 +11,11 @@ sys.path.insert(0, ROOT)
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
+    # a fresh checkout has no built artefacts (they are git-ignored): build them once, like __graft_entry__.build()
+    need = [os.path.join(ROOT, "cuda-raytracer_b200", "libb2rt.so"), os.path.join(ROOT, "oracle", "liboracle.so")]
+    if not all(os.path.exists(f) for f in need):
+        import __graft_entry__
+        __graft_entry__.build()
 
 
 @pytest.fixture(scope="session")
